@@ -1,0 +1,71 @@
+"""ctypes loader for libhevcb200.so (built in-tree by hevcbitstream_b200/csrc/Makefile)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhevcb200.so")
+
+HEVCB_OK = 0
+ERRORS = {
+    -100: "HEVCB_E_NODEVICE",
+    -101: "HEVCB_E_CUDA",
+    -102: "HEVCB_E_ARG",
+    -103: "HEVCB_E_ALIGN",
+    -104: "HEVCB_E_CAPACITY",
+    -105: "HEVCB_E_NOMEM",
+}
+
+
+class HevcbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class ScanSummary(C.Structure):
+    _fields_ = [
+        ("n_nals", C.c_int64),
+        ("n_terminated", C.c_int64),
+        ("last_rc", C.c_int32),
+        ("overflow", C.c_int32),
+        ("last_start", C.c_int64),
+        ("last_end", C.c_int64),
+        ("rbsp_bytes", C.c_int64),
+        ("n_epb", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; fails loudly when it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C hevcbitstream_b200/csrc` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.hevcb_create.restype = C.c_int
+    L.hevcb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.hevcb_destroy.restype = None
+    L.hevcb_destroy.argtypes = [vp]
+    L.hevcb_last_error.restype = C.c_char_p
+    L.hevcb_last_error.argtypes = [vp]
+    L.hevcb_version.restype = C.c_int
+    L.hevcb_launch_count.restype = i64
+    L.hevcb_launch_count.argtypes = [vp]
+    L.hevcb_sm_count.restype = C.c_int
+    L.hevcb_sm_count.argtypes = [vp]
+    L.hevcb_scan_strip_device.restype = C.c_int
+    L.hevcb_scan_strip_device.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.hevcb_scan_strip_host.restype = C.c_int
+    L.hevcb_scan_strip_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(ScanSummary)]
+    _lib = L
+    return L

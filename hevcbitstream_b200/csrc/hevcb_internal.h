@@ -1,0 +1,65 @@
+// hevcb_internal.h -- context object and helpers shared by the translation units of libhevcb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hevcb.h"
+
+struct hevcb_devbuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct hevcb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // scan scratch: [0,64) counters, then one 16-byte state word per tile
+    hevcb_devbuf scan_scratch;
+    // staging used by the *_host entry points
+    hevcb_devbuf h_in, h_rbsp, h_a0, h_a1, h_a2, h_a3, h_misc;
+    void* pinned = nullptr; // small pinned block for summaries
+    size_t pinned_bytes = 0;
+    cudaStream_t stream = nullptr; // stream used by *_host entry points
+    int scan_blocks_per_sm = 0;
+};
+
+extern char g_hevcb_create_error[512];
+
+#define HEVCB_SET_ERR(ctx, ...)                                         \
+    do {                                                                \
+        if (ctx) { snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); } \
+    } while (0)
+
+#define HEVCB_CUDA(ctx, call)                                                                          \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            HEVCB_SET_ERR(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return HEVCB_E_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+// grow-only device buffer
+static inline int hevcb_reserve(hevcb_ctx* ctx, hevcb_devbuf* b, size_t bytes)
+{
+    if (b->bytes >= bytes && b->p) { return HEVCB_OK; }
+    if (b->p) { cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&b->p, want);
+    if (e != cudaSuccess) {
+        HEVCB_SET_ERR(ctx, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        b->p = nullptr;
+        return HEVCB_E_NOMEM;
+    }
+    b->bytes = want;
+    return HEVCB_OK;
+}
+
+// kernels / launchers implemented in the .cu files
+int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int64_t* d_nal_start, int64_t* d_nal_end,
+                            int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
+                            hevcb_scan_summary* d_summary, cudaStream_t stream);

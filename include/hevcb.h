@@ -1,0 +1,109 @@
+/*
+ * hevcb.h -- C ABI of libhevcb200: batched, B200-native (sm_100a) entry points for the bitstream hot
+ * path of leslie-wang/hevcbitstream.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Each entry point replaces a per-NAL loop over the reference's functions (file:line in the reference):
+ *
+ *   hevcb_scan_strip_*   while (find_nal_unit(p, sz, &s, &e) > 0) ...      h264_nal.c:38-76, loop hevc_analyze.c:135-176
+ *                        + nal_to_rbsp(nal, &nal_size, rbsp, &rbsp_size)   h264_nal.c:147-200 (called at hevc_stream.c:165)
+ *   hevcb_insert_*       rbsp_to_nal(rbsp, &rbsp_size, nal, &nal_size)     h264_nal.c:92-132   (called at hevc_stream.c:1326)
+ *   hevcb_parse_*        read_hevc_nal_unit(h, buf, size)                  hevc_stream.c:155-241 (+ :243-1218, bs.h:126-221)
+ *   hevcb_materialize    the hevc_stream_t state read_hevc_nal_unit leaves behind (hevc_stream.h:556-569)
+ *   hevcb_rewrite_*      read -> edit -> write_hevc_nal_unit -> rbsp_to_nal   hevc_stream.c:1249-1335
+ *
+ * There is NO CPU implementation behind these calls: every one of them fails with HEVCB_E_NODEVICE
+ * when no CUDA device is usable.  `_device` variants take device pointers and a cudaStream_t (passed
+ * as void*); `_host` variants take host pointers and include the host<->device copies.
+ *
+ * Semantics shared by all entry points
+ *   - offsets are absolute byte offsets into the input buffer, 64-bit;
+ *   - a buffer behaves as if it were followed by zero bytes (the reference reads up to buf[size+2];
+ *     its behaviour there is defined here as "zero padded");
+ *   - per-NAL status codes are the reference's: >= 0 success, -1 failure.
+ */
+#ifndef HEVCB_H
+#define HEVCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEVCB_API __attribute__((visibility("default")))
+
+#define HEVCB_VERSION_MAJOR 0
+#define HEVCB_VERSION_MINOR 1
+
+/* error codes (negative, distinct from the reference's -1 per-NAL status) */
+#define HEVCB_OK 0
+#define HEVCB_E_NODEVICE (-100) /* no usable CUDA device / driver: there is no CPU fallback */
+#define HEVCB_E_CUDA (-101)     /* a CUDA runtime call failed; see hevcb_last_error() */
+#define HEVCB_E_ARG (-102)      /* invalid argument */
+#define HEVCB_E_ALIGN (-103)    /* device buffers must be 16-byte aligned */
+#define HEVCB_E_CAPACITY (-104) /* more NALs / bytes than the output arrays can hold */
+#define HEVCB_E_NOMEM (-105)
+
+typedef struct hevcb_ctx hevcb_ctx;
+
+/* Result of one scan (+strip) pass.  Mirrors what the canonical loop
+ *     while (find_nal_unit(p, sz, &s, &e) > 0) { ...; p += e; sz -= e; }
+ * leaves behind: the NALs it visited and the outputs of the call that ended it. */
+typedef struct hevcb_scan_summary {
+    int64_t n_nals;       /* NAL units a reference reader visits: terminated ones + the unterminated last NAL */
+    int64_t n_terminated; /* NALs for which find_nal_unit returned > 0 */
+    int32_t last_rc;      /* return value of the call that ended the loop: 0 (no start / zero-length NAL) or -1 */
+    int32_t overflow;     /* 1 when n_nals exceeds cap_nals (arrays hold the first cap_nals entries) */
+    int64_t last_start;   /* *nal_start / *nal_end of that last call, as absolute offsets */
+    int64_t last_end;
+    int64_t rbsp_bytes;   /* bytes of the EPB-free image written to `rbsp` (= size - n_epb) */
+    int64_t n_epb;        /* emulation prevention bytes (00 00 03) removed over the whole buffer */
+} hevcb_scan_summary;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+
+/* Creates a context bound to CUDA device `device`.  Returns HEVCB_E_NODEVICE if CUDA is unusable. */
+HEVCB_API int hevcb_create(int device, hevcb_ctx** out);
+HEVCB_API void hevcb_destroy(hevcb_ctx* ctx);
+/* Human-readable description of the last error on this context (or of the last failed hevcb_create
+ * when ctx is NULL). */
+HEVCB_API const char* hevcb_last_error(const hevcb_ctx* ctx);
+HEVCB_API int hevcb_version(void);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+HEVCB_API int64_t hevcb_launch_count(const hevcb_ctx* ctx);
+/* SM count of the bound device (grid sizing is a multiple of it). */
+HEVCB_API int hevcb_sm_count(const hevcb_ctx* ctx);
+
+/* ---- scan + EPB strip --------------------------------------------------------------------------
+ *
+ * One pass over `size` bytes of Annex-B data:
+ *   nal_start[k], nal_end[k]   what find_nal_unit reports for the k-th NAL of the canonical loop
+ *                              (h264_nal.c:38-76); the unterminated last NAL (rc -1) has nal_end == size.
+ *   rbsp                       (optional) the input with every emulation prevention byte removed
+ *                              (byte p is removed iff b[p]==3 && b[p-1]==0 && b[p-2]==0).  The RBSP that
+ *                              nal_to_rbsp (h264_nal.c:147-200) produces for NAL k is
+ *                              rbsp[rbsp_off[k] .. rbsp_end[k]); start codes stay in between.
+ *   rbsp_off[k], rbsp_end[k]   extent of NAL k's RBSP inside `rbsp`; rbsp_end[k] == -1 when nal_to_rbsp
+ *                              returns -1 for that NAL (00 00 0{0,1,2} inside, or 00 00 03 followed by > 3).
+ * `rbsp` may be NULL (scan only; rbsp_off / rbsp_end are still produced).  `rbsp` needs `size` bytes.
+ * All arrays hold cap_nals entries.  `summary` is written on the device for the _device variant (read it
+ * after synchronising the stream).  Device pointers `buf` and `rbsp` must be 16-byte aligned.
+ */
+HEVCB_API int hevcb_scan_strip_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size,
+                                      int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals,
+                                      uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
+                                      hevcb_scan_summary* d_summary, void* stream);
+
+/* Same with host buffers: copies `buf` to the device, runs the pass, copies the results back.
+ * Any of rbsp / rbsp_off / rbsp_end may be NULL.  Returns HEVCB_E_CAPACITY if summary->overflow. */
+HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size,
+                                    int64_t* nal_start, int64_t* nal_end, int64_t cap_nals,
+                                    uint8_t* rbsp, int64_t* rbsp_off, int64_t* rbsp_end,
+                                    hevcb_scan_summary* summary);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HEVCB_H */

