@@ -62,6 +62,7 @@ HEVCB_API int hevcb_create(int device, hevcb_ctx** out)
         delete ctx;
         return HEVCB_E_CUDA;
     }
+    if (const char* e2 = getenv("HEVCB_SCAN_STAGGER")) { ctx->scan_stagger_cycles = atoll(e2); }
     *out = ctx;
     return HEVCB_OK;
 }

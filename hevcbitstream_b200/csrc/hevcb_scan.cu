@@ -25,17 +25,18 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kWorkers = 8;                    // warps that analyse / write tiles
+constexpr int kSyncThreads = (kWorkers + 1) * 32; // workers + the control warp (publishes aggregates, fetches prefixes, issues TMA)
+constexpr int kThreads = (kWorkers + 2) * 32;     // + the scanner warp (only active in CTA 0)
+constexpr int kWorkerThreads = kWorkers * 32;
 constexpr int kRowBytes = 512;  // one warp-row: 32 lanes x 16 B
 constexpr int kRowsPerWarp = 8; // rows a warp walks in order (its carries stay in registers)
-constexpr int kRows = kWarps * kRowsPerWarp;
+constexpr int kRows = kWorkers * kRowsPerWarp;
 constexpr int kTileBytes = kRows * kRowBytes; // 32 KiB
-constexpr int kLead = 16;                     // leading halo
+constexpr int kLead = 128;                    // leading halo: a whole 128-byte line so that every bulk copy starts line-aligned
 constexpr int kStageBytes = kLead + kTileBytes + 16;
-constexpr int kStages = 2;
-constexpr int kOutBytes = kTileBytes + 32;
-constexpr int kLookPerLane = 2; // predecessor tile states per lane; every warp takes a 64-tile slice: window = 512 tiles per round
+constexpr int kStages = 3;       // tile i-1 being written out, tile i being analysed, tile i+1 in flight
+constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
 struct WarpAgg {
     uint32_t n;     // start codes in the warp's rows
@@ -59,10 +60,9 @@ struct LookPart {
 // dynamic shared memory layout
 struct __align__(16) SmemLayout {
     uint8_t stage[kStages][kStageBytes];
-    uint8_t out[kOutBytes];
     unsigned long long mbar[kStages];
-    WarpAgg wagg[kWarps];
-    LookPart look[kWarps];
+    WarpAgg wagg[2][kWorkers]; // per-warp aggregates of the tile analysed in iteration i (index i & 1)
+    LookPart pref[2];          // exclusive prefix of this CTA's i-th tile (index i & 1), written by the look-back warp
 };
 
 // ---- tile state for the decoupled look-back: one 16-byte word, read/written with single 128-bit accesses
@@ -78,12 +78,12 @@ __device__ __forceinline__ ulonglong2 pack_state(unsigned long long status, unsi
 __device__ __forceinline__ ulonglong2 ld_state(const ulonglong2* p)
 {
     ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_state(ulonglong2* p, ulonglong2 v)
 {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 
 // ---- TMA / mbarrier helpers (PTX)
@@ -118,6 +118,11 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// named barriers: 0 is __syncthreads; kBarWork = the worker warps only; kBarS1 / kBarE = workers + look-back warp
+constexpr int kBarWork = 1, kBarS1 = 2, kBarE = 3;
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // issue the bulk copies for tile `t` into stage buffer `st` (one elected thread)
 __device__ __forceinline__ void issue_tile_load(uint8_t* st, unsigned long long* bar, const uint8_t* buf, int64_t size, long long t)
@@ -156,7 +161,8 @@ struct DevSink {
 struct ScanHeader {
     unsigned long long reserved;
     long long first_empty;
-    unsigned long long pad[6];
+    ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
+    unsigned long long pad[4];
 };
 
 // ordered-carry resolution inside a warp: lane l receives the (kind, err) state produced by lanes < l.
@@ -197,324 +203,463 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
+// exact "does [g0-2, g0+17] contain two adjacent zero bytes" test: byte j of (w | w>>8) is zero iff b[j] and
+// b[j+1] are both zero, and (m - 0x01..) & ~m & 0x80.. is non-zero iff some byte of m is zero.
+__device__ __forceinline__ uint32_t zero_pair_any(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn)
+{
+    const uint32_t mp = (wp | __funnelshift_r(wp, w0, 8)) | 0x0000FFFFu; // only pairs starting at g0-2, g0-1
+    const uint32_t m0 = w0 | __funnelshift_r(w0, w1, 8);
+    const uint32_t m1 = w1 | __funnelshift_r(w1, w2, 8);
+    const uint32_t m2 = w2 | __funnelshift_r(w2, w3, 8);
+    const uint32_t m3 = w3 | __funnelshift_r(w3, wn, 8);
+    const uint32_t c = 0x01010101u, h = 0x80808080u;
+    return (((mp - c) & ~mp) | ((m0 - c) & ~m0) | ((m1 - c) & ~m1) | ((m2 - c) & ~m2) | ((m3 - c) & ~m3)) & h;
+}
+
+// cold path, kept out of line so that the hot loop stays small in the instruction cache
+__device__ __noinline__ uint3 analyze_cold(uint32_t wp, uint4 v, uint32_t wn, int64_t g0, int64_t size)
+{
+    const hevcb_chunk_masks m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, g0, size);
+    return make_uint3(m.ev | (m.sc << 16), m.del | (m.err << 16), m.valid | (m.scb << 16));
+}
+
+__device__ __noinline__ void emit_cold(uint32_t evsc, uint32_t deler, uint32_t misc, int64_t g0, int64_t nbase, int64_t kbase, uint32_t ck,
+                                       uint32_t ce, DevSink sink)
+{
+    hevcb_chunk_masks m;
+    m.ev = evsc & 0xFFFFu;
+    m.sc = evsc >> 16;
+    m.del = deler & 0xFFFFu;
+    m.err = deler >> 16;
+    m.valid = misc & 0xFFFFu;
+    m.scb = misc >> 16;
+    hevcb_chunk_emit(m, g0, nbase, kbase, ck, ce, sink);
+}
+
+// copy `nv` 16-byte vectors from shared memory (16-byte aligned `src16`, byte offset Q*4 + sh/8 into it) to the
+// 16-byte aligned global destination; Q selects the word offset at compile time, sh is the byte shift in bits.
+template <int Q>
+__device__ __forceinline__ void copy_vectors(uint8_t* __restrict__ dst16, const uint8_t* __restrict__ src16, uint32_t nv, uint32_t sh, int tid)
+{
+    for (uint32_t vi = tid; vi < nv; vi += kWorkerThreads) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(src16 + (vi << 4));
+        const uint4 hi = *reinterpret_cast<const uint4*>(src16 + (vi << 4) + 16);
+        const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint4 o4;
+        o4.x = __funnelshift_r(W[Q], W[Q + 1], sh);
+        o4.y = __funnelshift_r(W[Q + 1], W[Q + 2], sh);
+        o4.z = __funnelshift_r(W[Q + 2], W[Q + 3], sh);
+        o4.w = __funnelshift_r(W[Q + 3], W[Q + 4], sh);
+        __stcs(reinterpret_cast<uint4*>(dst16 + (vi << 4)), o4);
+    }
+}
+
+#ifndef HEVCB_SPIN_PAUSE
+#define HEVCB_SPIN_PAUSE __nanosleep(32)
+#endif
+#ifdef HEVCB_SCAN_TIMING
+__device__ unsigned long long g_scan_timing[4][16];
+#define TSTAMP(slot)                                                                      \
+    do {                                                                                  \
+        const long long now__ = clock64();                                                \
+        if (trec) { g_scan_timing[tcta][slot] += (unsigned long long)(now__ - tlast); }  \
+        tlast = now__;                                                                    \
+    } while (0)
+#else
+#define TSTAMP(slot) do {} while (0)
+#endif
+
+// one warp copies a clean 512-byte row (16-byte aligned in shared memory) to an arbitrarily aligned global address
+__device__ __forceinline__ void copy_row_clean(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int lane)
+{
+    const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    if ((uint32_t)lane < head) { dst[lane] = src[lane]; }
+    const uint32_t nv = (kRowBytes - head) >> 4; // 31 or 32 vectors
+    if ((uint32_t)lane < nv) {
+        const uint32_t so = head + ((uint32_t)lane << 4);
+        uint4 o4;
+        if (head == 0u) {
+            o4 = *reinterpret_cast<const uint4*>(src + so);
+        } else {
+            const uint32_t a = so & ~15u, q = (so & 15u) >> 2, sh = (so & 3u) * 8u;
+            const uint4 lo = *reinterpret_cast<const uint4*>(src + a);
+            const uint4 hi = *reinterpret_cast<const uint4*>(src + a + 16); // at most 16 bytes past the row: still inside the stage
+            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            uint32_t x[5];
+#pragma unroll
+            for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
+            o4.x = __funnelshift_r(x[0], x[1], sh);
+            o4.y = __funnelshift_r(x[1], x[2], sh);
+            o4.z = __funnelshift_r(x[2], x[3], sh);
+            o4.w = __funnelshift_r(x[3], x[4], sh);
+        }
+        __stcs(reinterpret_cast<uint4*>(dst + so), o4);
+    }
+    const uint32_t done = head + (nv << 4);
+    if ((uint32_t)lane < kRowBytes - done) { dst[done + lane] = src[done + lane]; }
+}
+
+// Scanner warp (one per grid): the chained scan over the tile aggregates.  Batch by batch (320 tiles, 10 per lane, in
+// stream order) it waits for the aggregates, combines them with shuffles / ballots and publishes every tile's
+// EXCLUSIVE prefix (start codes, kept bytes, ordered carry) into tile_excl[].  One reader per aggregate and one
+// 16-byte poll per CTA and tile replace the all-to-all look-back, whose polling traffic on a few cache lines was
+// measured to cost ~14k cycles per wave of 296 tiles.
+// A batch is exactly one wave of the grid (tiles w*G .. w*G+G-1, G <= 320): the prefixes of wave w must not wait for
+// aggregates of wave w+1, which the CTAs only publish after they have received their wave-w prefix.
+__device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl,
+                                             long long n_tiles, long long G, ScanHeader* __restrict__ hdr, int lane)
+{
+    unsigned long long runN = 0, runK = 0;
+    uint32_t runKind = HEVCB_KIND_Z3, runErr = 0;
+    for (long long base = 0; base < n_tiles; base += G) {
+        const long long first = base + (long long)lane * kScanPerLane;
+        const long long lim = (base + G < n_tiles) ? base + G : n_tiles; // end of this wave
+        ulonglong2 sv[kScanPerLane];
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; j++) {
+            const long long idx = first + j;
+            if (idx < lim) { sv[j] = ld_state(&tile_state[idx]); }
+            else { sv[j] = pack_state(kStatusAgg, 0, 0, HEVCB_KIND_PASS, 0); } // past the wave: identity
+        }
+        for (;;) { // re-poll, one batch per round trip, the aggregates that are not published yet
+            bool missing = false;
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; j++) { missing = missing || ((sv[j].x >> 62) == 0ull); }
+            if (!missing) { break; }
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; j++) {
+                if ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[first + j]); }
+            }
+        }
+        // lane totals
+        uint32_t ln = 0, lk = 0, lkind = HEVCB_KIND_PASS, lerr = 0;
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; j++) {
+            ln += (uint32_t)(sv[j].x & ((1ull << 40) - 1));
+            lk += (uint32_t)sv[j].y;
+            hevcb_carry_combine(lkind, lerr, (uint32_t)(sv[j].x >> 60) & 3u, (uint32_t)(sv[j].x >> 59) & 1u);
+        }
+        // exclusive scan over lanes (ascending lane = stream order)
+        const uint32_t nin = warp_incl_scan(ln, lane), kin = warp_incl_scan(lk, lane);
+        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, lkind != HEVCB_KIND_PASS);
+        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lkind == HEVCB_KIND_SC3);
+        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, lerr != 0u);
+        uint32_t ck, ce;
+        warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+        uint32_t cKind = runKind, cErr = runErr; // carry entering this lane's first tile
+        hevcb_carry_combine(cKind, cErr, ck, ce);
+        unsigned long long cN = runN + (nin - ln), cK = runK + (kin - lk);
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; j++) {
+            const long long idx = first + j;
+            if (idx < lim) { st_state(&tile_excl[idx], pack_state(kStatusPrefix, cN, cK, cKind, cErr)); }
+            cN += (uint32_t)(sv[j].x & ((1ull << 40) - 1));
+            cK += (uint32_t)sv[j].y;
+            hevcb_carry_combine(cKind, cErr, (uint32_t)(sv[j].x >> 60) & 3u, (uint32_t)(sv[j].x >> 59) & 1u);
+        }
+        // running state after the batch = lane 31's state after its last tile
+        runN = __shfl_sync(0xFFFFFFFFu, cN, 31);
+        runK = __shfl_sync(0xFFFFFFFFu, cK, 31);
+        runKind = __shfl_sync(0xFFFFFFFFu, cKind, 31);
+        runErr = __shfl_sync(0xFFFFFFFFu, cErr, 31);
+    }
+    if (lane == 0) { hdr->final_state = pack_state(kStatusPrefix, runN, runK, runKind, runErr); }
+}
+
 __global__ void __launch_bounds__(kThreads, 2) hevcb_scan_strip_kernel(
     const uint8_t* __restrict__ buf, int64_t size, long long n_tiles, ScanHeader* __restrict__ hdr,
-    ulonglong2* __restrict__ tile_state, int64_t* __restrict__ nal_start, int64_t* __restrict__ nal_end,
-    int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off, int64_t* __restrict__ rbsp_end)
+    ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, int64_t* __restrict__ nal_start,
+    int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off,
+    int64_t* __restrict__ rbsp_end, long long debug_flags)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const long long G = gridDim.x;
+    const unsigned dbg = (unsigned)debug_flags; // experiment switches, 0 in production
 
-    if (tid == 0) {
+    if (tid == kWorkerThreads) {
         for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        for (int s = 0; s < kStages; s++) {
-            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+        for (int s = 0; s < kStages; s++) { // this CTA's first three tiles
+            const long long t = (long long)blockIdx.x + (long long)s * G;
             if (t < n_tiles) { issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, t); }
         }
     }
     __syncthreads();
 
+    if (warp == kWorkers + 1) { // scanner warp: one per grid, never joins the CTA's barriers
+        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, G, hdr, lane); }
+        return;
+    }
+
+    // Iteration i of a CTA: its i-th tile t_i = blockIdx.x + i * grid (stage i mod 3).
+    //   workers  : analyse t_i -> per-warp aggregates -> [S1] -> emit + write out t_(i-1) with the prefix the look-back
+    //              warp produced during the previous iteration -> arrive on [E] (no wait) -> next iteration
+    //   look-back: [S1] -> publish aggregate(t_i) -> look-back(t_i) (hidden behind the workers' write-out of t_(i-1) and
+    //              analysis of t_(i+1)) -> publish prefix(t_i) -> [E] wait -> TMA load of t_(i+2) into the freed stage
+    if (warp == kWorkers) {
+        // =================================== look-back / TMA warp ===================================
+        int s = 0;
+        long long prev_t = -1;
+        for (long long t = blockIdx.x, it = 0;; t += G, it++) {
+            const bool have_cur = t < n_tiles;
+            if (!have_cur && prev_t < 0) { break; }
+            bar_sync(kBarS1, kSyncThreads);
+            if (have_cur) {
+                uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0;
+#pragma unroll
+                for (int w = 0; w < kWorkers; w++) {
+                    const WarpAgg a = sm.wagg[it & 1][w];
+                    tile_n += a.n;
+                    tile_k += a.k;
+                    hevcb_carry_combine(ak, ae, a.kind, a.err);
+                }
+                if (lane == 0) {
+                    if (!(dbg & 16u)) { st_state(&tile_state[t], pack_state(kStatusAgg, tile_n, tile_k, ak, ae)); }
+                    // fetch this tile's exclusive prefix from the scanner: needed only after the next [S1]
+                    ulonglong2 ex;
+                    if (dbg & 1u) { ex = pack_state(kStatusPrefix, 0, (unsigned long long)t * kTileBytes, HEVCB_KIND_Z3, 0); }
+                    else {
+                        ex = ld_state(&tile_excl[t]);
+                        while ((ex.x >> 62) == 0ull) { __nanosleep(64); ex = ld_state(&tile_excl[t]); }
+                    }
+                    LookPart lp;
+                    lp.n = ex.x & ((1ull << 40) - 1); lp.k = ex.y; lp.kind = (uint32_t)(ex.x >> 60) & 3u; lp.err = (uint32_t)(ex.x >> 59) & 1u;
+                    lp.has_prefix = 1; lp.pad = 0;
+                    sm.pref[it & 1] = lp;
+                }
+                __syncwarp();
+            }
+            if (prev_t >= 0) {
+                bar_sync(kBarE, kSyncThreads); // every worker finished reading the stage of the previous tile
+                const int ps = (s == 0) ? kStages - 1 : s - 1;
+                const long long nt = prev_t + (long long)kStages * G; // the tile that reuses this stage
+                if (lane == 0 && nt < n_tiles) {
+                    fence_proxy_async();
+                    issue_tile_load(sm.stage[ps], &sm.mbar[ps], buf, size, nt);
+                }
+            }
+            prev_t = have_cur ? t : -1;
+            s = (s + 1 == kStages) ? 0 : s + 1;
+        }
+        return;
+    }
+
+    // ========================================= worker warps =========================================
     DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
     uint32_t phase_bits = 0;
     int s = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t t0 = (int64_t)t * kTileBytes;
-        uint8_t* st = sm.stage[s];
-        while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
-        phase_bits ^= (1u << s);
+    // state of the previous tile between its analysis and its write-out
+    long long prev_t = -1;
+    uint32_t p_evsc[kRowsPerWarp], p_deler[kRowsPerWarp], p_misc[kRowsPerWarp];
+    uint32_t p_rowflags = 0, p_rN = 0, p_rK = 0, p_rKind = HEVCB_KIND_PASS, p_rErr = 0, p_tile_k = 0, p_compact = 0;
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; i++) { p_evsc[i] = p_deler[i] = p_misc[i] = 0; }
 
-        // ---- boundary fix-ups: positions < 0 read as non-zero, positions >= size read as zero
-        const int64_t valid_end = (int64_t)kLead + (size - t0); // smem offset of position `size`
-        if (t == 0 || valid_end < kStageBytes) {
-            if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
-            if (valid_end < kStageBytes) {
-                for (int i = (int)valid_end + tid; i < kStageBytes; i += kThreads) { st[i] = 0; }
-            }
-            __syncthreads();
-        }
+    for (long long t = blockIdx.x, it = 0;; t += G, it++) {
+        const bool have_cur = t < n_tiles;
+        if (!have_cur && prev_t < 0) { break; }
+        uint32_t c_evsc[kRowsPerWarp], c_deler[kRowsPerWarp], c_misc[kRowsPerWarp];
+        uint32_t c_rowflags = 0;
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; i++) { c_evsc[i] = c_deler[i] = 0; c_misc[i] = 0xFFFFu; }
 
-        // ---- phase 1: per-lane masks; the warp walks its rows in order and keeps the carries in registers
-        uint32_t m_evsc[kRowsPerWarp];  // ev | sc << 16
-        uint32_t m_deler[kRowsPerWarp]; // del | err << 16
-        uint32_t m_misc[kRowsPerWarp];  // valid | scb << 16
-        uint32_t rowflags = 0;          // bit i: row has events/errors; bit 16+i: row has removed bytes / partial validity
-        uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; i++) {
-            const int r = warp * kRowsPerWarp + i;
-            const int off = kLead + r * kRowBytes + lane * 16;
-            const uint4 v = *reinterpret_cast<const uint4*>(st + off);
-            uint32_t wp = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
-            uint32_t wn = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-            if (lane == 0) { wp = *reinterpret_cast<const uint32_t*>(st + off - 4); }
-            if (lane == 31) { wn = *reinterpret_cast<const uint32_t*>(st + off + 16); }
-            const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
-            hevcb_chunk_masks m;
-            const bool slow = hevcb_maybe_zero_pair(wp, v.x, v.y, v.z, v.w, wn) != 0u;
-            const int64_t rem = size - g0;
-            if (slow) {
-                m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, g0, size);
-            } else {
-                m.ev = m.sc = m.scb = m.del = m.err = 0u;
-                m.valid = rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+        if (have_cur) {
+            const int64_t t0 = (int64_t)t * kTileBytes;
+            uint8_t* st = sm.stage[s];
+            while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
+            phase_bits ^= (1u << s);
+            // ---- boundary fix-ups: positions < 0 read as non-zero, positions >= size read as zero
+            const int64_t valid_end = (int64_t)kLead + (size - t0); // smem offset of position `size`
+            // interior tile: every byte (and its halo) is inside the buffer and below the tail zone
+            const bool interior = valid_end >= (int64_t)kStageBytes + HEVCB_TAIL_ZONE + 16;
+            if (t == 0 || valid_end < kStageBytes) {
+                if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
+                if (valid_end < kStageBytes) {
+                    for (int i = (int)valid_end + tid; i < kStageBytes; i += kWorkerThreads) { st[i] = 0; }
+                }
+                bar_sync(kBarWork, kWorkerThreads);
             }
-            m_evsc[i] = m.ev | (m.sc << 16);
-            m_deler[i] = m.del | (m.err << 16);
-            m_misc[i] = m.valid | (m.scb << 16);
-            const uint32_t Ab = __ballot_sync(0xFFFFFFFFu, slow || rem < 16);
-            if (Ab == 0u) { // whole row on the fast path: 512 kept bytes, nothing else
-                wK += kRowBytes;
-                continue;
-            }
-            uint32_t lk, le;
-            hevcb_chunk_summary(m, lk, le);
-            const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, m.ev != 0u);
-            const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-            const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-            const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (m.ev | m.err) != 0u);
-            const uint32_t Db = __ballot_sync(0xFFFFFFFFu, (m.del != 0u) || (m.valid != 0xFFFFu));
-            wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(m.sc));
-            wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(m.valid & ~m.del));
-            uint32_t rk, re;
-            warp_carry_total(Eb, Sb, Rb, rk, re);
-            hevcb_carry_combine(wKind, wErr, rk, re);
-            rowflags |= (Xb != 0u ? 1u : 0u) << i;
-            rowflags |= (Db != 0u ? 1u : 0u) << (16 + i);
-        }
-        if (lane == 0) {
-            WarpAgg a;
-            a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = (rowflags >> 16) != 0u;
-            a.pad[0] = a.pad[1] = a.pad[2] = 0;
-            sm.wagg[warp] = a;
-        }
-        __syncthreads();
 
-        // ---- cross-tile look-back: every warp examines a 64-tile slice of the window (512 tiles per round trip)
-        uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0;
-        bool compact = false;
+            // ---- phase 1: per-lane masks; the warp walks its rows in order and keeps the carries in registers
+            uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            const WarpAgg a = sm.wagg[w];
-            tile_n += a.n;
-            tile_k += a.k;
-            hevcb_carry_combine(ak, ae, a.kind, a.err);
-            compact = compact || (a.del != 0u);
-        }
-        unsigned long long exN = 0, exK = 0;
-        uint32_t exKind = HEVCB_KIND_Z3, exErr = 0;
-        if (t > 0) {
-            if (tid == 0) { st_state(&tile_state[t], pack_state(kStatusAgg, tile_n, tile_k, ak, ae)); }
-            uint32_t kindF = HEVCB_KIND_PASS, errF = 0;
-            long long base = t - 1;
-            for (;;) {
-                // lane-local ordered summary of its tiles (j = 0 is the nearer one)
-                uint32_t aggN = 0, aggK = 0, lkind = HEVCB_KIND_PASS, lerr = 0;
-                unsigned long long pN = 0, pK = 0;
-                bool hasP = false;
-                ulonglong2 sv[kLookPerLane];
-                const long long first = base - (long long)((warp * 32 + lane) * kLookPerLane);
-#pragma unroll
-                for (int j = 0; j < kLookPerLane; j++) {
-                    const long long idx = first - j;
-                    if (idx >= 0) { sv[j] = ld_state(&tile_state[idx]); }
-                    else { sv[j] = pack_state(kStatusPrefix, 0, 0, HEVCB_KIND_Z3, 0); } // before the stream
-                }
-#pragma unroll
-                for (int j = 0; j < kLookPerLane; j++) {
-                    const long long idx = first - j;
-                    while ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[idx]); }
-                    if (!hasP) {
-                        const uint32_t skind = (uint32_t)(sv[j].x >> 60) & 3u;
-                        const uint32_t serr = (uint32_t)(sv[j].x >> 59) & 1u;
-                        if (lkind == HEVCB_KIND_PASS) { lerr |= serr; lkind = skind; }
-                        if ((sv[j].x >> 62) == kStatusPrefix) {
-                            hasP = true;
-                            pN = sv[j].x & ((1ull << 40) - 1);
-                            pK = sv[j].y;
-                        } else {
-                            aggN += (uint32_t)(sv[j].x & ((1ull << 40) - 1));
-                            aggK += (uint32_t)sv[j].y;
-                        }
-                    }
-                }
-                // warp-level ordered summary of the slice
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, hasP);
-                const int pl = pm ? (__ffs((int)pm) - 1) : 32;
-                const bool act = lane <= pl;
-                unsigned long long sN = __reduce_add_sync(0xFFFFFFFFu, act ? aggN : 0u);
-                unsigned long long sK = __reduce_add_sync(0xFFFFFFFFu, act ? aggK : 0u);
-                if (pl < 32) {
-                    sN += __shfl_sync(0xFFFFFFFFu, pN, pl);
-                    sK += __shfl_sync(0xFFFFFFFFu, pK, pl);
-                }
-                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, act && lkind != HEVCB_KIND_PASS);
-                const uint32_t rb = __ballot_sync(0xFFFFFFFFu, act && lerr != 0u);
-                uint32_t skind = HEVCB_KIND_PASS, serr;
-                if (eb) {
-                    const int f = __ffs((int)eb) - 1; // nearest lane whose tiles saw an event
-                    skind = __shfl_sync(0xFFFFFFFFu, lkind, f);
-                    const uint32_t upto = (f == 31) ? 0xFFFFFFFFu : ((2u << f) - 1u);
-                    serr = (rb & upto) != 0u;
-                } else {
-                    serr = rb != 0u;
-                }
-                if (lane == 0) {
-                    LookPart lp;
-                    lp.n = sN; lp.k = sK; lp.kind = skind; lp.err = serr; lp.has_prefix = (pl < 32) ? 1u : 0u; lp.pad = 0;
-                    sm.look[warp] = lp;
-                }
-                __syncthreads();
-                // every thread combines the slices nearest-first
-                bool found = false;
-#pragma unroll
-                for (int w = 0; w < kWarps; w++) {
-                    if (!found) {
-                        const LookPart lp = sm.look[w];
-                        exN += lp.n;
-                        exK += lp.k;
-                        if (kindF == HEVCB_KIND_PASS) { errF |= lp.err; kindF = lp.kind; }
-                        found = lp.has_prefix != 0u;
-                    }
-                }
-                if (found) { break; }
-                base -= (long long)kThreads * kLookPerLane;
-                __syncthreads(); // sm.look is rewritten by the next round
-            }
-            exKind = kindF;
-            exErr = errF;
-        }
-        if (tid == 0) {
-            uint32_t ik = exKind, ie = exErr;
-            hevcb_carry_combine(ik, ie, ak, ae);
-            st_state(&tile_state[t], pack_state(kStatusPrefix, exN + tile_n, exK + tile_k, ik, ie));
-        }
-
-        // ---- phase 2: ordered emission of NAL boundaries; compaction when bytes were removed
-        const long long tileN = (long long)exN;
-        const long long tileK = (long long)exK;
-        // carry entering this warp = tile carry (+) aggregates of the warps before it
-        uint32_t rN = 0, rK = 0, rKind = exKind, rErr = exErr;
-        const uint32_t tileKept = tile_k;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            if (w < warp) {
-                const WarpAgg a = sm.wagg[w];
-                rN += a.n; rK += a.k; hevcb_carry_combine(rKind, rErr, a.kind, a.err);
-            }
-        }
-        const bool do_compact = compact && (rbsp != nullptr);
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; i++) {
-            const bool rowX = ((rowflags >> i) & 1u) != 0u;
-            const bool rowD = ((rowflags >> (16 + i)) & 1u) != 0u;
-            if (!rowX && !rowD && !do_compact) { rK += kRowBytes; continue; }
-            const int r = warp * kRowsPerWarp + i;
-            hevcb_chunk_masks m;
-            m.ev = m_evsc[i] & 0xFFFFu;
-            m.sc = m_evsc[i] >> 16;
-            m.del = m_deler[i] & 0xFFFFu;
-            m.err = m_deler[i] >> 16;
-            m.valid = m_misc[i] & 0xFFFFu;
-            m.scb = m_misc[i] >> 16;
-            const uint32_t keep = m.valid & ~m.del;
-            uint32_t klane, rowKept;
-            if (rowD) {
-                const uint32_t c = (uint32_t)__popc(keep);
-                const uint32_t inc = warp_incl_scan(c, lane);
-                klane = inc - c;
-                rowKept = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            } else {
-                klane = (uint32_t)lane * 16u;
-                rowKept = kRowBytes;
-            }
-            klane += rK;
-            if (rowX) {
-                uint32_t lk, le;
-                hevcb_chunk_summary(m, lk, le);
-                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, m.ev != 0u);
-                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-                uint32_t ck, ce;
-                warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
-                if (ck == HEVCB_KIND_PASS) { ck = rKind; ce |= rErr; } // inherit the carry entering the row
-                const uint32_t c = (uint32_t)__popc(m.sc);
-                const uint32_t ninc = warp_incl_scan(c, lane);
-                if ((m.ev | m.err) != 0u) {
-                    const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
-                    hevcb_chunk_emit(m, g0, (int64_t)(tileN + rN + (ninc - c)), (int64_t)(tileK + klane), ck, ce, sink);
-                }
-                uint32_t rk, re;
-                warp_carry_total(Eb, Sb, Rb, rk, re);
-                hevcb_carry_combine(rKind, rErr, rk, re);
-                rN += __shfl_sync(0xFFFFFFFFu, ninc, 31);
-            }
-            if (do_compact) {
-                // byte-granular compaction of this lane's kept bytes into sm.out
+            for (int i = 0; i < kRowsPerWarp; i++) {
+                if (dbg & 2u) { wK += kRowBytes; continue; }
+                const int r = warp * kRowsPerWarp + i;
                 const int off = kLead + r * kRowBytes + lane * 16;
                 const uint4 v = *reinterpret_cast<const uint4*>(st + off);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t o = klane;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if ((keep >> j) & 1u) { sm.out[o++] = (uint8_t)(w[j >> 2] >> (8 * (j & 3))); }
+                uint32_t wp = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
+                uint32_t wn = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
+                if (lane == 0) { wp = *reinterpret_cast<const uint32_t*>(st + off - 4); }
+                if (lane == 31) { wn = *reinterpret_cast<const uint32_t*>(st + off + 16); }
+                const bool slow = zero_pair_any(wp, v.x, v.y, v.z, v.w, wn) != 0u;
+                if (!__any_sync(0xFFFFFFFFu, slow) && interior) { // whole row on the fast path: 512 kept bytes
+                    wK += kRowBytes;
+                    continue;
                 }
+                const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
+                const int64_t rem = size - g0;
+                uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
+                if (slow) { m3 = analyze_cold(wp, v, wn, g0, size); }
+                c_evsc[i] = m3.x;
+                c_deler[i] = m3.y;
+                c_misc[i] = m3.z;
+                const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
+                uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
+                if (ev != 0u) {
+                    const int tp = 31 - __clz((int)ev);
+                    lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                    le = ((er >> tp) >> 1) != 0u;
+                }
+                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
+                const uint32_t Db = __ballot_sync(0xFFFFFFFFu, (del != 0u) || (valid != 0xFFFFu));
+                wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
+                wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid & ~del));
+                uint32_t rk, re;
+                warp_carry_total(Eb, Sb, Rb, rk, re);
+                hevcb_carry_combine(wKind, wErr, rk, re);
+                c_rowflags |= 1u << i;
+                c_rowflags |= (Xb != 0u ? 1u : 0u) << (8 + i);
+                c_rowflags |= (Db != 0u ? 1u : 0u) << (16 + i);
             }
-            rK += rowKept;
+            if (lane == 0) {
+                WarpAgg a;
+                a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = (c_rowflags >> 16) != 0u;
+                a.pad[0] = a.pad[1] = a.pad[2] = 0;
+                sm.wagg[it & 1][warp] = a;
+            }
+        }
+        bar_sync(kBarS1, kSyncThreads);
+
+        // tile aggregate and the aggregate of the warps before this one
+        uint32_t c_rN = 0, c_rK = 0, c_rKind = HEVCB_KIND_PASS, c_rErr = 0, c_tile_k = 0, c_compact = 0;
+        if (have_cur) {
+            uint32_t tn = 0, ak = HEVCB_KIND_PASS, ae = 0;
+#pragma unroll
+            for (int w = 0; w < kWorkers; w++) {
+                const WarpAgg a = sm.wagg[it & 1][w];
+                if (w == warp) { c_rN = tn; c_rK = c_tile_k; c_rKind = ak; c_rErr = ae; }
+                tn += a.n;
+                c_tile_k += a.k;
+                hevcb_carry_combine(ak, ae, a.kind, a.err);
+                c_compact |= a.del;
+            }
         }
 
-        // ---- copy-out: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
-        if (rbsp != nullptr) {
-            if (compact) { __syncthreads(); }
-            const uint8_t* src = compact ? sm.out : (st + kLead);
-            const uint32_t L = tileKept;
-            uint8_t* dst = rbsp + tileK;
-            const uint32_t head0 = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-            const uint32_t head = head0 < L ? head0 : L;
-            if ((uint32_t)tid < head) { dst[tid] = src[tid]; }
-            const uint32_t nv = (L - head) >> 4;
-            const uint32_t r16 = head & 15u; // source misalignment, uniform over the tile
-            const uint32_t q = r16 >> 2;
-            const uint32_t sh = (r16 & 3u) * 8u;
-            for (uint32_t vi = tid; vi < nv; vi += kThreads) {
-                const uint32_t so = head + (vi << 4);
-                const uint32_t a = so & ~15u;
-                const uint4 lo = *reinterpret_cast<const uint4*>(src + a);
-                uint4 o4;
-                if (r16 == 0u) {
-                    o4 = lo;
-                } else {
-                    const uint4 hi = *reinterpret_cast<const uint4*>(src + a + 16);
-                    const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                    uint32_t x[5];
+        if (prev_t >= 0) {
+            const long long pt = prev_t;
+            const int ps = (s == 0) ? kStages - 1 : s - 1; // stage holding the previous tile
+            uint8_t* st = sm.stage[ps];
+            const int64_t t0 = (int64_t)pt * kTileBytes;
+            const LookPart pref = sm.pref[(it - 1) & 1];
+            const long long tileN = (long long)pref.n;
+            const long long tileK = (long long)pref.k;
+            const bool do_compact = (p_compact != 0u) && (rbsp != nullptr);
+
+            // ---- phase 2: ordered emission of NAL boundaries; tiles with removed bytes are also written out here, row by row
+            const bool dirty_out = do_compact && !(dbg & 4u);
+            if ((p_rowflags >> 8) != 0u || dirty_out) { // warp-uniform: something to emit, or a dirty tile to write
+                uint32_t rN = p_rN, rK = p_rK;
+                uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
+                hevcb_carry_combine(cKind, cErr, p_rKind, p_rErr);
 #pragma unroll
-                    for (int e = 0; e < 5; e++) {
-                        // q is tile-uniform: select without dynamic register indexing
-                        x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7];
+                for (int i = 0; i < kRowsPerWarp; i++) {
+                    const bool rowS = ((p_rowflags >> i) & 1u) != 0u;
+                    const bool rowX = ((p_rowflags >> (8 + i)) & 1u) != 0u;
+                    const bool rowD = ((p_rowflags >> (16 + i)) & 1u) != 0u;
+                    const int r = warp * kRowsPerWarp + i;
+                    if (!rowD) {
+                        if (dirty_out) { // clean row of a dirty tile: shifted 16-byte vector copy by this warp
+                            copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane);
+                        }
+                        if (!rowX) { rK += kRowBytes; continue; } // nothing to emit
                     }
-                    o4.x = __funnelshift_r(x[0], x[1], sh);
-                    o4.y = __funnelshift_r(x[1], x[2], sh);
-                    o4.z = __funnelshift_r(x[2], x[3], sh);
-                    o4.w = __funnelshift_r(x[3], x[4], sh);
+                    const uint32_t evsc = rowS ? p_evsc[i] : 0u, deler = rowS ? p_deler[i] : 0u, misc = rowS ? p_misc[i] : 0xFFFFu;
+                    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16, valid = misc & 0xFFFFu;
+                    const uint32_t keep = valid & ~del;
+                    uint32_t klane, rowKept;
+                    if (rowD) {
+                        const uint32_t c = (uint32_t)__popc(keep);
+                        const uint32_t inc = warp_incl_scan(c, lane);
+                        klane = inc - c;
+                        rowKept = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    } else {
+                        klane = (uint32_t)lane * 16u;
+                        rowKept = kRowBytes;
+                    }
+                    klane += rK;
+                    if (rowX) {
+                        uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+                        if (ev != 0u) {
+                            const int tp = 31 - __clz((int)ev);
+                            lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                            le = ((er >> tp) >> 1) != 0u;
+                        }
+                        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                        uint32_t ck, ce;
+                        warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+                        if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the row
+                        const uint32_t c = (uint32_t)__popc(sc);
+                        const uint32_t ninc = warp_incl_scan(c, lane);
+                        if ((ev | er) != 0u) {
+                            const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
+                            emit_cold(evsc, deler, misc, g0, (int64_t)(tileN + rN + (ninc - c)), (int64_t)(tileK + klane), ck, ce, sink);
+                        }
+                        uint32_t rk, re;
+                        warp_carry_total(Eb, Sb, Rb, rk, re);
+                        hevcb_carry_combine(cKind, cErr, rk, re);
+                        rN += __shfl_sync(0xFFFFFFFFu, ninc, 31);
+                    }
+                    if (rowD && dirty_out) { // row with removed / out-of-range bytes: byte-granular stores of the kept bytes
+                        const uint4 v = *reinterpret_cast<const uint4*>(st + kLead + r * kRowBytes + lane * 16);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint8_t* o = rbsp + tileK + klane;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if ((keep >> j) & 1u) { *o++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3))); }
+                        }
+                    }
+                    rK += rowKept;
                 }
-                __stcs(reinterpret_cast<uint4*>(dst + so), o4);
             }
-            const uint32_t done = head + (nv << 4);
-            if ((uint32_t)tid < L - done) { dst[done + tid] = src[done + tid]; }
-        }
-        __syncthreads(); // every read of stage s (and of sm.out) is finished
 
-        if (tid == 0) {
-            const long long nt = t + (long long)kStages * gridDim.x; // the tile that reuses this stage
-            if (nt < n_tiles) {
-                fence_proxy_async();
-                issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, nt);
+            // ---- copy-out of a clean tile: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
+            if (rbsp != nullptr && !do_compact && !(dbg & 4u)) {
+                const uint8_t* src = st + kLead;
+                const uint32_t L = p_tile_k;
+                uint8_t* dst = rbsp + tileK;
+                const uint32_t head0 = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+                const uint32_t head = head0 < L ? head0 : L;
+                if ((uint32_t)tid < head) { dst[tid] = src[tid]; }
+                const uint32_t nv = (L - head) >> 4;
+                const uint32_t sh = (head & 3u) * 8u; // source misalignment is tile-uniform
+                switch (head >> 2) {
+                    case 0: copy_vectors<0>(dst + head, src, nv, sh, tid); break;
+                    case 1: copy_vectors<1>(dst + head, src, nv, sh, tid); break;
+                    case 2: copy_vectors<2>(dst + head, src, nv, sh, tid); break;
+                    default: copy_vectors<3>(dst + head, src, nv, sh, tid); break;
+                }
+                const uint32_t done = head + (nv << 4);
+                if ((uint32_t)tid < L - done) { dst[done + tid] = src[done + tid]; }
             }
+            bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
         }
+
+        // the tile analysed in this iteration becomes the one to write out in the next
+        prev_t = have_cur ? t : -1;
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; i++) { p_evsc[i] = c_evsc[i]; p_deler[i] = c_deler[i]; p_misc[i] = c_misc[i]; }
+        p_rowflags = c_rowflags; p_rN = c_rN; p_rK = c_rK; p_rKind = c_rKind; p_rErr = c_rErr; p_tile_k = c_tile_k; p_compact = c_compact;
         s = (s + 1 == kStages) ? 0 : s + 1;
     }
 }
@@ -529,7 +674,7 @@ __global__ void hevcb_scan_finalize_kernel(const uint8_t* __restrict__ buf, int6
     int64_t N = 0, K = 0;
     uint32_t kind = HEVCB_KIND_Z3, err = 0;
     if (n_tiles > 0) {
-        const ulonglong2 sv = tile_state[n_tiles - 1];
+        const ulonglong2 sv = hdr->final_state;
         N = (int64_t)(sv.x & ((1ull << 40) - 1));
         K = (int64_t)sv.y;
         kind = (uint32_t)(sv.x >> 60) & 3u;
@@ -560,6 +705,15 @@ __global__ void hevcb_scan_init_kernel(ScanHeader* hdr)
 
 } // namespace
 
+#ifdef HEVCB_SCAN_TIMING
+extern "C" __attribute__((visibility("default"))) int hevcb_debug_scan_timing(unsigned long long* out, int reset)
+{
+    if (out) { cudaMemcpyFromSymbol(out, g_scan_timing, sizeof(g_scan_timing)); }
+    if (reset) { unsigned long long z[4][16] = {}; cudaMemcpyToSymbol(g_scan_timing, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int64_t* d_nal_start, int64_t* d_nal_end,
                             int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
                             hevcb_scan_summary* d_summary, cudaStream_t stream)
@@ -573,11 +727,13 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
         return HEVCB_E_ALIGN;
     }
     const long long n_tiles = (long long)((size + kTileBytes - 1) / kTileBytes);
-    const size_t need = sizeof(ScanHeader) + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(ulonglong2);
+    const size_t n_states = (size_t)(n_tiles > 0 ? n_tiles : 1);
+    const size_t need = sizeof(ScanHeader) + 2 * n_states * sizeof(ulonglong2);
     int rc = hevcb_reserve(ctx, &ctx->scan_scratch, need);
     if (rc != HEVCB_OK) { return rc; }
     ScanHeader* hdr = reinterpret_cast<ScanHeader*>(ctx->scan_scratch.p);
     ulonglong2* states = reinterpret_cast<ulonglong2*>(reinterpret_cast<uint8_t*>(ctx->scan_scratch.p) + sizeof(ScanHeader));
+    ulonglong2* excl = states + n_states;
 
     HEVCB_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch.p, 0, need, stream));
     hevcb_scan_init_kernel<<<1, 32, 0, stream>>>(hdr);
@@ -594,11 +750,13 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
             ctx->scan_blocks_per_sm = nb;
         }
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
+        if (grid > 32 * kScanPerLane) { grid = 32 * kScanPerLane; } // one wave must fit one scanner batch
         if (grid > n_tiles) { grid = n_tiles; }
         // cooperative launch: the chained look-back needs every CTA of the grid to be resident
         long long nt = n_tiles;
-        void* args[] = {(void*)&d_buf, (void*)&size, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&d_nal_start, (void*)&d_nal_end,
-                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end};
+        long long stagger = ctx->scan_stagger_cycles;
+        void* args[] = {(void*)&d_buf, (void*)&size, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
+                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&stagger};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
         ctx->launches++;
     }
