@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the bitstream hot path (BASELINE.json `metric`, config[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size-gib G] [--nal-size B] [--no-sweep]
+
+One "step" = one pass of the fused start-code scan + EPB strip (hevcb_scan_strip_device) over a synthetic Annex-B
+buffer that is already resident in HBM.  N = 1 runs BASELINE config[1]: a 4 GiB buffer; the headline `value` is quoted
+on 16 KiB NALs (escaped uniform-random payload) and `sweep` carries the other NAL sizes (64 B .. 1 MiB) plus the
+EPB-dense worst case.  N > 1 (torchrun, one rank per GPU) shards independent 4 GiB streams over the ranks (weak
+scaling, BASELINE config[5] first form); the only exchange is an all-gather of the per-shard NAL / RBSP-byte counts.
+
+Printed (rank 0, one JSON line): metric/value/unit + `roofline` (algorithmic bytes / CUDA-event time of the step vs the
+measured HBM peak), `cpu_baseline` (the UNMODIFIED reference's find_nal_unit + nal_to_rbsp loop, oracle/_ref, one host
+thread, bounded sample), `e2e` (the same pass through the host-pointer C ABI with pinned buffers, H2D + D2H inside the
+timed region), `clocks`, `gpu_launches`.
+
+`--impl reference` times the reference's own CPU implementation on the same workload shape (bounded sample per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "annexb_scan_epb_strip_input_GBps"
+UNIT = "GB/s"
+UNIT_BYTES = 64 << 20  # synthetic stream unit that is tiled to the full buffer on the device
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic Annex-B generator (numpy only -- the oracle is not used to build inputs)
+# ------------------------------------------------------------------------------------------------
+
+def escape_rbsp(rbsp: np.ndarray) -> np.ndarray:
+    """Emulation prevention as rbsp_to_nal does it (h264_nal.c:92-132): insert 03 before a byte <= 3 that follows two
+    zeros, restarting the zero count after each insertion.  Candidates are found vectorised, then walked in order."""
+    z = rbsp == 0
+    cand = np.nonzero(z[:-2] & z[1:-1] & (rbsp[2:] <= 3))[0] + 2  # positions whose two predecessors are zero
+    if cand.size == 0:
+        return rbsp
+    ins = []
+    last_ins = -10
+    for p in cand.tolist():
+        # zero count at p: zeros immediately before p, counted since the last insertion point
+        c = 0
+        q = p - 1
+        while q >= 0 and rbsp[q] == 0 and q >= last_ins and c < 2:
+            c += 1
+            q -= 1
+        if c == 2:
+            ins.append(p)
+            last_ins = p
+    return np.insert(rbsp, ins, 3) if ins else rbsp
+
+
+def make_unit(nal_size: int, total: int, seed: int, dense: bool) -> np.ndarray:
+    """`total` bytes (approximately) of NALs: 00 00 01 + 2-byte TRAIL_R header + escaped payload + 0x80."""
+    rng = np.random.default_rng(seed)
+    body = max(4, nal_size - 3)
+    if dense:
+        reps = max(1, (body - 3) // 4)
+        nal = np.concatenate([np.array([0, 0, 1, 0x02, 0x01], np.uint8), np.tile(np.array([0, 0, 3, 1], np.uint8), reps), np.array([0x80], np.uint8)])
+        return np.tile(nal, max(1, total // nal.size))
+    n = max(1, total // nal_size)
+    pay = body - 3
+    rb = rng.integers(0, 256, (n, pay + 6), dtype=np.uint8)
+    rb[:, 0] = 0
+    rb[:, 1] = 0
+    rb[:, 2] = 1
+    rb[:, 3] = 0x02
+    rb[:, 4] = 0x01
+    rb[:, -1] = 0x80
+    # escape the payload region of every NAL; start codes must stay intact, so escape NAL by NAL only where needed
+    flat = rb.reshape(-1)
+    z = flat == 0
+    hit = np.nonzero(z[:-2] & z[1:-1] & (flat[2:] <= 3))[0] + 2
+    hit = hit[(hit % (pay + 6)) >= 5]  # start codes (columns 0..2) are not payload
+    rows = np.unique(hit // (pay + 6)).tolist()
+    if not rows:
+        return flat
+    out = []
+    prev = 0
+    for r in rows:
+        out.append(flat[prev * (pay + 6): r * (pay + 6)])
+        row = rb[r]
+        out.append(np.concatenate([row[:3], escape_rbsp(row[3:])]))
+        prev = r + 1
+    out.append(flat[prev * (pay + 6):])
+    return np.concatenate(out)
+
+
+WORKLOADS = [("nal64", 64, False), ("nal256", 256, False), ("nal1k", 1024, False), ("nal4k", 4096, False), ("nal16k", 16384, False),
+             ("nal64k", 65536, False), ("nal256k", 262144, False), ("nal1m", 1 << 20, False), ("epb_dense_4k", 4096, True)]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.dev)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for nme, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def cpu_reference_sample(unit: np.ndarray, reps: int = 3):
+    """find_nal_unit + nal_to_rbsp loop of the UNMODIFIED reference (oracle/_ref) on one host thread."""
+    from oracle import ref
+
+    size = unit.size
+    buf = ref.padded(unit)
+    t, n = ref.time_loop(buf, size, 1, reps)
+    return size / t / 1e9, n, t
+
+
+# ------------------------------------------------------------------------------------------------
+# arms
+# ------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhevcref.so missing (reference sources not compiled)"}))
+        return
+    name, nal_size, dense = next(w for w in WORKLOADS if w[0] == args.workload)
+    unit = make_unit(nal_size, args.ref_sample_mib << 20, 1234, dense)
+    buf = ref.padded(unit)
+    size = unit.size
+    for _ in range(args.warmup):
+        ref.time_loop(buf, size, 1, 1)
+    ts = []
+    for _ in range(args.steps):
+        t, n = ref.time_loop(buf, size, 1, 1)
+        ts.append(t)
+    mean = float(np.mean(ts))
+    val = size / mean / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"reference find_nal_unit + nal_to_rbsp loop over a {args.ref_sample_mib} MiB sample of {name} (NAL {nal_size} B)", "nal_size": nal_size},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"{args.ref_sample_mib} MiB of the {name} stream per step, 1 thread (the reference is single-threaded and not re-entrant)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import hevcbitstream_b200 as hb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = hb.Context(local)
+    size_target = int(args.size_gib * (1 << 30))
+    peak, peak_src = measured_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_workload(name, nal_size, dense, steps, warmup, sampler=None):
+        unit = make_unit(nal_size, UNIT_BYTES, 1234 + rank * 7919, dense)
+        reps = max(1, size_target // unit.size)
+        d = torch.from_numpy(unit).to(dev).repeat(reps)
+        size = d.numel()
+        cap = size // max(16, (nal_size if not dense else 4096) // 2) + (1 << 16)
+        outs = ctx.scan_strip_device(d, size=size, cap_nals=cap, want_rbsp=True, sync=False)
+        torch.cuda.synchronize()
+        for _ in range(warmup):
+            ctx.scan_strip_device(d, size=size, cap_nals=cap, out=outs, sync=False)
+        barrier()
+        l0 = ctx.launch_count
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ctx.scan_strip_device(d, size=size, cap_nals=cap, out=outs, sync=False)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        launches = ctx.launch_count - l0
+        s = outs["summary"].cpu().numpy()
+        n_nals, rbsp_bytes, n_epb = int(s[0]), int(s[5]), int(s[6])
+        assert int(s[2] >> 32) == 0, "NAL capacity overflow in bench"
+        # NCCL exchange of the per-shard counts (the only collective of the sharded path)
+        tot = torch.tensor([ms, float(size), float(n_nals), float(rbsp_bytes)], dtype=torch.float64, device=dev)
+        if world > 1:
+            allv = [torch.zeros_like(tot) for _ in range(world)]
+            dist.all_gather(allv, tot)
+            allv = torch.stack(allv).cpu().numpy()
+        else:
+            allv = tot.cpu().numpy()[None, :]
+        ms_max = float(allv[:, 0].max())
+        tot_size = float(allv[:, 1].sum())
+        tot_nals = float(allv[:, 2].sum())
+        tot_rbsp = float(allv[:, 3].sum())
+        alg = tot_size + tot_rbsp + 24.0 * tot_nals
+        res = dict(name=name, nal_size=nal_size, ms=ms_max, size=tot_size, n_nals=tot_nals, rbsp_bytes=tot_rbsp, n_epb=n_epb,
+                   in_gbs=tot_size / (ms_max * 1e-3) / 1e9, alg_gbs=alg / (ms_max * 1e-3) / 1e9, launches=launches,
+                   alg_bytes_per_gpu=(size + rbsp_bytes + 24.0 * n_nals), unit=unit, d=d, outs=outs, cap=cap, size_local=size)
+        return res
+
+    name, nal_size, dense = next(w for w in WORKLOADS if w[0] == args.workload)
+    with ClockSampler(local) as cs:
+        head = time_workload(name, nal_size, dense, args.steps, args.warmup)
+    clocks = cs.summary()
+
+    # ---- e2e: host-pointer C ABI with pinned buffers, H2D + D2H inside the timed region (per rank, summed)
+    e2e = None
+    try:
+        import ctypes as C
+
+        from hevcbitstream_b200._lib import ScanSummary
+
+        size = min(head["size_local"], int(args.e2e_gib * (1 << 30)))
+        size -= size % head["unit"].size if size >= head["unit"].size else 0
+        cap = head["cap"]
+        h_in = torch.empty(size, dtype=torch.uint8).pin_memory()
+        h_in.copy_(head["d"][:size].cpu())
+        h_rbsp = torch.empty(size + 16, dtype=torch.uint8).pin_memory()
+        h_arr = [torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(4)]
+        sm = ScanSummary()
+        L = ctx._L
+
+        def one():
+            rc = L.hevcb_scan_strip_host(ctx._h, h_in.data_ptr(), size, h_arr[0].data_ptr(), h_arr[1].data_ptr(), cap, h_rbsp.data_ptr(),
+                                         h_arr[2].data_ptr(), h_arr[3].data_ptr(), C.byref(sm))
+            assert rc == 0, rc
+
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, 5))
+        for _ in range(k):
+            one()
+        barrier()
+        dt = (time.perf_counter() - t0) / k
+        v = torch.tensor([dt, float(size)], dtype=torch.float64, device=dev)
+        if world > 1:
+            allv = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+            allv = torch.stack(allv).cpu().numpy()
+        else:
+            allv = v.cpu().numpy()[None, :]
+        e2e = {"value": float(allv[:, 1].sum() / allv[:, 0].max() / 1e9), "unit": UNIT, "h2d_bytes_per_step": int(size),
+               "d2h_bytes_per_step": int(sm.rbsp_bytes + 4 * 8 * sm.n_nals + C.sizeof(ScanSummary)), "bytes_per_rank": int(size),
+               "note": "hevcb_scan_strip_host: pinned host buffers, copies inside the timed region; PCIe-bound"}
+        del h_in, h_rbsp, h_arr
+    except Exception as ex:  # report, never fake
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+
+    # ---- sweep over the other BASELINE config[1] shapes (fewer steps each)
+    sweep = {}
+    if not args.no_sweep and world == 1:
+        unit_keep = head["unit"]
+        for wname, wnal, wdense in WORKLOADS:
+            if wname == name:
+                r = head
+            else:
+                head_d = None
+                r = time_workload(wname, wnal, wdense, max(2, args.steps // 4), 3)
+            sweep[wname] = {"nal_size": wnal, "ms": round(r["ms"], 4), "input_GBps": round(r["in_gbs"], 1), "algorithmic_GBps": round(r["alg_gbs"], 1),
+                            "frac_of_peak": round(r["alg_gbs"] / peak, 4), "n_nals": int(r["n_nals"]), "n_epb": int(r["n_epb"])}
+            if r is not head:
+                del r
+                torch.cuda.empty_cache()
+
+    # ---- CPU baseline: the unmodified reference on rank 0's host cores, bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 or (rank == 0 and args.cpu_baseline_multi):
+        try:
+            sample = head["unit"][: args.ref_sample_mib << 20]
+            v, n, t = cpu_reference_sample(sample, reps=3)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"first {sample.size >> 20} MiB of the {name} stream, find_nal_unit + nal_to_rbsp loop (oracle/_ref), best of 3, {n} NALs"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "error": repr(ex)}
+
+    if rank == 0:
+        per_gpu_alg_gbs = head["alg_bytes_per_gpu"] / (head["ms"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": head["in_gbs"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"BASELINE config[1]: fused start-code scan + EPB strip, {args.size_gib:g} GiB Annex-B buffer per GPU, NAL size {nal_size} B "
+                                   f"({name}); 64 MiB synthetic unit (escaped uniform-random payload) tiled on the device; input > L2 so no flush needed",
+                       "nal_size": nal_size, "bytes_per_gpu": int(head["size_local"]), "nals_per_step": int(head["n_nals"]),
+                       "nal_headers_located_per_s": head["n_nals"] / (head["ms"] * 1e-3), "l2": "inputs larger than L2 (4 GiB vs 126 MB)",
+                       "sharding": "independent stream per rank, all_gather of (nals, rbsp_bytes) only" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": per_gpu_alg_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_alg_gbs / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": "N_in + N_rbsp + 24*NALs per launch (SURVEY 8d), per GPU; time = CUDA-event mean over the timed steps (memset + init + scan + finalize launches)"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(head["launches"]),
+            "clocks": clocks,
+        }
+        if sweep:
+            line["sweep"] = sweep
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size-gib", type=float, default=4.0)
+    ap.add_argument("--e2e-gib", type=float, default=1.0)
+    ap.add_argument("--workload", default="nal16k", choices=[w[0] for w in WORKLOADS])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--ref-sample-mib", type=int, default=64)
+    ap.add_argument("--cpu-baseline-multi", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

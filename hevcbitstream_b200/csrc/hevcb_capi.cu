@@ -62,7 +62,7 @@ HEVCB_API int hevcb_create(int device, hevcb_ctx** out)
         delete ctx;
         return HEVCB_E_CUDA;
     }
-    if (const char* e2 = getenv("HEVCB_SCAN_STAGGER")) { ctx->scan_stagger_cycles = atoll(e2); }
+    if (const char* e2 = getenv("HEVCB_SCAN_DEBUG")) { ctx->scan_debug_flags = atoll(e2); } // kernel experiment switches
     *out = ctx;
     return HEVCB_OK;
 }

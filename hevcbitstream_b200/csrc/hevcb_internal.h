@@ -25,7 +25,7 @@ struct hevcb_ctx {
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr; // stream used by *_host entry points
     int scan_blocks_per_sm = 0;
-    long long scan_stagger_cycles = 0; // start skew spread over the grid (tunable: HEVCB_SCAN_STAGGER)
+    long long scan_debug_flags = 0; // experiment switches of the scan kernel (HEVCB_SCAN_DEBUG); 0 in production
 };
 
 extern char g_hevcb_create_error[512];

@@ -25,7 +25,13 @@
 
 namespace {
 
-constexpr int kWorkers = 8;                    // warps that analyse / write tiles
+#ifndef HEVCB_SCAN_WORKERS
+#define HEVCB_SCAN_WORKERS 8
+#endif
+#ifndef HEVCB_SCAN_CTAS
+#define HEVCB_SCAN_CTAS 2
+#endif
+constexpr int kWorkers = HEVCB_SCAN_WORKERS;   // warps that analyse / write tiles
 constexpr int kSyncThreads = (kWorkers + 1) * 32; // workers + the control warp (publishes aggregates, fetches prefixes, issues TMA)
 constexpr int kThreads = (kWorkers + 2) * 32;     // + the scanner warp (only active in CTA 0)
 constexpr int kWorkerThreads = kWorkers * 32;
@@ -311,9 +317,10 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 {
     unsigned long long runN = 0, runK = 0;
     uint32_t runKind = HEVCB_KIND_Z3, runErr = 0;
-    for (long long base = 0; base < n_tiles; base += G) {
+    for (long long wbase = 0; wbase < n_tiles; wbase += G) {
+      const long long lim = (wbase + G < n_tiles) ? wbase + G : n_tiles; // end of this wave
+      for (long long base = wbase; base < lim; base += 32 * kScanPerLane) { // the wave in batches of 320 tiles
         const long long first = base + (long long)lane * kScanPerLane;
-        const long long lim = (base + G < n_tiles) ? base + G : n_tiles; // end of this wave
         ulonglong2 sv[kScanPerLane];
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
@@ -362,11 +369,12 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
         runK = __shfl_sync(0xFFFFFFFFu, cK, 31);
         runKind = __shfl_sync(0xFFFFFFFFu, cKind, 31);
         runErr = __shfl_sync(0xFFFFFFFFu, cErr, 31);
+      }
     }
     if (lane == 0) { hdr->final_state = pack_state(kStatusPrefix, runN, runK, runKind, runErr); }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) hevcb_scan_strip_kernel(
+__global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_kernel(
     const uint8_t* __restrict__ buf, int64_t size, long long n_tiles, ScanHeader* __restrict__ hdr,
     ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, int64_t* __restrict__ nal_start,
     int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off,
@@ -485,50 +493,74 @@ __global__ void __launch_bounds__(kThreads, 2) hevcb_scan_strip_kernel(
                 bar_sync(kBarWork, kWorkerThreads);
             }
 
-            // ---- phase 1: per-lane masks; the warp walks its rows in order and keeps the carries in registers
+            // ---- phase 1: per-lane masks; the warp walks its rows in order and keeps the carries in registers.
+            // Rows are taken four at a time: the four loads, halo exchanges and zero-pair tests are independent
+            // instruction chains, and one vote sends the common "no two adjacent zero bytes anywhere" case on.
             uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
 #pragma unroll
-            for (int i = 0; i < kRowsPerWarp; i++) {
-                if (dbg & 2u) { wK += kRowBytes; continue; }
-                const int r = warp * kRowsPerWarp + i;
-                const int off = kLead + r * kRowBytes + lane * 16;
-                const uint4 v = *reinterpret_cast<const uint4*>(st + off);
-                uint32_t wp = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
-                uint32_t wn = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-                if (lane == 0) { wp = *reinterpret_cast<const uint32_t*>(st + off - 4); }
-                if (lane == 31) { wn = *reinterpret_cast<const uint32_t*>(st + off + 16); }
-                const bool slow = zero_pair_any(wp, v.x, v.y, v.z, v.w, wn) != 0u;
-                if (!__any_sync(0xFFFFFFFFu, slow) && interior) { // whole row on the fast path: 512 kept bytes
-                    wK += kRowBytes;
+            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
+                if (dbg & 2u) { wK += 4 * kRowBytes; continue; }
+                const int rbase = warp * kRowsPerWarp + i0;
+                const uint8_t* rp = st + kLead + rbase * kRowBytes + lane * 16;
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { v[k] = *reinterpret_cast<const uint4*>(rp + k * kRowBytes); }
+                uint32_t wp[4], wn[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    wp[k] = __shfl_up_sync(0xFFFFFFFFu, v[k].w, 1);
+                    wn[k] = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
+                }
+                // lane 0 / lane 31 take the neighbouring row's edge words (from registers inside the group of four)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t prev_last = (k > 0) ? __shfl_sync(0xFFFFFFFFu, v[k > 0 ? k - 1 : 0].w, 31) : 0u;
+                    const uint32_t next_first = (k < 3) ? __shfl_sync(0xFFFFFFFFu, v[k < 3 ? k + 1 : 3].x, 0) : 0u;
+                    if (lane == 0) { wp[k] = (k > 0) ? prev_last : *reinterpret_cast<const uint32_t*>(rp - 4); }
+                    if (lane == 31) { wn[k] = (k < 3) ? next_first : *reinterpret_cast<const uint32_t*>(rp + 3 * kRowBytes + 16); }
+                }
+                uint32_t slowmask = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    slowmask |= (zero_pair_any(wp[k], v[k].x, v[k].y, v[k].z, v[k].w, wn[k]) != 0u ? 1u : 0u) << k;
+                }
+                if (!__any_sync(0xFFFFFFFFu, slowmask != 0u) && interior) { // four rows on the fast path: 2 KiB kept
+                    wK += 4 * kRowBytes;
                     continue;
                 }
-                const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
-                const int64_t rem = size - g0;
-                uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
-                if (slow) { m3 = analyze_cold(wp, v, wn, g0, size); }
-                c_evsc[i] = m3.x;
-                c_deler[i] = m3.y;
-                c_misc[i] = m3.z;
-                const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
-                uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
-                if (ev != 0u) {
-                    const int tp = 31 - __clz((int)ev);
-                    lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
-                    le = ((er >> tp) >> 1) != 0u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = i0 + k;
+                    const bool slow = ((slowmask >> k) & 1u) != 0u;
+                    if (!__any_sync(0xFFFFFFFFu, slow) && interior) { wK += kRowBytes; continue; }
+                    const int64_t g0 = t0 + (int64_t)(rbase + k) * kRowBytes + lane * 16;
+                    const int64_t rem = size - g0;
+                    uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
+                    if (slow) { m3 = analyze_cold(wp[k], v[k], wn[k], g0, size); }
+                    c_evsc[i] = m3.x;
+                    c_deler[i] = m3.y;
+                    c_misc[i] = m3.z;
+                    const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
+                    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
+                    if (ev != 0u) {
+                        const int tp = 31 - __clz((int)ev);
+                        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                        le = ((er >> tp) >> 1) != 0u;
+                    }
+                    const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                    const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                    const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
+                    const uint32_t Db = __ballot_sync(0xFFFFFFFFu, (del != 0u) || (valid != 0xFFFFu));
+                    wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
+                    wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid & ~del));
+                    uint32_t rk, re;
+                    warp_carry_total(Eb, Sb, Rb, rk, re);
+                    hevcb_carry_combine(wKind, wErr, rk, re);
+                    c_rowflags |= 1u << i;
+                    c_rowflags |= (Xb != 0u ? 1u : 0u) << (8 + i);
+                    c_rowflags |= (Db != 0u ? 1u : 0u) << (16 + i);
                 }
-                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
-                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-                const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
-                const uint32_t Db = __ballot_sync(0xFFFFFFFFu, (del != 0u) || (valid != 0xFFFFu));
-                wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
-                wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid & ~del));
-                uint32_t rk, re;
-                warp_carry_total(Eb, Sb, Rb, rk, re);
-                hevcb_carry_combine(wKind, wErr, rk, re);
-                c_rowflags |= 1u << i;
-                c_rowflags |= (Xb != 0u ? 1u : 0u) << (8 + i);
-                c_rowflags |= (Db != 0u ? 1u : 0u) << (16 + i);
             }
             if (lane == 0) {
                 WarpAgg a;
@@ -750,11 +782,10 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
             ctx->scan_blocks_per_sm = nb;
         }
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
-        if (grid > 32 * kScanPerLane) { grid = 32 * kScanPerLane; } // one wave must fit one scanner batch
         if (grid > n_tiles) { grid = n_tiles; }
         // cooperative launch: the chained look-back needs every CTA of the grid to be resident
         long long nt = n_tiles;
-        long long stagger = ctx->scan_stagger_cycles;
+        long long stagger = ctx->scan_debug_flags;
         void* args[] = {(void*)&d_buf, (void*)&size, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&stagger};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
