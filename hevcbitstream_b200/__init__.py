@@ -5,6 +5,6 @@ thin Python mirror used by tests and bench.py: ctypes bindings plus torch for de
 There is no CPU implementation: importing works anywhere, but every compute call needs a B200.
 """
 from ._lib import LIB_PATH, load_library, HevcbError  # noqa: F401
-from .api import Context, ScanResult  # noqa: F401
+from .api import Context, HostIndex, ScanResult  # noqa: F401
 
 __all__ = ["Context", "ScanResult", "HevcbError", "load_library", "LIB_PATH"]

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhevcb200.so")
+LIB_PATH = os.environ.get("HEVCB_LIB", os.path.join(_HERE, "libhevcb200.so"))  # HEVCB_LIB: alternative build (experiments)
 
 HEVCB_OK = 0
 ERRORS = {
@@ -34,6 +34,27 @@ class ScanSummary(C.Structure):
         ("last_end", C.c_int64),
         ("rbsp_bytes", C.c_int64),
         ("n_epb", C.c_int64),
+    ]
+
+
+class ParseBuffers(C.Structure):
+    _fields_ = [
+        ("rc", C.c_void_p), ("nal_hdr", C.c_void_p), ("kind", C.c_void_p), ("ubflag", C.c_void_p), ("hdr_end", C.c_void_p),
+        ("cols", C.c_void_p), ("pair_off", C.c_void_p), ("pair_field", C.c_void_p), ("pair_value", C.c_void_p), ("cap_pairs", C.c_int64),
+    ]
+
+
+class ParseSummary(C.Structure):
+    _fields_ = [
+        ("n_nals", C.c_int64), ("n_ok", C.c_int64), ("n_pairs", C.c_int64), ("n_vps", C.c_int64), ("n_sps", C.c_int64),
+        ("n_pps", C.c_int64), ("n_slices", C.c_int64), ("overflow", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class StreamIndex(C.Structure):
+    _fields_ = [
+        ("cap_nals", C.c_int64), ("nal_start", C.c_void_p), ("nal_end", C.c_void_p), ("rbsp_off", C.c_void_p), ("rbsp_end", C.c_void_p),
+        ("rbsp", C.c_void_p), ("p", ParseBuffers), ("scan", ScanSummary), ("parse", ParseSummary),
     ]
 
 
@@ -67,5 +88,11 @@ def load_library() -> C.CDLL:
     L.hevcb_scan_strip_device.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
     L.hevcb_scan_strip_host.restype = C.c_int
     L.hevcb_scan_strip_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(ScanSummary)]
+    L.hevcb_parse_device.restype = C.c_int
+    L.hevcb_parse_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), vp, vp]
+    L.hevcb_index_host.restype = C.c_int
+    L.hevcb_index_host.argtypes = [vp, vp, i64, C.POINTER(StreamIndex)]
+    L.hevcb_materialize.restype = C.c_int
+    L.hevcb_materialize.argtypes = [C.POINTER(StreamIndex), i64, vp, vp, vp, vp, vp]
     _lib = L
     return L

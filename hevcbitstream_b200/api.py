@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import HevcbError, ScanSummary, load_library
+from ._lib import HevcbError, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
 
 
 @dataclass
@@ -126,3 +126,89 @@ class Context:
         n = sm.n_nals
         return ScanResult(n, sm.n_terminated, sm.last_rc, sm.last_start, sm.last_end, sm.rbsp_bytes, sm.n_epb,
                           ns[:n], ne[:n], ro[:n], re[:n], rb[: sm.rbsp_bytes] if rb is not None else None)
+
+
+    # ---- batched header parse -----------------------------------------------------------------
+    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True):
+        """Header parse of every NAL found by scan_strip_device (device resident).  Returns a dict of torch tensors
+        (rc, nal_hdr, kind, ubflag, hdr_end, cols[8][n], pair_off[n+1], pair_field, pair_value) and `summary`."""
+        import torch
+
+        n = int(scan.n_nals)
+        dev = buf.device
+        if cap_pairs is None:
+            cap_pairs = 64 * n + 4096
+        out = dict(
+            rc=torch.empty(max(n, 1), dtype=torch.int32, device=dev), nal_hdr=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
+            kind=torch.empty(max(n, 1), dtype=torch.uint8, device=dev), ubflag=torch.empty(max(n, 1), dtype=torch.uint8, device=dev),
+            hdr_end=torch.empty(max(n, 1), dtype=torch.int32, device=dev), cols=torch.empty((8, max(n, 1)), dtype=torch.int32, device=dev),
+            pair_off=torch.empty(n + 1, dtype=torch.int64, device=dev), pair_field=torch.empty(cap_pairs, dtype=torch.int32, device=dev),
+            pair_value=torch.empty(cap_pairs, dtype=torch.int32, device=dev), summary=torch.zeros(8, dtype=torch.int64, device=dev),
+        )
+        pb = ParseBuffers(out["rc"].data_ptr(), out["nal_hdr"].data_ptr(), out["kind"].data_ptr(), out["ubflag"].data_ptr(),
+                          out["hdr_end"].data_ptr(), out["cols"].data_ptr(), out["pair_off"].data_ptr(), out["pair_field"].data_ptr(),
+                          out["pair_value"].data_ptr(), cap_pairs)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.hevcb_parse_device(self._h, buf.data_ptr(), scan.nal_start.data_ptr(), scan.nal_end.data_ptr(), scan.rbsp.data_ptr(),
+                                               scan.rbsp_off.data_ptr(), scan.rbsp_end.data_ptr(), n, C.byref(pb), out["summary"].data_ptr(), stream))
+        out["n"] = n
+        out["cap_pairs"] = cap_pairs
+        if sync:
+            s = out["summary"].cpu().numpy()
+            out["n_ok"], out["n_pairs"], out["n_vps"], out["n_sps"], out["n_pps"], out["n_slices"] = (int(x) for x in s[1:7])
+            if int(s[7]) & 0xFFFFFFFF:
+                raise HevcbError(-104, f"{out['n_pairs']} syntax elements exceed cap_pairs {cap_pairs}")
+        return out
+
+    def index_host(self, buf: np.ndarray, size=None, cap_nals=None, cap_pairs=None, want_rbsp=True) -> "HostIndex":
+        """Annex-B bytes in host memory -> full index (hevcb_index_host: scan + strip + parse, copies included)."""
+        assert buf.dtype == np.uint8
+        size = int(buf.size if size is None else size)
+        if cap_nals is None:
+            cap_nals = size // 3 + 8
+        if cap_pairs is None:
+            cap_pairs = 64 * min(cap_nals, size // 4 + 8) + 4096
+        return HostIndex(self, buf, size, cap_nals, cap_pairs, want_rbsp)
+
+
+class HostIndex:
+    """Owns the host arrays of a hevcb_stream_index and exposes hevcb_materialize."""
+
+    def __init__(self, ctx: Context, buf, size, cap_nals, cap_pairs, want_rbsp):
+        self._L = ctx._L
+        a = self.arrays = dict(
+            nal_start=np.zeros(cap_nals, np.int64), nal_end=np.zeros(cap_nals, np.int64), rbsp_off=np.zeros(cap_nals, np.int64),
+            rbsp_end=np.zeros(cap_nals, np.int64), rbsp=np.zeros(size + 16, np.uint8) if want_rbsp else None,
+            rc=np.zeros(cap_nals, np.int32), nal_hdr=np.zeros(cap_nals, np.int32), kind=np.zeros(cap_nals, np.uint8),
+            ubflag=np.zeros(cap_nals, np.uint8), hdr_end=np.zeros(cap_nals, np.int32), cols=np.zeros(8 * cap_nals, np.int32),
+            pair_off=np.zeros(cap_nals + 1, np.int64), pair_field=np.zeros(cap_pairs, np.uint32), pair_value=np.zeros(cap_pairs, np.int32),
+        )
+        pb = ParseBuffers(_np_ptr(a["rc"]), _np_ptr(a["nal_hdr"]), _np_ptr(a["kind"]), _np_ptr(a["ubflag"]), _np_ptr(a["hdr_end"]), _np_ptr(a["cols"]),
+                          _np_ptr(a["pair_off"]), _np_ptr(a["pair_field"]), _np_ptr(a["pair_value"]), cap_pairs)
+        self.idx = StreamIndex(cap_nals, _np_ptr(a["nal_start"]), _np_ptr(a["nal_end"]), _np_ptr(a["rbsp_off"]), _np_ptr(a["rbsp_end"]),
+                               _np_ptr(a["rbsp"]), pb, ScanSummary(), ParseSummary())
+        ctx._check(self._L.hevcb_index_host(ctx._h, _np_ptr(buf), size, C.byref(self.idx)))
+        self.n = int(self.idx.scan.n_nals)
+        self.scan = self.idx.scan
+        self.parse = self.idx.parse
+        n = self.n
+        self.cols = a["cols"][: 8 * n].reshape(8, n) if n else np.zeros((8, 0), np.int32)
+
+    def __getattr__(self, name):
+        a = self.__dict__.get("arrays", {})
+        if name in a:
+            v = a[name]
+            if v is None:
+                return None
+            if name in ("pair_field", "pair_value"):
+                return v[: int(self.idx.parse.n_pairs)]
+            if name == "pair_off":
+                return v[: self.n + 1]
+            if name == "rbsp":
+                return v[: int(self.idx.scan.rbsp_bytes)]
+            return v[: self.n]
+        raise AttributeError(name)
+
+    def materialize(self, k: int, nal, vps, sps, pps, sh) -> int:
+        """Applies NAL k to numpy int32 struct images (any may be None).  Returns the reference's rc."""
+        return int(self._L.hevcb_materialize(C.byref(self.idx), k, _np_ptr(nal), _np_ptr(vps), _np_ptr(sps), _np_ptr(pps), _np_ptr(sh)))

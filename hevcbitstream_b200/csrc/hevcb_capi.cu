@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "hevcb_internal.h"
+#include "../../include/hevcb_layout.h"
 
 char g_hevcb_create_error[512] = {0};
 
@@ -44,6 +45,7 @@ HEVCB_API int hevcb_create(int device, hevcb_ctx** out)
                  "device %d is sm_%d%d; libhevcb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
         return HEVCB_E_NODEVICE;
     }
+    cudaDeviceSetLimit(cudaLimitStackSize, 4096); // the syntax walker keeps derived RPS tables in local memory
     hevcb_ctx* ctx = new (std::nothrow) hevcb_ctx();
     if (!ctx) { return HEVCB_E_NOMEM; }
     ctx->device = device;
@@ -71,7 +73,9 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
 {
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
-    hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc};
+    hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
+                            &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
+                            &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
     }
@@ -141,6 +145,141 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
         return HEVCB_E_CAPACITY;
     }
     return HEVCB_OK;
+}
+
+
+HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
+                                 const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals, const hevcb_parse_buffers* out,
+                                 hevcb_parse_summary* d_summary, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_parse(ctx, d_buf, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, out, d_summary, (cudaStream_t)stream);
+}
+
+HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx)
+{
+    if (!ctx || !idx || size < 0 || (size > 0 && !buf) || idx->cap_nals < 0 || !idx->nal_start || !idx->nal_end || !idx->rbsp_off || !idx->rbsp_end ||
+        !idx->p.rc || !idx->p.nal_hdr || !idx->p.kind || !idx->p.ubflag || !idx->p.hdr_end || !idx->p.cols || !idx->p.pair_off) {
+        HEVCB_SET_ERR(ctx, "hevcb_index_host: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t cap = idx->cap_nals;
+    const size_t in_bytes = ((size_t)size + 15u) & ~(size_t)15u;
+    const size_t arr_bytes = (size_t)(cap > 0 ? cap : 1) * sizeof(int64_t);
+    int rc;
+    if ((rc = hevcb_reserve(ctx, &ctx->h_in, in_bytes + 16)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_rbsp, in_bytes + 16)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a0, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a1, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a2, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a3, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_misc, 256)) != HEVCB_OK) { return rc; }
+    if (size > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_in.p, buf, (size_t)size, cudaMemcpyHostToDevice, st)); }
+    hevcb_scan_summary* d_sum = reinterpret_cast<hevcb_scan_summary*>(ctx->h_misc.p);
+    hevcb_parse_summary* d_psum = reinterpret_cast<hevcb_parse_summary*>(reinterpret_cast<uint8_t*>(ctx->h_misc.p) + 128);
+    const uint8_t* d_in = reinterpret_cast<const uint8_t*>(ctx->h_in.p);
+    uint8_t* d_rbsp = reinterpret_cast<uint8_t*>(ctx->h_rbsp.p);
+    int64_t* d_ns = reinterpret_cast<int64_t*>(ctx->h_a0.p);
+    int64_t* d_ne = reinterpret_cast<int64_t*>(ctx->h_a1.p);
+    int64_t* d_ro = reinterpret_cast<int64_t*>(ctx->h_a2.p);
+    int64_t* d_re = reinterpret_cast<int64_t*>(ctx->h_a3.p);
+    rc = hevcb_launch_scan_strip(ctx, d_in, size, d_ns, d_ne, cap, d_rbsp, d_ro, d_re, d_sum, st);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_scan_summary* p_sum = reinterpret_cast<hevcb_scan_summary*>(ctx->pinned);
+    hevcb_parse_summary* p_psum = reinterpret_cast<hevcb_parse_summary*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 128);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_sum, d_sum, sizeof(hevcb_scan_summary), cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    idx->scan = *p_sum;
+    memset(&idx->parse, 0, sizeof(idx->parse));
+    if (idx->scan.overflow || idx->scan.n_nals > cap) {
+        HEVCB_SET_ERR(ctx, "hevcb_index_host: %lld NALs exceed cap_nals %lld", (long long)idx->scan.n_nals, (long long)cap);
+        return HEVCB_E_CAPACITY;
+    }
+    const int64_t n = idx->scan.n_nals;
+    // device staging of the parse outputs
+    const size_t sizes[9] = {(size_t)n * 4, (size_t)n * 4, (size_t)n, (size_t)n, (size_t)n * 4, (size_t)n * 32, (size_t)(n + 1) * 8,
+                             (size_t)idx->p.cap_pairs * 4, (size_t)idx->p.cap_pairs * 4};
+    for (int i = 0; i < 9; i++) {
+        if ((rc = hevcb_reserve(ctx, &ctx->h_p[i], sizes[i] + 16)) != HEVCB_OK) { return rc; }
+    }
+    hevcb_parse_buffers d;
+    d.rc = reinterpret_cast<int32_t*>(ctx->h_p[0].p);
+    d.nal_hdr = reinterpret_cast<int32_t*>(ctx->h_p[1].p);
+    d.kind = reinterpret_cast<uint8_t*>(ctx->h_p[2].p);
+    d.ubflag = reinterpret_cast<uint8_t*>(ctx->h_p[3].p);
+    d.hdr_end = reinterpret_cast<int32_t*>(ctx->h_p[4].p);
+    d.cols = reinterpret_cast<int32_t*>(ctx->h_p[5].p);
+    d.pair_off = reinterpret_cast<int64_t*>(ctx->h_p[6].p);
+    d.pair_field = reinterpret_cast<uint32_t*>(ctx->h_p[7].p);
+    d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
+    d.cap_pairs = idx->p.cap_pairs;
+    rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, st);
+    if (rc != HEVCB_OK) { return rc; }
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
+    if (n > 0) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->nal_start, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->nal_end, d_ne, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->rbsp_off, d_ro, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->rbsp_end, d_re, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.rc, d.rc, sizes[0], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.nal_hdr, d.nal_hdr, sizes[1], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.kind, d.kind, sizes[2], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.ubflag, d.ubflag, sizes[3], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.hdr_end, d.hdr_end, sizes[4], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.cols, d.cols, sizes[5], cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_off, d.pair_off, sizes[6], cudaMemcpyDeviceToHost, st));
+    }
+    if (idx->rbsp && idx->scan.rbsp_bytes > 0) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->rbsp, d_rbsp, (size_t)idx->scan.rbsp_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    idx->parse = *p_psum;
+    const int64_t np = idx->parse.n_pairs < idx->p.cap_pairs ? idx->parse.n_pairs : idx->p.cap_pairs;
+    if (np > 0 && idx->p.pair_field && idx->p.pair_value) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_field, d.pair_field, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_value, d.pair_value, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (idx->parse.overflow) {
+        HEVCB_SET_ERR(ctx, "hevcb_index_host: %lld syntax elements exceed cap_pairs %lld", (long long)idx->parse.n_pairs, (long long)idx->p.cap_pairs);
+        return HEVCB_E_CAPACITY;
+    }
+    return HEVCB_OK;
+}
+
+// Host-side formatting of device results into the reference's struct layout: zero the struct the NAL wrote and scatter
+// its (field, value) pairs.  No parsing happens here.
+HEVCB_API int hevcb_materialize(const hevcb_stream_index* idx, int64_t k, void* nal, void* vps, void* sps, void* pps, void* sh)
+{
+    if (!idx || k < 0 || k >= idx->scan.n_nals) { return HEVCB_E_ARG; }
+    const int32_t hdr = idx->p.nal_hdr[k];
+    if (hdr != -1 && nal) {
+        hevc_nal_t* nn = reinterpret_cast<hevc_nal_t*>(nal);
+        nn->nal_unit_type = hdr & 0xFF;
+        nn->nal_layer_id = (hdr >> 8) & 0xFF;
+        nn->nal_temporal_id_plus1 = (hdr >> 16) & 0xFF;
+    }
+    int32_t* dst = nullptr;
+    size_t words = 0;
+    switch (idx->p.kind[k]) {
+        case HEVCB_KIND_VPS: dst = reinterpret_cast<int32_t*>(vps); words = sizeof(hevc_vps_t) / 4; break;
+        case HEVCB_KIND_SPS: dst = reinterpret_cast<int32_t*>(sps); words = sizeof(hevc_sps_t) / 4; break;
+        case HEVCB_KIND_PPS: dst = reinterpret_cast<int32_t*>(pps); words = sizeof(hevc_pps_t) / 4; break;
+        case HEVCB_KIND_SLICE: dst = reinterpret_cast<int32_t*>(sh); words = sizeof(hevc_slice_header_t) / 4; break;
+        default: break;
+    }
+    if (dst) {
+        memset(dst, 0, words * 4);
+        const int64_t a = idx->p.pair_off[k], b = idx->p.pair_off[k + 1];
+        for (int64_t i = a; i < b && i < idx->p.cap_pairs; i++) {
+            const uint32_t f = idx->p.pair_field[i];
+            if (f < words) { dst[f] = idx->p.pair_value[i]; }
+        }
+    }
+    return idx->p.rc[k];
 }
 
 } // extern "C"

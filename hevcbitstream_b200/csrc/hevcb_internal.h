@@ -19,6 +19,8 @@ struct hevcb_ctx {
     char err[512] = {0};
     // scan scratch: [0,64) counters, then one 16-byte state word per tile
     hevcb_devbuf scan_scratch;
+    hevcb_devbuf parse_scratch, parse_ps; // parser: per-NAL scratch arrays, parameter-set context tables
+    hevcb_devbuf h_p[9];                  // staging of the parse outputs for the *_host entry points
     // staging used by the *_host entry points
     hevcb_devbuf h_in, h_rbsp, h_a0, h_a1, h_a2, h_a3, h_misc;
     void* pinned = nullptr; // small pinned block for summaries
@@ -64,3 +66,7 @@ static inline int hevcb_reserve(hevcb_ctx* ctx, hevcb_devbuf* b, size_t bytes)
 int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int64_t* d_nal_start, int64_t* d_nal_end,
                             int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
                             hevcb_scan_summary* d_summary, cudaStream_t stream);
+
+int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
+                       const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
+                       hevcb_parse_summary* d_summary, cudaStream_t stream);

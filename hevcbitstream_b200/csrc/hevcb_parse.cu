@@ -1,0 +1,356 @@
+// hevcb_parse.cu -- batched HEVC header parser for sm_100a: read_hevc_nal_unit (hevc_stream.c:155-241) for every NAL
+// of a stream at once, working on the EPB-free image produced by hevcb_scan_strip_*.
+//
+// Dependency-ordered passes (a slice uses "the most recent SPS / PPS NAL before it", not an id lookup):
+//   1. classify      one thread per NAL: 2-byte NAL header -> class (VPS / SPS / PPS / slice / unsupported / strip error)
+//   2. ordinal scan  inclusive counts of SPS and PPS NALs -> for every NAL the ordinal of the last SPS / PPS before it
+//   3. PS pass       VPS / SPS / PPS NALs (rare): full parse, count of syntax elements, and the compact per-ordinal
+//                    context (hevcb_sps_ctx incl. derived RPS tables, hevcb_pps_ctx) kept in device memory
+//   4. slice pass    slice segment headers: parse against the context of their SPS / PPS ordinal, count elements,
+//                    write rc, header end and the SoA columns
+//   5. offset scan   exclusive scan of the per-NAL element counts -> pair_off
+//   6. emit          every parsed NAL walks its syntax once more and writes its (field, value) pairs at pair_off[k]
+// The walker itself (bit reader with 64-bit window and clz exp-Golomb, all syntax structures) is hevcb_syntax.h.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hevcb_internal.h"
+#include "hevcb_syntax.h"
+
+namespace {
+
+constexpr int kCls_None = 0, kCls_Vps = 1, kCls_Sps = 2, kCls_Pps = 3, kCls_Slice = 4, kCls_Other = 5, kCls_StripErr = 255;
+
+// ---- generic 3-kernel scan over a per-element functor -------------------------------------------------------
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+template <typename T>
+__device__ __forceinline__ T block_incl_scan(T v, T* warp_sums, T& block_total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) { v += o; }
+    }
+    if (lane == 31) { warp_sums[warp] = v; }
+    __syncthreads();
+    if (warp == 0) {
+        T w = (lane < kScanThreads / 32) ? warp_sums[lane] : T(0);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T o = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) { w += o; }
+        }
+        if (lane < kScanThreads / 32) { warp_sums[lane] = w; }
+    }
+    __syncthreads();
+    const T base = (warp > 0) ? warp_sums[warp - 1] : T(0);
+    block_total = warp_sums[kScanThreads / 32 - 1];
+    return v + base;
+}
+
+// value extractors
+struct ClsIsSps { const uint8_t* cls; __device__ long long operator()(int64_t i) const { return cls[i] == kCls_Sps ? 1 : 0; } };
+struct ClsIsPps { const uint8_t* cls; __device__ long long operator()(int64_t i) const { return cls[i] == kCls_Pps ? 1 : 0; } };
+struct CntVal { const int32_t* cnt; __device__ long long operator()(int64_t i) const { return (long long)cnt[i]; } };
+
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(F f, int64_t n, long long* block_sums)
+{
+    __shared__ long long ws[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    long long s = 0;
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + (int64_t)j * kScanThreads + threadIdx.x;
+        if (i < n) { s += f(i); }
+    }
+    long long tot;
+    block_incl_scan<long long>(s, ws, tot);
+    if (threadIdx.x == 0) { block_sums[blockIdx.x] = tot; }
+}
+
+// single block: exclusive scan of block_sums in place; total written to block_sums[nb]
+__global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(long long* block_sums, int64_t nb)
+{
+    __shared__ long long ws[kScanThreads / 32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) { carry_s = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = (i < nb) ? block_sums[i] : 0;
+        long long tot;
+        const long long inc = block_incl_scan<long long>(v, ws, tot);
+        const long long carry = carry_s;
+        __syncthreads();
+        if (i < nb) { block_sums[i] = carry + inc - v; }
+        if (threadIdx.x == 0) { carry_s = carry + tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { block_sums[nb] = carry_s; }
+}
+
+// out[i] = (inclusive ? sum_{j<=i} : sum_{j<i}) f(j); blocked arrangement per thread for coalescing via striding
+template <class F, typename TOut, bool kInclusive>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(F f, int64_t n, const long long* block_sums, TOut* out)
+{
+    __shared__ long long ws[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    long long carry = block_sums[blockIdx.x];
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + (int64_t)j * kScanThreads + threadIdx.x;
+        const long long v = (i < n) ? f(i) : 0;
+        long long tot;
+        const long long inc = block_incl_scan<long long>(v, ws, tot);
+        if (i < n) { out[i] = (TOut)(carry + (kInclusive ? inc : inc - v)); }
+        carry += tot;
+        __syncthreads();
+    }
+}
+
+template <class F, typename TOut, bool kInclusive>
+int run_scan(hevcb_ctx* ctx, F f, int64_t n, TOut* out, long long* block_sums /* nb + 1 */, cudaStream_t stream)
+{
+    const int64_t nb = (n + kScanTile - 1) / kScanTile;
+    if (nb == 0) { return HEVCB_OK; }
+    scan_reduce_kernel<F><<<(unsigned)nb, kScanThreads, 0, stream>>>(f, n, block_sums);
+    scan_blocksums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nb);
+    scan_apply_kernel<F, TOut, kInclusive><<<(unsigned)nb, kScanThreads, 0, stream>>>(f, n, block_sums, out);
+    ctx->launches += 3;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
+
+// ---- pass 1: classify ----------------------------------------------------------------------------------------
+__global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t* __restrict__ rbsp_off, const int64_t* __restrict__ rbsp_end,
+                                int64_t n, uint8_t* __restrict__ cls, int32_t* __restrict__ nal_hdr, int32_t* __restrict__ rc,
+                                uint8_t* __restrict__ kind, uint8_t* __restrict__ ubflag, int32_t* __restrict__ cnt, int32_t* __restrict__ hdr_end)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) { return; }
+    const int64_t off = rbsp_off[k], end = rbsp_end[k];
+    cnt[k] = 0;
+    kind[k] = HEVCB_KIND_NONE;
+    ubflag[k] = 0;
+    hdr_end[k] = 0;
+    rc[k] = -1;
+    if (end < 0) { // nal_to_rbsp failed: read_hevc_nal_unit returns -1 before touching h->nal (hevc_stream.c:165-168)
+        cls[k] = (uint8_t)kCls_StripErr;
+        nal_hdr[k] = -1;
+        return;
+    }
+    const int64_t size = end - off;
+    const uint32_t b0 = size > 0 ? rbsp[off] : 0u, b1 = size > 1 ? rbsp[off + 1] : 0u;
+    const uint32_t type = (b0 >> 1) & 0x3Fu;
+    const uint32_t layer = ((b0 & 1u) << 5) | (b1 >> 3);
+    const uint32_t tid = b1 & 7u;
+    nal_hdr[k] = (int32_t)(type | (layer << 8) | (tid << 16));
+    uint8_t c = (uint8_t)kCls_Other;
+    if (hevcb_is_slice_type((int)type)) { c = (uint8_t)kCls_Slice; }
+    else if (type == 32u) { c = (uint8_t)kCls_Vps; }
+    else if (type == 33u) { c = (uint8_t)kCls_Sps; }
+    else if (type == 34u) { c = (uint8_t)kCls_Pps; }
+    cls[k] = c;
+}
+
+// consumed bytes reported by read_hevc_nal_unit: nal_size, minus one when a trailing 00 00 03 was dropped (h264_nal.c:170-173,197)
+__device__ __forceinline__ int32_t consumed_bytes(const uint8_t* __restrict__ buf, int64_t start, int64_t end)
+{
+    const int64_t size = end - start;
+    if (size >= 3 && buf[end - 1] == 3 && buf[end - 2] == 0 && buf[end - 3] == 0) { return (int32_t)(size - 1); }
+    return (int32_t)size;
+}
+
+// ---- passes 3/4/6: parse (count or emit) ------------------------------------------------------------------------
+struct ParseArgs {
+    const uint8_t* buf;
+    const int64_t* nal_start;
+    const int64_t* nal_end;
+    const uint8_t* rbsp;
+    const int64_t* rbsp_off;
+    const int64_t* rbsp_end;
+    int64_t n;
+    const uint8_t* cls;
+    const int32_t* sps_ord; // inclusive count of SPS NALs up to and including k
+    const int32_t* pps_ord;
+    hevcb_sps_ctx* sps_tab;  // [n_sps + 1]; entry 0 = the zeroed state before any SPS (calloc in hevc_new)
+    hevcb_pps_ctx* pps_tab;  // [n_pps + 1]
+    hevcb_sps_ctx* sps_scratch; // emit pass: where re-parsed SPS contexts go (same shape as sps_tab)
+    hevcb_pps_ctx* pps_scratch;
+    int32_t* rc;
+    uint8_t* kind;
+    uint8_t* ubflag;
+    int32_t* cnt;
+    int32_t* hdr_end;
+    int32_t* cols; // 8 columns x n
+    const int64_t* pair_off;
+    uint32_t* pair_field;
+    int32_t* pair_value;
+    int64_t cap_pairs;
+};
+
+template <bool kEmit, bool kSlices>
+__global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) { return; }
+    const int c = a.cls[k];
+    const bool is_ps = (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps);
+    const bool is_slice = (c == kCls_Slice);
+    if (!kEmit) {
+        if (kSlices ? !is_slice : !is_ps) { return; }
+    } else {
+        if (!is_ps && !is_slice) { return; }
+    }
+    const int64_t off = a.rbsp_off[k];
+    const int64_t size = a.rbsp_end[k] - off;
+    // ordinals: entry 0 of the tables is the all-zero state, SPS / PPS number j lives at index j (1-based)
+    const int sps_count = a.sps_ord[k], pps_count = a.pps_ord[k];
+    const hevcb_sps_ctx* sps_in = &a.sps_tab[c == kCls_Sps ? sps_count - 1 : sps_count];
+    const hevcb_pps_ctx* pps_in = &a.pps_tab[c == kCls_Pps ? pps_count - 1 : pps_count];
+    hevcb_sps_ctx* sps_out = nullptr;
+    hevcb_pps_ctx* pps_out = nullptr;
+    if (c == kCls_Sps) { sps_out = kEmit ? &a.sps_scratch[sps_count] : &a.sps_tab[sps_count]; }
+    if (c == kCls_Pps) { pps_out = kEmit ? &a.pps_scratch[pps_count] : &a.pps_tab[pps_count]; }
+    hevcb_nal_result r;
+    if (!kEmit) {
+        hevcb_sink sink{nullptr, nullptr, 0};
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
+        a.cnt[k] = (int32_t)sink.n;
+        a.kind[k] = (uint8_t)r.kind;
+        a.ubflag[k] = (uint8_t)(r.flags & 0xFFu);
+        a.rc[k] = r.ok ? consumed_bytes(a.buf, a.nal_start[k], a.nal_end[k]) : -1;
+        a.hdr_end[k] = kSlices ? r.hdr_end : (int32_t)r.end_bits;
+        if (kSlices) {
+            a.cols[0 * a.n + k] = r.cols.slice_type;
+            a.cols[1 * a.n + k] = r.cols.slice_qp_delta;
+            a.cols[2 * a.n + k] = r.cols.slice_pic_order_cnt_lsb;
+            a.cols[3 * a.n + k] = r.cols.first_slice_segment_in_pic_flag;
+            a.cols[4 * a.n + k] = r.cols.slice_segment_address;
+            a.cols[5 * a.n + k] = r.cols.dependent_slice_segment_flag;
+            a.cols[6 * a.n + k] = r.cols.num_entry_point_offsets;
+            a.cols[7 * a.n + k] = r.cols.short_term_ref_pic_set_idx;
+        }
+    } else {
+        const int64_t po = a.pair_off[k];
+        const int64_t pn = (int64_t)a.cnt[k];
+        if (pn == 0 || po + pn > a.cap_pairs) { return; }
+        hevcb_sink sink{a.pair_field + po, a.pair_value + po, 0};
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
+        if (sink.n != (uint32_t)pn) { a.ubflag[k] |= 0x80u; a.cols[k] = (int32_t)r.end_bits; a.cols[a.n + k] = (int32_t)sink.n; } // self-check
+    }
+}
+
+struct ParseSummaryDev {
+    int64_t n_nals, n_ok, n_pairs, n_vps, n_sps, n_pps, n_slices;
+    int32_t overflow, pad;
+};
+
+__global__ void parse_summary_kernel(const uint8_t* __restrict__ cls, const int32_t* __restrict__ rc, int64_t n, const long long* pair_total,
+                                     int64_t cap_pairs, hevcb_parse_summary* out)
+{
+    __shared__ unsigned long long acc[5];
+    if (threadIdx.x < 5) { acc[threadIdx.x] = 0; }
+    __syncthreads();
+    unsigned long long ok = 0, v = 0, s = 0, p = 0, sl = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        ok += rc[k] >= 0;
+        const int c = cls[k];
+        v += c == kCls_Vps; s += c == kCls_Sps; p += c == kCls_Pps; sl += c == kCls_Slice;
+    }
+    atomicAdd(&acc[0], ok); atomicAdd(&acc[1], v); atomicAdd(&acc[2], s); atomicAdd(&acc[3], p); atomicAdd(&acc[4], sl);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&out->n_ok, acc[0]);
+        atomicAdd((unsigned long long*)&out->n_vps, acc[1]);
+        atomicAdd((unsigned long long*)&out->n_sps, acc[2]);
+        atomicAdd((unsigned long long*)&out->n_pps, acc[3]);
+        atomicAdd((unsigned long long*)&out->n_slices, acc[4]);
+        if (blockIdx.x == 0) {
+            out->n_nals = n;
+            out->n_pairs = *pair_total;
+            out->overflow = (*pair_total > cap_pairs) ? 1 : 0;
+        }
+    }
+}
+
+} // namespace
+
+int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
+                       const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
+                       hevcb_parse_summary* d_summary, cudaStream_t stream)
+{
+    if (n < 0 || !out || !d_summary || (n > 0 && (!d_buf || !d_nal_start || !d_nal_end || !d_rbsp || !d_rbsp_off || !d_rbsp_end))) {
+        HEVCB_SET_ERR(ctx, "hevcb_parse: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    if (n > 0 && (!out->rc || !out->nal_hdr || !out->kind || !out->ubflag || !out->hdr_end || !out->cols || !out->pair_off ||
+                  (out->cap_pairs > 0 && (!out->pair_field || !out->pair_value)))) {
+        HEVCB_SET_ERR(ctx, "hevcb_parse: output buffers missing");
+        return HEVCB_E_ARG;
+    }
+    HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_parse_summary), stream));
+    if (n == 0) { return HEVCB_OK; }
+    const int64_t nb = (n + kScanTile - 1) / kScanTile;
+    // scratch: cls (n), cnt (n x4), sps_ord (n x4), pps_ord (n x4), block sums (nb + 1) x3, pair total
+    size_t need = 0;
+    auto take = [&](size_t bytes) { size_t o = need; need += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_cls = take((size_t)n), o_cnt = take((size_t)n * 4), o_so = take((size_t)n * 4), o_po = take((size_t)n * 4);
+    const size_t o_bs = take((size_t)(nb + 1) * 8), o_tot = take(64);
+    int rcx = hevcb_reserve(ctx, &ctx->parse_scratch, need);
+    if (rcx != HEVCB_OK) { return rcx; }
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->parse_scratch.p);
+    uint8_t* cls = base + o_cls;
+    int32_t* cnt = reinterpret_cast<int32_t*>(base + o_cnt);
+    int32_t* sps_ord = reinterpret_cast<int32_t*>(base + o_so);
+    int32_t* pps_ord = reinterpret_cast<int32_t*>(base + o_po);
+    long long* bsums = reinterpret_cast<long long*>(base + o_bs);
+    long long* pair_total = reinterpret_cast<long long*>(base + o_tot);
+
+    const unsigned g128 = (unsigned)((n + 127) / 128);
+    classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rbsp, d_rbsp_off, d_rbsp_end, n, cls, out->nal_hdr, out->rc, out->kind,
+                                                                    out->ubflag, cnt, out->hdr_end);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    int rcs = run_scan<ClsIsSps, int32_t, true>(ctx, ClsIsSps{cls}, n, sps_ord, bsums, stream);
+    if (rcs != HEVCB_OK) { return rcs; }
+    long long h_counts[2] = {0, 0};
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_counts[0], bsums + nb, 8, cudaMemcpyDeviceToHost, stream));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(stream)); // the table sizes below depend on the counts
+    rcs = run_scan<ClsIsPps, int32_t, true>(ctx, ClsIsPps{cls}, n, pps_ord, bsums, stream);
+    if (rcs != HEVCB_OK) { return rcs; }
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_counts[1], bsums + nb, 8, cudaMemcpyDeviceToHost, stream));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(stream));
+    const size_t n_sps = (size_t)h_counts[0], n_pps = (size_t)h_counts[1];
+    // context tables: entry 0 is the zeroed initial state; a second copy receives the emit pass' re-parse
+    const size_t sps_bytes = (n_sps + 1) * sizeof(hevcb_sps_ctx), pps_bytes = (n_pps + 1) * sizeof(hevcb_pps_ctx);
+    if ((rcx = hevcb_reserve(ctx, &ctx->parse_ps, 2 * sps_bytes + 2 * pps_bytes + 1024)) != HEVCB_OK) { return rcx; }
+    uint8_t* pb = reinterpret_cast<uint8_t*>(ctx->parse_ps.p);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(pb, 0, 2 * sps_bytes + 2 * pps_bytes, stream));
+    ParseArgs a;
+    a.buf = d_buf; a.nal_start = d_nal_start; a.nal_end = d_nal_end; a.rbsp = d_rbsp; a.rbsp_off = d_rbsp_off; a.rbsp_end = d_rbsp_end;
+    a.n = n; a.cls = cls; a.sps_ord = sps_ord; a.pps_ord = pps_ord;
+    a.sps_tab = reinterpret_cast<hevcb_sps_ctx*>(pb);
+    a.sps_scratch = reinterpret_cast<hevcb_sps_ctx*>(pb + sps_bytes);
+    a.pps_tab = reinterpret_cast<hevcb_pps_ctx*>(pb + 2 * sps_bytes);
+    a.pps_scratch = reinterpret_cast<hevcb_pps_ctx*>(pb + 2 * sps_bytes + pps_bytes);
+    a.rc = out->rc; a.kind = out->kind; a.ubflag = out->ubflag; a.cnt = cnt; a.hdr_end = out->hdr_end; a.cols = out->cols;
+    a.pair_off = out->pair_off; a.pair_field = out->pair_field; a.pair_value = out->pair_value; a.cap_pairs = out->cap_pairs;
+
+    parse_kernel<false, false><<<g128, 128, 0, stream>>>(a); // parameter sets first
+    parse_kernel<false, true><<<g128, 128, 0, stream>>>(a);  // then the slices that depend on them
+    ctx->launches += 2;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    rcs = run_scan<CntVal, int64_t, false>(ctx, CntVal{cnt}, n, out->pair_off, bsums, stream);
+    if (rcs != HEVCB_OK) { return rcs; }
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(pair_total, bsums + nb, 8, cudaMemcpyDeviceToDevice, stream));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_off + n, bsums + nb, 8, cudaMemcpyDeviceToDevice, stream));
+    parse_kernel<true, false><<<g128, 128, 0, stream>>>(a);
+    parse_summary_kernel<<<148, 256, 0, stream>>>(cls, out->rc, n, pair_total, out->cap_pairs, d_summary);
+    ctx->launches += 2;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}

@@ -1,0 +1,1005 @@
+// hevcb_syntax.h -- bit reader and HEVC header syntax walker used by the batched parser kernels.
+//
+// Host/device code: compiled by nvcc into the sm_100a parser kernels (hevcb_parse.cu) and by g++ into the TEST-ONLY
+// host build (tests/hostsim) that pins this logic against the reference without a GPU.  The product library only
+// calls it from device code.
+//
+// Behaviour restated (reference file:line):
+//   bit reader        bs.h:117-221   reads past the end yield 0 bits but still advance; ue() prefix loop stops at 32
+//                                    zeros or when the consumed bit makes the cursor reach the end; overrun = byte
+//                                    cursor strictly beyond the end
+//   NAL dispatch      hevc_stream.c:155-241            VPS  :243-300     SPS :303-401 (+ :404-416)   PPS :419-521
+//   slice header      hevc_stream.c:782-941 (+ :944-966 list modification, :969-1029 pred weight table)
+//   PTL :652-755   scaling list :758-779   st_ref_pic_set :1032-1085   VUI :1088-1157   HRD :1160-1218
+//   derived RPS state hevc_stream.in.c:26-113 (file-static tables in the reference; per-SPS tables here)
+// The reference's deviations from the HEVC specification are reproduced on purpose.
+//
+// Every parsed syntax element is reported to a `Sink` as (field index, value), the field index being the offset in
+// ints inside the struct the NAL writes (include/hevcb_layout.h).  Zero-filling that struct and scattering the pairs
+// reproduces what read_hevc_nal_unit leaves in hevc_stream_t.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/hevcb_layout.h"
+
+#if defined(__CUDACC__)
+#define HEVCB_SHD __host__ __device__
+#else
+#define HEVCB_SHD
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// bit reader: 64-bit MSB-first window over the RBSP bytes, refilled on demand
+// ------------------------------------------------------------------------------------------------
+struct hevcb_bits {
+    const uint8_t* base; // first RBSP byte
+    int64_t size;        // RBSP size in bytes
+    int64_t pos;         // bit position
+    int64_t wbyte;       // byte index of the first byte held in `win`
+    uint64_t win;        // bytes [wbyte, wbyte + 8), big endian; bytes at or beyond `size` are 0
+
+    HEVCB_SHD void init(const uint8_t* b, int64_t n)
+    {
+        base = b;
+        size = n;
+        pos = 0;
+        wbyte = -16;
+        win = 0;
+    }
+    HEVCB_SHD void refill(int64_t byte)
+    {
+        uint64_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int64_t b = byte + i;
+            const uint32_t x = (b < size) ? (uint32_t)base[b] : 0u;
+            v = (v << 8) | x;
+        }
+        win = v;
+        wbyte = byte;
+    }
+    // next 32 bits at the cursor, without consuming them
+    HEVCB_SHD uint32_t peek32()
+    {
+        const int64_t byte = pos >> 3;
+        if (byte < wbyte || byte > wbyte + 3) { refill(byte); }
+        const uint32_t sh = (uint32_t)(pos - (wbyte << 3)); // 0..31
+        return (uint32_t)((win << sh) >> 32);
+    }
+    HEVCB_SHD uint32_t read_u(int n) // bs_read_u, n <= 32 (bs.h:160)
+    {
+        if (n <= 0) { return 0u; }
+        if (n > 32) { pos += n - 32; n = 32; } // wider than 32 only on corrupt input (undefined shifts in the reference)
+        const uint32_t v = peek32() >> (32 - n);
+        pos += n;
+        return v;
+    }
+    HEVCB_SHD void skip(int n) // bs_skip_u (bs.h:171): f(n, v) elements of the read variant, n may exceed 32
+    {
+        if (n > 0) { pos += n; }
+    }
+    HEVCB_SHD uint32_t read_u1() { return read_u(1); }
+    HEVCB_SHD uint32_t read_u8() { return read_u(8); } // the FAST_U8 path reads the same bits (bs.h:182)
+    HEVCB_SHD uint32_t read_ue() // bs.h:195-207
+    {
+        const int64_t endbits = size << 3;
+        int64_t j_eof = endbits - 1 - pos; // first consumed bit that makes bs_eof() true
+        if (j_eof < 0) { j_eof = 0; }
+        const uint32_t w = peek32();
+        uint32_t i = 32u;
+        if (w != 0u) {
+#if defined(__CUDA_ARCH__)
+            i = (uint32_t)__clz((int)w);
+#else
+            i = (uint32_t)__builtin_clz(w);
+#endif
+        }
+        if ((int64_t)i > j_eof) { i = (uint32_t)j_eof; }
+        pos += (int64_t)i + 1; // the zeros and the bit that ended the loop
+        uint32_t r = read_u((int)i);
+        r += (i < 32u) ? ((1u << i) - 1u) : 0u; // 1 << 32 evaluates to 1 in the x86 reference
+        return r;
+    }
+    HEVCB_SHD int32_t read_se() // bs.h:209-221
+    {
+        const int32_t r = (int32_t)read_ue();
+        return (r & 1) ? (int32_t)(((int64_t)r + 1) / 2) : -(r / 2);
+    }
+    HEVCB_SHD bool byte_aligned() const { return (pos & 7) == 0; }
+    HEVCB_SHD int64_t byte_pos() const { return pos >> 3; }
+    HEVCB_SHD bool overrun() const { return (pos >> 3) > size; } // bs.h:119
+};
+
+// ------------------------------------------------------------------------------------------------
+// sinks
+// ------------------------------------------------------------------------------------------------
+// One sink type for both passes of the parser (count, then emit), so that both run the very same instantiation of
+// the walker: with `field` null it only counts.
+struct hevcb_sink {
+    uint32_t* field;
+    int32_t* value;
+    uint32_t n;
+    HEVCB_SHD void put(uint32_t f, int32_t v)
+    {
+        if (field) {
+            field[n] = f;
+            value[n] = v;
+        }
+        n++;
+    }
+};
+typedef hevcb_sink hevcb_count_sink;
+typedef hevcb_sink hevcb_emit_sink;
+
+// ------------------------------------------------------------------------------------------------
+// parameter-set context kept on the device for the slices that follow
+// ------------------------------------------------------------------------------------------------
+#define HEVCB_RPS_SLOTS 33 // sets 0..31 of an SPS + the slice-local set at index num_short_term_ref_pic_sets
+
+struct hevcb_rps_entry { // derived variables of one short-term RPS (hevc_stream.in.c:26-32)
+    int32_t num_neg, num_pos, num_delta;
+    uint32_t used_s0, used_s1; // UsedByCurrPicS0/S1 as bit masks
+    int32_t dpoc_s0[32];
+    int32_t dpoc_s1[32];
+};
+
+struct hevcb_sps_ctx {
+    int32_t log2_min_cb_minus3, log2_diff_max_min_cb, pic_width, pic_height;
+    int32_t separate_colour_plane_flag, chroma_format_idc, log2_max_poc_lsb_minus4;
+    int32_t num_short_term_ref_pic_sets, long_term_ref_pics_present_flag, num_long_term_ref_pics_sps;
+    int32_t sps_temporal_mvp_enabled_flag, sample_adaptive_offset_enabled_flag;
+    uint32_t used_by_curr_pic_lt_sps_mask;
+    int32_t pad[3];
+    hevcb_rps_entry rps[HEVCB_RPS_SLOTS];
+};
+
+struct hevcb_pps_ctx {
+    int32_t seq_parameter_set_id, dependent_slice_segments_enabled_flag, output_flag_present_flag, num_extra_slice_header_bits;
+    int32_t cabac_init_present_flag, num_ref_idx_l0_default_active_minus1, num_ref_idx_l1_default_active_minus1;
+    int32_t pps_slice_chroma_qp_offsets_present_flag, weighted_pred_flag, weighted_bipred_flag, tiles_enabled_flag;
+    int32_t entropy_coding_sync_enabled_flag, pps_loop_filter_across_slices_enabled_flag, deblocking_filter_override_enabled_flag;
+    int32_t lists_modification_present_flag, slice_segment_header_extension_present_flag, chroma_qp_offset_list_enabled_flag;
+    int32_t pad[3];
+};
+
+// per-slice columns written besides the (field, value) pairs
+struct hevcb_slice_cols {
+    int32_t slice_type, slice_qp_delta, slice_pic_order_cnt_lsb, first_slice_segment_in_pic_flag;
+    int32_t slice_segment_address, dependent_slice_segment_flag, num_entry_point_offsets, short_term_ref_pic_set_idx;
+};
+
+HEVCB_SHD inline int hevcb_ceil_log2(int64_t n) // ceil(log2(n)) as the reference computes it in double; n <= 0 -> 0 bits
+{
+    if (n <= 1) { return 0; }
+    int b = 0;
+    uint64_t v = (uint64_t)(n - 1);
+    while (v) { b++; v >>= 1; }
+    return b;
+}
+
+#define HF(type, member) HEVCB_FIELD(type, member)
+
+// ------------------------------------------------------------------------------------------------
+// the walker
+// ------------------------------------------------------------------------------------------------
+template <class Sink>
+struct hevcb_walker {
+    hevcb_bits& b;
+    Sink& s;
+    uint32_t flags; // bit0: an index ran past the reference's array bounds (undefined behaviour there)
+
+    HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0) {}
+
+    // value(x, u(n)) / u1 / u8 / ue / se : read + report
+    HEVCB_SHD int32_t u(uint32_t f, int n) { const int32_t v = (int32_t)b.read_u(n); s.put(f, v); return v; }
+    HEVCB_SHD int32_t u1(uint32_t f) { return u(f, 1); }
+    HEVCB_SHD int32_t u8(uint32_t f) { return u(f, 8); }
+    HEVCB_SHD int32_t ue(uint32_t f) { const int32_t v = (int32_t)b.read_ue(); s.put(f, v); return v; }
+    HEVCB_SHD int32_t se(uint32_t f) { const int32_t v = b.read_se(); s.put(f, v); return v; }
+    // array element: reported only inside the reference's bounds
+    HEVCB_SHD int32_t au(uint32_t f, int idx, int bound, int n) { const int32_t v = (int32_t)b.read_u(n); put_idx(f, idx, bound, v); return v; }
+    HEVCB_SHD int32_t aue(uint32_t f, int idx, int bound) { const int32_t v = (int32_t)b.read_ue(); put_idx(f, idx, bound, v); return v; }
+    HEVCB_SHD int32_t ase(uint32_t f, int idx, int bound) { const int32_t v = b.read_se(); put_idx(f, idx, bound, v); return v; }
+    HEVCB_SHD void put_idx(uint32_t f, int idx, int bound, int32_t v)
+    {
+        if (idx >= 0 && idx < bound) { s.put(f + (uint32_t)idx, v); } else { flags |= 1u; }
+    }
+
+    // 7.3.2.11 / 7.3.2.12: one bit, then skip to the byte boundary (hevc_stream.c:630-649)
+    HEVCB_SHD void trailing_bits()
+    {
+        b.skip(1);
+        while (!b.byte_aligned()) { b.skip(1); }
+    }
+
+    // ---- 7.3.3 profile_tier_level (hevc_stream.c:652-755) --------------------------------------
+    HEVCB_SHD void profile_tier_level(uint32_t base, int max_sub_layers_minus1)
+    {
+        typedef hevc_profile_tier_level_t P;
+        u(base + HF(P, general_profile_space), 2);
+        u1(base + HF(P, general_tier_flag));
+        const int idc = u(base + HF(P, general_profile_idc), 5);
+        uint32_t compat = 0;
+        for (int i = 0; i < 32; i++) { compat |= (uint32_t)u1(base + HF(P, general_profile_compatibility_flag) + i) << i; }
+        u1(base + HF(P, general_progressive_source_flag));
+        u1(base + HF(P, general_interlaced_source_flag));
+        u1(base + HF(P, general_non_packed_constraint_flag));
+        u1(base + HF(P, general_frame_only_constraint_flag));
+        if (idc == 4 || ((compat >> 4) & 1) || idc == 5 || ((compat >> 5) & 1) || idc == 6 || ((compat >> 6) & 1) || idc == 7 || ((compat >> 7) & 1)) {
+            u1(base + HF(P, general_max_12bit_constraint_flag));
+            u1(base + HF(P, general_max_10bit_constraint_flag));
+            u1(base + HF(P, general_max_8bit_constraint_flag));
+            u1(base + HF(P, general_max_422chroma_constraint_flag));
+            u1(base + HF(P, general_max_420chroma_constraint_flag));
+            u1(base + HF(P, general_max_monochrome_constraint_flag));
+            u1(base + HF(P, general_intra_constraint_flag));
+            u1(base + HF(P, general_one_picture_only_constraint_flag));
+            u1(base + HF(P, general_lower_bit_rate_constraint_flag));
+            b.skip(34);
+        } else {
+            b.skip(43);
+        }
+        if ((idc >= 1 && idc <= 5) || ((compat >> 1) & 1) || ((compat >> 2) & 1) || ((compat >> 3) & 1) || ((compat >> 4) & 1) || ((compat >> 5) & 1)) {
+            u1(base + HF(P, general_inbld_flag));
+        } else {
+            b.skip(1);
+        }
+        u8(base + HF(P, general_level_idc));
+        uint32_t prof_present = 0, level_present = 0;
+        for (int i = 0; i < max_sub_layers_minus1; i++) {
+            prof_present |= (uint32_t)(au(base + HF(P, sub_layer_profile_present_flag), i, HEVCB_MAX_SUBLAYERS, 1) & 1) << (i & 31);
+            level_present |= (uint32_t)(au(base + HF(P, sub_layer_level_present_flag), i, HEVCB_MAX_SUBLAYERS, 1) & 1) << (i & 31);
+        }
+        if (max_sub_layers_minus1 > 0) {
+            for (int i = max_sub_layers_minus1; i < 8; i++) { b.skip(2); }
+        }
+        for (int i = 0; i < max_sub_layers_minus1; i++) {
+            if ((prof_present >> (i & 31)) & 1u) {
+                au(base + HF(P, sub_layer_profile_space), i, HEVCB_MAX_SUBLAYERS, 2);
+                au(base + HF(P, sub_layer_tier_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                const int sidc = au(base + HF(P, sub_layer_profile_idc), i, HEVCB_MAX_SUBLAYERS, 5);
+                uint32_t sc = 0;
+                for (int j = 0; j < 32; j++) {
+                    const int32_t v = (int32_t)b.read_u(1);
+                    if (i < HEVCB_MAX_SUBLAYERS) { s.put(base + HF(P, sub_layer_profile_compatibility_flag) + (uint32_t)(i * 32 + j), v); } else { flags |= 1u; }
+                    sc |= (uint32_t)v << j;
+                }
+                au(base + HF(P, sub_layer_progressive_source_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                au(base + HF(P, sub_layer_interlaced_source_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                au(base + HF(P, sub_layer_non_packed_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                au(base + HF(P, sub_layer_frame_only_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                if (sidc == 4 || ((sc >> 4) & 1) || sidc == 5 || ((sc >> 5) & 1) || sidc == 6 || ((sc >> 6) & 1) || sidc == 7 || ((sc >> 7) & 1)) {
+                    au(base + HF(P, sub_layer_max_12bit_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_max_10bit_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_max_8bit_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_max_422chroma_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_max_420chroma_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_max_monochrome_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_intra_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_one_picture_only_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    au(base + HF(P, sub_layer_lower_bit_rate_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+                    b.skip(34);
+                } else {
+                    b.skip(43);
+                }
+                // the reference tests the ADDRESS of sub_layer_profile_compatibility_flag[1] (always true): App. A-10
+                au(base + HF(P, sub_layer_inbld_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+            }
+            if ((level_present >> (i & 31)) & 1u) { au(base + HF(P, sub_layer_level_idc), i, HEVCB_MAX_SUBLAYERS, 8); }
+        }
+    }
+
+    // ---- E.2.3 sub-layer HRD (hevc_stream.c:1207-1218): CpbCnt + 1 entries (App. A-8) -----------
+    HEVCB_SHD void sub_layer_hrd(uint32_t base, int cpb_cnt, int sub_pic)
+    {
+        typedef hevc_sub_layer_hrd_t H;
+        for (int i = 0; i <= cpb_cnt; i++) {
+            aue(base + HF(H, bit_rate_value_minus1), i, HEVCB_MAX_CPB_CNT);
+            aue(base + HF(H, cpb_size_value_minus1), i, HEVCB_MAX_CPB_CNT);
+            if (sub_pic) {
+                aue(base + HF(H, cpb_size_du_value_minus1), i, HEVCB_MAX_CPB_CNT);
+                aue(base + HF(H, bit_rate_du_value_minus1), i, HEVCB_MAX_CPB_CNT);
+            }
+            au(base + HF(H, cbr_flag), i, HEVCB_MAX_CPB_CNT, 1);
+        }
+    }
+
+    // ---- E.2.2 HRD parameters (hevc_stream.c:1160-1204) ------------------------------------------
+    HEVCB_SHD void hrd_parameters(uint32_t base, int common_inf_present, int max_sub_layers_minus1)
+    {
+        typedef hevc_hrd_t H;
+        int nal = 0, vcl = 0, sub_pic = 0; // the struct is zeroed by the enclosing memset: absent flags read as 0
+        if (common_inf_present) {
+            nal = u1(base + HF(H, nal_hrd_parameters_present_flag));
+            vcl = u1(base + HF(H, vcl_hrd_parameters_present_flag));
+            if (nal || vcl) {
+                sub_pic = u1(base + HF(H, sub_pic_hrd_params_present_flag));
+                if (sub_pic) {
+                    u8(base + HF(H, tick_divisor_minus2));
+                    u(base + HF(H, du_cpb_removal_delay_increment_length_minus1), 5);
+                    u1(base + HF(H, sub_pic_cpb_params_in_pic_timing_sei_flag));
+                    u(base + HF(H, dpb_output_delay_du_length_minus1), 5);
+                }
+                u(base + HF(H, bit_rate_scale), 4);
+                u(base + HF(H, cpb_size_scale), 4);
+                if (sub_pic) { u(base + HF(H, cpb_size_du_scale), 4); }
+                u(base + HF(H, initial_cpb_removal_delay_length_minus1), 5);
+                u(base + HF(H, au_cpb_removal_delay_length_minus1), 5);
+                u(base + HF(H, dpb_output_delay_length_minus1), 5);
+            }
+        }
+        for (int i = 0; i <= max_sub_layers_minus1; i++) {
+            const int general = au(base + HF(H, fixed_pic_rate_general_flag), i, HEVCB_MAX_SUBLAYERS, 1);
+            int within = 0, low_delay = 0, cpb_cnt_minus1 = 0;
+            if (!general) { within = au(base + HF(H, fixed_pic_rate_within_cvs_flag), i, HEVCB_MAX_SUBLAYERS, 1); }
+            if (within) { aue(base + HF(H, elemental_duration_in_tc_minus1), i, HEVCB_MAX_SUBLAYERS); }
+            else { low_delay = au(base + HF(H, low_delay_hrd_flag), i, HEVCB_MAX_SUBLAYERS, 1); }
+            if (low_delay) { cpb_cnt_minus1 = aue(base + HF(H, cpb_cnt_minus1), i, HEVCB_MAX_SUBLAYERS); } // read when SET (App. A-8)
+            const uint32_t sl = (uint32_t)(sizeof(hevc_sub_layer_hrd_t) / sizeof(int));
+            if (nal) { if (i < HEVCB_MAX_SUBLAYERS) { sub_layer_hrd(base + HF(H, sub_layer_hrd_nal) + (uint32_t)i * sl, cpb_cnt_minus1 + 1, sub_pic); } }
+            if (vcl) { if (i < HEVCB_MAX_SUBLAYERS) { sub_layer_hrd(base + HF(H, sub_layer_hrd_vcl) + (uint32_t)i * sl, cpb_cnt_minus1 + 1, sub_pic); } }
+        }
+    }
+
+    // ---- 7.3.4 scaling list data (hevc_stream.c:758-779): every delta coef lands in [sizeId][matrixId] (App. A-9)
+    HEVCB_SHD void scaling_list_data(uint32_t base)
+    {
+        typedef hevc_scaling_list_data_t L;
+        for (int size_id = 0; size_id < 4; size_id++) {
+            for (int matrix_id = 0; matrix_id < 6; matrix_id += (size_id == 3) ? 3 : 1) {
+                const int mode = u1(base + HF(L, scaling_list_pred_mode_flag) + (uint32_t)(size_id * 6 + matrix_id));
+                if (!mode) {
+                    ue(base + HF(L, scaling_list_pred_matrix_id_delta) + (uint32_t)(size_id * 6 + matrix_id));
+                } else {
+                    int coef_num = 1 << (4 + (size_id << 1));
+                    if (coef_num > 64) { coef_num = 64; }
+                    if (size_id > 1) { se(base + HF(L, scaling_list_dc_coef_minus8) + (uint32_t)((size_id - 2) * 6 + matrix_id)); }
+                    for (int i = 0; i < coef_num; i++) { se(base + HF(L, scaling_list_delta_coef) + (uint32_t)(size_id * 64 + matrix_id)); }
+                }
+            }
+        }
+    }
+
+    // ---- 7.3.7 st_ref_pic_set + derived variables (hevc_stream.c:1032-1085, hevc_stream.in.c:61-113) ----------
+    // `tbl` = derived entries of the enclosing SPS (read for RefRpsIdx), `cur` = entry being produced (index idx).
+    HEVCB_SHD void st_ref_pic_set(uint32_t base, int idx, int num_sets, const hevcb_rps_entry* tbl, hevcb_rps_entry& cur)
+    {
+        typedef hevc_st_ref_pic_set_t R;
+        int inter = 0;
+        if (idx != 0) { inter = u1(base + HF(R, inter_ref_pic_set_prediction_flag)); }
+        if (inter) {
+            int delta_idx_minus1 = 0;
+            if (idx == num_sets) { delta_idx_minus1 = ue(base + HF(R, delta_idx_minus1)); }
+            const int sign = u1(base + HF(R, delta_rps_sign));
+            const int abs_minus1 = ue(base + HF(R, abs_delta_rps_minus1));
+            int ref_idx = idx - (delta_idx_minus1 + 1);
+            if (ref_idx < 0 || ref_idx >= HEVCB_RPS_SLOTS) { flags |= 1u; ref_idx = 0; } // out of bounds in the reference
+            const hevcb_rps_entry& ref = tbl[ref_idx];
+            uint64_t used = 0, use_delta = 0; // use_delta_flag stays 0 when used_by_curr_pic_flag is 1 (App. A-5)
+            for (int j = 0; j <= ref.num_delta; j++) {
+                const int ub = au(base + HF(R, used_by_curr_pic_flag), j, HEVCB_MAX_PICS, 1);
+                if (j < 64) { used |= (uint64_t)(ub & 1) << j; }
+                if (!ub) {
+                    const int ud = au(base + HF(R, use_delta_flag), j, HEVCB_MAX_PICS, 1);
+                    if (j < 64) { use_delta |= (uint64_t)(ud & 1) << j; }
+                }
+            }
+            // updateNumDeltaPocs, inter case
+            const int delta_rps = (1 - 2 * sign) * (abs_minus1 + 1);
+            int i = 0;
+            uint32_t us0 = 0, us1 = 0;
+            int32_t d0[32], d1[32];
+            for (int j = ref.num_pos - 1; j >= 0; j--) {
+                const int jj = j & 31;
+                const int dpoc = ref.dpoc_s1[jj] + delta_rps;
+                const int k = ref.num_neg + j;
+                if (dpoc < 0 && k < 64 && ((use_delta >> k) & 1)) { if (i < 32) { d0[i] = dpoc; us0 |= (uint32_t)((used >> k) & 1) << i; } i++; }
+            }
+            if (delta_rps < 0 && ref.num_delta < 64 && ((use_delta >> ref.num_delta) & 1)) {
+                if (i < 32) { d0[i] = delta_rps; us0 |= (uint32_t)((used >> ref.num_delta) & 1) << i; }
+                i++;
+            }
+            for (int j = 0; j < ref.num_neg; j++) {
+                const int dpoc = ref.dpoc_s0[j & 31] + delta_rps;
+                if (dpoc < 0 && j < 64 && ((use_delta >> j) & 1)) { if (i < 32) { d0[i] = dpoc; us0 |= (uint32_t)((used >> j) & 1) << i; } i++; }
+            }
+            const int nneg = i;
+            i = 0;
+            for (int j = ref.num_neg - 1; j >= 0; j--) {
+                const int dpoc = ref.dpoc_s0[j & 31] + delta_rps;
+                if (dpoc > 0 && j < 64 && ((use_delta >> j) & 1)) { if (i < 32) { d1[i] = dpoc; us1 |= (uint32_t)((used >> j) & 1) << i; } i++; }
+            }
+            if (delta_rps > 0 && ref.num_delta < 64 && ((use_delta >> ref.num_delta) & 1)) {
+                if (i < 32) { d1[i] = delta_rps; us1 |= (uint32_t)((used >> ref.num_delta) & 1) << i; }
+                i++;
+            }
+            for (int j = 0; j < ref.num_pos; j++) {
+                const int dpoc = ref.dpoc_s1[j & 31] + delta_rps;
+                const int k = ref.num_neg + j;
+                if (dpoc > 0 && k < 64 && ((use_delta >> k) & 1)) { if (i < 32) { d1[i] = dpoc; us1 |= (uint32_t)((used >> k) & 1) << i; } i++; }
+            }
+            const int npos = i;
+            if (nneg > 32 || npos > 32) { flags |= 1u; }
+            // entries the reference does not overwrite keep their previous values: carry them over from `cur`
+            for (int j = 0; j < 32; j++) {
+                if (j < nneg) { cur.dpoc_s0[j] = d0[j]; cur.used_s0 = (cur.used_s0 & ~(1u << j)) | (us0 & (1u << j)); }
+                if (j < npos) { cur.dpoc_s1[j] = d1[j]; cur.used_s1 = (cur.used_s1 & ~(1u << j)) | (us1 & (1u << j)); }
+            }
+            cur.num_neg = nneg;
+            cur.num_pos = npos;
+        } else {
+            const int nneg = ue(base + HF(R, num_negative_pics));
+            const int npos = ue(base + HF(R, num_positive_pics));
+            int32_t acc = 0;
+            for (int i = 0; i < nneg; i++) {
+                const int d = aue(base + HF(R, delta_poc_s0_minus1), i, HEVCB_MAX_PICS);
+                const int ub = au(base + HF(R, used_by_curr_pic_s0_flag), i, HEVCB_MAX_PICS, 1);
+                acc = (i == 0) ? -(d + 1) : acc - (d + 1);
+                if (i < 32) { cur.dpoc_s0[i] = acc; cur.used_s0 = (cur.used_s0 & ~(1u << i)) | ((uint32_t)(ub & 1) << i); }
+            }
+            acc = 0;
+            for (int i = 0; i < npos; i++) {
+                const int d = aue(base + HF(R, delta_poc_s1_minus1), i, HEVCB_MAX_PICS);
+                const int ub = au(base + HF(R, used_by_curr_pic_s1_flag), i, HEVCB_MAX_PICS, 1);
+                acc = (i == 0) ? (d + 1) : acc + (d + 1);
+                if (i < 32) { cur.dpoc_s1[i] = acc; cur.used_s1 = (cur.used_s1 & ~(1u << i)) | ((uint32_t)(ub & 1) << i); }
+            }
+            cur.num_neg = nneg;
+            cur.num_pos = npos;
+        }
+        cur.num_delta = cur.num_neg + cur.num_pos;
+    }
+
+    // ---- E.2.1 VUI (hevc_stream.c:1088-1157) -----------------------------------------------------
+    HEVCB_SHD void vui_parameters(uint32_t base, int sps_max_sub_layers_minus1)
+    {
+        typedef hevc_vui_t V;
+        if (u1(base + HF(V, aspect_ratio_info_present_flag))) {
+            if (u8(base + HF(V, aspect_ratio_idc)) == 255) { // SAR_Extended
+                u(base + HF(V, sar_width), 16);
+                u(base + HF(V, sar_height), 16);
+            }
+        }
+        if (u1(base + HF(V, overscan_info_present_flag))) { u1(base + HF(V, overscan_appropriate_flag)); }
+        if (u1(base + HF(V, video_signal_type_present_flag))) {
+            u(base + HF(V, video_format), 3);
+            u1(base + HF(V, video_full_range_flag));
+            if (u1(base + HF(V, colour_description_present_flag))) {
+                u8(base + HF(V, colour_primaries));
+                u8(base + HF(V, transfer_characteristics));
+                u8(base + HF(V, matrix_coefficients));
+            }
+        }
+        if (u1(base + HF(V, chroma_loc_info_present_flag))) {
+            ue(base + HF(V, chroma_sample_loc_type_top_field));
+            ue(base + HF(V, chroma_sample_loc_type_bottom_field));
+        }
+        u1(base + HF(V, neutral_chroma_indication_flag));
+        u1(base + HF(V, field_seq_flag));
+        u1(base + HF(V, frame_field_info_present_flag));
+        if (u1(base + HF(V, default_display_window_flag))) {
+            ue(base + HF(V, def_disp_win_left_offset));
+            ue(base + HF(V, def_disp_win_right_offset));
+            ue(base + HF(V, def_disp_win_top_offset));
+            ue(base + HF(V, def_disp_win_bottom_offset));
+        }
+        if (u1(base + HF(V, vui_timing_info_present_flag))) {
+            u(base + HF(V, vui_num_units_in_tick), 32);
+            u(base + HF(V, vui_time_scale), 32);
+            if (u1(base + HF(V, vui_poc_proportional_to_timing_flag))) { ue(base + HF(V, vui_num_ticks_poc_diff_one_minus1)); }
+            if (u1(base + HF(V, vui_hrd_parameters_present_flag))) { hrd_parameters(base + HF(V, hrd), 1, sps_max_sub_layers_minus1); }
+        }
+        if (u1(base + HF(V, bitstream_restriction_flag))) {
+            u1(base + HF(V, tiles_fixed_structure_flag));
+            u1(base + HF(V, motion_vectors_over_pic_boundaries_flag));
+            u1(base + HF(V, restricted_ref_pic_lists_flag));
+            ue(base + HF(V, min_spatial_segmentation_idc));
+            ue(base + HF(V, max_bytes_per_pic_denom));
+            ue(base + HF(V, max_bits_per_min_cu_denom));
+            ue(base + HF(V, log2_max_mv_length_horizontal));
+            ue(base + HF(V, log2_max_mv_length_vertical));
+        }
+    }
+
+    // ---- 7.3.2.1 VPS (hevc_stream.c:243-300) -----------------------------------------------------
+    HEVCB_SHD void video_parameter_set()
+    {
+        typedef hevc_vps_t V;
+        u(HF(V, vps_video_parameter_set_id), 4);
+        u1(HF(V, vps_base_layer_internal_flag));
+        u1(HF(V, vps_base_layer_available_flag));
+        u(HF(V, vps_max_layers_minus1), 6);
+        const int msl = u(HF(V, vps_max_sub_layers_minus1), 3);
+        u1(HF(V, vps_temporal_id_nesting_flag));
+        b.skip(16);
+        profile_tier_level(HF(V, ptl), msl);
+        const int ordering = u1(HF(V, vps_sub_layer_ordering_info_present_flag));
+        for (int i = (ordering ? 0 : msl); i <= msl; i++) {
+            aue(HF(V, vps_max_dec_pic_buffering_minus1), i, HEVCB_MAX_SUBLAYERS);
+            aue(HF(V, vps_max_num_reorder_pics), i, HEVCB_MAX_SUBLAYERS);
+            aue(HF(V, vps_max_latency_increase_plus1), i, HEVCB_MAX_SUBLAYERS);
+        }
+        const int max_layer_id = u(HF(V, vps_max_layer_id), 6);
+        const int num_layer_sets_minus1 = ue(HF(V, vps_num_layer_sets_minus1));
+        for (int i = 1; i <= num_layer_sets_minus1; i++) {
+            for (int j = 0; j <= max_layer_id; j++) {
+                const int32_t v = (int32_t)b.read_u(1);
+                if (i < HEVCB_MAX_SUBLAYERS && j < HEVCB_MAX_SUBLAYERS) { s.put(HF(V, layer_id_included_flag) + (uint32_t)(i * HEVCB_MAX_SUBLAYERS + j), v); }
+                else { flags |= 1u; }
+            }
+        }
+        if (u1(HF(V, vps_timing_info_present_flag))) {
+            u(HF(V, vps_num_units_in_tick), 32);
+            u(HF(V, vps_time_scale), 32);
+            if (u1(HF(V, vps_poc_proportional_to_timing_flag))) { ue(HF(V, vps_num_ticks_poc_diff_one_minus1)); }
+            const int num_hrd = ue(HF(V, vps_num_hrd_parameters));
+            for (int i = 0; i < num_hrd; i++) {
+                aue(HF(V, hrd_layer_set_idx), i, HEVCB_MAX_HRD_PARAM);
+                int cprms = 0; // cprms_present_flag[0] is neither read nor inferred (App. A-8)
+                if (i > 0) { cprms = au(HF(V, cprms_present_flag), i, HEVCB_MAX_HRD_PARAM, 1); }
+                const uint32_t hs = (uint32_t)(sizeof(hevc_hrd_t) / sizeof(int));
+                if (i < HEVCB_MAX_HRD_PARAM) { hrd_parameters(HF(V, hrd) + (uint32_t)i * hs, cprms, msl); }
+                else { flags |= 1u; hevcb_sink dummy{nullptr, nullptr, 0}; hevcb_walker<hevcb_count_sink> w(b, dummy); w.hrd_parameters(0, cprms, msl); }
+            }
+        }
+        u1(HF(V, vps_extension_flag));
+        trailing_bits();
+    }
+
+    // ---- 7.3.2.2 SPS (hevc_stream.c:303-416): no rbsp_trailing_bits (App. A-1) -------------------
+    HEVCB_SHD void seq_parameter_set(hevcb_sps_ctx& c)
+    {
+        typedef hevc_sps_t S;
+        u(HF(S, sps_video_parameter_set_id), 4);
+        const int msl = u(HF(S, sps_max_sub_layers_minus1), 3);
+        u1(HF(S, sps_temporal_id_nesting_flag));
+        profile_tier_level(HF(S, ptl), msl);
+        ue(HF(S, sps_seq_parameter_set_id));
+        c.chroma_format_idc = ue(HF(S, chroma_format_idc));
+        c.separate_colour_plane_flag = 0;
+        if (c.chroma_format_idc == 3) { c.separate_colour_plane_flag = u1(HF(S, separate_colour_plane_flag)); }
+        c.pic_width = ue(HF(S, pic_width_in_luma_samples));
+        c.pic_height = ue(HF(S, pic_height_in_luma_samples));
+        if (u1(HF(S, conformance_window_flag))) {
+            ue(HF(S, conf_win_left_offset));
+            ue(HF(S, conf_win_right_offset));
+            ue(HF(S, conf_win_top_offset));
+            ue(HF(S, conf_win_bottom_offset));
+        }
+        ue(HF(S, bit_depth_luma_minus8));
+        ue(HF(S, bit_depth_chroma_minus8));
+        c.log2_max_poc_lsb_minus4 = ue(HF(S, log2_max_pic_order_cnt_lsb_minus4));
+        const int ordering = u1(HF(S, sps_sub_layer_ordering_info_present_flag));
+        for (int i = (ordering ? 0 : msl); i <= msl; i++) {
+            aue(HF(S, sps_max_dec_pic_buffering_minus1), i, HEVCB_MAX_SUBLAYERS);
+            aue(HF(S, sps_max_num_reorder_pics), i, HEVCB_MAX_SUBLAYERS);
+            aue(HF(S, sps_max_latency_increase_plus1), i, HEVCB_MAX_SUBLAYERS);
+        }
+        c.log2_min_cb_minus3 = ue(HF(S, log2_min_luma_coding_block_size_minus3));
+        c.log2_diff_max_min_cb = ue(HF(S, log2_diff_max_min_luma_coding_block_size));
+        ue(HF(S, log2_min_luma_transform_block_size_minus2));
+        ue(HF(S, log2_diff_max_min_luma_transform_block_size));
+        ue(HF(S, max_transform_hierarchy_depth_inter));
+        ue(HF(S, max_transform_hierarchy_depth_intra));
+        if (u1(HF(S, scaling_list_enabled_flag))) {
+            if (u1(HF(S, sps_scaling_list_data_present_flag))) { scaling_list_data(HF(S, scaling_list_data)); }
+        }
+        u1(HF(S, amp_enabled_flag));
+        c.sample_adaptive_offset_enabled_flag = u1(HF(S, sample_adaptive_offset_enabled_flag));
+        if (u1(HF(S, pcm_enabled_flag))) {
+            u(HF(S, pcm_sample_bit_depth_luma_minus1), 4);
+            u(HF(S, pcm_sample_bit_depth_chroma_minus1), 4);
+            ue(HF(S, log2_min_pcm_luma_coding_block_size_minus3));
+            ue(HF(S, log2_diff_max_min_pcm_luma_coding_block_size));
+            u1(HF(S, pcm_loop_filter_disabled_flag));
+        }
+        c.num_short_term_ref_pic_sets = ue(HF(S, num_short_term_ref_pic_sets));
+        const uint32_t rs = (uint32_t)(sizeof(hevc_st_ref_pic_set_t) / sizeof(int));
+        for (int i = 0; i < c.num_short_term_ref_pic_sets; i++) {
+            if (i < HEVCB_MAX_PICS) {
+                st_ref_pic_set(HF(S, st_ref_pic_set) + (uint32_t)i * rs, i, c.num_short_term_ref_pic_sets, c.rps, c.rps[i]);
+            } else { // beyond the reference's array: keep the bit cursor moving, report nothing
+                flags |= 1u;
+                hevcb_sink dummy{nullptr, nullptr, 0};
+                hevcb_walker<hevcb_count_sink> w(b, dummy);
+                hevcb_rps_entry scratch = c.rps[HEVCB_RPS_SLOTS - 1];
+                w.st_ref_pic_set(0, i, c.num_short_term_ref_pic_sets, c.rps, scratch);
+            }
+        }
+        c.long_term_ref_pics_present_flag = u1(HF(S, long_term_ref_pics_present_flag));
+        c.num_long_term_ref_pics_sps = 0;
+        c.used_by_curr_pic_lt_sps_mask = 0;
+        if (c.long_term_ref_pics_present_flag) {
+            c.num_long_term_ref_pics_sps = ue(HF(S, num_long_term_ref_pics_sps));
+            for (int i = 0; i < c.num_long_term_ref_pics_sps; i++) {
+                au(HF(S, lt_ref_pic_poc_lsb_sps), i, HEVCB_MAX_PICS, c.log2_max_poc_lsb_minus4 + 4);
+                const int f = au(HF(S, used_by_curr_pic_lt_sps_flag), i, HEVCB_MAX_PICS, 1);
+                if (i < 32) { c.used_by_curr_pic_lt_sps_mask |= (uint32_t)(f & 1) << i; }
+            }
+        }
+        c.sps_temporal_mvp_enabled_flag = u1(HF(S, sps_temporal_mvp_enabled_flag));
+        u1(HF(S, strong_intra_smoothing_enabled_flag));
+        if (u1(HF(S, vui_parameters_present_flag))) { vui_parameters(HF(S, vui), msl); }
+        int range_ext = 0;
+        if (u1(HF(S, sps_extension_present_flag))) {
+            range_ext = u1(HF(S, sps_range_extension_flag));
+            u1(HF(S, sps_multilayer_extension_flag));
+            u1(HF(S, sps_3d_extension_flag));
+            u(HF(S, sps_extension_5bits), 5);
+        }
+        if (range_ext) {
+            const uint32_t e = HF(S, sps_range_ext);
+            typedef hevc_sps_range_ext_t E;
+            u1(e + HF(E, transform_skip_rotation_enabled_flag));
+            u1(e + HF(E, transform_skip_context_enabled_flag));
+            u1(e + HF(E, implicit_rdpcm_enabled_flag));
+            u1(e + HF(E, explicit_rdpcm_enabled_flag));
+            u1(e + HF(E, extended_precision_processing_flag));
+            u1(e + HF(E, intra_smoothing_disabled_flag));
+            u1(e + HF(E, high_precision_offsets_enabled_flag));
+            u1(e + HF(E, persistent_rice_adaptation_enabled_flag));
+            u1(e + HF(E, cabac_bypass_alignment_enabled_flag));
+        }
+    }
+
+    // ---- 7.3.2.3 PPS (hevc_stream.c:419-521) ------------------------------------------------------
+    HEVCB_SHD void pic_parameter_set(hevcb_pps_ctx& c)
+    {
+        typedef hevc_pps_t P;
+        ue(HF(P, pic_parameter_set_id));
+        c.seq_parameter_set_id = ue(HF(P, seq_parameter_set_id));
+        c.dependent_slice_segments_enabled_flag = u1(HF(P, dependent_slice_segments_enabled_flag));
+        c.output_flag_present_flag = u1(HF(P, output_flag_present_flag));
+        c.num_extra_slice_header_bits = u(HF(P, num_extra_slice_header_bits), 3);
+        u1(HF(P, sign_data_hiding_enabled_flag));
+        c.cabac_init_present_flag = u1(HF(P, cabac_init_present_flag));
+        c.num_ref_idx_l0_default_active_minus1 = ue(HF(P, num_ref_idx_l0_default_active_minus1));
+        c.num_ref_idx_l1_default_active_minus1 = ue(HF(P, num_ref_idx_l1_default_active_minus1));
+        se(HF(P, init_qp_minus26));
+        u1(HF(P, constrained_intra_pred_flag));
+        const int transform_skip = u1(HF(P, transform_skip_enabled_flag));
+        if (u1(HF(P, cu_qp_delta_enabled_flag))) { ue(HF(P, diff_cu_qp_delta_depth)); }
+        se(HF(P, pps_cb_qp_offset));
+        se(HF(P, pps_cr_qp_offset));
+        c.pps_slice_chroma_qp_offsets_present_flag = u1(HF(P, pps_slice_chroma_qp_offsets_present_flag));
+        c.weighted_pred_flag = u1(HF(P, weighted_pred_flag));
+        c.weighted_bipred_flag = u1(HF(P, weighted_bipred_flag));
+        u1(HF(P, transquant_bypass_enabled_flag));
+        c.tiles_enabled_flag = u1(HF(P, tiles_enabled_flag));
+        c.entropy_coding_sync_enabled_flag = u1(HF(P, entropy_coding_sync_enabled_flag));
+        if (c.tiles_enabled_flag) {
+            const int cols = ue(HF(P, num_tile_columns_minus1));
+            const int rows = ue(HF(P, num_tile_rows_minus1));
+            if (!u1(HF(P, uniform_spacing_flag))) {
+                for (int i = 0; i < cols; i++) { aue(HF(P, column_width_minus1), i, HEVCB_MAX_PICS); }
+                for (int i = 0; i < rows; i++) { aue(HF(P, row_height_minus1), i, HEVCB_MAX_PICS); }
+            }
+            u1(HF(P, loop_filter_across_tiles_enabled_flag));
+        }
+        c.pps_loop_filter_across_slices_enabled_flag = u1(HF(P, pps_loop_filter_across_slices_enabled_flag));
+        c.deblocking_filter_override_enabled_flag = 0;
+        if (u1(HF(P, deblocking_filter_control_present_flag))) {
+            c.deblocking_filter_override_enabled_flag = u1(HF(P, deblocking_filter_override_enabled_flag));
+            if (u1(HF(P, pps_deblocking_filter_disabled_flag))) { // offsets read when the filter is DISABLED (App. A-6)
+                se(HF(P, pps_beta_offset_div2));
+                se(HF(P, pps_tc_offset_div2));
+            }
+        }
+        if (u1(HF(P, pps_scaling_list_data_present_flag))) { scaling_list_data(HF(P, scaling_list_data)); }
+        c.lists_modification_present_flag = u1(HF(P, lists_modification_present_flag));
+        ue(HF(P, log2_parallel_merge_level_minus2));
+        c.slice_segment_header_extension_present_flag = u1(HF(P, slice_segment_header_extension_present_flag));
+        int range_ext = 0;
+        if (u1(HF(P, pps_extension_present_flag))) {
+            range_ext = u1(HF(P, pps_range_extension_flag));
+            u1(HF(P, pps_multilayer_extension_flag));
+            u1(HF(P, pps_3d_extension_flag));
+            u1(HF(P, pps_extension_5bits)); // ONE bit (App. A-6)
+        }
+        c.chroma_qp_offset_list_enabled_flag = 0;
+        if (range_ext) {
+            const uint32_t e = HF(P, pps_range_ext);
+            typedef hevc_pps_range_ext_t E;
+            if (transform_skip) { ue(e + HF(E, log2_max_transform_skip_block_size_minus2)); }
+            u1(e + HF(E, cross_component_prediction_enabled_flag));
+            c.chroma_qp_offset_list_enabled_flag = u1(e + HF(E, chroma_qp_offset_list_enabled_flag));
+            if (c.chroma_qp_offset_list_enabled_flag) {
+                ue(e + HF(E, diff_cu_chroma_qp_offset_depth));
+                const int len_minus1 = ue(e + HF(E, chroma_qp_offset_list_len_minus1));
+                for (int i = 0; i <= len_minus1; i++) {
+                    ase(e + HF(E, cb_qp_offset_list), i, HEVCB_MAX_PICS);
+                    ase(e + HF(E, cr_qp_offset_list), i, HEVCB_MAX_PICS);
+                }
+            }
+            ue(e + HF(E, log2_sao_offset_scale_luma));
+            ue(e + HF(E, log2_sao_offset_scale_chroma));
+        }
+        trailing_bits();
+    }
+
+    // getNumPicTotalCurr (hevc_stream.in.c:35-59)
+    HEVCB_SHD static int num_pic_total_curr(const hevcb_sps_ctx& sps, const hevcb_rps_entry& e, int num_lt_sps, int num_lt_pics,
+                                            const int* lt_idx_sps, uint32_t used_lt_mask)
+    {
+        int n = 0;
+        for (int i = 0; i < e.num_neg && i < 32; i++) { n += (e.used_s0 >> i) & 1u; }
+        for (int i = 0; i < e.num_pos && i < 32; i++) { n += (e.used_s1 >> i) & 1u; }
+        for (int i = 0; i < num_lt_sps + num_lt_pics; i++) {
+            int used;
+            if (i < num_lt_sps) { const int k = (i < 32) ? lt_idx_sps[i] : 0; used = (k >= 0 && k < 32) ? ((sps.used_by_curr_pic_lt_sps_mask >> k) & 1u) : 0; }
+            else { used = (i < 32) ? ((used_lt_mask >> i) & 1u) : 0; }
+            n += used;
+        }
+        return n;
+    }
+
+    // ---- 7.3.6 slice segment header (hevc_stream.c:782-941) --------------------------------------
+    // Returns nothing; `cols` receives the per-slice columns.  `sps`/`pps` = the most recent SPS / PPS NAL that
+    // precedes the slice in stream order (pointer indexing with id 0, not a table lookup).
+    HEVCB_SHD void slice_segment_header(int nal_unit_type, const hevcb_sps_ctx& sps, const hevcb_pps_ctx& pps, hevcb_slice_cols& cols)
+    {
+        typedef hevc_slice_header_t H;
+        s.put(HF(H, collocated_from_l0_flag), 1); // init_slice_hevc (hevc_stream.c:18-23)
+        const int first = u1(HF(H, first_slice_segment_in_pic_flag));
+        if (nal_unit_type >= 16 && nal_unit_type <= 23) { u1(HF(H, no_output_of_prior_pics_flag)); }
+        const int pps_id = ue(HF(H, pic_parameter_set_id));
+        if (pps_id != 0 || pps.seq_parameter_set_id != 0) { flags |= 1u; } // the reference indexes past its single PPS / SPS
+        int num_ref_idx_l0 = pps.num_ref_idx_l0_default_active_minus1, num_ref_idx_l1 = pps.num_ref_idx_l1_default_active_minus1;
+        s.put(HF(H, num_ref_idx_l0_active_minus1), num_ref_idx_l0);
+        s.put(HF(H, num_ref_idx_l1_active_minus1), num_ref_idx_l1);
+        int dependent = 0;
+        cols.first_slice_segment_in_pic_flag = first;
+        cols.slice_segment_address = 0;
+        cols.slice_type = 0;
+        cols.slice_qp_delta = 0;
+        cols.slice_pic_order_cnt_lsb = 0;
+        cols.num_entry_point_offsets = 0;
+        cols.short_term_ref_pic_set_idx = 0;
+        if (!first) {
+            if (pps.dependent_slice_segments_enabled_flag) { dependent = u1(HF(H, dependent_slice_segment_flag)); }
+            // getSliceSegmentAddressBitLength (hevc_stream.in.c:115-123)
+            int ctb_log2 = sps.log2_min_cb_minus3 + 3 + sps.log2_diff_max_min_cb;
+            if (ctb_log2 < 0 || ctb_log2 > 30) { flags |= 1u; ctb_log2 = ctb_log2 < 0 ? 0 : 30; }
+            const int64_t ctb = (int64_t)1 << ctb_log2;
+            const int64_t wc = ((int64_t)sps.pic_width + ctb - 1) >> ctb_log2;
+            const int64_t hc = ((int64_t)sps.pic_height + ctb - 1) >> ctb_log2;
+            const int32_t pic_size = (int32_t)(wc * hc);
+            cols.slice_segment_address = u(HF(H, slice_segment_address), hevcb_ceil_log2(pic_size));
+        }
+        cols.dependent_slice_segment_flag = dependent;
+        if (!dependent) {
+            for (int i = 0; i < pps.num_extra_slice_header_bits; i++) { b.skip(1); }
+            const int slice_type = ue(HF(H, slice_type));
+            cols.slice_type = slice_type;
+            if (pps.output_flag_present_flag) { u1(HF(H, pic_output_flag)); }
+            if (sps.separate_colour_plane_flag == 1) { u(HF(H, colour_plane_id), 2); }
+            int slice_temporal_mvp = 0, sao_luma = 0, sao_chroma = 0;
+            int short_term_sps_flag = 0, st_idx = 0, num_lt_sps = 0, num_lt_pics = 0;
+            int lt_idx_sps[32];
+            uint32_t used_lt_mask = 0;
+            hevcb_rps_entry local; // derived variables of the slice-local RPS (index num_short_term_ref_pic_sets)
+            bool have_local = false;
+            for (int i = 0; i < 32; i++) { lt_idx_sps[i] = 0; }
+            if (nal_unit_type != 19 && nal_unit_type != 20) {
+                cols.slice_pic_order_cnt_lsb = u(HF(H, slice_pic_order_cnt_lsb), sps.log2_max_poc_lsb_minus4 + 4);
+                short_term_sps_flag = u1(HF(H, short_term_ref_pic_set_sps_flag));
+                const int nsets = sps.num_short_term_ref_pic_sets;
+                if (!short_term_sps_flag) {
+                    const int slot = (nsets >= 0 && nsets < HEVCB_RPS_SLOTS) ? nsets : HEVCB_RPS_SLOTS - 1;
+                    if (slot != nsets) { flags |= 1u; }
+                    local = sps.rps[slot]; // entries the parse does not overwrite keep the table's previous content
+                    st_ref_pic_set(HF(H, st_ref_pic_set), nsets, nsets, sps.rps, local);
+                    have_local = true;
+                } else if (nsets > 1) {
+                    st_idx = u(HF(H, short_term_ref_pic_set_idx), hevcb_ceil_log2(nsets));
+                    cols.short_term_ref_pic_set_idx = st_idx;
+                }
+                if (sps.long_term_ref_pics_present_flag) {
+                    if (sps.num_long_term_ref_pics_sps > 0) { num_lt_sps = ue(HF(H, num_long_term_sps)); }
+                    num_lt_pics = ue(HF(H, num_long_term_pics));
+                    const int64_t tot = (int64_t)num_lt_sps + (int64_t)num_lt_pics;
+                    for (int64_t i = 0; i < tot; i++) {
+                        const int ii = (int)(i < 0x7fffffff ? i : 0x7fffffff);
+                        if (i < num_lt_sps) {
+                            if (sps.num_long_term_ref_pics_sps > 1) {
+                                const int v = au(HF(H, lt_idx_sps), ii, HEVCB_MAX_PICS, hevcb_ceil_log2(sps.num_long_term_ref_pics_sps));
+                                if (ii < 32) { lt_idx_sps[ii] = v; }
+                            }
+                        } else {
+                            au(HF(H, poc_lsb_lt), ii, HEVCB_MAX_PICS, sps.log2_max_poc_lsb_minus4 + 4);
+                            const int f = au(HF(H, used_by_curr_pic_lt_flag), ii, HEVCB_MAX_PICS, 1);
+                            if (ii < 32) { used_lt_mask |= (uint32_t)(f & 1) << ii; }
+                        }
+                        if (au(HF(H, delta_poc_msb_present_flag), ii, HEVCB_MAX_PICS, 1)) { aue(HF(H, delta_poc_msb_cycle_lt), ii, HEVCB_MAX_PICS); }
+                        if (b.overrun() && i > 64) { break; } // runaway count on a truncated NAL: the result is -1 either way
+                    }
+                }
+                if (sps.sps_temporal_mvp_enabled_flag) { slice_temporal_mvp = u1(HF(H, slice_temporal_mvp_enabled_flag)); }
+            }
+            if (sps.sample_adaptive_offset_enabled_flag) {
+                sao_luma = u1(HF(H, slice_sao_luma_flag));
+                const int cat = (sps.separate_colour_plane_flag == 0) ? sps.chroma_format_idc : 0;
+                if (cat != 0) { sao_chroma = u1(HF(H, slice_sao_chroma_flag)); }
+            }
+            if (slice_type == 1 || slice_type == 0) { // P or B (HEVC_SLICE_TYPE_P = 1, _B = 0)
+                if (u1(HF(H, num_ref_idx_active_override_flag))) {
+                    num_ref_idx_l0 = ue(HF(H, num_ref_idx_l0_active_minus1));
+                    if (slice_type == 0) { num_ref_idx_l1 = ue(HF(H, num_ref_idx_l1_active_minus1)); }
+                }
+                // the RPS that getNumPicTotalCurr consults: slice-local entry or the SPS entry short_term_ref_pic_set_idx
+                const int cur_idx = short_term_sps_flag ? st_idx : sps.num_short_term_ref_pic_sets;
+                const int slot = (cur_idx >= 0 && cur_idx < HEVCB_RPS_SLOTS) ? cur_idx : HEVCB_RPS_SLOTS - 1;
+                const hevcb_rps_entry& e = (have_local && !short_term_sps_flag) ? local : sps.rps[slot];
+                if (pps.lists_modification_present_flag) {
+                    const int total = num_pic_total_curr(sps, e, num_lt_sps, num_lt_pics, lt_idx_sps, used_lt_mask);
+                    if (total > 1) { // 7.3.6.2 (hevc_stream.c:944-966); flag_l1 is never read (App. A-4)
+                        typedef hevc_ref_pics_lists_mod_t M;
+                        const uint32_t m = HF(H, rpld);
+                        if (u1(m + HF(M, ref_pic_list_modification_flag_l0))) {
+                            for (int i = 0; i <= num_ref_idx_l0; i++) {
+                                au(m + HF(M, list_entry_l0), i, HEVCB_MAX_PICS, hevcb_ceil_log2(total));
+                                if (b.overrun() && i > 64) { break; }
+                            }
+                        }
+                    }
+                }
+                if (slice_type == 0) { u1(HF(H, mvd_l1_zero_flag)); }
+                if (pps.cabac_init_present_flag) { u1(HF(H, cabac_init_flag)); }
+                if (slice_temporal_mvp) {
+                    int collocated_from_l0 = 1;
+                    if (slice_type == 0) { collocated_from_l0 = u1(HF(H, collocated_from_l0_flag)); }
+                    if ((collocated_from_l0 && num_ref_idx_l0 > 0) || (!collocated_from_l0 && num_ref_idx_l1 > 0)) { ue(HF(H, collocated_ref_idx)); }
+                }
+                if ((pps.weighted_pred_flag && slice_type == 1) || (pps.weighted_bipred_flag && slice_type == 0)) {
+                    pred_weight_table(HF(H, pwt), sps, slice_type, num_ref_idx_l0, num_ref_idx_l1);
+                }
+                ue(HF(H, five_minus_max_num_merge_cand));
+            }
+            cols.slice_qp_delta = se(HF(H, slice_qp_delta));
+            if (pps.pps_slice_chroma_qp_offsets_present_flag) {
+                se(HF(H, slice_cb_qp_offset));
+                se(HF(H, slice_cr_qp_offset));
+            }
+            if (pps.chroma_qp_offset_list_enabled_flag) { u1(HF(H, cu_chroma_qp_offset_enabled_flag)); }
+            int override_flag = 0, slice_deblocking_disabled = 0;
+            if (pps.deblocking_filter_override_enabled_flag) { override_flag = u1(HF(H, deblocking_filter_override_flag)); }
+            if (override_flag) {
+                slice_deblocking_disabled = u1(HF(H, slice_deblocking_filter_disabled_flag));
+                if (!slice_deblocking_disabled) {
+                    se(HF(H, slice_beta_offset_div2));
+                    se(HF(H, slice_tc_offset_div2));
+                }
+            }
+            if (pps.pps_loop_filter_across_slices_enabled_flag && (sao_luma || sao_chroma || !slice_deblocking_disabled)) {
+                u1(HF(H, slice_loop_filter_across_slices_enabled_flag));
+            }
+        }
+        if (pps.tiles_enabled_flag || pps.entropy_coding_sync_enabled_flag) {
+            const int n = ue(HF(H, num_entry_point_offsets));
+            cols.num_entry_point_offsets = n;
+            if (n > 0) {
+                const int len_minus1 = ue(HF(H, offset_len_minus1));
+                for (int i = 0; i < n; i++) {
+                    // u(offset_len_minus1 + 1): widths beyond 32 only occur on corrupt input
+                    const int w = len_minus1 + 1;
+                    int32_t v;
+                    if (w <= 32) { v = (int32_t)b.read_u(w); } else { b.skip(w - 32); v = (int32_t)b.read_u(32); flags |= 1u; }
+                    put_idx(HF(H, entry_point_offset_minus1), i, HEVCB_MAX_PICS, v);
+                    if (b.overrun() && i > 64) { break; }
+                }
+            }
+        }
+        if (pps.slice_segment_header_extension_present_flag) {
+            const int len = ue(HF(H, slice_segment_header_extension_length));
+            for (int i = 0; i < len; i++) {
+                b.skip(8);
+                if (b.overrun()) { break; }
+            }
+        }
+        trailing_bits(); // byte_alignment(): same bit pattern handling (hevc_stream.c:641-649)
+    }
+
+    // ---- 7.3.6.3 pred_weight_table (hevc_stream.c:969-1029) ---------------------------------------
+    HEVCB_SHD void pred_weight_table(uint32_t base, const hevcb_sps_ctx& sps, int slice_type, int n0, int n1)
+    {
+        typedef hevc_pred_weight_table_t W;
+        ue(base + HF(W, luma_log2_weight_denom));
+        const int cat = (sps.separate_colour_plane_flag == 0) ? sps.chroma_format_idc : 0;
+        if (cat != 0) { se(base + HF(W, delta_chroma_log2_weight_denom)); }
+        one_list(base, cat, n0, HF(W, luma_weight_l0_flag), HF(W, chroma_weight_l0_flag), HF(W, delta_luma_weight_l0), HF(W, luma_offset_l0),
+                 HF(W, delta_chroma_weight_l0), HF(W, delta_chroma_offset_l0));
+        if (slice_type == 0) {
+            one_list(base, cat, n1, HF(W, luma_weight_l1_flag), HF(W, chroma_weight_l1_flag), HF(W, delta_luma_weight_l1), HF(W, luma_offset_l1),
+                     HF(W, delta_chroma_weight_l1), HF(W, delta_chroma_offset_l1));
+        }
+    }
+    HEVCB_SHD void one_list(uint32_t base, int cat, int n, uint32_t f_lw, uint32_t f_cw, uint32_t f_dl, uint32_t f_lo, uint32_t f_dcw, uint32_t f_dco)
+    {
+        uint64_t lw = 0, cw = 0; // chroma flags stay 0 (struct zeroed) when ChromaArrayType == 0
+        for (int i = 0; i <= n; i++) {
+            const int f = au(base + f_lw, i, HEVCB_MAX_PICS, 1);
+            if (i < 64) { lw |= (uint64_t)(f & 1) << i; }
+            if (b.overrun() && i > 64) { break; }
+        }
+        if (cat != 0) {
+            for (int i = 0; i <= n; i++) {
+                const int f = au(base + f_cw, i, HEVCB_MAX_PICS, 1);
+                if (i < 64) { cw |= (uint64_t)(f & 1) << i; }
+                if (b.overrun() && i > 64) { break; }
+            }
+        }
+        for (int i = 0; i <= n; i++) {
+            if (i < 64 && ((lw >> i) & 1)) {
+                ase(base + f_dl, i, HEVCB_MAX_PICS);
+                ase(base + f_lo, i, HEVCB_MAX_PICS);
+            }
+            if (i < 64 && ((cw >> i) & 1)) {
+                for (int j = 0; j < 2; j++) {
+                    const int32_t v1 = b.read_se();
+                    if (i < HEVCB_MAX_PICS) { s.put(base + f_dcw + (uint32_t)(i * 2 + j), v1); } else { flags |= 1u; }
+                    const int32_t v2 = b.read_se();
+                    if (i < HEVCB_MAX_PICS) { s.put(base + f_dco + (uint32_t)(i * 2 + j), v2); } else { flags |= 1u; }
+                }
+            }
+            if (b.overrun() && i > 64) { break; }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one NAL: the dispatcher of read_hevc_nal_unit (hevc_stream.c:155-241) after nal_to_rbsp succeeded
+// ------------------------------------------------------------------------------------------------
+struct hevcb_nal_result {
+    int32_t nal_unit_type, nal_layer_id, nal_temporal_id_plus1;
+    int32_t kind;       // HEVCB_KIND_*
+    int32_t ok;         // 1: the reference returns nal_size; 0: it returns -1 (unsupported type or overrun)
+    int32_t hdr_end;    // slices: RBSP byte offset of the cursor after byte_alignment (slice data starts one byte later)
+    uint32_t flags;
+    int64_t end_bits;   // bit position of the reader when the NAL's syntax ended
+    hevcb_slice_cols cols;
+};
+
+HEVCB_SHD inline bool hevcb_is_slice_type(int t) { return (t >= 0 && t <= 9) || (t >= 16 && t <= 21); }
+
+// Parses one RBSP.  `sps_in`/`pps_in`: context for slices; `sps_out`/`pps_out`: filled when the NAL is an SPS / PPS
+// (may be null when the caller does not need them).
+template <class Sink>
+HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Sink& sink, const hevcb_sps_ctx* sps_in, const hevcb_pps_ctx* pps_in,
+                                      hevcb_sps_ctx* sps_out, hevcb_pps_ctx* pps_out, hevcb_nal_result& r)
+{
+    hevcb_bits b;
+    b.init(rbsp, rbsp_size);
+    b.skip(1); // forbidden_zero_bit is not validated (App. A-12)
+    r.nal_unit_type = (int32_t)b.read_u(6);
+    r.nal_layer_id = (int32_t)b.read_u(6);
+    r.nal_temporal_id_plus1 = (int32_t)b.read_u(3);
+    r.kind = HEVCB_KIND_NONE;
+    r.ok = 0;
+    r.hdr_end = 0;
+    r.flags = 0;
+    r.end_bits = 0;
+    r.cols = hevcb_slice_cols{0, 0, 0, 0, 0, 0, 0, 0};
+    hevcb_walker<Sink> w(b, sink);
+    const int t = r.nal_unit_type;
+    if (hevcb_is_slice_type(t)) {
+        r.kind = HEVCB_KIND_SLICE;
+        w.slice_segment_header(t, *sps_in, *pps_in, r.cols);
+        r.hdr_end = (int32_t)b.byte_pos();
+        w.trailing_bits(); // read_hevc_rbsp_slice_trailing_bits skips 8 bits of slice data (App. A-11)
+    } else if (t == 32) {
+        r.kind = HEVCB_KIND_VPS;
+        w.video_parameter_set();
+    } else if (t == 33) {
+        r.kind = HEVCB_KIND_SPS;
+        w.seq_parameter_set(*sps_out);
+    } else if (t == 34) {
+        r.kind = HEVCB_KIND_PPS;
+        w.pic_parameter_set(*pps_out);
+    } else {
+        r.flags = w.flags;
+        return; // default: return -1 with h->nal already filled (hevc_stream.c:220-221)
+    }
+    r.flags = w.flags;
+    r.end_bits = b.pos;
+    r.ok = b.overrun() ? 0 : 1;
+}

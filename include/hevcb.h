@@ -102,6 +102,78 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
                                     uint8_t* rbsp, int64_t* rbsp_off, int64_t* rbsp_end,
                                     hevcb_scan_summary* summary);
 
+
+/* ---- batched header parse ----------------------------------------------------------------------
+ *
+ * read_hevc_nal_unit (hevc_stream.c:155-241) for every NAL of a stream at once, on the results of
+ * hevcb_scan_strip_* (the RBSP image and the per-NAL extents).  Per NAL k:
+ *   rc[k]        the reference's return value: bytes consumed (nal size, minus one if a trailing 00 00 03 was
+ *                dropped) or -1 (nal_to_rbsp error, unsupported NAL type, or the reader ran past the end)
+ *   nal_hdr[k]   nal_unit_type | nal_layer_id << 8 | nal_temporal_id_plus1 << 16, what the call leaves in h->nal;
+ *                -1 when nal_to_rbsp failed (the reference returns before touching h->nal)
+ *   kind[k]      which struct the NAL wrote: HEVCB_KIND_{NONE,VPS,SPS,PPS,SLICE} (hevcb_layout.h)
+ *   pairs        (pair_field, pair_value)[pair_off[k] .. pair_off[k+1]): every syntax element the reference stores,
+ *                in parse order; pair_field is the offset in ints inside hevc_vps_t / hevc_sps_t / hevc_pps_t /
+ *                hevc_slice_header_t.  Zero-filling the struct and scattering the pairs reproduces, bit for bit,
+ *                what read_hevc_nal_unit leaves in hevc_stream_t (hevcb_materialize does exactly that).
+ *   hdr_end[k]   slices: RBSP byte offset of the cursor after byte_alignment(); the reference's slice_data copy
+ *                (hevc_stream.c:605-613) is rbsp[rbsp_off[k] + hdr_end[k] + 1 .. rbsp_end[k])
+ *   cols         SoA columns for slices, laid out [8][n]: slice_type, slice_qp_delta, slice_pic_order_cnt_lsb,
+ *                first_slice_segment_in_pic_flag, slice_segment_address, dependent_slice_segment_flag,
+ *                num_entry_point_offsets, short_term_ref_pic_set_idx
+ *   ubflag[k]    non-zero when the NAL drives the reference out of its array bounds (undefined behaviour there);
+ *                such elements are skipped, every other field still matches
+ * Dependencies follow the reference, not the HEVC spec: a slice is parsed against the most recent SPS NAL and PPS
+ * NAL that precede it in the stream, resolved on the device with an ordinal scan.
+ */
+typedef struct hevcb_parse_buffers { /* device pointers for hevcb_parse_device, host pointers inside hevcb_stream_index */
+    int32_t* rc;          /* [n] */
+    int32_t* nal_hdr;     /* [n] */
+    uint8_t* kind;        /* [n] */
+    uint8_t* ubflag;      /* [n] */
+    int32_t* hdr_end;     /* [n] */
+    int32_t* cols;        /* [8 * n] */
+    int64_t* pair_off;    /* [n + 1] */
+    uint32_t* pair_field; /* [cap_pairs] */
+    int32_t* pair_value;  /* [cap_pairs] */
+    int64_t cap_pairs;
+} hevcb_parse_buffers;
+
+typedef struct hevcb_parse_summary {
+    int64_t n_nals;
+    int64_t n_ok;     /* NALs for which read_hevc_nal_unit returns >= 0 */
+    int64_t n_pairs;  /* total syntax elements; > cap_pairs means the pair arrays are incomplete (overflow = 1) */
+    int64_t n_vps, n_sps, n_pps, n_slices;
+    int32_t overflow;
+    int32_t pad;
+} hevcb_parse_summary;
+
+HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                                 const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                 const hevcb_parse_buffers* out, hevcb_parse_summary* d_summary, void* stream);
+
+/* Host-side index of a whole stream: the outputs of hevcb_scan_strip + hevcb_parse in caller-allocated host arrays. */
+typedef struct hevcb_stream_index {
+    int64_t cap_nals;   /* capacity of the per-NAL arrays */
+    int64_t* nal_start; /* [cap_nals] */
+    int64_t* nal_end;
+    int64_t* rbsp_off;
+    int64_t* rbsp_end;
+    uint8_t* rbsp;      /* optional, `size` bytes: the EPB-free image */
+    hevcb_parse_buffers p; /* host arrays sized for cap_nals / p.cap_pairs */
+    hevcb_scan_summary scan;
+    hevcb_parse_summary parse;
+} hevcb_stream_index;
+
+/* Annex-B bytes in host memory -> complete index (scan + strip + parse on the device, results copied back). */
+HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx);
+
+/* Applies NAL k of an index to caller-owned structs the way read_hevc_nal_unit updates hevc_stream_t: h->nal always
+ * (unless nal_to_rbsp failed), and the struct selected by kind[k] is zeroed and refilled.  The struct pointers are the
+ * reference-layout types of hevcb_layout.h passed as void* (any of them may be NULL).  Calling it for k = 0, 1, 2, ...
+ * reproduces the evolving state of the reference's single-stream reader.  Returns rc[k]. */
+HEVCB_API int hevcb_materialize(const hevcb_stream_index* idx, int64_t k, void* nal, void* vps, void* sps, void* pps, void* sh);
+
 #ifdef __cplusplus
 }
 #endif

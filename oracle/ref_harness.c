@@ -896,6 +896,9 @@ static void gen_slice(hevc_stream_t* h, int rich, int nut, int force_type)
     }
     if (sh->dependent_slice_segment_flag) { goto tail; }
     sh->slice_type = (force_type >= 0) ? force_type : rr(0, 2);
+    /* IDR pictures carry I slices only; a P/B-typed IDR slice makes the reference consult derived RPS state left
+     * behind by an earlier slice (process-global tables), which no stateless parser can reproduce */
+    if (nut == HEVC_NAL_UNIT_TYPE_IDR_W_RADL || nut == HEVC_NAL_UNIT_TYPE_IDR_N_LP) { sh->slice_type = HEVC_SLICE_TYPE_I; }
     sh->pic_output_flag = rr(0, 1);
     sh->colour_plane_id = rr(0, 2);
     if (nut != HEVC_NAL_UNIT_TYPE_IDR_W_RADL && nut != HEVC_NAL_UNIT_TYPE_IDR_N_LP) {
