@@ -330,6 +330,56 @@ def run_ours(args):
                 del r
                 torch.cuda.empty_cache()
 
+    # ---- BASELINE config[3]: batched header parse of >= 1M header-bearing NALs (reference-written fixture, tiled)
+    parse = None
+    if not args.no_parse:
+        try:
+            unit_h = np.fromfile(os.path.join(ROOT, "tests", "golden", "headers_unit.bin"), dtype=np.uint8)
+            probe = ctx.scan_strip_device(torch.from_numpy(unit_h).to(dev), size=unit_h.size)
+            nals_per_unit = int(probe.n_nals)
+            reps = max(1, -(-args.parse_nals // nals_per_unit))
+            dh = torch.from_numpy(unit_h).to(dev).repeat(reps)
+            hsize = dh.numel()
+            scan = ctx.scan_strip_device(dh, size=hsize, cap_nals=hsize // 8 + 1024)
+            n_h = int(scan.n_nals)
+            for _ in range(3):
+                pout = ctx.parse_device(dh, scan)
+            barrier()
+            l0 = ctx.launch_count
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            k = max(3, args.steps // 2)
+            e0.record()
+            for _ in range(k):
+                pout = ctx.parse_device(dh, scan, sync=False)
+            e1.record()
+            barrier()
+            pms = e0.elapsed_time(e1) / k
+            pl = (ctx.launch_count - l0) // k
+            pout = ctx.parse_device(dh, scan)
+            # full pipeline (scan + strip + parse) device resident
+            e0.record()
+            for _ in range(k):
+                sc2 = ctx.scan_strip_device(dh, size=hsize, cap_nals=hsize // 8 + 1024, sync=False)
+            e1.record()
+            barrier()
+            sms = e0.elapsed_time(e1) / k
+            parse = {"n_nals": n_h, "ms_parse": pms, "nal_headers_per_s": n_h / (pms * 1e-3), "syntax_elements": int(pout["n_pairs"]),
+                     "elements_per_s": pout["n_pairs"] / (pms * 1e-3), "n_ok": int(pout["n_ok"]), "launches_per_parse": int(pl),
+                     "ms_scan_strip": sms, "nal_headers_per_s_incl_scan_strip": n_h / ((pms + sms) * 1e-3),
+                     "workload": f"tests/golden/headers_unit.bin (reference-written, {nals_per_unit} NALs: multi-slice, tiles/WPP, long-term refs, "
+                                 f"RPS, pred-weight, VUI/HRD) tiled x{reps} on the device; per rank"}
+            if rank == 0 and world == 1:
+                from oracle import ref as _ref
+                if _ref.available():
+                    ub = _ref.padded(unit_h)
+                    t_cpu, n_cpu = _ref.time_loop(ub, unit_h.size, 2, 5)
+                    parse["cpu_reference_nal_headers_per_s"] = n_cpu / t_cpu
+                    parse["cpu_reference_note"] = "find_nal_unit + read_hevc_nal_unit loop of the unmodified reference, 1 thread, one unit, best of 5"
+            del dh, scan, pout
+        except Exception as ex:
+            parse = {"error": repr(ex)}
+
     # ---- CPU baseline: the unmodified reference on rank 0's host cores, bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 or (rank == 0 and args.cpu_baseline_multi):
@@ -341,6 +391,14 @@ def run_ours(args):
         except Exception as ex:
             cpu = {"value": None, "unit": UNIT, "error": repr(ex)}
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same workload (profiles/)
+    traffic = None
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_strip_ncu.json")))
+        if pj.get("workload") == name and abs(pj.get("size_gib", 0) - args.size_gib) < 1e-6:
+            traffic = pj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     if rank == 0:
         per_gpu_alg_gbs = head["alg_bytes_per_gpu"] / (head["ms"] * 1e-3) / 1e9
         line = {
@@ -352,7 +410,7 @@ def run_ours(args):
                        "nal_headers_located_per_s": head["n_nals"] / (head["ms"] * 1e-3), "l2": "inputs larger than L2 (4 GiB vs 126 MB)",
                        "sharding": "independent stream per rank, all_gather of (nals, rbsp_bytes) only" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_alg_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_alg_gbs / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": head["alg_bytes_per_gpu"], "peak_source": peak_src,
                          "algorithmic_bytes": "N_in + N_rbsp + 24*NALs per launch (SURVEY 8d), per GPU; time = CUDA-event mean over the timed steps (memset + init + scan + finalize launches)"},
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -361,6 +419,8 @@ def run_ours(args):
         }
         if sweep:
             line["sweep"] = sweep
+        if parse:
+            line["parse"] = parse
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +436,8 @@ def main():
     ap.add_argument("--e2e-gib", type=float, default=1.0)
     ap.add_argument("--workload", default="nal16k", choices=[w[0] for w in WORKLOADS])
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-parse", action="store_true")
+    ap.add_argument("--parse-nals", type=int, default=1_000_000)
     ap.add_argument("--ref-sample-mib", type=int, default=64)
     ap.add_argument("--cpu-baseline-multi", action="store_true")
     args = ap.parse_args()

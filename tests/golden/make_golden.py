@@ -52,6 +52,12 @@ def main():
         rcases.append(bytes(a[rng.integers(0, len(a), int(rng.integers(0, 40)))]))
     for c in rcases:
         out["rbsp_to_nal"].append({"rbsp": HEX(c), "nal": HEX(ref.rbsp_to_nal(c))})
+    # header-bearing stream written by the reference's own writer (BASELINE config 3 shape), used by bench.py
+    hs = ref.gen_stream(seed=2026, profile=1, n_slices=4000, payload_min=1, payload_max=48, zero_heavy_pct=10, extra_zero_pct=5,
+                        ps_period=400, unsupported_pct=2)
+    hpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "headers_unit.bin")
+    hs[: hs.size - ref.PAD].tofile(hpath)
+    print("wrote", hpath, hs.size - ref.PAD, "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "byte_layer.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0)
