@@ -51,6 +51,10 @@ class ParseSummary(C.Structure):
     ]
 
 
+class InsertSummary(C.Structure):
+    _fields_ = [("n_nals", C.c_int64), ("out_bytes", C.c_int64), ("n_inserted", C.c_int64), ("overflow", C.c_int32), ("pad", C.c_int32)]
+
+
 class StreamIndex(C.Structure):
     _fields_ = [
         ("cap_nals", C.c_int64), ("nal_start", C.c_void_p), ("nal_end", C.c_void_p), ("rbsp_off", C.c_void_p), ("rbsp_end", C.c_void_p),
@@ -88,6 +92,10 @@ def load_library() -> C.CDLL:
     L.hevcb_scan_strip_device.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
     L.hevcb_scan_strip_host.restype = C.c_int
     L.hevcb_scan_strip_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(ScanSummary)]
+    L.hevcb_insert_device.restype = C.c_int
+    L.hevcb_insert_device.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp, i64, vp, vp, vp]
+    L.hevcb_insert_host.restype = C.c_int
+    L.hevcb_insert_host.argtypes = [vp, vp, i64, vp, vp, i64, C.c_int, vp, i64, vp, C.POINTER(InsertSummary)]
     L.hevcb_parse_device.restype = C.c_int
     L.hevcb_parse_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), vp, vp]
     L.hevcb_index_host.restype = C.c_int

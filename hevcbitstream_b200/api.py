@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import HevcbError, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
+from ._lib import HevcbError, InsertSummary, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
 
 
 @dataclass
@@ -127,6 +127,44 @@ class Context:
         return ScanResult(n, sm.n_terminated, sm.last_rc, sm.last_start, sm.last_end, sm.rbsp_bytes, sm.n_epb,
                           ns[:n], ne[:n], ro[:n], re[:n], rb[: sm.rbsp_bytes] if rb is not None else None)
 
+    # ---- EPB insertion (rbsp_to_nal) ----------------------------------------------------------
+    def insert_device(self, rbsp, rbsp_off, rbsp_end, n_nals=None, start_code_len=0, out_cap=None, sync=True):
+        """rbsp_to_nal for every segment rbsp[rbsp_off[k]:rbsp_end[k]] (torch CUDA tensors).  Returns dict(out, out_off,
+        summary) plus out_bytes / n_inserted when sync."""
+        import torch
+
+        n = int(rbsp_off.numel() if n_nals is None else n_nals)
+        dev = rbsp.device
+        if out_cap is None:  # worst case: one 03 per two payload bytes
+            payload = int((rbsp_end[:n] - rbsp_off[:n]).clamp(min=0).sum().item()) if n else 0
+            out_cap = payload * 3 // 2 + (start_code_len + 1) * n + 64
+        out = dict(out=torch.empty(out_cap + 16, dtype=torch.uint8, device=dev), out_off=torch.empty(n + 1, dtype=torch.int64, device=dev),
+                   summary=torch.zeros(4, dtype=torch.int64, device=dev))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.hevcb_insert_device(self._h, rbsp.data_ptr(), rbsp_off.data_ptr(), rbsp_end.data_ptr(), n, start_code_len,
+                                                out["out"].data_ptr(), out_cap, out["out_off"].data_ptr(), out["summary"].data_ptr(), stream))
+        if sync:
+            s = out["summary"].cpu().numpy()
+            out["out_bytes"], out["n_inserted"] = int(s[1]), int(s[2])
+            if int(s[3]) & 0xFFFFFFFF:
+                raise HevcbError(-104, f"{out['out_bytes']} output bytes exceed out_cap {out_cap}")
+        return out
+
+    def insert_host(self, rbsp: np.ndarray, rbsp_off: np.ndarray, rbsp_end: np.ndarray, start_code_len=0, out_cap=None):
+        """Host arrays in, (out bytes, out_off[n+1], n_inserted) out; includes the copies (hevcb_insert_host)."""
+        assert rbsp.dtype == np.uint8
+        rbsp_off = np.ascontiguousarray(rbsp_off, dtype=np.int64)
+        rbsp_end = np.ascontiguousarray(rbsp_end, dtype=np.int64)
+        n = int(rbsp_off.size)
+        if out_cap is None:  # worst case: one 03 per two payload bytes
+            payload = int(np.maximum(rbsp_end - rbsp_off, 0).sum()) if n else 0
+            out_cap = payload * 3 // 2 + (start_code_len + 1) * n + 64
+        out = np.empty(out_cap, dtype=np.uint8)
+        out_off = np.empty(n + 1, dtype=np.int64)
+        sm = InsertSummary()
+        self._check(self._L.hevcb_insert_host(self._h, _np_ptr(rbsp), int(rbsp.size), _np_ptr(rbsp_off), _np_ptr(rbsp_end), n, start_code_len,
+                                              _np_ptr(out), out_cap, _np_ptr(out_off), C.byref(sm)))
+        return out[: sm.out_bytes], out_off, int(sm.n_inserted)
 
     # ---- batched header parse -----------------------------------------------------------------
     def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True):

@@ -74,7 +74,7 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
     hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
-                            &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
+                            &ctx->insert_scratch, &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
                             &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
@@ -147,6 +147,61 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
     return HEVCB_OK;
 }
 
+
+HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                  int start_code_len, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary,
+                                  void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_insert(ctx, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, start_code_len, d_out, out_cap, d_out_off, d_summary,
+                               (cudaStream_t)stream);
+}
+
+HEVCB_API int hevcb_insert_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t rbsp_bytes, const int64_t* rbsp_off, const int64_t* rbsp_end,
+                                int64_t n_nals, int start_code_len, uint8_t* out, int64_t out_cap, int64_t* out_off, hevcb_insert_summary* summary)
+{
+    if (!ctx || !summary || !out_off || rbsp_bytes < 0 || n_nals < 0 || out_cap < 0 || (n_nals > 0 && (!rbsp_off || !rbsp_end)) ||
+        (rbsp_bytes > 0 && !rbsp) || (out_cap > 0 && !out)) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert_host: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t in_bytes = ((size_t)rbsp_bytes + 15u) & ~(size_t)15u;
+    const size_t arr_bytes = (size_t)(n_nals + 1) * sizeof(int64_t);
+    int rc;
+    if ((rc = hevcb_reserve(ctx, &ctx->h_rbsp, in_bytes + 16)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_in, (size_t)out_cap + 16)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a0, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a2, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a3, arr_bytes)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_misc, 256)) != HEVCB_OK) { return rc; }
+    if (rbsp_bytes > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_rbsp.p, rbsp, (size_t)rbsp_bytes, cudaMemcpyHostToDevice, st)); }
+    if (n_nals > 0) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_a2.p, rbsp_off, (size_t)n_nals * 8, cudaMemcpyHostToDevice, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_a3.p, rbsp_end, (size_t)n_nals * 8, cudaMemcpyHostToDevice, st));
+    }
+    hevcb_insert_summary* d_sum = reinterpret_cast<hevcb_insert_summary*>(ctx->h_misc.p);
+    rc = hevcb_launch_insert(ctx, reinterpret_cast<const uint8_t*>(ctx->h_rbsp.p), reinterpret_cast<const int64_t*>(ctx->h_a2.p),
+                             reinterpret_cast<const int64_t*>(ctx->h_a3.p), n_nals, start_code_len, reinterpret_cast<uint8_t*>(ctx->h_in.p), out_cap,
+                             reinterpret_cast<int64_t*>(ctx->h_a0.p), d_sum, st);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_insert_summary* p_sum = reinterpret_cast<hevcb_insert_summary*>(ctx->pinned);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_sum, d_sum, sizeof(hevcb_insert_summary), cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out_off, ctx->h_a0.p, arr_bytes, cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    *summary = *p_sum;
+    if (summary->overflow) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert_host: %lld output bytes exceed out_cap %lld", (long long)summary->out_bytes, (long long)out_cap);
+        return HEVCB_E_CAPACITY;
+    }
+    if (summary->out_bytes > 0) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(out, ctx->h_in.p, (size_t)summary->out_bytes, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return HEVCB_OK;
+}
 
 HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
                                  const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals, const hevcb_parse_buffers* out,

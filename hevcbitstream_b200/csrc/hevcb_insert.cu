@@ -1,0 +1,322 @@
+// hevcb_insert.cu -- batched emulation-prevention insertion for sm_100a: rbsp_to_nal (h264_nal.c:92-132) for every
+// NAL of a batch, optionally framing the result as Annex-B (start code before every NAL).
+//
+// rbsp_to_nal is a 3-state machine (count of zero bytes since the last non-zero byte or the last insertion): before a
+// byte <= 3 that arrives with count == 2 it emits 03 and restarts the count.  After a run of m zero bytes the state is
+// 0 / 1 / 2 for m = 0 / odd / even, so the only thing that crosses a 16-byte chunk is the length of the zero run that
+// precedes it; that is a "distance to the last non-zero byte", resolved inside a warp row with one ballot and carried
+// between rows in a register.  One warp walks one NAL (512 bytes per step, 16 per lane); NALs are distributed over the
+// warps of a persistent grid.  Two passes: count insertions per NAL -> exclusive scan of the output sizes -> write.
+// Rows without insertions are written as aligned 16-byte vectors assembled with shuffles + funnel shifts, rows with
+// insertions byte by byte.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hevcb_internal.h"
+
+namespace {
+
+constexpr int kInsThreads = 256;
+constexpr int kInsWarps = kInsThreads / 32;
+
+__device__ __forceinline__ uint32_t zero_flags(uint32_t w)
+{
+    const uint32_t t = (w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | w | 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t gather4(uint32_t f) { return (((f >> 7) * 0x00204081u) >> 21) & 0xFu; }
+__device__ __forceinline__ uint32_t zero_mask16(const uint4& v)
+{
+    return gather4(zero_flags(v.x)) | (gather4(zero_flags(v.y)) << 4) | (gather4(zero_flags(v.z)) << 8) | (gather4(zero_flags(v.w)) << 12);
+}
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, int j)
+{
+    const uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
+    return (w >> (8 * (j & 3))) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) { v += o; }
+    }
+    return v;
+}
+
+struct RowInfo {
+    uint4 v;        // this lane's 16 bytes (aligned chunk of the image)
+    uint32_t valid; // bit j: byte belongs to the NAL
+    uint32_t ins;   // bit j: 03 is inserted before byte j
+};
+
+// One 512-byte row of a NAL: loads, zero-run carry, insertion mask.  run_m = zero-run length in front of the row
+// (warp uniform), updated for the next row.
+__device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, int64_t row, int64_t off, int64_t end, int lane, uint32_t& run_m)
+{
+    RowInfo r;
+    const int64_t cpos = row + lane * 16;
+    r.v = make_uint4(0, 0, 0, 0);
+    if (cpos < end && cpos + 16 > off) { r.v = *reinterpret_cast<const uint4*>(img + cpos); }
+    // validity of the 16 positions
+    const int64_t lo = off - cpos, hi = end - cpos; // valid j in [lo, hi)
+    uint32_t valid = 0xFFFFu;
+    if (lo > 0) { valid &= (lo >= 16) ? 0u : (0xFFFFu << (int)lo); }
+    if (hi < 16) { valid &= (hi <= 0) ? 0u : ((1u << (int)hi) - 1u); }
+    valid &= 0xFFFFu;
+    r.valid = valid;
+    const uint32_t Z = zero_mask16(r.v) & valid;
+    // R: bytes that end a zero run: non-zero bytes of the NAL, and positions in front of the NAL start
+    const uint32_t before = (lo > 0) ? ((lo >= 16) ? 0xFFFFu : ((1u << (int)lo) - 1u)) : 0u;
+    const uint32_t R = (valid & ~Z) | before;
+    const uint32_t tz = R ? (uint32_t)(15 - (31 - __clz((int)R))) : 16u; // zero bytes after the last run-ending byte
+    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, R != 0u);
+    const uint32_t lower = Rb & ((1u << lane) - 1u);
+    uint32_t m_in;
+    {
+        const int p = lower ? (31 - __clz((int)lower)) : 0;
+        const uint32_t tzp = __shfl_sync(0xFFFFFFFFu, tz, p);
+        m_in = lower ? (tzp + 16u * (uint32_t)(lane - p - 1)) : (run_m + 16u * (uint32_t)lane);
+    }
+    // next row's carry
+    {
+        const int p = Rb ? (31 - __clz((int)Rb)) : 0;
+        const uint32_t tzp = __shfl_sync(0xFFFFFFFFu, tz, p);
+        run_m = Rb ? (tzp + 16u * (uint32_t)(31 - p)) : (run_m + 512u);
+    }
+    // state machine only where an insertion is possible: two zeros in a row somewhere, or a run reaching into the chunk
+    uint32_t ins = 0;
+    const bool need = ((Z & (Z >> 1)) != 0u) || (m_in >= 2u) || (m_in >= 1u && (Z & 1u));
+    if (need && valid) {
+        uint32_t count = (m_in == 0u) ? 0u : ((m_in & 1u) ? 1u : 2u);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if ((valid >> j) & 1u) {
+                const uint32_t bv = byte_of(r.v, j);
+                if (count == 2u && bv <= 3u) { ins |= 1u << j; count = 0u; }
+                count = (bv == 0u) ? count + 1u : 0u;
+            }
+        }
+    }
+    r.ins = ins;
+    return r;
+}
+
+// pass 1: output size of every NAL (start code + bytes + insertions); NALs whose nal_to_rbsp failed (end < 0) emit nothing
+__global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const uint8_t* __restrict__ img, const int64_t* __restrict__ off_a,
+                                                                   const int64_t* __restrict__ end_a, int64_t n, int sc_len,
+                                                                   int64_t* __restrict__ out_size, unsigned long long* __restrict__ n_ins_total)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * kInsWarps;
+    unsigned long long local_ins = 0;
+    for (int64_t k = wid; k < n; k += nw) {
+        const int64_t off = off_a[k], end = end_a[k];
+        if (end < 0 || end < off) {
+            if (lane == 0) { out_size[k] = 0; }
+            continue;
+        }
+        uint32_t run_m = 0, total = 0;
+        for (int64_t row = off & ~(int64_t)15; row < end; row += 512) {
+            const RowInfo r = insert_row(img, row, off, end, lane, run_m);
+            total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
+        }
+        if (lane == 0) { out_size[k] = (int64_t)sc_len + (end - off) + (int64_t)total; }
+        local_ins += total;
+    }
+    if (lane == 0 && local_ins) { atomicAdd(n_ins_total, local_ins); }
+}
+
+// pass 2: write start code + escaped bytes of every NAL at out_off[k]
+__global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const uint8_t* __restrict__ img, const int64_t* __restrict__ off_a,
+                                                                   const int64_t* __restrict__ end_a, int64_t n, int sc_len,
+                                                                   const int64_t* __restrict__ out_off, uint8_t* __restrict__ out, int64_t out_cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * kInsWarps;
+    for (int64_t k = wid; k < n; k += nw) {
+        const int64_t off = off_a[k], end = end_a[k];
+        if (end < 0 || end < off) { continue; }
+        int64_t o = out_off[k];
+        if (out_off[k + 1] > out_cap) { continue; } // capacity overflow is reported by the summary
+        if (lane < sc_len) { out[o + lane] = (lane == sc_len - 1) ? 1 : 0; }
+        o += sc_len;
+        uint32_t run_m = 0;
+        for (int64_t row = off & ~(int64_t)15; row < end; row += 512) {
+            const RowInfo r = insert_row(img, row, off, end, lane, run_m);
+            const uint32_t cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
+            const uint32_t inc = warp_incl_scan_u32(cnt, lane);
+            const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
+            uint8_t* dst = out + o;
+            if (clean) {
+                // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
+                const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+                if ((uint32_t)lane == 0u) {
+                    for (uint32_t j = 0; j < head; j++) { dst[j] = (uint8_t)byte_of(r.v, (int)j); }
+                }
+                // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
+                uint4 nx;
+                nx.x = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
+                nx.y = __shfl_down_sync(0xFFFFFFFFu, r.v.y, 1);
+                nx.z = __shfl_down_sync(0xFFFFFFFFu, r.v.z, 1);
+                nx.w = __shfl_down_sync(0xFFFFFFFFu, r.v.w, 1);
+                if (head == 0u) {
+                    *reinterpret_cast<uint4*>(dst + lane * 16) = r.v;
+                } else {
+                    const uint32_t W[8] = {r.v.x, r.v.y, r.v.z, r.v.w, nx.x, nx.y, nx.z, nx.w};
+                    const uint32_t q = head >> 2, sh = (head & 3u) * 8u;
+                    uint32_t x[5];
+#pragma unroll
+                    for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
+                    uint4 o4;
+                    o4.x = __funnelshift_r(x[0], x[1], sh);
+                    o4.y = __funnelshift_r(x[1], x[2], sh);
+                    o4.z = __funnelshift_r(x[2], x[3], sh);
+                    o4.w = __funnelshift_r(x[3], x[4], sh);
+                    if (lane < 31) {
+                        *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4;
+                    } else { // last lane: only 16 - head bytes remain
+                        for (uint32_t j = head; j < 16u; j++) { dst[496 + j] = (uint8_t)byte_of(r.v, (int)j); }
+                    }
+                }
+            } else {
+                uint8_t* p = dst + (inc - cnt);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if ((r.valid >> j) & 1u) {
+                        if ((r.ins >> j) & 1u) { *p++ = 3; }
+                        *p++ = (uint8_t)byte_of(r.v, j);
+                    }
+                }
+            }
+            o += row_total;
+        }
+    }
+}
+
+__global__ void insert_summary_kernel(const int64_t* out_off, int64_t n, int64_t out_cap, const unsigned long long* n_ins, hevcb_insert_summary* s)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        s->n_nals = n;
+        s->out_bytes = out_off[n];
+        s->n_inserted = (int64_t)*n_ins;
+        s->overflow = out_off[n] > out_cap ? 1 : 0;
+        s->pad = 0;
+    }
+}
+
+// ---- exclusive scan of int64 sizes (3 kernels) -----------------------------------------------------------------
+constexpr int kSThreads = 512, kSItems = 8, kSTile = kSThreads * kSItems;
+__device__ __forceinline__ long long block_incl_scan_ll(long long v, long long* ws, long long& tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) { v += o; }
+    }
+    if (lane == 31) { ws[warp] = v; }
+    __syncthreads();
+    if (warp == 0) {
+        long long w = (lane < kSThreads / 32) ? ws[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) { w += o; }
+        }
+        if (lane < kSThreads / 32) { ws[lane] = w; }
+    }
+    __syncthreads();
+    const long long base = warp > 0 ? ws[warp - 1] : 0;
+    tot = ws[kSThreads / 32 - 1];
+    return v + base;
+}
+__global__ void __launch_bounds__(kSThreads) sizes_reduce_kernel(const int64_t* in, int64_t n, long long* bs)
+{
+    __shared__ long long ws[kSThreads / 32];
+    long long s = 0;
+    for (int j = 0; j < kSItems; j++) {
+        const int64_t i = (int64_t)blockIdx.x * kSTile + (int64_t)j * kSThreads + threadIdx.x;
+        if (i < n) { s += in[i]; }
+    }
+    long long tot;
+    block_incl_scan_ll(s, ws, tot);
+    if (threadIdx.x == 0) { bs[blockIdx.x] = tot; }
+}
+__global__ void __launch_bounds__(kSThreads) sizes_blocksums_kernel(long long* bs, int64_t nb)
+{
+    __shared__ long long ws[kSThreads / 32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) { carry_s = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += kSThreads) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < nb ? bs[i] : 0;
+        long long tot;
+        const long long inc = block_incl_scan_ll(v, ws, tot);
+        const long long carry = carry_s;
+        __syncthreads();
+        if (i < nb) { bs[i] = carry + inc - v; }
+        if (threadIdx.x == 0) { carry_s = carry + tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { bs[nb] = carry_s; }
+}
+__global__ void __launch_bounds__(kSThreads) sizes_apply_kernel(const int64_t* in, int64_t n, const long long* bs, int64_t nb, int64_t* out)
+{
+    __shared__ long long ws[kSThreads / 32];
+    long long carry = bs[blockIdx.x];
+    for (int j = 0; j < kSItems; j++) {
+        const int64_t i = (int64_t)blockIdx.x * kSTile + (int64_t)j * kSThreads + threadIdx.x;
+        const long long v = i < n ? in[i] : 0;
+        long long tot;
+        const long long inc = block_incl_scan_ll(v, ws, tot);
+        if (i < n) { out[i] = carry + inc - v; }
+        carry += tot;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[n] = bs[nb]; }
+}
+
+} // namespace
+
+int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,
+                        int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    if (n < 0 || (sc_len != 0 && sc_len != 3 && sc_len != 4) || !d_out_off || !d_summary || (n > 0 && (!d_rbsp || !d_off || !d_end || !d_out))) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    if ((uintptr_t)d_rbsp & 15u) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert: rbsp must be 16-byte aligned");
+        return HEVCB_E_ALIGN;
+    }
+    const int64_t nb = (n + kSTile - 1) / kSTile;
+    const size_t need = (size_t)(n > 0 ? n : 1) * 8 + (size_t)(nb + 2) * 8 + 64;
+    int rc = hevcb_reserve(ctx, &ctx->insert_scratch, need);
+    if (rc != HEVCB_OK) { return rc; }
+    int64_t* sizes = reinterpret_cast<int64_t*>(ctx->insert_scratch.p);
+    long long* bs = reinterpret_cast<long long*>(sizes + (n > 0 ? n : 1));
+    unsigned long long* n_ins = reinterpret_cast<unsigned long long*>(bs + nb + 1);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(n_ins, 0, 8, stream));
+    if (n == 0) {
+        HEVCB_CUDA(ctx, cudaMemsetAsync(d_out_off, 0, 8, stream));
+        HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_insert_summary), stream));
+        return HEVCB_OK;
+    }
+    long long grid = (long long)ctx->sm_count * 8;
+    const long long max_grid = (n + kInsWarps - 1) / kInsWarps;
+    if (grid > max_grid) { grid = max_grid; }
+    insert_count_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(d_rbsp, d_off, d_end, n, sc_len, sizes, n_ins);
+    sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs);
+    sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
+    sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs, nb, d_out_off);
+    insert_write_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(d_rbsp, d_off, d_end, n, sc_len, d_out_off, d_out, out_cap);
+    insert_summary_kernel<<<1, 32, 0, stream>>>(d_out_off, n, out_cap, n_ins, d_summary);
+    ctx->launches += 6;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}

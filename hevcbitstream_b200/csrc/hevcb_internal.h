@@ -19,6 +19,7 @@ struct hevcb_ctx {
     char err[512] = {0};
     // scan scratch: [0,64) counters, then one 16-byte state word per tile
     hevcb_devbuf scan_scratch;
+    hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
     hevcb_devbuf parse_scratch, parse_ps; // parser: per-NAL scratch arrays, parameter-set context tables
     hevcb_devbuf h_p[9];                  // staging of the parse outputs for the *_host entry points
     // staging used by the *_host entry points
@@ -70,3 +71,6 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
 int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
                        const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
                        hevcb_parse_summary* d_summary, cudaStream_t stream);
+
+int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,
+                        int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream);

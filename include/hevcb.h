@@ -103,6 +103,37 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
                                     hevcb_scan_summary* summary);
 
 
+/* ---- batched EPB insertion (rbsp_to_nal) ---------------------------------------------------------
+ *
+ * rbsp_to_nal (h264_nal.c:92-132) for n RBSP segments at once.  Segment k is rbsp[rbsp_off[k] .. rbsp_end[k]) of one
+ * device buffer (for instance the image + extents hevcb_scan_strip_* produced, or the payloads a writer laid out);
+ * segments with rbsp_end[k] < 0 (nal_to_rbsp failed) produce nothing.  The output is one contiguous buffer:
+ *     out[out_off[k] .. out_off[k] + start_code_len)            00 00 01 / 00 00 00 01 (start_code_len 3 / 4; 0: none)
+ *     out[out_off[k] + start_code_len .. out_off[k+1])          the bytes rbsp_to_nal writes for segment k
+ * out_off has n + 1 entries; out_off[n] is the total size.  The reference's capacity check is commented out
+ * (h264_nal.c:101-107: it writes past a short buffer); here summary.overflow = 1 when out_cap is too small: nothing is
+ * written for the NALs that do not fit, out_off is still complete so the caller can re-run with out_off[n] bytes.
+ * `rbsp` must be 16-byte aligned and readable up to the next 16-byte boundary after the last segment; the segments
+ * may start anywhere.
+ */
+typedef struct hevcb_insert_summary {
+    int64_t n_nals;
+    int64_t out_bytes;  /* = out_off[n] */
+    int64_t n_inserted; /* emulation prevention bytes inserted */
+    int32_t overflow;
+    int32_t pad;
+} hevcb_insert_summary;
+
+HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                  int start_code_len, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                                  hevcb_insert_summary* d_summary, void* stream);
+
+/* Host buffers: `rbsp` holds rbsp_bytes bytes; copies in, runs the pass, copies `out` (up to out_cap) and out_off back.
+ * Returns HEVCB_E_CAPACITY if summary->overflow. */
+HEVCB_API int hevcb_insert_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t rbsp_bytes, const int64_t* rbsp_off, const int64_t* rbsp_end,
+                                int64_t n_nals, int start_code_len, uint8_t* out, int64_t out_cap, int64_t* out_off,
+                                hevcb_insert_summary* summary);
+
 /* ---- batched header parse ----------------------------------------------------------------------
  *
  * read_hevc_nal_unit (hevc_stream.c:155-241) for every NAL of a stream at once, on the results of
