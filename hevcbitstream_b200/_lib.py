@@ -55,6 +55,33 @@ class InsertSummary(C.Structure):
     _fields_ = [("n_nals", C.c_int64), ("out_bytes", C.c_int64), ("n_inserted", C.c_int64), ("overflow", C.c_int32), ("pad", C.c_int32)]
 
 
+class ShardSummary(C.Structure):
+    _fields_ = [
+        ("own", C.c_int64), ("n_nals", C.c_int64), ("first_empty", C.c_int64), ("first_empty_start", C.c_int64), ("rbsp_bytes", C.c_int64),
+        ("n_epb", C.c_int64), ("head_end", C.c_int64), ("head_rbsp_end", C.c_int64), ("last_nal_start", C.c_int64),
+        ("last_rbsp_off", C.c_int64), ("last_nal_end", C.c_int64), ("is_first", C.c_int32), ("is_last", C.c_int32),
+        ("open_at_end", C.c_int32), ("open_err", C.c_int32), ("overflow", C.c_int32), ("tail_len", C.c_int32), ("tail", C.c_uint8 * 32),
+        ("pad", C.c_int32),
+    ]
+
+
+MAX_SHARDS = 64
+
+
+class StitchPatch(C.Structure):
+    _fields_ = [("shard", C.c_int32), ("set_start", C.c_int32), ("index", C.c_int64), ("nal_start", C.c_int64), ("rbsp_off", C.c_int64),
+                ("nal_end", C.c_int64), ("rbsp_end", C.c_int64)]
+
+
+class StitchResult(C.Structure):
+    _fields_ = [
+        ("glob", ScanSummary), ("n_shards", C.c_int32), ("n_patches", C.c_int32),
+        ("byte_base", C.c_int64 * MAX_SHARDS), ("rbsp_base", C.c_int64 * MAX_SHARDS), ("first_local", C.c_int64 * MAX_SHARDS),
+        ("n_owned", C.c_int64 * MAX_SHARDS), ("nal_base", C.c_int64 * MAX_SHARDS), ("cont_last_shard", C.c_int32 * MAX_SHARDS),
+        ("cont_last_bytes", C.c_int64 * MAX_SHARDS), ("cont_bytes", C.c_int64 * MAX_SHARDS), ("patches", StitchPatch * (MAX_SHARDS + 8)),
+    ]
+
+
 class StreamIndex(C.Structure):
     _fields_ = [
         ("cap_nals", C.c_int64), ("nal_start", C.c_void_p), ("nal_end", C.c_void_p), ("rbsp_off", C.c_void_p), ("rbsp_end", C.c_void_p),
@@ -92,6 +119,12 @@ def load_library() -> C.CDLL:
     L.hevcb_scan_strip_device.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
     L.hevcb_scan_strip_host.restype = C.c_int
     L.hevcb_scan_strip_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(ScanSummary)]
+    L.hevcb_scan_strip_shard_device.restype = C.c_int
+    L.hevcb_scan_strip_shard_device.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.hevcb_plan_shards.restype = C.c_int
+    L.hevcb_plan_shards.argtypes = [vp, i64, C.c_int, vp]
+    L.hevcb_stitch.restype = C.c_int
+    L.hevcb_stitch.argtypes = [C.POINTER(ShardSummary), C.c_int, C.POINTER(StitchResult)]
     L.hevcb_insert_device.restype = C.c_int
     L.hevcb_insert_device.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp, i64, vp, vp, vp]
     L.hevcb_insert_host.restype = C.c_int

@@ -148,6 +148,16 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
 }
 
 
+HEVCB_API int hevcb_scan_strip_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t own, int64_t halo, int is_first, int is_last,
+                                            int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off,
+                                            int64_t* d_rbsp_end, hevcb_shard_summary* d_summary, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_scan_strip_shard(ctx, d_buf, own, halo, is_first, is_last, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off,
+                                         d_rbsp_end, d_summary, (cudaStream_t)stream);
+}
+
 HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
                                   int start_code_len, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary,
                                   void* stream)

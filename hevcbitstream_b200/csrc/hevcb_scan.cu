@@ -44,6 +44,15 @@ constexpr int kStageBytes = kLead + kTileBytes + 16;
 constexpr int kStages = 3;       // tile i-1 being written out, tile i being analysed, tile i+1 in flight
 constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
+// byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
+struct ScanGeom {
+    int64_t size;       // bytes present (owned + following halo)
+    int64_t own;        // owned bytes: tiles, image and reported positions stop here
+    int64_t evl;        // events / error positions honoured below this
+    uint32_t init_n;    // 1: a NAL is considered open at position 0 (local index 0: the piece of a NAL begun in an earlier shard)
+    uint32_t init_kind; // carry entering the range
+};
+
 struct WarpAgg {
     uint32_t n;     // start codes in the warp's rows
     uint32_t k;     // kept bytes
@@ -223,9 +232,9 @@ __device__ __forceinline__ uint32_t zero_pair_any(uint32_t wp, uint32_t w0, uint
 }
 
 // cold path, kept out of line so that the hot loop stays small in the instruction cache
-__device__ __noinline__ uint3 analyze_cold(uint32_t wp, uint4 v, uint32_t wn, int64_t g0, int64_t size)
+__device__ __noinline__ uint3 analyze_cold(uint32_t wp, uint4 v, uint32_t wn, int64_t g0, int64_t size, int64_t own, int64_t evl)
 {
-    const hevcb_chunk_masks m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, g0, size);
+    const hevcb_chunk_masks m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, g0, size, own, evl);
     return make_uint3(m.ev | (m.sc << 16), m.del | (m.err << 16), m.valid | (m.scb << 16));
 }
 
@@ -262,17 +271,6 @@ __device__ __forceinline__ void copy_vectors(uint8_t* __restrict__ dst16, const 
 
 #ifndef HEVCB_SPIN_PAUSE
 #define HEVCB_SPIN_PAUSE __nanosleep(32)
-#endif
-#ifdef HEVCB_SCAN_TIMING
-__device__ unsigned long long g_scan_timing[4][16];
-#define TSTAMP(slot)                                                                      \
-    do {                                                                                  \
-        const long long now__ = clock64();                                                \
-        if (trec) { g_scan_timing[tcta][slot] += (unsigned long long)(now__ - tlast); }  \
-        tlast = now__;                                                                    \
-    } while (0)
-#else
-#define TSTAMP(slot) do {} while (0)
 #endif
 
 // one warp copies a clean 512-byte row (16-byte aligned in shared memory) to an arbitrarily aligned global address
@@ -313,10 +311,11 @@ __device__ __forceinline__ void copy_row_clean(uint8_t* __restrict__ dst, const 
 // A batch is exactly one wave of the grid (tiles w*G .. w*G+G-1, G <= 320): the prefixes of wave w must not wait for
 // aggregates of wave w+1, which the CTAs only publish after they have received their wave-w prefix.
 __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl,
-                                             long long n_tiles, long long G, ScanHeader* __restrict__ hdr, int lane)
+                                             long long n_tiles, long long G, ScanHeader* __restrict__ hdr, int lane, uint32_t init_n,
+                                             uint32_t init_kind)
 {
-    unsigned long long runN = 0, runK = 0;
-    uint32_t runKind = HEVCB_KIND_Z3, runErr = 0;
+    unsigned long long runN = init_n, runK = 0;
+    uint32_t runKind = init_kind, runErr = 0;
     for (long long wbase = 0; wbase < n_tiles; wbase += G) {
       const long long lim = (wbase + G < n_tiles) ? wbase + G : n_tiles; // end of this wave
       for (long long base = wbase; base < lim; base += 32 * kScanPerLane) { // the wave in batches of 320 tiles
@@ -375,7 +374,7 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 }
 
 __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_kernel(
-    const uint8_t* __restrict__ buf, int64_t size, long long n_tiles, ScanHeader* __restrict__ hdr,
+    const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, ScanHeader* __restrict__ hdr,
     ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, int64_t* __restrict__ nal_start,
     int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off,
     int64_t* __restrict__ rbsp_end, long long debug_flags)
@@ -387,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     const int warp = tid >> 5;
     const long long G = gridDim.x;
     const unsigned dbg = (unsigned)debug_flags; // experiment switches, 0 in production
+    const int64_t size = geom.size;
 
     if (tid == kWorkerThreads) {
         for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); }
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     __syncthreads();
 
     if (warp == kWorkers + 1) { // scanner warp: one per grid, never joins the CTA's barriers
-        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, G, hdr, lane); }
+        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, G, hdr, lane, geom.init_n, geom.init_kind); }
         return;
     }
 
@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             phase_bits ^= (1u << s);
             // ---- boundary fix-ups: positions < 0 read as non-zero, positions >= size read as zero
             const int64_t valid_end = (int64_t)kLead + (size - t0); // smem offset of position `size`
-            // interior tile: every byte (and its halo) is inside the buffer and below the tail zone
-            const bool interior = valid_end >= (int64_t)kStageBytes + HEVCB_TAIL_ZONE + 16;
+            // interior tile: every byte (and its halo) is owned and below the event limit
+            const bool interior = geom.evl - t0 >= (int64_t)kTileBytes + 32;
             if (t == 0 || valid_end < kStageBytes) {
                 if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
                 if (valid_end < kStageBytes) {
@@ -534,9 +534,9 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const bool slow = ((slowmask >> k) & 1u) != 0u;
                     if (!__any_sync(0xFFFFFFFFu, slow) && interior) { wK += kRowBytes; continue; }
                     const int64_t g0 = t0 + (int64_t)(rbase + k) * kRowBytes + lane * 16;
-                    const int64_t rem = size - g0;
+                    const int64_t rem = geom.own - g0;
                     uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
-                    if (slow) { m3 = analyze_cold(wp[k], v[k], wn[k], g0, size); }
+                    if (slow) { m3 = analyze_cold(wp[k], v[k], wn[k], g0, size, geom.own, geom.evl); }
                     c_evsc[i] = m3.x;
                     c_deler[i] = m3.y;
                     c_misc[i] = m3.z;
@@ -727,38 +727,48 @@ __global__ void hevcb_scan_finalize_kernel(const uint8_t* __restrict__ buf, int6
     summary->n_epb = core.n_epb;
 }
 
-__global__ void hevcb_scan_init_kernel(ScanHeader* hdr)
+__global__ void hevcb_scan_init_kernel(ScanHeader* hdr, uint32_t init_n, int64_t* nal_start, int64_t* rbsp_off, int64_t cap_nals)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         hdr->reserved = 0ull;
         hdr->first_empty = 0x7FFFFFFFFFFFFFFFll;
+        if (init_n && cap_nals > 0) { nal_start[0] = 0; rbsp_off[0] = 0; } // the NAL piece that enters the shard
     }
+}
+
+// epilogue of a shard pass: no end-of-buffer rules here (hevcb_stitch applies them once, to the last shard)
+__global__ void hevcb_scan_shard_finalize_kernel(const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles,
+                                                 const ScanHeader* __restrict__ hdr, int64_t* nal_start, int64_t* nal_end, int64_t* rbsp_off,
+                                                 int64_t* rbsp_end, int64_t cap_nals, int is_first, int is_last, hevcb_shard_summary* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+    int64_t N = geom.init_n, K = 0;
+    uint32_t kind = geom.init_kind, err = 0;
+    if (n_tiles > 0) {
+        const ulonglong2 sv = hdr->final_state;
+        N = (int64_t)(sv.x & ((1ull << 40) - 1));
+        K = (int64_t)sv.y;
+        kind = (uint32_t)(sv.x >> 60) & 3u;
+        err = (uint32_t)(sv.x >> 59) & 1u;
+    }
+    long long fe = hdr->first_empty;
+    if (fe == 0x7FFFFFFFFFFFFFFFll) { fe = -1; }
+    auto fetch = [buf](int64_t pos) -> uint32_t { return (uint32_t)buf[pos]; };
+    hevcb_shard_finalize(geom.own, N, kind, err, K, (int64_t)fe, fetch, nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, is_first, is_last, out);
 }
 
 } // namespace
 
-#ifdef HEVCB_SCAN_TIMING
-extern "C" __attribute__((visibility("default"))) int hevcb_debug_scan_timing(unsigned long long* out, int reset)
-{
-    if (out) { cudaMemcpyFromSymbol(out, g_scan_timing, sizeof(g_scan_timing)); }
-    if (reset) { unsigned long long z[4][16] = {}; cudaMemcpyToSymbol(g_scan_timing, z, sizeof(z)); }
-    return 0;
-}
-#endif
 
-int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int64_t* d_nal_start, int64_t* d_nal_end,
-                            int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
-                            hevcb_scan_summary* d_summary, cudaStream_t stream)
+static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGeom& geom, int64_t* d_nal_start, int64_t* d_nal_end,
+                              int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end, ScanHeader** hdr_out,
+                              long long* n_tiles_out, cudaStream_t stream)
 {
-    if (size < 0 || cap_nals < 0 || !d_nal_start || !d_nal_end || !d_rbsp_off || !d_rbsp_end || !d_summary || (size > 0 && !d_buf)) {
-        HEVCB_SET_ERR(ctx, "hevcb_scan_strip: invalid argument");
-        return HEVCB_E_ARG;
-    }
     if (((uintptr_t)d_buf & 15u) || ((uintptr_t)d_rbsp & 15u)) {
         HEVCB_SET_ERR(ctx, "hevcb_scan_strip: buf and rbsp must be 16-byte aligned");
         return HEVCB_E_ALIGN;
     }
-    const long long n_tiles = (long long)((size + kTileBytes - 1) / kTileBytes);
+    const long long n_tiles = (long long)((geom.own + kTileBytes - 1) / kTileBytes);
     const size_t n_states = (size_t)(n_tiles > 0 ? n_tiles : 1);
     const size_t need = sizeof(ScanHeader) + 2 * n_states * sizeof(ulonglong2);
     int rc = hevcb_reserve(ctx, &ctx->scan_scratch, need);
@@ -768,7 +778,7 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
     ulonglong2* excl = states + n_states;
 
     HEVCB_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch.p, 0, need, stream));
-    hevcb_scan_init_kernel<<<1, 32, 0, stream>>>(hdr);
+    hevcb_scan_init_kernel<<<1, 32, 0, stream>>>(hdr, geom.init_n, d_nal_start, d_rbsp_off, cap_nals);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
 
@@ -783,16 +793,62 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
         }
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
         if (grid > n_tiles) { grid = n_tiles; }
-        // cooperative launch: the chained look-back needs every CTA of the grid to be resident
+        // cooperative launch: the chained scan needs every CTA of the grid to be resident
         long long nt = n_tiles;
-        long long stagger = ctx->scan_debug_flags;
-        void* args[] = {(void*)&d_buf, (void*)&size, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
-                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&stagger};
+        long long dbg = ctx->scan_debug_flags;
+        ScanGeom g = geom;
+        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
+                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
         ctx->launches++;
     }
-    hevcb_scan_finalize_kernel<<<1, 32, 0, stream>>>(d_buf, size, n_tiles, hdr, states, d_nal_start, d_nal_end, d_rbsp_off, d_rbsp_end,
+    *hdr_out = hdr;
+    *n_tiles_out = n_tiles;
+    return HEVCB_OK;
+}
+
+int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int64_t* d_nal_start, int64_t* d_nal_end,
+                            int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off, int64_t* d_rbsp_end,
+                            hevcb_scan_summary* d_summary, cudaStream_t stream)
+{
+    if (size < 0 || cap_nals < 0 || !d_nal_start || !d_nal_end || !d_rbsp_off || !d_rbsp_end || !d_summary || (size > 0 && !d_buf)) {
+        HEVCB_SET_ERR(ctx, "hevcb_scan_strip: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    ScanGeom geom;
+    geom.size = size; geom.own = size; geom.evl = size - HEVCB_TAIL_ZONE; geom.init_n = 0; geom.init_kind = HEVCB_KIND_Z3;
+    ScanHeader* hdr = nullptr;
+    long long n_tiles = 0;
+    int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_scan_finalize_kernel<<<1, 32, 0, stream>>>(d_buf, size, n_tiles, hdr, nullptr, d_nal_start, d_nal_end, d_rbsp_off, d_rbsp_end,
                                                      cap_nals, d_summary);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
+
+int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t own, int64_t halo, int is_first, int is_last,
+                                  int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off,
+                                  int64_t* d_rbsp_end, hevcb_shard_summary* d_summary, cudaStream_t stream)
+{
+    if (own < 0 || halo < 0 || halo > 16 || cap_nals < 1 || !d_nal_start || !d_nal_end || !d_rbsp_off || !d_rbsp_end || !d_summary ||
+        (own > 0 && !d_buf) || (is_last && halo != 0) || (!is_last && own > 0 && halo < 3)) {
+        HEVCB_SET_ERR(ctx, "hevcb_scan_strip_shard: invalid argument (inner shards need a halo of 3..16 bytes, the last shard none)");
+        return HEVCB_E_ARG;
+    }
+    ScanGeom geom;
+    geom.size = own + halo;
+    geom.own = own;
+    geom.evl = is_last ? own - HEVCB_TAIL_ZONE : own;
+    geom.init_n = is_first ? 0u : 1u;
+    geom.init_kind = is_first ? HEVCB_KIND_Z3 : HEVCB_KIND_SC3;
+    ScanHeader* hdr = nullptr;
+    long long n_tiles = 0;
+    int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_scan_shard_finalize_kernel<<<1, 32, 0, stream>>>(d_buf, geom, n_tiles, hdr, d_nal_start, d_nal_end, d_rbsp_off, d_rbsp_end, cap_nals,
+                                                           is_first, is_last, d_summary);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;

@@ -17,6 +17,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/hevcb.h"
+
 #if defined(__CUDACC__)
 #define HEVCB_HD __host__ __device__ __forceinline__
 #else
@@ -71,8 +73,14 @@ struct hevcb_chunk_masks {
 // Exact masks for the 16-byte chunk at global position g0.  wp = bytes g0-4..g0-1, wn = bytes
 // g0+16..g0+19.  Bytes at positions < 0 must be presented as non-zero, bytes >= size as zero (the
 // product's zero-padding rule).
+//
+// Three limits describe the byte range (a whole stream, or one shard of a byte-range partition):
+//   size  bytes that exist as data (for a shard: the owned bytes + the halo that follows them)
+//   own   bytes that are kept / reported by this pass (image, removal and error masks stop here)
+//   evl   events and error positions are honoured below evl (whole stream and last shard: own - HEVCB_TAIL_ZONE, the rest
+//         is resolved by hevcb_scan_tail; inner shard: own, the patterns read on into the halo)
 HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn,
-                                               int64_t g0, int64_t size)
+                                               int64_t g0, int64_t size, int64_t own, int64_t evl)
 {
     hevcb_chunk_masks m;
     // 21-bit masks, bit (j+3) <-> position g0+j, j in [-3, 17]
@@ -90,9 +98,9 @@ HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_
                    ((hevcb_gather4(hevcb_zero_flags(wn & cfc)) & 1u) << 19);
 
     // position limits
-    int64_t rem = size - g0;                     // positions j < rem are inside the buffer
+    int64_t rem = own - g0;                      // positions j < rem are owned
     uint32_t valid = rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
-    int64_t remT = size - HEVCB_TAIL_ZONE - g0;  // events honoured for j < remT (j may be -3..-1)
+    int64_t remT = evl - g0;                     // events honoured for j < remT (j may be -3..-1)
     uint32_t evlim = remT >= 16 ? 0x7FFFFu : (remT <= -3 ? 0u : ((1u << (int)(remT + 3)) - 1u));
 
     uint32_t P = Z & (Z >> 1);                   // bit (j+3): b[j]==0 && b[j+1]==0, j in [-3, 16]
@@ -103,7 +111,8 @@ HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_
     uint32_t LT3 = LE3 & ~T3;
     uint32_t ERR1 = LT3 & PP & ~(EV << 2);       // third byte of an honoured event is not an error
     uint32_t GT3n = (~LE3) >> 1;                 // bit (j+3): b[j+1] > 3
-    uint32_t v1 = rem - 1 >= 16 ? 0xFFFFu : (rem - 1 <= 0 ? 0u : ((1u << (int)(rem - 1)) - 1u));
+    int64_t remS = size - 1 - g0;                // positions j with j + 1 inside the data
+    uint32_t v1 = remS >= 16 ? 0xFFFFu : (remS <= 0 ? 0u : ((1u << (int)remS) - 1u));
     uint32_t ERR2 = DEL & GT3n & (v1 << 3);      // EPB followed by > 3, only when that byte exists
 
     m.ev = (EV >> 3) & 0xFFFFu;
@@ -115,6 +124,13 @@ HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_
     m.err = ((ERR1 | ERR2) >> 3) & valid & errlim;
     m.valid = valid;
     return m;
+}
+
+// whole stream: everything is owned, the last HEVCB_TAIL_ZONE bytes are left to hevcb_scan_tail
+HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn,
+                                               int64_t g0, int64_t size)
+{
+    return hevcb_chunk_analyze(wp, w0, w1, w2, w3, wn, g0, size, size, size - HEVCB_TAIL_ZONE);
 }
 
 HEVCB_HD int hevcb_popc(uint32_t x)
@@ -430,4 +446,40 @@ HEVCB_HD void hevcb_scan_finalize(int64_t size, int64_t n_main, uint32_t kind, u
     out->last_rc = t.last_rc;
     out->last_start = t.last_start;
     out->last_end = t.last_end;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shard epilogue: the record one shard of a byte-range partition contributes to hevcb_stitch.  No end-of-buffer rules
+// here; (N, kind, err, K) is the state after the honoured events of the shard.
+// ------------------------------------------------------------------------------------------------
+template <typename Fetch>
+HEVCB_HD void hevcb_shard_finalize(int64_t own, int64_t N, uint32_t kind, uint32_t err, int64_t K, int64_t first_empty, const Fetch& fetch,
+                                   const int64_t* nal_start, const int64_t* nal_end, const int64_t* rbsp_off, const int64_t* rbsp_end,
+                                   int64_t cap, int is_first, int is_last, hevcb_shard_summary* out)
+{
+    int64_t fe = first_empty;
+    if (fe < 0 || fe >= N) { fe = -1; }
+    out->own = own;
+    out->n_nals = N;
+    out->first_empty = fe;
+    out->first_empty_start = (fe >= 0 && fe < cap) ? nal_start[fe] : -1;
+    out->rbsp_bytes = K;
+    out->n_epb = own - K;
+    out->is_first = is_first;
+    out->is_last = is_last;
+    out->open_at_end = (kind == HEVCB_KIND_SC3) ? 1 : 0;
+    out->open_err = (int32_t)err;
+    out->overflow = N > cap ? 1 : 0;
+    out->pad = 0;
+    const bool have0 = N > 0 && cap > 0;
+    const bool closed0 = have0 && (N > 1 || kind != HEVCB_KIND_SC3);
+    out->head_end = closed0 ? nal_end[0] : -1;
+    out->head_rbsp_end = closed0 ? rbsp_end[0] : -1;
+    const bool havel = N > 0 && N <= cap;
+    out->last_nal_start = havel ? nal_start[N - 1] : -1;
+    out->last_nal_end = (havel && kind != HEVCB_KIND_SC3) ? nal_end[N - 1] : -1;
+    out->last_rbsp_off = havel ? rbsp_off[N - 1] : -1;
+    const int64_t nt = own < 32 ? own : 32;
+    out->tail_len = (int32_t)nt;
+    for (int i = 0; i < 32; i++) { out->tail[i] = (i < nt) ? (uint8_t)fetch(own - nt + i) : (uint8_t)0; }
 }

@@ -1,0 +1,126 @@
+"""Byte-range sharding of one Annex-B stream over several GPUs (include/hevcb.h: hevcb_plan_shards,
+hevcb_scan_strip_shard_device, hevcb_stitch).
+
+One process per GPU.  Every rank scans + strips its own bytes (plus a halo of the 16 bytes that follow them); the only
+exchange is an all_gather of one ~170-byte record per shard, after which every rank runs the same host-side stitch and
+patches the (at most two) entries of its own arrays that depend on a neighbour.  Payload bytes only move when a caller
+asks for the continuation of a NAL that crosses into the next shard (`fetch_continuation`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import HevcbError, ShardSummary, StitchResult, load_library
+
+HALO = 16
+
+
+def plan_shards(buf: np.ndarray, n_shards: int, size=None) -> np.ndarray:
+    """Cut points (n_shards + 1 offsets) such that no start-code / EPB pattern reaches back across a cut."""
+    assert buf.dtype == np.uint8
+    size = int(buf.size if size is None else size)
+    bounds = np.zeros(n_shards + 1, dtype=np.int64)
+    rc = load_library().hevcb_plan_shards(buf.ctypes.data_as(C.c_void_p), size, n_shards, bounds.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise HevcbError(rc, "hevcb_plan_shards")
+    return bounds
+
+
+def shard_flags(bounds: np.ndarray, r: int):
+    """(own, halo, is_first, is_last) of shard r for the cut points of plan_shards."""
+    size = int(bounds[-1])
+    lo, hi = int(bounds[r]), int(bounds[r + 1])
+    own = hi - lo
+    is_first = own > 0 and lo == 0
+    is_last = own > 0 and hi == size
+    halo = 0 if is_last else min(HALO, size - hi)
+    return own, halo, is_first, is_last
+
+
+def stitch(records) -> StitchResult:
+    """records: ShardSummary per shard, in stream order."""
+    n = len(records)
+    arr = (ShardSummary * n)(*records)
+    out = StitchResult()
+    rc = load_library().hevcb_stitch(arr, n, C.byref(out))
+    if rc != 0:
+        raise HevcbError(rc, "hevcb_stitch: inconsistent shard records")
+    return out
+
+
+def record_to_tensor(rec: ShardSummary, device):
+    import torch
+
+    raw = np.frombuffer(bytes(rec), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
+def gather_records(rec: ShardSummary, device, group=None):
+    """all_gather of the shard records (NCCL on the GPU box, gloo in the CPU tests): the only collective of the scan."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    mine = record_to_tensor(rec, device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [ShardSummary.from_buffer_copy(t.cpu().numpy().tobytes()) for t in out]
+
+
+def patches_for(res: StitchResult, shard: int):
+    return [res.patches[i] for i in range(res.n_patches) if res.patches[i].shard == shard]
+
+
+def apply_patches(res: StitchResult, shard: int, nal_start, nal_end, rbsp_off, rbsp_end):
+    """Writes the stitched entries into shard `shard`'s arrays (numpy arrays or torch tensors, local coordinates)."""
+    for p in patches_for(res, shard):
+        k = int(p.index)
+        if p.set_start:
+            nal_start[k] = int(p.nal_start)
+            rbsp_off[k] = int(p.rbsp_off)
+        nal_end[k] = int(p.nal_end)
+        rbsp_end[k] = int(p.rbsp_end)
+
+
+class ShardScan:
+    """Result of scan_strip_shard on one rank: device arrays in local coordinates + the shard record."""
+
+    def __init__(self, record, nal_start, nal_end, rbsp_off, rbsp_end, rbsp):
+        self.record, self.nal_start, self.nal_end, self.rbsp_off, self.rbsp_end, self.rbsp = record, nal_start, nal_end, rbsp_off, rbsp_end, rbsp
+
+
+def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: bool, cap_nals=None, want_rbsp=True, extra_rbsp=0) -> ShardScan:
+    """buf: torch.uint8 CUDA tensor with own + halo bytes (16-byte aligned).  extra_rbsp: spare bytes behind the image for
+    the continuation of the last NAL."""
+    import torch
+
+    assert buf.is_cuda and buf.dtype == torch.uint8 and buf.numel() >= own + halo
+    dev = buf.device
+    if cap_nals is None:
+        cap_nals = own // 3 + 8
+    a = [torch.empty(cap_nals, dtype=torch.int64, device=dev) for _ in range(4)]
+    rbsp = torch.empty(own + 16 + extra_rbsp, dtype=torch.uint8, device=dev) if want_rbsp else None
+    d_sum = torch.zeros(C.sizeof(ShardSummary), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = ctx._L.hevcb_scan_strip_shard_device(ctx._h, buf.data_ptr(), own, halo, int(is_first), int(is_last), a[0].data_ptr(), a[1].data_ptr(),
+                                              cap_nals, rbsp.data_ptr() if rbsp is not None else None, a[2].data_ptr(), a[3].data_ptr(),
+                                              d_sum.data_ptr(), stream)
+    ctx._check(rc)
+    rec = ShardSummary.from_buffer_copy(d_sum.cpu().numpy().tobytes())
+    if rec.overflow:
+        raise HevcbError(-104, f"{rec.n_nals} NALs exceed cap_nals {cap_nals}")
+    return ShardScan(rec, a[0], a[1], a[2], a[3], rbsp)
+
+
+def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw):
+    """The distributed pass: local shard scan, all_gather of the records, stitch, local patches.  Returns
+    (ShardScan, StitchResult); global NAL index of local NAL j is res.nal_base[rank] + j - res.first_local[rank]."""
+    import torch.distributed as dist
+
+    sc = scan_strip_shard(ctx, buf, own, halo, is_first, is_last, **kw)
+    records = gather_records(sc.record, buf.device, group)
+    res = stitch(records)
+    apply_patches(res, dist.get_rank(group), sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)
+    return sc, res

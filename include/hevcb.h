@@ -103,6 +103,84 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
                                     hevcb_scan_summary* summary);
 
 
+/* ---- byte-range sharding of one stream (multi-GPU) -----------------------------------------------
+ *
+ * One long Annex-B stream is cut into contiguous shards, one per GPU.  Every GPU runs the scan + strip pass
+ * over its own bytes only; the pieces are joined from one small record per shard (all-gathered by the caller, e.g. with
+ * ncclAllGather) by hevcb_stitch, which is pure host arithmetic over those records.  No payload moves for the scan.
+ *
+ * Cut points: hevcb_plan_shards moves every nominal cut forward to the next position p whose preceding byte is >= 2.
+ * No start code or emulation-prevention pattern can straddle such a cut backwards, so a shard needs no bytes from
+ * before its start -- only a HALO of the 3..16 bytes that follow it (patterns that begin in its last two bytes).
+ *
+ * Inside a shard that is not the first, local NAL index 0 is the piece of the NAL that was open at the cut
+ * (nal_start[0] = rbsp_off[0] = 0); whether such a NAL really exists is only known after stitching.  All offsets in the
+ * per-shard arrays are local to the shard (and to its image).
+ */
+typedef struct hevcb_shard_summary {
+    int64_t own;            /* owned bytes */
+    int64_t n_nals;         /* local NAL indices in use (including the entering piece when !is_first) */
+    int64_t first_empty;    /* local index of the first zero-length NAL (the reference loop stops there), -1: none */
+    int64_t first_empty_start; /* its nal_start */
+    int64_t rbsp_bytes;     /* bytes of the shard's EPB-free image */
+    int64_t n_epb;
+    int64_t head_end;       /* nal_end / rbsp_end of local NAL 0 when it was closed inside the shard, else -1 / -1 */
+    int64_t head_rbsp_end;
+    int64_t last_nal_start; /* nal_start / rbsp_off of local NAL n_nals-1; nal_end of it, or -1 while it is open */
+    int64_t last_rbsp_off;
+    int64_t last_nal_end;
+    int32_t is_first, is_last;
+    int32_t open_at_end;    /* local NAL n_nals-1 is still open where the shard ends */
+    int32_t open_err;       /* a nal_to_rbsp error was already seen inside it */
+    int32_t overflow;       /* n_nals > cap_nals */
+    int32_t tail_len;       /* the last min(32, own) bytes of the shard: the last shard's end-of-stream rules are */
+    uint8_t tail[32];       /* applied to them by hevcb_stitch (h264_nal.c:46-72 at the end of the buffer) */
+    int32_t pad;
+} hevcb_shard_summary;
+
+/* Scan + strip of one shard.  d_buf holds own + halo bytes (halo: the bytes that follow the shard in the stream, 3..16;
+ * 0 for the last shard).  Events are honoured for positions < own (last shard: < own - 8, the rest is resolved by
+ * hevcb_stitch).  cap_nals >= 1. */
+HEVCB_API int hevcb_scan_strip_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t own, int64_t halo, int is_first, int is_last,
+                                            int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, uint8_t* d_rbsp,
+                                            int64_t* d_rbsp_off, int64_t* d_rbsp_end, hevcb_shard_summary* d_summary, void* stream);
+
+/* Host helper: cut points for n_shards shards of buf[0..size).  bounds has n_shards + 1 entries, bounds[0] = 0,
+ * bounds[n_shards] = size; trailing shards may be empty.  The last non-empty shard is at least 64 bytes long (or the
+ * stream is one shard). */
+HEVCB_API int hevcb_plan_shards(const uint8_t* buf, int64_t size, int n_shards, int64_t* bounds);
+
+#define HEVCB_MAX_SHARDS 64
+
+typedef struct hevcb_stitch_patch { /* overwrite entry `index` of shard `shard`'s arrays (local coordinates) */
+    int32_t shard;
+    int32_t set_start; /* 1: nal_start / rbsp_off are to be written too (NALs found by the end-of-stream rules) */
+    int64_t index;
+    int64_t nal_start, rbsp_off;
+    int64_t nal_end;   /* may exceed the shard's own size: the NAL ends in a later shard */
+    int64_t rbsp_end;  /* -1, or the end in the shard's image extended by the continuation bytes (cont_bytes) */
+} hevcb_stitch_patch;
+
+typedef struct hevcb_stitch_result {
+    hevcb_scan_summary global;               /* what hevcb_scan_strip_* reports for the whole stream (global offsets) */
+    int32_t n_shards;
+    int32_t n_patches;
+    int64_t byte_base[HEVCB_MAX_SHARDS];     /* global offset of the shard's byte 0 */
+    int64_t rbsp_base[HEVCB_MAX_SHARDS];     /* global offset of the shard's image in the whole-stream image */
+    int64_t first_local[HEVCB_MAX_SHARDS];   /* local index of the first NAL the shard owns (0, or 1 when local NAL 0 is a piece) */
+    int64_t n_owned[HEVCB_MAX_SHARDS];       /* NALs owned (those that start in the shard and that the reference loop visits) */
+    int64_t nal_base[HEVCB_MAX_SHARDS];      /* global index of the first owned NAL */
+    /* continuation of the shard's last owned NAL in later shards: image bytes [0, cont_last_bytes) of shard
+     * cont_last_shard plus the whole images of the shards in between; cont_bytes is their sum (0: none) */
+    int32_t cont_last_shard[HEVCB_MAX_SHARDS];
+    int64_t cont_last_bytes[HEVCB_MAX_SHARDS];
+    int64_t cont_bytes[HEVCB_MAX_SHARDS];
+    hevcb_stitch_patch patches[HEVCB_MAX_SHARDS + 8];
+} hevcb_stitch_result;
+
+/* Joins the shard records (in stream order).  Pure host code, identical on every rank. */
+HEVCB_API int hevcb_stitch(const hevcb_shard_summary* shards, int n_shards, hevcb_stitch_result* out);
+
 /* ---- batched EPB insertion (rbsp_to_nal) ---------------------------------------------------------
  *
  * rbsp_to_nal (h264_nal.c:92-132) for n RBSP segments at once.  Segment k is rbsp[rbsp_off[k] .. rbsp_end[k]) of one

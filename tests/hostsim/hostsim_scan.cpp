@@ -73,3 +73,44 @@ extern "C" int64_t hostsim_scan_strip(const uint8_t* buf, int64_t size, int64_t*
     hevcb_scan_finalize(size, N, kind, err, K, sink.first_empty, fetch, nal_start, nal_end, rbsp_off, rbsp_end, cap, summary);
     return summary->n_nals;
 }
+
+// one shard of a byte-range partition: buf holds own + halo bytes; mirrors hevcb_scan_strip_shard_device
+extern "C" int64_t hostsim_scan_strip_shard(const uint8_t* buf, int64_t own, int64_t halo, int is_first, int is_last, int64_t* nal_start,
+                                            int64_t* nal_end, int64_t* rbsp_off, int64_t* rbsp_end, int64_t cap, uint8_t* rbsp_out,
+                                            hevcb_shard_summary* summary)
+{
+    const int64_t LEAD = 16;
+    const int64_t size = own + halo;
+    const int64_t evl = is_last ? own - HEVCB_TAIL_ZONE : own;
+    int64_t nchunks = (own + 15) / 16;
+    std::vector<uint8_t> img((size_t)(LEAD + nchunks * 16 + 48), 0);
+    memset(img.data(), 0xFF, LEAD);
+    if (size > 0) { memcpy(img.data() + LEAD, buf, (size_t)size); }
+
+    Sink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap, -1};
+    int64_t N = is_first ? 0 : 1, K = 0;
+    uint32_t kind = is_first ? HEVCB_KIND_Z3 : HEVCB_KIND_SC3, err = 0;
+    if (!is_first && cap > 0) { nal_start[0] = 0; rbsp_off[0] = 0; }
+    for (int64_t c = 0; c < nchunks; c++) {
+        int64_t g0 = c * 16;
+        int64_t o = LEAD + g0;
+        uint32_t wp = ld32(img, o - 4), w0 = ld32(img, o), w1 = ld32(img, o + 4), w2 = ld32(img, o + 8),
+                 w3 = ld32(img, o + 12), wn = ld32(img, o + 16);
+        hevcb_chunk_masks m = hevcb_chunk_analyze(wp, w0, w1, w2, w3, wn, g0, size, own, evl);
+        hevcb_chunk_emit(m, g0, N, K, kind, err, sink);
+        uint32_t keep = m.valid & ~m.del;
+        if (rbsp_out) {
+            for (int j = 0; j < 16; j++) {
+                if ((keep >> j) & 1u) { rbsp_out[K + hevcb_popc(keep & ((1u << j) - 1u))] = buf[g0 + j]; }
+            }
+        }
+        uint32_t ck, ce;
+        hevcb_chunk_summary(m, ck, ce);
+        hevcb_carry_combine(kind, err, ck, ce);
+        N += hevcb_popc(m.sc);
+        K += hevcb_popc(keep);
+    }
+    auto fetch = [&](int64_t pos) -> uint32_t { return buf[pos]; };
+    hevcb_shard_finalize(own, N, kind, err, K, sink.first_empty, fetch, nal_start, nal_end, rbsp_off, rbsp_end, cap, is_first, is_last, summary);
+    return N;
+}

@@ -1,0 +1,71 @@
+"""GPU parity tests of the byte-range sharding: every shard goes through hevcb_scan_strip_shard_device (the CUDA path),
+the records are stitched by hevcb_stitch, and the assembled result must equal the oracle's whole-stream result.  All
+shards run on cuda:0 one after the other; the multi-process exchange is covered by tests/test_shard_cpu.py (gloo) and
+by bench.py --gpus N (NCCL)."""
+import numpy as np
+import pytest
+
+from oracle import ref
+from tests import shard_check, util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
+
+
+@pytest.mark.parametrize("alphabet", [0, 1, 2, 3])
+def test_adversarial_small(ctx, alphabet):
+    run = shard_check.device_shard_runner(ctx)
+    rng = np.random.default_rng(400 + alphabet)
+    for it in range(60):
+        size = int(rng.integers(0, 600))
+        buf = util.adversarial(rng, size, alphabet, density=[1.0, 0.5, 0.1][it % 3])
+        for g in (2, 3, 5):
+            shard_check.check_sharded(buf, size, g, run, tag=f"a{alphabet}-{it}")
+
+
+def test_adversarial_multi_tile(ctx):
+    """shards of several 32 KiB tiles, cuts at arbitrary (unaligned) stream positions"""
+    run = shard_check.device_shard_runner(ctx)
+    rng = np.random.default_rng(13)
+    for it in range(8):
+        size = int(rng.integers(300_000, 2_000_000))
+        buf = util.adversarial(rng, size, it, density=[1.0, 0.3, 0.01][it % 3])
+        for g in (2, 8):
+            shard_check.check_sharded(buf, size, g, run, tag=f"multi{it}")
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_generated_rich_streams(ctx, seed):
+    run = shard_check.device_shard_runner(ctx)
+    s = ref.gen_stream(seed=seed, profile=1, n_slices=20000, payload_min=1, payload_max=400, zero_heavy_pct=30, extra_zero_pct=20, ps_period=40,
+                       unsupported_pct=5)
+    size = s.size - ref.PAD
+    for g, cut in ((2, 0), (4, 3), (8, 7)):
+        buf = util.padded(s[: size - cut])
+        n = shard_check.check_sharded(buf, size - cut, g, run, tag=f"gen{seed}-{cut}")
+        assert n > 20000
+
+
+def test_large_nals_span_shards(ctx):
+    """1 MiB NALs over 8 shards of ~0.9 MiB: most shards hold no start code at all"""
+    run = shard_check.device_shard_runner(ctx)
+    s = util.c2_stream(1 << 20, 7 << 20, seed=3)
+    size = s.size - ref.PAD
+    g, image, res, bounds = shard_check.run_sharded(s, size, 8, run)
+    util.compare_scan(s, size, g, image, tag="big")
+    assert sum(1 for r in range(8) if res.n_owned[r] == 0) >= 1
+
+
+def test_single_shard_equals_whole_stream_entry_point(ctx):
+    run = shard_check.device_shard_runner(ctx)
+    rng = np.random.default_rng(2)
+    for it in range(20):
+        size = int(rng.integers(0, 100_000))
+        buf = util.adversarial(rng, size, it, density=0.2)
+        g, image, res, bounds = shard_check.run_sharded(buf, size, 1, run)
+        whole = ctx.scan_strip_host(buf[:size], size=size)
+        assert (g.n_nals, g.n_terminated, g.last_rc, g.last_start, g.last_end, g.rbsp_bytes, g.n_epb) == (
+            whole.n_nals, whole.n_terminated, whole.last_rc, whole.last_start, whole.last_end, whole.rbsp_bytes, whole.n_epb)
+        n = whole.n_nals
+        assert np.array_equal(g.nal_start[:n], whole.nal_start[:n]) and np.array_equal(g.nal_end[:n], whole.nal_end[:n])
+        assert np.array_equal(g.rbsp_off[:n], whole.rbsp_off[:n]) and np.array_equal(g.rbsp_end[:n], whole.rbsp_end[:n])
+        assert np.array_equal(image, whole.rbsp)
