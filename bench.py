@@ -212,6 +212,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the JSON line only: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = hb.Context(local)
@@ -226,27 +230,59 @@ def run_ours(args):
     def time_workload(name, nal_size, dense, steps, warmup, sampler=None):
         unit = make_unit(nal_size, UNIT_BYTES, 1234 + rank * 7919, dense)
         reps = max(1, size_target // unit.size)
-        d = torch.from_numpy(unit).to(dev).repeat(reps)
-        size = d.numel()
+        ut = torch.from_numpy(unit).to(dev)
+        size = ut.numel() * reps
+        d = torch.zeros(size + 32, dtype=torch.uint8, device=dev)[: size + 16]  # + room for the halo of the next shard
+        d[:size].view(reps, -1).copy_(ut.unsqueeze(0).expand(reps, -1))
         cap = size // max(16, (nal_size if not dense else 4096) // 2) + (1 << 16)
-        outs = ctx.scan_strip_device(d, size=size, cap_nals=cap, want_rbsp=True, sync=False)
+        stitched = None
+        if world == 1:
+            outs = ctx.scan_strip_device(d, size=size, cap_nals=cap, want_rbsp=True, sync=False)
+
+            def step():
+                ctx.scan_strip_device(d, size=size, cap_nals=cap, out=outs, sync=False)
+        else:
+            # BASELINE config[4]: the ranks' buffers are consecutive byte ranges of ONE stream.  Halo = the first 16 bytes of
+            # the next rank's range (all_gather of 16 B, once); per step: shard scan, all_gather of the ~190-byte shard
+            # records over NCCL, host stitch, patch of the boundary entries.
+            from hevcbitstream_b200 import shard as hs
+
+            assert unit[-1] >= 2, "rank boundary must follow a byte >= 2 (hevcb_plan_shards rule)"
+            heads = [torch.empty(16, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(heads, d[:16].clone())
+            is_first, is_last = rank == 0, rank == world - 1
+            halo = 0 if is_last else 16
+            if not is_last:
+                d[size: size + 16] = heads[rank + 1]
+            outs = hs.alloc_shard_outputs(d, size, cap)
+            box = {}
+
+            def step():
+                box["sc"], box["res"] = hs.scan_strip_sharded(ctx, d, size, halo, is_first, is_last, out=outs)
+        step()
         torch.cuda.synchronize()
         for _ in range(warmup):
-            ctx.scan_strip_device(d, size=size, cap_nals=cap, out=outs, sync=False)
+            step()
         barrier()
         l0 = ctx.launch_count
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            ctx.scan_strip_device(d, size=size, cap_nals=cap, out=outs, sync=False)
+            step()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / steps
         launches = ctx.launch_count - l0
-        s = outs["summary"].cpu().numpy()
-        n_nals, rbsp_bytes, n_epb = int(s[0]), int(s[5]), int(s[6])
-        assert int(s[2] >> 32) == 0, "NAL capacity overflow in bench"
+        if world == 1:
+            s = outs["summary"].cpu().numpy()
+            n_nals, rbsp_bytes, n_epb = int(s[0]), int(s[5]), int(s[6])
+            assert int(s[2] >> 32) == 0, "NAL capacity overflow in bench"
+        else:
+            sc, res = box["sc"], box["res"]
+            n_nals, rbsp_bytes, n_epb = int(res.n_owned[rank]), int(sc.record.rbsp_bytes), int(sc.record.n_epb)
+            stitched = {"global_n_nals": int(res.glob.n_nals), "global_rbsp_bytes": int(res.glob.rbsp_bytes), "last_rc": int(res.glob.last_rc),
+                        "patches": int(res.n_patches), "owned_per_rank": [int(res.n_owned[r]) for r in range(world)]}
         # NCCL exchange of the per-shard counts (the only collective of the sharded path)
         tot = torch.tensor([ms, float(size), float(n_nals), float(rbsp_bytes)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -262,7 +298,9 @@ def run_ours(args):
         alg = tot_size + tot_rbsp + 24.0 * tot_nals
         res = dict(name=name, nal_size=nal_size, ms=ms_max, size=tot_size, n_nals=tot_nals, rbsp_bytes=tot_rbsp, n_epb=n_epb,
                    in_gbs=tot_size / (ms_max * 1e-3) / 1e9, alg_gbs=alg / (ms_max * 1e-3) / 1e9, launches=launches,
-                   alg_bytes_per_gpu=(size + rbsp_bytes + 24.0 * n_nals), unit=unit, d=d, outs=outs, cap=cap, size_local=size)
+                   alg_bytes_per_gpu=(size + rbsp_bytes + 24.0 * n_nals), unit=unit, d=d, outs=outs, cap=cap, size_local=size, stitched=stitched)
+        if stitched is not None:
+            assert stitched["global_n_nals"] == int(tot_nals) and stitched["global_rbsp_bytes"] == int(tot_rbsp), (stitched, tot_nals, tot_rbsp)
         return res
 
     name, nal_size, dense = next(w for w in WORKLOADS if w[0] == args.workload)
@@ -408,7 +446,8 @@ def run_ours(args):
                                    f"({name}); 64 MiB synthetic unit (escaped uniform-random payload) tiled on the device; input > L2 so no flush needed",
                        "nal_size": nal_size, "bytes_per_gpu": int(head["size_local"]), "nals_per_step": int(head["n_nals"]),
                        "nal_headers_located_per_s": head["n_nals"] / (head["ms"] * 1e-3), "l2": "inputs larger than L2 (4 GiB vs 126 MB)",
-                       "sharding": "independent stream per rank, all_gather of (nals, rbsp_bytes) only" if world > 1 else "single GPU"},
+                       "sharding": ("one stream cut by byte range, one shard per rank: 16-byte halo, NCCL all_gather of the shard records, host stitch "
+                                    "(BASELINE config[4]); every step includes the exchange") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_alg_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_alg_gbs / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": head["alg_bytes_per_gpu"], "peak_source": peak_src,
                          "algorithmic_bytes": "N_in + N_rbsp + 24*NALs per launch (SURVEY 8d), per GPU; time = CUDA-event mean over the timed steps (memset + init + scan + finalize launches)"},
@@ -417,11 +456,14 @@ def run_ours(args):
             "gpu_launches": int(head["launches"]),
             "clocks": clocks,
         }
+        if head.get("stitched"):
+            line["stitched"] = head["stitched"]
         if sweep:
             line["sweep"] = sweep
         if parse:
             line["parse"] = parse
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -121,6 +121,8 @@ def load_library() -> C.CDLL:
     L.hevcb_scan_strip_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(ScanSummary)]
     L.hevcb_scan_strip_shard_device.restype = C.c_int
     L.hevcb_scan_strip_shard_device.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.hevcb_apply_patches_device.restype = C.c_int
+    L.hevcb_apply_patches_device.argtypes = [vp, C.POINTER(StitchResult), C.c_int, vp, vp, vp, vp, i64, vp]
     L.hevcb_plan_shards.restype = C.c_int
     L.hevcb_plan_shards.argtypes = [vp, i64, C.c_int, vp]
     L.hevcb_stitch.restype = C.c_int

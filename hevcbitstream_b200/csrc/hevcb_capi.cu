@@ -158,6 +158,40 @@ HEVCB_API int hevcb_scan_strip_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf
                                          d_rbsp_end, d_summary, (cudaStream_t)stream);
 }
 
+namespace {
+struct PatchPack {
+    int n;
+    hevcb_stitch_patch p[8];
+};
+__global__ void apply_patches_kernel(PatchPack pk, int64_t* ns, int64_t* ne, int64_t* ro, int64_t* re, int64_t cap)
+{
+    const int i = threadIdx.x;
+    if (i < pk.n && pk.p[i].index >= 0 && pk.p[i].index < cap) {
+        const hevcb_stitch_patch& p = pk.p[i];
+        if (p.set_start) { ns[p.index] = p.nal_start; ro[p.index] = p.rbsp_off; }
+        ne[p.index] = p.nal_end;
+        re[p.index] = p.rbsp_end;
+    }
+}
+} // namespace
+
+HEVCB_API int hevcb_apply_patches_device(hevcb_ctx* ctx, const hevcb_stitch_result* res, int shard, int64_t* d_nal_start, int64_t* d_nal_end,
+                                         int64_t* d_rbsp_off, int64_t* d_rbsp_end, int64_t cap_nals, void* stream)
+{
+    if (!ctx || !res || !d_nal_start || !d_nal_end || !d_rbsp_off || !d_rbsp_end) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PatchPack pk;
+    pk.n = 0;
+    for (int i = 0; i < res->n_patches; i++) {
+        if (res->patches[i].shard == shard && pk.n < 8) { pk.p[pk.n++] = res->patches[i]; }
+    }
+    if (pk.n == 0) { return HEVCB_OK; }
+    apply_patches_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pk, d_nal_start, d_nal_end, d_rbsp_off, d_rbsp_end, cap_nals);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
+
 HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
                                   int start_code_len, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary,
                                   void* stream)

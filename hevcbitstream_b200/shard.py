@@ -91,36 +91,66 @@ class ShardScan:
         self.record, self.nal_start, self.nal_end, self.rbsp_off, self.rbsp_end, self.rbsp = record, nal_start, nal_end, rbsp_off, rbsp_end, rbsp
 
 
-def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: bool, cap_nals=None, want_rbsp=True, extra_rbsp=0) -> ShardScan:
+def alloc_shard_outputs(buf, own: int, cap_nals: int, want_rbsp=True, extra_rbsp=0):
+    import torch
+
+    dev = buf.device
+    return dict(arrays=[torch.empty(cap_nals, dtype=torch.int64, device=dev) for _ in range(4)],
+                rbsp=torch.empty(own + 16 + extra_rbsp, dtype=torch.uint8, device=dev) if want_rbsp else None,
+                summary=torch.zeros(C.sizeof(ShardSummary), dtype=torch.uint8, device=dev), cap_nals=cap_nals)
+
+
+def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: bool, cap_nals=None, want_rbsp=True, extra_rbsp=0, out=None,
+                     sync=True) -> ShardScan:
     """buf: torch.uint8 CUDA tensor with own + halo bytes (16-byte aligned).  extra_rbsp: spare bytes behind the image for
-    the continuation of the last NAL."""
+    the continuation of the last NAL.  out: buffers of alloc_shard_outputs to reuse.  sync=False leaves the record on the
+    device (ShardScan.record is None, ShardScan.summary holds the raw bytes)."""
     import torch
 
     assert buf.is_cuda and buf.dtype == torch.uint8 and buf.numel() >= own + halo
-    dev = buf.device
-    if cap_nals is None:
-        cap_nals = own // 3 + 8
-    a = [torch.empty(cap_nals, dtype=torch.int64, device=dev) for _ in range(4)]
-    rbsp = torch.empty(own + 16 + extra_rbsp, dtype=torch.uint8, device=dev) if want_rbsp else None
-    d_sum = torch.zeros(C.sizeof(ShardSummary), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    if out is None:
+        out = alloc_shard_outputs(buf, own, own // 3 + 8 if cap_nals is None else cap_nals, want_rbsp, extra_rbsp)
+    a, rbsp, d_sum, cap_nals = out["arrays"], out["rbsp"], out["summary"], out["cap_nals"]
+    stream = torch.cuda.current_stream(buf.device).cuda_stream
     rc = ctx._L.hevcb_scan_strip_shard_device(ctx._h, buf.data_ptr(), own, halo, int(is_first), int(is_last), a[0].data_ptr(), a[1].data_ptr(),
                                               cap_nals, rbsp.data_ptr() if rbsp is not None else None, a[2].data_ptr(), a[3].data_ptr(),
                                               d_sum.data_ptr(), stream)
     ctx._check(rc)
-    rec = ShardSummary.from_buffer_copy(d_sum.cpu().numpy().tobytes())
-    if rec.overflow:
-        raise HevcbError(-104, f"{rec.n_nals} NALs exceed cap_nals {cap_nals}")
-    return ShardScan(rec, a[0], a[1], a[2], a[3], rbsp)
+    sc = ShardScan(None, a[0], a[1], a[2], a[3], rbsp)
+    sc.summary, sc.cap_nals = d_sum, cap_nals
+    if sync:
+        sc.record = ShardSummary.from_buffer_copy(d_sum.cpu().numpy().tobytes())
+        if sc.record.overflow:
+            raise HevcbError(-104, f"{sc.record.n_nals} NALs exceed cap_nals {cap_nals}")
+    return sc
+
+
+def apply_patches_device(ctx, res: StitchResult, shard: int, sc: ShardScan):
+    """One tiny kernel writes the stitched entries of this shard into its device arrays (hevcb_apply_patches_device)."""
+    import torch
+
+    stream = torch.cuda.current_stream(sc.nal_start.device).cuda_stream
+    ctx._check(ctx._L.hevcb_apply_patches_device(ctx._h, C.byref(res), shard, sc.nal_start.data_ptr(), sc.nal_end.data_ptr(), sc.rbsp_off.data_ptr(),
+                                                 sc.rbsp_end.data_ptr(), sc.cap_nals, stream))
 
 
 def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw):
-    """The distributed pass: local shard scan, all_gather of the records, stitch, local patches.  Returns
-    (ShardScan, StitchResult); global NAL index of local NAL j is res.nal_base[rank] + j - res.first_local[rank]."""
+    """The distributed pass: local shard scan, all_gather of the device-resident records (the only collective), one
+    device->host read, host stitch, one patch kernel.  Returns (ShardScan, StitchResult); the global index of local NAL j
+    is res.nal_base[rank] + j - res.first_local[rank]."""
+    import torch
     import torch.distributed as dist
 
-    sc = scan_strip_shard(ctx, buf, own, halo, is_first, is_last, **kw)
-    records = gather_records(sc.record, buf.device, group)
+    sc = scan_strip_shard(ctx, buf, own, halo, is_first, is_last, sync=False, **kw)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    allrec = torch.empty(world * sc.summary.numel(), dtype=torch.uint8, device=buf.device)
+    dist.all_gather_into_tensor(allrec, sc.summary, group=group)
+    raw = allrec.cpu().numpy().tobytes()
+    n = C.sizeof(ShardSummary)
+    records = [ShardSummary.from_buffer_copy(raw[i * n:(i + 1) * n]) for i in range(world)]
+    sc.record = records[rank]
+    if sc.record.overflow:
+        raise HevcbError(-104, f"{sc.record.n_nals} NALs exceed cap_nals {sc.cap_nals}")
     res = stitch(records)
-    apply_patches(res, dist.get_rank(group), sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)
+    apply_patches_device(ctx, res, rank, sc)
     return sc, res

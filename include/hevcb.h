@@ -181,6 +181,10 @@ typedef struct hevcb_stitch_result {
 /* Joins the shard records (in stream order).  Pure host code, identical on every rank. */
 HEVCB_API int hevcb_stitch(const hevcb_shard_summary* shards, int n_shards, hevcb_stitch_result* out);
 
+/* Writes the patches that concern shard `shard` into its device arrays (one small kernel, no copies). */
+HEVCB_API int hevcb_apply_patches_device(hevcb_ctx* ctx, const hevcb_stitch_result* res, int shard, int64_t* d_nal_start, int64_t* d_nal_end,
+                                         int64_t* d_rbsp_off, int64_t* d_rbsp_end, int64_t cap_nals, void* stream);
+
 /* ---- batched EPB insertion (rbsp_to_nal) ---------------------------------------------------------
  *
  * rbsp_to_nal (h264_nal.c:92-132) for n RBSP segments at once.  Segment k is rbsp[rbsp_off[k] .. rbsp_end[k]) of one

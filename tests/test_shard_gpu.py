@@ -69,3 +69,29 @@ def test_single_shard_equals_whole_stream_entry_point(ctx):
         assert np.array_equal(g.nal_start[:n], whole.nal_start[:n]) and np.array_equal(g.nal_end[:n], whole.nal_end[:n])
         assert np.array_equal(g.rbsp_off[:n], whole.rbsp_off[:n]) and np.array_equal(g.rbsp_end[:n], whole.rbsp_end[:n])
         assert np.array_equal(image, whole.rbsp)
+
+
+def test_apply_patches_device_matches_host_patching(ctx):
+    import torch
+
+    from hevcbitstream_b200 import shard as hs
+
+    s = ref.gen_stream(seed=5, profile=1, n_slices=3000, payload_min=1, payload_max=2000, zero_heavy_pct=20, extra_zero_pct=10, ps_period=40)
+    size = s.size - ref.PAD
+    bounds = hs.plan_shards(s, 4, size)
+    scans = []
+    for r in range(4):
+        own, halo, first, last = hs.shard_flags(bounds, r)
+        lo = int(bounds[r])
+        d = torch.zeros(own + halo + 32, dtype=torch.uint8, device="cuda")
+        d[: own + halo] = torch.from_numpy(s[lo: lo + own + halo].copy())
+        scans.append(hs.scan_strip_shard(ctx, d, own, halo, first, last))
+    res = hs.stitch([sc.record for sc in scans])
+    assert res.n_patches >= 3
+    for r, sc in enumerate(scans):
+        host = [t.cpu().numpy().copy() for t in (sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)]
+        hs.apply_patches(res, r, *host)
+        hs.apply_patches_device(ctx, res, r, sc)
+        n = int(res.first_local[r] + res.n_owned[r])
+        for h, t in zip(host, (sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)):
+            assert np.array_equal(h[:n], t.cpu().numpy()[:n])
