@@ -20,6 +20,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/hevcb.h"
 #include "../../include/hevcb_layout.h"
 
 #if defined(__CUDACC__)
@@ -180,36 +181,197 @@ HEVCB_SHD inline int hevcb_ceil_log2(int64_t n) // ceil(log2(n)) as the referenc
 #define HF(type, member) HEVCB_FIELD(type, member)
 
 // ------------------------------------------------------------------------------------------------
+// write side: bit writer (bs.h:224-331) and the source of the values a writer walks over
+// ------------------------------------------------------------------------------------------------
+struct hevcb_bitwriter {
+    uint8_t* dst;  // null: count only
+    int64_t cap;   // bytes that may be stored (bits beyond are dropped like bs_write_u1 past the end, bs.h:228)
+    int64_t pos;   // bits written
+    uint64_t acc;  // pending bits of the current byte (nacc < 8 between calls)
+    int nacc;
+
+    HEVCB_SHD void init(uint8_t* d, int64_t c) { dst = d; cap = c; pos = 0; acc = 0; nacc = 0; }
+    HEVCB_SHD void put_bits(int n, uint32_t v) // 0 <= n <= 32: low n bits of v, MSB first
+    {
+        if (n <= 0) { return; }
+        const uint64_t m = (n >= 32) ? 0xFFFFFFFFull : ((1ull << n) - 1ull);
+        acc = (acc << n) | ((uint64_t)v & m);
+        nacc += n;
+        pos += n;
+        while (nacc >= 8) {
+            const int64_t byte = ((pos - nacc) >> 3);
+            const uint8_t x = (uint8_t)(acc >> (nacc - 8));
+            if (dst && byte < cap) { dst[byte] = x; }
+            nacc -= 8;
+        }
+        acc &= 0xFFull;
+    }
+    // bs_write_u (bs.h:240): bit i is (v >> (n - i - 1)) & 1; shift counts >= 32 wrap on the x86 reference
+    HEVCB_SHD void write_u(int n, uint32_t v)
+    {
+        if (n <= 32) { put_bits(n, v); return; }
+        for (int i = 0; i < n; i++) { put_bits(1, (v >> ((n - i - 1) & 31)) & 1u); }
+    }
+    HEVCB_SHD void write_ue(uint32_t v) // bs.h:264-319
+    {
+        if (v == 0u) { put_bits(1, 1u); return; }
+        const uint32_t vv = v + 1u;
+        int len = 1; // len_table[0] == 1: v == 0xFFFFFFFF wraps to 0
+        if (vv != 0u) {
+#if defined(__CUDA_ARCH__)
+            len = 32 - __clz((int)vv);
+#else
+            len = 32 - __builtin_clz(vv);
+#endif
+        }
+        write_u(2 * len - 1, vv);
+    }
+    HEVCB_SHD void write_se(int32_t v) // bs.h:321-331
+    {
+        if (v <= 0) { write_ue((uint32_t)(-v * 2)); } else { write_ue((uint32_t)(v * 2 - 1)); }
+    }
+    HEVCB_SHD bool byte_aligned() const { return (pos & 7) == 0; }
+    HEVCB_SHD int64_t bytes() const { return pos >> 3; } // bs_pos: whole bytes only, a trailing partial byte is not counted
+    HEVCB_SHD bool overrun() const { return (pos >> 3) > cap; } // bs.h:119: the byte cursor strictly beyond the end
+};
+
+// edits applied while rewriting: hevcb_edit_set (include/hevcb.h)
+// The values of one parsed NAL, i.e. the struct read_hevc_nal_unit filled (zero + scatter of the pairs), consulted the
+// way write_hevc_nal_unit reads that struct: field by field, last write wins, absent = 0.  The pairs are in syntax
+// order, so the common case is a hit at the cursor.
+struct hevcb_replay {
+    const uint32_t* field;
+    const int32_t* value;
+    uint32_t n, cur;
+    int32_t kind;
+    const hevcb_edit_set* edits;
+
+    HEVCB_SHD int32_t load(uint32_t f, bool multi)
+    {
+        int32_t v = 0;
+        if (!multi && cur < n && field[cur] == f) {
+            v = value[cur];
+            cur++;
+        } else {
+            for (int64_t i = (int64_t)n - 1; i >= 0; i--) {
+                if (field[i] == f) {
+                    v = value[i];
+                    if (!multi) { cur = (uint32_t)i + 1u; }
+                    break;
+                }
+            }
+        }
+        if (edits) {
+            for (int i = 0; i < edits->n; i++) {
+                const hevcb_edit_rule& e = edits->e[i];
+                if (e.kind == kind && e.field == f) {
+                    v = (e.op == HEVCB_EDIT_ADD) ? v + e.arg : (e.op == HEVCB_EDIT_SET) ? e.arg : (v ^ e.arg);
+                }
+            }
+        }
+        return v;
+    }
+    HEVCB_SHD void skip_if(uint32_t f) // a value the reader stored without reading bits
+    {
+        if (cur < n && field[cur] == f) { cur++; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // the walker
 // ------------------------------------------------------------------------------------------------
-template <class Sink>
+// kWrite = false: the read variant (read_hevc_*): bits -> (field, value) pairs in `s`.
+// kWrite = true : the write variant (write_hevc_*, hevc_stream.c:1249-2312): the same walk with every value taken from
+//                 `rp` (the struct the reader filled) and written to `bw`.  The two variants of the reference are
+//                 generated from one template and differ only in what is listed at fx(), level8() and ovr() below.
+template <class Sink, bool kWrite = false>
 struct hevcb_walker {
     hevcb_bits& b;
     Sink& s;
     uint32_t flags; // bit0: an index ran past the reference's array bounds (undefined behaviour there)
+    hevcb_bitwriter* bw;
+    hevcb_replay* rp;
 
-    HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0) {}
+    HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0), bw(nullptr), rp(nullptr) {}
+    HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss, hevcb_bitwriter* w, hevcb_replay* r) : b(bb), s(ss), flags(0), bw(w), rp(r) {}
 
-    // value(x, u(n)) / u1 / u8 / ue / se : read + report
-    HEVCB_SHD int32_t u(uint32_t f, int n) { const int32_t v = (int32_t)b.read_u(n); s.put(f, v); return v; }
+    // value(x, u(n)) / u1 / u8 / ue / se : read + report, or load + write
+    HEVCB_SHD int32_t u(uint32_t f, int n)
+    {
+        if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_u(n, (uint32_t)v); return v; }
+        else { const int32_t v = (int32_t)b.read_u(n); s.put(f, v); return v; }
+    }
     HEVCB_SHD int32_t u1(uint32_t f) { return u(f, 1); }
     HEVCB_SHD int32_t u8(uint32_t f) { return u(f, 8); }
-    HEVCB_SHD int32_t ue(uint32_t f) { const int32_t v = (int32_t)b.read_ue(); s.put(f, v); return v; }
-    HEVCB_SHD int32_t se(uint32_t f) { const int32_t v = b.read_se(); s.put(f, v); return v; }
+    HEVCB_SHD int32_t ue(uint32_t f)
+    {
+        if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_ue((uint32_t)v); return v; }
+        else { const int32_t v = (int32_t)b.read_ue(); s.put(f, v); return v; }
+    }
+    HEVCB_SHD int32_t se(uint32_t f)
+    {
+        if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_se(v); return v; }
+        else { const int32_t v = b.read_se(); s.put(f, v); return v; }
+    }
+    // a field the reader stores several times (only the last value survives in the struct the writer reads)
+    HEVCB_SHD int32_t se_multi(uint32_t f)
+    {
+        if constexpr (kWrite) { const int32_t v = rp->load(f, true); bw->write_se(v); return v; }
+        else { return se(f); }
+    }
     // array element: reported only inside the reference's bounds
-    HEVCB_SHD int32_t au(uint32_t f, int idx, int bound, int n) { const int32_t v = (int32_t)b.read_u(n); put_idx(f, idx, bound, v); return v; }
-    HEVCB_SHD int32_t aue(uint32_t f, int idx, int bound) { const int32_t v = (int32_t)b.read_ue(); put_idx(f, idx, bound, v); return v; }
-    HEVCB_SHD int32_t ase(uint32_t f, int idx, int bound) { const int32_t v = b.read_se(); put_idx(f, idx, bound, v); return v; }
+    HEVCB_SHD int32_t au(uint32_t f, int idx, int bound, int n) { return raw_u(f + (uint32_t)idx, idx >= 0 && idx < bound, n); }
+    HEVCB_SHD int32_t aue(uint32_t f, int idx, int bound)
+    {
+        const bool in = idx >= 0 && idx < bound;
+        if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f + (uint32_t)idx, false); } else { flags |= 1u; } bw->write_ue((uint32_t)v); return v; }
+        else { const int32_t v = (int32_t)b.read_ue(); if (in) { s.put(f + (uint32_t)idx, v); } else { flags |= 1u; } return v; }
+    }
+    HEVCB_SHD int32_t ase(uint32_t f, int idx, int bound) { return raw_se(f + (uint32_t)idx, idx >= 0 && idx < bound); }
+    // element at an already computed field index; `in` = inside the reference's array
+    HEVCB_SHD int32_t raw_u(uint32_t f, bool in, int n)
+    {
+        if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f, false); } else { flags |= 1u; } bw->write_u(n, (uint32_t)v); return v; }
+        else { const int32_t v = (int32_t)b.read_u(n); if (in) { s.put(f, v); } else { flags |= 1u; } return v; }
+    }
+    HEVCB_SHD int32_t raw_se(uint32_t f, bool in)
+    {
+        if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f, false); } else { flags |= 1u; } bw->write_se(v); return v; }
+        else { const int32_t v = b.read_se(); if (in) { s.put(f, v); } else { flags |= 1u; } return v; }
+    }
     HEVCB_SHD void put_idx(uint32_t f, int idx, int bound, int32_t v)
     {
         if (idx >= 0 && idx < bound) { s.put(f + (uint32_t)idx, v); } else { flags |= 1u; }
     }
+    // f(n, v): bits the reader skips (bs_skip_u) and the writer emits as the constant v
+    HEVCB_SHD void fx(int n, uint32_t v)
+    {
+        if constexpr (kWrite) { bw->write_u(n, v); } else { b.skip(n); }
+    }
+    // a value the reader stores without reading bits (init_slice_hevc, defaults): nothing is written
+    HEVCB_SHD void syn(uint32_t f, int32_t v)
+    {
+        if constexpr (kWrite) { rp->skip_if(f); } else { s.put(f, v); }
+    }
+    // num_ref_idx_l{0,1}_active_minus1: write_hevc_slice_header first overwrites the struct member with the PPS default
+    // (hevc_stream.c:1898-1899) and then writes THAT value where the reader parses the override (:1965-1967)
+    HEVCB_SHD int32_t ovr(uint32_t f, int32_t dflt)
+    {
+        if constexpr (kWrite) { rp->skip_if(f); bw->write_ue((uint32_t)dflt); return dflt; }
+        else { return ue(f); }
+    }
+    // sub_layer_level_idc: read as u(8), written with bs_write_u1 by the generated writer (hevc_stream.c:751 vs :1845)
+    HEVCB_SHD int32_t level8(uint32_t f, int idx, int bound) { return au(f, idx, bound, kWrite ? 1 : 8); }
+    HEVCB_SHD bool aligned() const
+    {
+        if constexpr (kWrite) { return bw->byte_aligned(); } else { return b.byte_aligned(); }
+    }
 
-    // 7.3.2.11 / 7.3.2.12: one bit, then skip to the byte boundary (hevc_stream.c:630-649)
+    // 7.3.2.11 / 7.3.2.12: a one bit, then zero bits up to the byte boundary (hevc_stream.c:630-649 / :1724-1743)
     HEVCB_SHD void trailing_bits()
     {
-        b.skip(1);
-        while (!b.byte_aligned()) { b.skip(1); }
+        fx(1, 1u);
+        while (!aligned()) { fx(1, 0u); }
     }
 
     // ---- 7.3.3 profile_tier_level (hevc_stream.c:652-755) --------------------------------------
@@ -235,14 +397,14 @@ struct hevcb_walker {
             u1(base + HF(P, general_intra_constraint_flag));
             u1(base + HF(P, general_one_picture_only_constraint_flag));
             u1(base + HF(P, general_lower_bit_rate_constraint_flag));
-            b.skip(34);
+            fx(34, 0u);
         } else {
-            b.skip(43);
+            fx(43, 0u);
         }
         if ((idc >= 1 && idc <= 5) || ((compat >> 1) & 1) || ((compat >> 2) & 1) || ((compat >> 3) & 1) || ((compat >> 4) & 1) || ((compat >> 5) & 1)) {
             u1(base + HF(P, general_inbld_flag));
         } else {
-            b.skip(1);
+            fx(1, 0u);
         }
         u8(base + HF(P, general_level_idc));
         uint32_t prof_present = 0, level_present = 0;
@@ -251,7 +413,7 @@ struct hevcb_walker {
             level_present |= (uint32_t)(au(base + HF(P, sub_layer_level_present_flag), i, HEVCB_MAX_SUBLAYERS, 1) & 1) << (i & 31);
         }
         if (max_sub_layers_minus1 > 0) {
-            for (int i = max_sub_layers_minus1; i < 8; i++) { b.skip(2); }
+            for (int i = max_sub_layers_minus1; i < 8; i++) { fx(2, 0u); }
         }
         for (int i = 0; i < max_sub_layers_minus1; i++) {
             if ((prof_present >> (i & 31)) & 1u) {
@@ -260,9 +422,8 @@ struct hevcb_walker {
                 const int sidc = au(base + HF(P, sub_layer_profile_idc), i, HEVCB_MAX_SUBLAYERS, 5);
                 uint32_t sc = 0;
                 for (int j = 0; j < 32; j++) {
-                    const int32_t v = (int32_t)b.read_u(1);
-                    if (i < HEVCB_MAX_SUBLAYERS) { s.put(base + HF(P, sub_layer_profile_compatibility_flag) + (uint32_t)(i * 32 + j), v); } else { flags |= 1u; }
-                    sc |= (uint32_t)v << j;
+                    const int32_t v = raw_u(base + HF(P, sub_layer_profile_compatibility_flag) + (uint32_t)(i * 32 + j), i < HEVCB_MAX_SUBLAYERS, 1);
+                    sc |= (uint32_t)(v & 1) << j;
                 }
                 au(base + HF(P, sub_layer_progressive_source_flag), i, HEVCB_MAX_SUBLAYERS, 1);
                 au(base + HF(P, sub_layer_interlaced_source_flag), i, HEVCB_MAX_SUBLAYERS, 1);
@@ -278,14 +439,14 @@ struct hevcb_walker {
                     au(base + HF(P, sub_layer_intra_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
                     au(base + HF(P, sub_layer_one_picture_only_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
                     au(base + HF(P, sub_layer_lower_bit_rate_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
-                    b.skip(34);
+                    fx(34, 0u);
                 } else {
-                    b.skip(43);
+                    fx(43, 0u);
                 }
                 // the reference tests the ADDRESS of sub_layer_profile_compatibility_flag[1] (always true): App. A-10
                 au(base + HF(P, sub_layer_inbld_flag), i, HEVCB_MAX_SUBLAYERS, 1);
             }
-            if ((level_present >> (i & 31)) & 1u) { au(base + HF(P, sub_layer_level_idc), i, HEVCB_MAX_SUBLAYERS, 8); }
+            if ((level_present >> (i & 31)) & 1u) { level8(base + HF(P, sub_layer_level_idc), i, HEVCB_MAX_SUBLAYERS); }
         }
     }
 
@@ -354,7 +515,7 @@ struct hevcb_walker {
                     int coef_num = 1 << (4 + (size_id << 1));
                     if (coef_num > 64) { coef_num = 64; }
                     if (size_id > 1) { se(base + HF(L, scaling_list_dc_coef_minus8) + (uint32_t)((size_id - 2) * 6 + matrix_id)); }
-                    for (int i = 0; i < coef_num; i++) { se(base + HF(L, scaling_list_delta_coef) + (uint32_t)(size_id * 64 + matrix_id)); }
+                    for (int i = 0; i < coef_num; i++) { se_multi(base + HF(L, scaling_list_delta_coef) + (uint32_t)(size_id * 64 + matrix_id)); }
                 }
             }
         }
@@ -511,7 +672,7 @@ struct hevcb_walker {
         u(HF(V, vps_max_layers_minus1), 6);
         const int msl = u(HF(V, vps_max_sub_layers_minus1), 3);
         u1(HF(V, vps_temporal_id_nesting_flag));
-        b.skip(16);
+        fx(16, 0xFFFFu); // vps_reserved_0xffff_16bits
         profile_tier_level(HF(V, ptl), msl);
         const int ordering = u1(HF(V, vps_sub_layer_ordering_info_present_flag));
         for (int i = (ordering ? 0 : msl); i <= msl; i++) {
@@ -523,9 +684,7 @@ struct hevcb_walker {
         const int num_layer_sets_minus1 = ue(HF(V, vps_num_layer_sets_minus1));
         for (int i = 1; i <= num_layer_sets_minus1; i++) {
             for (int j = 0; j <= max_layer_id; j++) {
-                const int32_t v = (int32_t)b.read_u(1);
-                if (i < HEVCB_MAX_SUBLAYERS && j < HEVCB_MAX_SUBLAYERS) { s.put(HF(V, layer_id_included_flag) + (uint32_t)(i * HEVCB_MAX_SUBLAYERS + j), v); }
-                else { flags |= 1u; }
+                raw_u(HF(V, layer_id_included_flag) + (uint32_t)(i * HEVCB_MAX_SUBLAYERS + j), i < HEVCB_MAX_SUBLAYERS && j < HEVCB_MAX_SUBLAYERS, 1);
             }
         }
         if (u1(HF(V, vps_timing_info_present_flag))) {
@@ -539,6 +698,7 @@ struct hevcb_walker {
                 if (i > 0) { cprms = au(HF(V, cprms_present_flag), i, HEVCB_MAX_HRD_PARAM, 1); }
                 const uint32_t hs = (uint32_t)(sizeof(hevc_hrd_t) / sizeof(int));
                 if (i < HEVCB_MAX_HRD_PARAM) { hrd_parameters(HF(V, hrd) + (uint32_t)i * hs, cprms, msl); }
+                else if constexpr (kWrite) { flags |= 1u; }
                 else { flags |= 1u; hevcb_sink dummy{nullptr, nullptr, 0}; hevcb_walker<hevcb_count_sink> w(b, dummy); w.hrd_parameters(0, cprms, msl); }
             }
         }
@@ -598,6 +758,8 @@ struct hevcb_walker {
         for (int i = 0; i < c.num_short_term_ref_pic_sets; i++) {
             if (i < HEVCB_MAX_PICS) {
                 st_ref_pic_set(HF(S, st_ref_pic_set) + (uint32_t)i * rs, i, c.num_short_term_ref_pic_sets, c.rps, c.rps[i]);
+            } else if constexpr (kWrite) {
+                flags |= 1u;
             } else { // beyond the reference's array: keep the bit cursor moving, report nothing
                 flags |= 1u;
                 hevcb_sink dummy{nullptr, nullptr, 0};
@@ -739,14 +901,14 @@ struct hevcb_walker {
     HEVCB_SHD void slice_segment_header(int nal_unit_type, const hevcb_sps_ctx& sps, const hevcb_pps_ctx& pps, hevcb_slice_cols& cols)
     {
         typedef hevc_slice_header_t H;
-        s.put(HF(H, collocated_from_l0_flag), 1); // init_slice_hevc (hevc_stream.c:18-23)
+        syn(HF(H, collocated_from_l0_flag), 1); // init_slice_hevc (hevc_stream.c:18-23)
         const int first = u1(HF(H, first_slice_segment_in_pic_flag));
         if (nal_unit_type >= 16 && nal_unit_type <= 23) { u1(HF(H, no_output_of_prior_pics_flag)); }
         const int pps_id = ue(HF(H, pic_parameter_set_id));
         if (pps_id != 0 || pps.seq_parameter_set_id != 0) { flags |= 1u; } // the reference indexes past its single PPS / SPS
         int num_ref_idx_l0 = pps.num_ref_idx_l0_default_active_minus1, num_ref_idx_l1 = pps.num_ref_idx_l1_default_active_minus1;
-        s.put(HF(H, num_ref_idx_l0_active_minus1), num_ref_idx_l0);
-        s.put(HF(H, num_ref_idx_l1_active_minus1), num_ref_idx_l1);
+        syn(HF(H, num_ref_idx_l0_active_minus1), num_ref_idx_l0);
+        syn(HF(H, num_ref_idx_l1_active_minus1), num_ref_idx_l1);
         int dependent = 0;
         cols.first_slice_segment_in_pic_flag = first;
         cols.slice_segment_address = 0;
@@ -768,7 +930,7 @@ struct hevcb_walker {
         }
         cols.dependent_slice_segment_flag = dependent;
         if (!dependent) {
-            for (int i = 0; i < pps.num_extra_slice_header_bits; i++) { b.skip(1); }
+            for (int i = 0; i < pps.num_extra_slice_header_bits; i++) { fx(1, 1u); } // slice_reserved_flag: the writer emits 1
             const int slice_type = ue(HF(H, slice_type));
             cols.slice_type = slice_type;
             if (pps.output_flag_present_flag) { u1(HF(H, pic_output_flag)); }
@@ -823,8 +985,8 @@ struct hevcb_walker {
             }
             if (slice_type == 1 || slice_type == 0) { // P or B (HEVC_SLICE_TYPE_P = 1, _B = 0)
                 if (u1(HF(H, num_ref_idx_active_override_flag))) {
-                    num_ref_idx_l0 = ue(HF(H, num_ref_idx_l0_active_minus1));
-                    if (slice_type == 0) { num_ref_idx_l1 = ue(HF(H, num_ref_idx_l1_active_minus1)); }
+                    num_ref_idx_l0 = ovr(HF(H, num_ref_idx_l0_active_minus1), num_ref_idx_l0);
+                    if (slice_type == 0) { num_ref_idx_l1 = ovr(HF(H, num_ref_idx_l1_active_minus1), num_ref_idx_l1); }
                 }
                 // the RPS that getNumPicTotalCurr consults: slice-local entry or the SPS entry short_term_ref_pic_set_idx
                 const int cur_idx = short_term_sps_flag ? st_idx : sps.num_short_term_ref_pic_sets;
@@ -882,9 +1044,13 @@ struct hevcb_walker {
                 for (int i = 0; i < n; i++) {
                     // u(offset_len_minus1 + 1): widths beyond 32 only occur on corrupt input
                     const int w = len_minus1 + 1;
-                    int32_t v;
-                    if (w <= 32) { v = (int32_t)b.read_u(w); } else { b.skip(w - 32); v = (int32_t)b.read_u(32); flags |= 1u; }
-                    put_idx(HF(H, entry_point_offset_minus1), i, HEVCB_MAX_PICS, v);
+                    if constexpr (kWrite) {
+                        raw_u(HF(H, entry_point_offset_minus1) + (uint32_t)i, i < HEVCB_MAX_PICS, w);
+                    } else {
+                        int32_t v;
+                        if (w <= 32) { v = (int32_t)b.read_u(w); } else { b.skip(w - 32); v = (int32_t)b.read_u(32); flags |= 1u; }
+                        put_idx(HF(H, entry_point_offset_minus1), i, HEVCB_MAX_PICS, v);
+                    }
                     if (b.overrun() && i > 64) { break; }
                 }
             }
@@ -892,7 +1058,7 @@ struct hevcb_walker {
         if (pps.slice_segment_header_extension_present_flag) {
             const int len = ue(HF(H, slice_segment_header_extension_length));
             for (int i = 0; i < len; i++) {
-                b.skip(8);
+                fx(8, 0u); // slice_segment_header_extension_data_byte
                 if (b.overrun()) { break; }
             }
         }
@@ -935,10 +1101,8 @@ struct hevcb_walker {
             }
             if (i < 64 && ((cw >> i) & 1)) {
                 for (int j = 0; j < 2; j++) {
-                    const int32_t v1 = b.read_se();
-                    if (i < HEVCB_MAX_PICS) { s.put(base + f_dcw + (uint32_t)(i * 2 + j), v1); } else { flags |= 1u; }
-                    const int32_t v2 = b.read_se();
-                    if (i < HEVCB_MAX_PICS) { s.put(base + f_dco + (uint32_t)(i * 2 + j), v2); } else { flags |= 1u; }
+                    raw_se(base + f_dcw + (uint32_t)(i * 2 + j), i < HEVCB_MAX_PICS);
+                    raw_se(base + f_dco + (uint32_t)(i * 2 + j), i < HEVCB_MAX_PICS);
                 }
             }
             if (b.overrun() && i > 64) { break; }
@@ -1002,4 +1166,53 @@ HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Si
     r.flags = w.flags;
     r.end_bits = b.pos;
     r.ok = b.overrun() ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one NAL, write side: write_hevc_nal_unit (hevc_stream.c:1249-1335) up to (not including) rbsp_to_nal
+// ------------------------------------------------------------------------------------------------
+struct hevcb_write_result {
+    int32_t ok;        // 1: the reference's writer returns > 0 for this NAL (supported type, no overrun)
+    int32_t hdr_bytes; // slices: bytes up to and including byte_alignment(); the writer then appends rbsp_trailing_bits (0x80)
+    int64_t bytes;     // RBSP bytes produced (bs_pos: a trailing partial byte is dropped, as happens for an SPS, App. A-1)
+    uint32_t flags;
+};
+
+// Writes the RBSP of one NAL from the values its parse produced (`rp`) into `bw` (count only when bw.dst is null).
+// nal_hdr = nal_unit_type | nal_layer_id << 8 | nal_temporal_id_plus1 << 16 (what the parse left in h->nal).
+// `sps_scratch`: working copy for the derived RPS tables an SPS builds while it is walked.
+HEVCB_SHD inline void hevcb_write_nal(hevcb_replay& rp, hevcb_bitwriter& bw, int32_t nal_hdr, const hevcb_sps_ctx* sps_in, const hevcb_pps_ctx* pps_in,
+                                      hevcb_sps_ctx* sps_scratch, hevcb_write_result& r)
+{
+    hevcb_bits nob;
+    nob.init(nullptr, 0);
+    hevcb_sink nos{nullptr, nullptr, 0};
+    const int t = nal_hdr & 0xFF;
+    r.ok = 0;
+    r.hdr_bytes = 0;
+    r.bytes = 0;
+    r.flags = 0;
+    bw.write_u(1, 0u); // forbidden_zero_bit
+    bw.write_u(6, (uint32_t)t);
+    bw.write_u(6, (uint32_t)((nal_hdr >> 8) & 0xFF));
+    bw.write_u(3, (uint32_t)((nal_hdr >> 16) & 0xFF));
+    hevcb_walker<hevcb_sink, true> w(nob, nos, &bw, &rp);
+    if (hevcb_is_slice_type(t)) {
+        hevcb_slice_cols cols;
+        w.slice_segment_header(t, *sps_in, *pps_in, cols);
+        r.hdr_bytes = (int32_t)bw.bytes();
+        w.trailing_bits(); // write_hevc_rbsp_slice_trailing_bits: no slice data is written
+    } else if (t == 32) {
+        w.video_parameter_set();
+    } else if (t == 33) {
+        w.seq_parameter_set(*sps_scratch);
+    } else if (t == 34) {
+        hevcb_pps_ctx pc;
+        w.pic_parameter_set(pc);
+    } else {
+        return;
+    }
+    r.flags = w.flags;
+    r.bytes = bw.bytes();
+    r.ok = (bw.overrun() || (w.flags & 1u)) ? 0 : 1;
 }

@@ -265,6 +265,53 @@ HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int
                                  const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
                                  const hevcb_parse_buffers* out, hevcb_parse_summary* d_summary, void* stream);
 
+/* ---- header rewrite ------------------------------------------------------------------------------
+ *
+ * The reference's edit loop: read_hevc_nal_unit -> change fields of h->sh / h->sps ... ->
+ * write_hevc_nal_unit (hevc_stream.c:1249-1335) -> rbsp_to_nal, for every NAL of a stream at once:
+ *   slices        new NAL = rbsp_to_nal( written header without the writer's final 0x80 byte ++ the original RBSP
+ *                 from the old header end (hdr_end[k]) on ); the writer emits no slice data itself
+ *   VPS/SPS/PPS   new NAL = what write_hevc_nal_unit produces from the parsed struct (+ edits)
+ *   anything else (unsupported types, NALs the reader or the writer fails on) is copied through unchanged
+ * Everything between two NALs (start codes, zero bytes) and after the last one is copied verbatim.
+ * An edit names a field by (kind, field index in ints inside the kind's struct, see hevcb_layout.h / hevcb_field_index)
+ * and must not change which syntax elements are present.
+ */
+#define HEVCB_EDIT_ADD 0
+#define HEVCB_EDIT_SET 1
+#define HEVCB_EDIT_XOR 2
+#define HEVCB_MAX_EDITS 8
+typedef struct hevcb_edit_rule {
+    int32_t kind;   /* HEVCB_KIND_{VPS,SPS,PPS,SLICE} */
+    uint32_t field;
+    int32_t op;     /* HEVCB_EDIT_* */
+    int32_t arg;
+} hevcb_edit_rule;
+typedef struct hevcb_edit_set {
+    int32_t n;
+    hevcb_edit_rule e[HEVCB_MAX_EDITS];
+} hevcb_edit_set;
+
+typedef struct hevcb_rewrite_summary {
+    int64_t n_nals;
+    int64_t n_rewritten; /* NALs that went through the writer (the rest was copied through) */
+    int64_t out_bytes;
+    int64_t n_inserted;  /* emulation prevention bytes inserted */
+    int32_t overflow;    /* out_cap too small: out_start / out_end are complete, bytes of NALs that do not fit are missing */
+    int32_t pad;
+} hevcb_rewrite_summary;
+
+/* Must follow hevcb_scan_strip_device + hevcb_parse_device on the same context, stream and arrays (it uses the
+ * parameter-set tables the parse left on the device).  out_start[k] / out_end[k]: extent of NAL k in `out`. */
+HEVCB_API int hevcb_rewrite_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                                   const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                   const hevcb_parse_buffers* parsed, const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap,
+                                   int64_t* d_out_start, int64_t* d_out_end, hevcb_rewrite_summary* d_summary, void* stream);
+
+/* Field index (offset in ints) of a member of the struct of `kind`, by name: "slice_qp_delta", "vui.video_full_range_flag",
+ * "pwt.luma_offset_l0[3]", "st_ref_pic_set[2].delta_poc_s0_minus1[0]".  -1 when the path does not exist. */
+HEVCB_API int64_t hevcb_field_index(int kind, const char* path);
+
 /* Host-side index of a whole stream: the outputs of hevcb_scan_strip + hevcb_parse in caller-allocated host arrays. */
 typedef struct hevcb_stream_index {
     int64_t cap_nals;   /* capacity of the per-NAL arrays */

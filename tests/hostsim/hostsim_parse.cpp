@@ -128,3 +128,95 @@ extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, 
     delete sps; delete pps; delete vps_s; delete sps_s; delete pps_s; delete sh_s;
     return ok;
 }
+
+// ------------------------------------------------------------------------------------------------
+// rewrite: parse -> edit -> write walker -> splice -> EPB insertion, NAL by NAL (mirrors SURVEY 3.4 / ref_rewrite_all)
+// ------------------------------------------------------------------------------------------------
+namespace {
+void insert_epb(const std::vector<uint8_t>& rbsp, std::vector<uint8_t>& out) // rbsp_to_nal restated (h264_nal.c:92-132), test only
+{
+    int count = 0;
+    for (size_t i = 0; i < rbsp.size(); i++) {
+        if (count == 2 && rbsp[i] <= 3) { out.push_back(3); count = 0; }
+        out.push_back(rbsp[i]);
+        count = rbsp[i] == 0 ? count + 1 : 0;
+    }
+}
+} // namespace
+
+extern "C" int64_t hostsim_rewrite_all(const uint8_t* buf, int64_t size, const int64_t* starts, const int64_t* ends, int64_t n,
+                                       const hevcb_edit_set* edits, uint8_t* out, int64_t out_cap, int64_t* out_starts, int64_t* out_ends,
+                                       int64_t* n_rewritten)
+{
+    std::vector<uint8_t> rbsp, o, nr, w;
+    std::vector<uint32_t> fld(1 << 16);
+    std::vector<int32_t> val(1 << 16);
+    hevcb_sps_ctx* sps = new hevcb_sps_ctx();
+    hevcb_sps_ctx* sps_new = new hevcb_sps_ctx();
+    hevcb_sps_ctx* sps_scr = new hevcb_sps_ctx();
+    hevcb_pps_ctx* pps = new hevcb_pps_ctx();
+    memset(sps, 0, sizeof(*sps));
+    memset(pps, 0, sizeof(*pps));
+    int64_t prev_end = 0, done_count = 0;
+    for (int64_t k = 0; k < n; k++) {
+        o.insert(o.end(), buf + prev_end, buf + starts[k]);
+        prev_end = ends[k];
+        out_starts[k] = (int64_t)o.size();
+        const int64_t nsz = ends[k] - starts[k];
+        int64_t consumed = 0;
+        const int64_t rs = strip(buf + starts[k], nsz, rbsp, &consumed);
+        bool done = false;
+        if (rs >= 0) {
+            rbsp.resize(rbsp.size() + 16, 0);
+            hevcb_nal_result res;
+            hevcb_sink cs{nullptr, nullptr, 0};
+            hevcb_pps_ctx pps_new;
+            memset(sps_new, 0, sizeof(*sps_new));
+            memset(&pps_new, 0, sizeof(pps_new));
+            hevcb_parse_nal(rbsp.data(), rs, cs, sps, pps, sps_new, &pps_new, res);
+            if (cs.n > fld.size()) { fld.resize(cs.n); val.resize(cs.n); }
+            hevcb_sink es{fld.data(), val.data(), 0};
+            memset(sps_new, 0, sizeof(*sps_new));
+            memset(&pps_new, 0, sizeof(pps_new));
+            hevcb_parse_nal(rbsp.data(), rs, es, sps, pps, sps_new, &pps_new, res);
+            if (res.kind == HEVCB_KIND_SPS) { *sps = *sps_new; }
+            if (res.kind == HEVCB_KIND_PPS) { *pps = pps_new; }
+            const int32_t hdr = res.nal_unit_type | (res.nal_layer_id << 8) | (res.nal_temporal_id_plus1 << 16);
+            if (res.ok && res.kind != HEVCB_KIND_NONE && !(res.kind == HEVCB_KIND_SLICE && res.hdr_end > rs)) {
+                // the writer's scratch: write_hevc_nal_unit gets size*3/4 bytes of RBSP room (hevc_stream.c:1266)
+                const int64_t wcap_nal = (res.kind == HEVCB_KIND_SLICE) ? 16384 : nsz * 2 + 64;
+                const int64_t wcap = wcap_nal * 3 / 4;
+                hevcb_write_result wr;
+                for (int pass = 0; pass < 2; pass++) { // count, then emit (as the kernels do)
+                    hevcb_replay rp{fld.data(), val.data(), es.n, 0, res.kind, edits};
+                    hevcb_bitwriter bw;
+                    if (pass == 1) { w.assign((size_t)wr.bytes + 8, 0); }
+                    bw.init(pass == 0 ? nullptr : w.data(), wcap);
+                    memset(sps_scr, 0, sizeof(*sps_scr));
+                    hevcb_write_nal(rp, bw, hdr, sps, pps, sps_scr, wr);
+                    if (!wr.ok) { break; }
+                }
+                if (wr.ok && wr.bytes > 0) {
+                    nr.clear();
+                    if (res.kind == HEVCB_KIND_SLICE) {
+                        nr.insert(nr.end(), w.begin(), w.begin() + wr.hdr_bytes);
+                        nr.insert(nr.end(), rbsp.begin() + res.hdr_end, rbsp.begin() + rs);
+                    } else {
+                        nr.insert(nr.end(), w.begin(), w.begin() + wr.bytes);
+                    }
+                    insert_epb(nr, o);
+                    done = true;
+                    done_count++;
+                }
+            }
+        }
+        if (!done) { o.insert(o.end(), buf + starts[k], buf + ends[k]); }
+        out_ends[k] = (int64_t)o.size();
+    }
+    if (size > prev_end) { o.insert(o.end(), buf + prev_end, buf + size); }
+    delete sps; delete sps_new; delete sps_scr; delete pps;
+    *n_rewritten = done_count;
+    if ((int64_t)o.size() > out_cap) { return -1; }
+    memcpy(out, o.data(), o.size());
+    return (int64_t)o.size();
+}
