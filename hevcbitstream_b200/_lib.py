@@ -55,6 +55,19 @@ class InsertSummary(C.Structure):
     _fields_ = [("n_nals", C.c_int64), ("out_bytes", C.c_int64), ("n_inserted", C.c_int64), ("overflow", C.c_int32), ("pad", C.c_int32)]
 
 
+class EditRule(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("field", C.c_uint32), ("op", C.c_int32), ("arg", C.c_int32)]
+
+
+class EditSet(C.Structure):
+    _fields_ = [("n", C.c_int32), ("e", EditRule * 8)]
+
+
+class RewriteSummary(C.Structure):
+    _fields_ = [("n_nals", C.c_int64), ("n_rewritten", C.c_int64), ("out_bytes", C.c_int64), ("n_inserted", C.c_int64), ("overflow", C.c_int32),
+                ("pad", C.c_int32)]
+
+
 class ShardSummary(C.Structure):
     _fields_ = [
         ("own", C.c_int64), ("n_nals", C.c_int64), ("first_empty", C.c_int64), ("first_empty_start", C.c_int64), ("rbsp_bytes", C.c_int64),
@@ -127,6 +140,10 @@ def load_library() -> C.CDLL:
     L.hevcb_plan_shards.argtypes = [vp, i64, C.c_int, vp]
     L.hevcb_stitch.restype = C.c_int
     L.hevcb_stitch.argtypes = [C.POINTER(ShardSummary), C.c_int, C.POINTER(StitchResult)]
+    L.hevcb_rewrite_device.restype = C.c_int
+    L.hevcb_rewrite_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), C.POINTER(EditSet), vp, i64, vp, vp, vp, vp]
+    L.hevcb_field_index.restype = i64
+    L.hevcb_field_index.argtypes = [C.c_int, C.c_char_p]
     L.hevcb_insert_device.restype = C.c_int
     L.hevcb_insert_device.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp, i64, vp, vp, vp]
     L.hevcb_insert_host.restype = C.c_int

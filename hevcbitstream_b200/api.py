@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import HevcbError, InsertSummary, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
+from ._lib import EditRule, EditSet, HevcbError, InsertSummary, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
 
 
 @dataclass
@@ -196,6 +196,43 @@ class Context:
             out["n_ok"], out["n_pairs"], out["n_vps"], out["n_sps"], out["n_pps"], out["n_slices"] = (int(x) for x in s[1:7])
             if int(s[7]) & 0xFFFFFFFF:
                 raise HevcbError(-104, f"{out['n_pairs']} syntax elements exceed cap_pairs {cap_pairs}")
+        return out
+
+    # ---- header rewrite -------------------------------------------------------------------------
+    def rewrite_device(self, buf, scan: "ScanResult", parsed: dict, edits=(), size=None, out_cap=None, sync=True):
+        """read -> edit -> write_hevc_nal_unit -> rbsp_to_nal for every NAL (hevcb_rewrite_device); must directly follow
+        parse_device(buf, scan).  edits: iterable of (kind, field index or name, op, arg).  Returns dict(out, out_start,
+        out_end, summary) + out_bytes / n_rewritten / n_inserted when sync."""
+        import torch
+
+        n = int(scan.n_nals)
+        size = int(buf.numel() if size is None else size)
+        dev = buf.device
+        es = EditSet()
+        for i, (kind, field, op, arg) in enumerate(edits):
+            if isinstance(field, str):
+                idx = int(self._L.hevcb_field_index(kind, field.encode()))
+                if idx < 0:
+                    raise HevcbError(-102, f"unknown field {field!r}")
+                field = idx
+            es.e[i] = EditRule(kind, field, op, arg)
+            es.n = i + 1
+        if out_cap is None:
+            out_cap = size + size // 2 + 64 * n + 4096
+        out = dict(out=torch.empty(out_cap + 16, dtype=torch.uint8, device=dev), out_start=torch.empty(max(n, 1), dtype=torch.int64, device=dev),
+                   out_end=torch.empty(max(n, 1), dtype=torch.int64, device=dev), summary=torch.zeros(5, dtype=torch.int64, device=dev))
+        pb = ParseBuffers(parsed["rc"].data_ptr(), parsed["nal_hdr"].data_ptr(), parsed["kind"].data_ptr(), parsed["ubflag"].data_ptr(),
+                          parsed["hdr_end"].data_ptr(), parsed["cols"].data_ptr(), parsed["pair_off"].data_ptr(), parsed["pair_field"].data_ptr(),
+                          parsed["pair_value"].data_ptr(), parsed["cap_pairs"])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.hevcb_rewrite_device(self._h, buf.data_ptr(), size, scan.nal_start.data_ptr(), scan.nal_end.data_ptr(), scan.rbsp.data_ptr(),
+                                                 scan.rbsp_off.data_ptr(), scan.rbsp_end.data_ptr(), n, C.byref(pb), C.byref(es), out["out"].data_ptr(),
+                                                 out_cap, out["out_start"].data_ptr(), out["out_end"].data_ptr(), out["summary"].data_ptr(), stream))
+        if sync:
+            s = out["summary"].cpu().numpy()
+            out["n_rewritten"], out["out_bytes"], out["n_inserted"] = int(s[1]), int(s[2]), int(s[3])
+            if int(s[4]) & 0xFFFFFFFF:
+                raise HevcbError(-104, f"{out['out_bytes']} output bytes exceed out_cap {out_cap}")
         return out
 
     def index_host(self, buf: np.ndarray, size=None, cap_nals=None, cap_pairs=None, want_rbsp=True) -> "HostIndex":

@@ -74,7 +74,7 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
     hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
-                            &ctx->insert_scratch, &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
+                            &ctx->insert_scratch, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
                             &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
@@ -190,6 +190,17 @@ HEVCB_API int hevcb_apply_patches_device(hevcb_ctx* ctx, const hevcb_stitch_resu
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
+}
+
+HEVCB_API int hevcb_rewrite_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                                   const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                   const hevcb_parse_buffers* parsed, const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap,
+                                   int64_t* d_out_start, int64_t* d_out_end, hevcb_rewrite_summary* d_summary, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_rewrite(ctx, d_buf, size, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, parsed, edits, d_out, out_cap,
+                                d_out_start, d_out_end, d_summary, (cudaStream_t)stream);
 }
 
 HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,

@@ -9,6 +9,10 @@
 // warps of a persistent grid.  Two passes: count insertions per NAL -> exclusive scan of the output sizes -> write.
 // Rows without insertions are written as aligned 16-byte vectors assembled with shuffles + funnel shifts, rows with
 // insertions byte by byte.
+//
+// The same kernels assemble the output of the header rewrite (hevcb_rewrite_device): a NAL is then made of up to three
+// parts -- bytes copied verbatim (what precedes the NAL in the input, or a NAL that is passed through), the rewritten
+// header (escaped) and the original payload (escaped, the zero-run state continuing across the junction).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -50,8 +54,8 @@ struct RowInfo {
     uint32_t ins;   // bit j: 03 is inserted before byte j
 };
 
-// One 512-byte row of a NAL: loads, zero-run carry, insertion mask.  run_m = zero-run length in front of the row
-// (warp uniform), updated for the next row.
+// One 512-byte row of a part: loads, zero-run carry, insertion mask.  run_m = length of the zero run that ends right in
+// front of the row's first byte of the part (warp uniform), updated to the run that reaches the end of the row.
 __device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, int64_t row, int64_t off, int64_t end, int lane, uint32_t& run_m)
 {
     RowInfo r;
@@ -65,28 +69,27 @@ __device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, i
     if (hi < 16) { valid &= (hi <= 0) ? 0u : ((1u << (int)hi) - 1u); }
     valid &= 0xFFFFu;
     r.valid = valid;
+    const uint32_t lead = (off > row) ? (uint32_t)(off - row) : 0u; // bytes of the row in front of the part (first row only, < 16)
     const uint32_t Z = zero_mask16(r.v) & valid;
-    // R: bytes that end a zero run: non-zero bytes of the NAL, and positions in front of the NAL start
-    const uint32_t before = (lo > 0) ? ((lo >= 16) ? 0xFFFFu : ((1u << (int)lo) - 1u)) : 0u;
-    const uint32_t R = (valid & ~Z) | before;
-    const uint32_t tz = R ? (uint32_t)(15 - (31 - __clz((int)R))) : 16u; // zero bytes after the last run-ending byte
+    const uint32_t R = valid & ~Z; // bytes that end a zero run
+    const uint32_t tz = R ? (uint32_t)(15 - (31 - __clz((int)R))) : 16u; // bytes after the last run-ending byte of the chunk
     const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, R != 0u);
     const uint32_t lower = Rb & ((1u << lane) - 1u);
     uint32_t m_in;
     {
         const int p = lower ? (31 - __clz((int)lower)) : 0;
         const uint32_t tzp = __shfl_sync(0xFFFFFFFFu, tz, p);
-        m_in = lower ? (tzp + 16u * (uint32_t)(lane - p - 1)) : (run_m + 16u * (uint32_t)lane);
+        m_in = lower ? (tzp + 16u * (uint32_t)(lane - p - 1)) : (run_m + 16u * (uint32_t)lane - (lane ? lead : 0u));
     }
-    // next row's carry
+    // next row's carry (bytes behind `end` are counted here; the caller takes them off after the last row)
     {
         const int p = Rb ? (31 - __clz((int)Rb)) : 0;
         const uint32_t tzp = __shfl_sync(0xFFFFFFFFu, tz, p);
-        run_m = Rb ? (tzp + 16u * (uint32_t)(31 - p)) : (run_m + 512u);
+        run_m = Rb ? (tzp + 16u * (uint32_t)(31 - p)) : (run_m + 512u - lead);
     }
     // state machine only where an insertion is possible: two zeros in a row somewhere, or a run reaching into the chunk
     uint32_t ins = 0;
-    const bool need = ((Z & (Z >> 1)) != 0u) || (m_in >= 2u) || (m_in >= 1u && (Z & 1u));
+    const bool need = ((Z & (Z >> 1)) != 0u) || (m_in >= 2u) || (m_in >= 1u && (Z & (valid & (0u - valid))) != 0u);
     if (need && valid) {
         uint32_t count = (m_in == 0u) ? 0u : ((m_in & 1u) ? 1u : 2u);
 #pragma unroll
@@ -102,98 +105,140 @@ __device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, i
     return r;
 }
 
-// pass 1: output size of every NAL (start code + bytes + insertions); NALs whose nal_to_rbsp failed (end < 0) emit nothing
-__global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const uint8_t* __restrict__ img, const int64_t* __restrict__ off_a,
-                                                                   const int64_t* __restrict__ end_a, int64_t n, int sc_len,
-                                                                   int64_t* __restrict__ out_size, unsigned long long* __restrict__ n_ins_total)
+// the parts of the NALs to assemble; a part is absent when its offset array is null or off >= end
+struct AssembleParts {
+    const uint8_t* raw_base; const int64_t* raw_off; const int64_t* raw_end; // copied verbatim
+    const uint8_t* a_base; const int64_t* a_off; const int64_t* a_end;       // escaped
+    const uint8_t* b_base; const int64_t* b_off; const int64_t* b_end;       // escaped, continues the state of A
+    int sc_len;      // start code written in front of every NAL (0: none)
+    int skip_neg_b;  // hevcb_insert semantics: b_end < 0 => the NAL emits nothing at all
+};
+
+// insertions of one escaped part (count pass)
+__device__ __forceinline__ uint32_t count_part(const uint8_t* __restrict__ base, int64_t off, int64_t end, int lane, uint32_t& run_m)
+{
+    if (end <= off) { return 0u; }
+    uint32_t total = 0;
+    int64_t row = off & ~(int64_t)15;
+    for (; row < end; row += 512) {
+        const RowInfo r = insert_row(base, row, off, end, lane, run_m);
+        total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
+    }
+    run_m -= (uint32_t)(row - end); // bytes of the last row behind the part
+    return total;
+}
+
+// pass 1: output size of every NAL (start code + verbatim bytes + escaped bytes)
+__global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const AssembleParts P, int64_t n, int64_t* __restrict__ out_size,
+                                                                   unsigned long long* __restrict__ n_ins_total)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * kInsWarps;
     unsigned long long local_ins = 0;
     for (int64_t k = wid; k < n; k += nw) {
-        const int64_t off = off_a[k], end = end_a[k];
-        if (end < 0 || end < off) {
+        const int64_t boff = P.b_off ? P.b_off[k] : 0, bend = P.b_off ? P.b_end[k] : 0;
+        if (P.skip_neg_b && (bend < 0 || bend < boff)) {
             if (lane == 0) { out_size[k] = 0; }
             continue;
         }
-        uint32_t run_m = 0, total = 0;
-        for (int64_t row = off & ~(int64_t)15; row < end; row += 512) {
-            const RowInfo r = insert_row(img, row, off, end, lane, run_m);
-            total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
+        const int64_t roff = P.raw_off ? P.raw_off[k] : 0, rend = P.raw_off ? P.raw_end[k] : 0;
+        const int64_t aoff = P.a_off ? P.a_off[k] : 0, aend = P.a_off ? P.a_end[k] : 0;
+        uint32_t run_m = 0;
+        uint32_t total = count_part(P.a_base, aoff, aend, lane, run_m);
+        total += count_part(P.b_base, boff, bend, lane, run_m);
+        if (lane == 0) {
+            out_size[k] = (int64_t)P.sc_len + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) + (bend > boff ? bend - boff : 0) +
+                          (int64_t)total;
         }
-        if (lane == 0) { out_size[k] = (int64_t)sc_len + (end - off) + (int64_t)total; }
         local_ins += total;
     }
     if (lane == 0 && local_ins) { atomicAdd(n_ins_total, local_ins); }
 }
 
-// pass 2: write start code + escaped bytes of every NAL at out_off[k]
-__global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const uint8_t* __restrict__ img, const int64_t* __restrict__ off_a,
-                                                                   const int64_t* __restrict__ end_a, int64_t n, int sc_len,
-                                                                   const int64_t* __restrict__ out_off, uint8_t* __restrict__ out, int64_t out_cap)
+// writes one escaped part at out + o; returns the bytes written (warp uniform)
+__device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, int64_t off, int64_t end, uint8_t* __restrict__ out, int64_t o, int lane,
+                                              uint32_t& run_m)
+{
+    if (end <= off) { return 0; }
+    const int64_t o0 = o;
+    int64_t row = off & ~(int64_t)15;
+    for (; row < end; row += 512) {
+        const RowInfo r = insert_row(base, row, off, end, lane, run_m);
+        const uint32_t cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
+        const uint32_t inc = warp_incl_scan_u32(cnt, lane);
+        const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
+        uint8_t* dst = out + o;
+        if (clean) {
+            // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
+            const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+            if ((uint32_t)lane == 0u) {
+                for (uint32_t j = 0; j < head; j++) { dst[j] = (uint8_t)byte_of(r.v, (int)j); }
+            }
+            // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
+            uint4 nx;
+            nx.x = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
+            nx.y = __shfl_down_sync(0xFFFFFFFFu, r.v.y, 1);
+            nx.z = __shfl_down_sync(0xFFFFFFFFu, r.v.z, 1);
+            nx.w = __shfl_down_sync(0xFFFFFFFFu, r.v.w, 1);
+            if (head == 0u) {
+                *reinterpret_cast<uint4*>(dst + lane * 16) = r.v;
+            } else {
+                const uint32_t W[8] = {r.v.x, r.v.y, r.v.z, r.v.w, nx.x, nx.y, nx.z, nx.w};
+                const uint32_t q = head >> 2, sh = (head & 3u) * 8u;
+                uint32_t x[5];
+#pragma unroll
+                for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
+                uint4 o4;
+                o4.x = __funnelshift_r(x[0], x[1], sh);
+                o4.y = __funnelshift_r(x[1], x[2], sh);
+                o4.z = __funnelshift_r(x[2], x[3], sh);
+                o4.w = __funnelshift_r(x[3], x[4], sh);
+                if (lane < 31) {
+                    *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4;
+                } else { // last lane: only 16 - head bytes remain
+                    for (uint32_t j = head; j < 16u; j++) { dst[496 + j] = (uint8_t)byte_of(r.v, (int)j); }
+                }
+            }
+        } else {
+            uint8_t* p = dst + (inc - cnt);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((r.valid >> j) & 1u) {
+                    if ((r.ins >> j) & 1u) { *p++ = 3; }
+                    *p++ = (uint8_t)byte_of(r.v, j);
+                }
+            }
+        }
+        o += row_total;
+    }
+    run_m -= (uint32_t)(row - end);
+    return o - o0;
+}
+
+// pass 2: write start code, verbatim bytes and escaped bytes of every NAL at out_off[k]
+__global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const AssembleParts P, int64_t n, const int64_t* __restrict__ out_off,
+                                                                   uint8_t* __restrict__ out, int64_t out_cap)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * kInsWarps;
     for (int64_t k = wid; k < n; k += nw) {
-        const int64_t off = off_a[k], end = end_a[k];
-        if (end < 0 || end < off) { continue; }
+        const int64_t boff = P.b_off ? P.b_off[k] : 0, bend = P.b_off ? P.b_end[k] : 0;
+        if (P.skip_neg_b && (bend < 0 || bend < boff)) { continue; }
         int64_t o = out_off[k];
         if (out_off[k + 1] > out_cap) { continue; } // capacity overflow is reported by the summary
-        if (lane < sc_len) { out[o + lane] = (lane == sc_len - 1) ? 1 : 0; }
-        o += sc_len;
-        uint32_t run_m = 0;
-        for (int64_t row = off & ~(int64_t)15; row < end; row += 512) {
-            const RowInfo r = insert_row(img, row, off, end, lane, run_m);
-            const uint32_t cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
-            const uint32_t inc = warp_incl_scan_u32(cnt, lane);
-            const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
-            uint8_t* dst = out + o;
-            if (clean) {
-                // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
-                const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-                if ((uint32_t)lane == 0u) {
-                    for (uint32_t j = 0; j < head; j++) { dst[j] = (uint8_t)byte_of(r.v, (int)j); }
-                }
-                // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
-                uint4 nx;
-                nx.x = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
-                nx.y = __shfl_down_sync(0xFFFFFFFFu, r.v.y, 1);
-                nx.z = __shfl_down_sync(0xFFFFFFFFu, r.v.z, 1);
-                nx.w = __shfl_down_sync(0xFFFFFFFFu, r.v.w, 1);
-                if (head == 0u) {
-                    *reinterpret_cast<uint4*>(dst + lane * 16) = r.v;
-                } else {
-                    const uint32_t W[8] = {r.v.x, r.v.y, r.v.z, r.v.w, nx.x, nx.y, nx.z, nx.w};
-                    const uint32_t q = head >> 2, sh = (head & 3u) * 8u;
-                    uint32_t x[5];
-#pragma unroll
-                    for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
-                    uint4 o4;
-                    o4.x = __funnelshift_r(x[0], x[1], sh);
-                    o4.y = __funnelshift_r(x[1], x[2], sh);
-                    o4.z = __funnelshift_r(x[2], x[3], sh);
-                    o4.w = __funnelshift_r(x[3], x[4], sh);
-                    if (lane < 31) {
-                        *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4;
-                    } else { // last lane: only 16 - head bytes remain
-                        for (uint32_t j = head; j < 16u; j++) { dst[496 + j] = (uint8_t)byte_of(r.v, (int)j); }
-                    }
-                }
-            } else {
-                uint8_t* p = dst + (inc - cnt);
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if ((r.valid >> j) & 1u) {
-                        if ((r.ins >> j) & 1u) { *p++ = 3; }
-                        *p++ = (uint8_t)byte_of(r.v, j);
-                    }
-                }
-            }
-            o += row_total;
+        if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
+        o += P.sc_len;
+        if (P.raw_off) {
+            const int64_t roff = P.raw_off[k], rend = P.raw_end[k];
+            for (int64_t i = roff + lane; i < rend; i += 32) { out[o + (i - roff)] = P.raw_base[i]; }
+            if (rend > roff) { o += rend - roff; }
         }
+        uint32_t run_m = 0;
+        if (P.a_off) { o += write_part(P.a_base, P.a_off[k], P.a_end[k], out, o, lane, run_m); }
+        o += write_part(P.b_base, boff, bend, out, o, lane, run_m);
     }
 }
 
@@ -283,17 +328,9 @@ __global__ void __launch_bounds__(kSThreads) sizes_apply_kernel(const int64_t* i
 
 } // namespace
 
-int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,
-                        int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream)
+static int launch_assemble(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                           hevcb_insert_summary* d_summary, cudaStream_t stream)
 {
-    if (n < 0 || (sc_len != 0 && sc_len != 3 && sc_len != 4) || !d_out_off || !d_summary || (n > 0 && (!d_rbsp || !d_off || !d_end || !d_out))) {
-        HEVCB_SET_ERR(ctx, "hevcb_insert: invalid argument");
-        return HEVCB_E_ARG;
-    }
-    if ((uintptr_t)d_rbsp & 15u) {
-        HEVCB_SET_ERR(ctx, "hevcb_insert: rbsp must be 16-byte aligned");
-        return HEVCB_E_ALIGN;
-    }
     const int64_t nb = (n + kSTile - 1) / kSTile;
     const size_t need = (size_t)(n > 0 ? n : 1) * 8 + (size_t)(nb + 2) * 8 + 64;
     int rc = hevcb_reserve(ctx, &ctx->insert_scratch, need);
@@ -310,13 +347,51 @@ int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_
     long long grid = (long long)ctx->sm_count * 8;
     const long long max_grid = (n + kInsWarps - 1) / kInsWarps;
     if (grid > max_grid) { grid = max_grid; }
-    insert_count_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(d_rbsp, d_off, d_end, n, sc_len, sizes, n_ins);
+    insert_count_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, sizes, n_ins);
     sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs);
     sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
     sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs, nb, d_out_off);
-    insert_write_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(d_rbsp, d_off, d_end, n, sc_len, d_out_off, d_out, out_cap);
+    insert_write_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, d_out_off, d_out, out_cap);
     insert_summary_kernel<<<1, 32, 0, stream>>>(d_out_off, n, out_cap, n_ins, d_summary);
     ctx->launches += 6;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
+}
+
+int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,
+                        int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    if (n < 0 || (sc_len != 0 && sc_len != 3 && sc_len != 4) || !d_out_off || !d_summary || (n > 0 && (!d_rbsp || !d_off || !d_end || !d_out))) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    if ((uintptr_t)d_rbsp & 15u) {
+        HEVCB_SET_ERR(ctx, "hevcb_insert: rbsp must be 16-byte aligned");
+        return HEVCB_E_ALIGN;
+    }
+    AssembleParts P;
+    P.raw_base = nullptr; P.raw_off = nullptr; P.raw_end = nullptr;
+    P.a_base = nullptr; P.a_off = nullptr; P.a_end = nullptr;
+    P.b_base = d_rbsp; P.b_off = d_off; P.b_end = d_end;
+    P.sc_len = sc_len;
+    P.skip_neg_b = 1;
+    return launch_assemble(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
+}
+
+// three-part assembly used by the header rewrite (hevcb_parse.cu): verbatim bytes, escaped header, escaped payload
+int hevcb_launch_assemble3(hevcb_ctx* ctx, const uint8_t* raw_base, const int64_t* raw_off, const int64_t* raw_end, const uint8_t* a_base,
+                           const int64_t* a_off, const int64_t* a_end, const uint8_t* b_base, const int64_t* b_off, const int64_t* b_end, int64_t n,
+                           uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    if (((uintptr_t)a_base & 15u) || ((uintptr_t)b_base & 15u)) {
+        HEVCB_SET_ERR(ctx, "hevcb_assemble: escaped sources must be 16-byte aligned");
+        return HEVCB_E_ALIGN;
+    }
+    AssembleParts P;
+    P.raw_base = raw_base; P.raw_off = raw_off; P.raw_end = raw_end;
+    P.a_base = a_base; P.a_off = a_off; P.a_end = a_end;
+    P.b_base = b_base; P.b_off = b_off; P.b_end = b_end;
+    P.sc_len = 0;
+    P.skip_neg_b = 0;
+    return launch_assemble(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
 }

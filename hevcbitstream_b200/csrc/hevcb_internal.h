@@ -20,6 +20,13 @@ struct hevcb_ctx {
     // scan scratch: [0,64) counters, then one 16-byte state word per tile
     hevcb_devbuf scan_scratch;
     hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
+    hevcb_devbuf rewrite_scratch, rewrite_staging; // rewrite: part arrays, written headers
+    // what the last hevcb_parse_* left on the device (consumed by hevcb_rewrite_*)
+    struct {
+        int64_t n = -1;
+        const void *cls = nullptr, *sps_ord = nullptr, *pps_ord = nullptr, *cnt = nullptr;
+        void *sps_tab = nullptr, *pps_tab = nullptr, *sps_scratch = nullptr;
+    } last_parse;
     hevcb_devbuf parse_scratch, parse_ps; // parser: per-NAL scratch arrays, parameter-set context tables
     hevcb_devbuf h_p[9];                  // staging of the parse outputs for the *_host entry points
     // staging used by the *_host entry points
@@ -78,3 +85,12 @@ int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_
 int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t own, int64_t halo, int is_first, int is_last,
                                   int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off,
                                   int64_t* d_rbsp_end, hevcb_shard_summary* d_summary, cudaStream_t stream);
+
+int hevcb_launch_assemble3(hevcb_ctx* ctx, const uint8_t* raw_base, const int64_t* raw_off, const int64_t* raw_end, const uint8_t* a_base,
+                           const int64_t* a_off, const int64_t* a_end, const uint8_t* b_base, const int64_t* b_off, const int64_t* b_end, int64_t n,
+                           uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream);
+
+int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                         const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* parsed,
+                         const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap, int64_t* d_out_start, int64_t* d_out_end,
+                         hevcb_rewrite_summary* d_summary, cudaStream_t stream);

@@ -277,7 +277,203 @@ __global__ void parse_summary_kernel(const uint8_t* __restrict__ cls, const int3
     }
 }
 
+// ---- header rewrite: write pass (count / emit), part composition, epilogue ----------------------------------------
+struct RewriteArgs {
+    const int64_t* nal_start;
+    const int64_t* nal_end;
+    const int64_t* rbsp_off;
+    const int64_t* rbsp_end;
+    int64_t n, size;
+    const uint8_t* cls;
+    const int32_t* sps_ord;
+    const int32_t* pps_ord;
+    const hevcb_sps_ctx* sps_tab;
+    const hevcb_pps_ctx* pps_tab;
+    hevcb_sps_ctx* sps_scratch;
+    const int32_t* rc;
+    const int32_t* nal_hdr;
+    const uint8_t* ubflag;
+    const int32_t* hdr_end;
+    const int64_t* pair_off;
+    const uint32_t* pair_field;
+    const int32_t* pair_value;
+    int64_t cap_pairs;
+    int32_t* wlen;       // [n] bytes of the written header part (0: the NAL is copied through)
+    const int64_t* woff; // exclusive scan of wlen
+    uint8_t* staging;
+    int64_t *raw_off, *raw_end, *a_off, *a_end, *b_off, *b_end; // [n + 1]
+    hevcb_edit_set edits;
+};
+
+template <bool kEmit>
+__global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) { return; }
+    const int c = a.cls[k];
+    const bool is_slice = (c == kCls_Slice);
+    if (!kEmit) { a.wlen[k] = 0; }
+    if (!(is_slice || c == kCls_Vps || c == kCls_Sps || c == kCls_Pps)) { return; }
+    if (kEmit && a.wlen[k] == 0) { return; }
+    const int64_t po = a.pair_off[k];
+    const int64_t pn = a.pair_off[k + 1] - po;
+    if (!kEmit) {
+        const int64_t rs = a.rbsp_end[k] - a.rbsp_off[k];
+        if (a.rc[k] < 0 || a.ubflag[k] != 0 || po + pn > a.cap_pairs || (is_slice && (int64_t)a.hdr_end[k] > rs)) { return; }
+    }
+    const int sps_count = a.sps_ord[k], pps_count = a.pps_ord[k];
+    const hevcb_sps_ctx* sps_in = &a.sps_tab[c == kCls_Sps ? sps_count - 1 : sps_count];
+    const hevcb_pps_ctx* pps_in = &a.pps_tab[c == kCls_Pps ? pps_count - 1 : pps_count];
+    hevcb_sps_ctx* scr = nullptr;
+    if (c == kCls_Sps) { // working copy for the derived RPS tables, zeroed like the struct the reference starts from
+        scr = &a.sps_scratch[sps_count];
+        int32_t* z = reinterpret_cast<int32_t*>(scr);
+        for (size_t i = 0; i < sizeof(hevcb_sps_ctx) / 4; i++) { z[i] = 0; }
+    }
+    const int64_t nsz = a.nal_end[k] - a.nal_start[k];
+    const int64_t wcap = ((is_slice ? (int64_t)16384 : nsz * 2 + 64) * 3) / 4; // write_hevc_nal_unit: rbsp_size = size * 3 / 4 (hevc_stream.c:1266)
+    const int kind = is_slice ? HEVCB_KIND_SLICE : (c == kCls_Vps ? HEVCB_KIND_VPS : (c == kCls_Sps ? HEVCB_KIND_SPS : HEVCB_KIND_PPS));
+    hevcb_replay rp{a.pair_field + po, a.pair_value + po, (uint32_t)pn, 0u, kind, &a.edits};
+    hevcb_bitwriter bw;
+    if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(nullptr, wcap); }
+    hevcb_write_result wr;
+    hevcb_write_nal(rp, bw, a.nal_hdr[k], sps_in, pps_in, scr, wr);
+    if (!kEmit) {
+        const int64_t len = is_slice ? (int64_t)wr.hdr_bytes : wr.bytes;
+        a.wlen[k] = (wr.ok && wr.bytes > 0 && len > 0 && len < (1 << 30)) ? (int32_t)len : 0;
+    }
+}
+
+__global__ void compose_parts_kernel(RewriteArgs a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > a.n) { return; }
+    const int64_t prev_end = k > 0 ? a.nal_end[k - 1] : 0;
+    int64_t ro = prev_end, re, ao = 0, ae = 0, bo = 0, be = 0;
+    if (k == a.n) {
+        re = a.size; // what follows the last NAL
+    } else if (a.wlen[k] > 0) {
+        re = a.nal_start[k];
+        ao = a.woff[k];
+        ae = ao + a.wlen[k];
+        if (a.cls[k] == kCls_Slice) { bo = a.rbsp_off[k] + a.hdr_end[k]; be = a.rbsp_end[k]; }
+    } else {
+        re = a.nal_end[k]; // copied through together with what precedes it
+    }
+    if (re < ro) { re = ro; }
+    a.raw_off[k] = ro; a.raw_end[k] = re; a.a_off[k] = ao; a.a_end[k] = ae; a.b_off[k] = bo; a.b_end[k] = be;
+}
+
+__global__ void rewrite_finish_kernel(RewriteArgs a, const int64_t* __restrict__ out_off, const hevcb_insert_summary* __restrict__ isum,
+                                      int64_t* __restrict__ out_start, int64_t* __restrict__ out_end, unsigned long long* n_rewritten,
+                                      hevcb_rewrite_summary* summary, int final_pass)
+{
+    if (final_pass) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            summary->n_nals = a.n;
+            summary->n_rewritten = (int64_t)*n_rewritten;
+            summary->out_bytes = isum->out_bytes;
+            summary->n_inserted = isum->n_inserted;
+            summary->overflow = isum->overflow;
+            summary->pad = 0;
+        }
+        return;
+    }
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < a.n;
+    int rew = 0;
+    if (live) {
+        const int64_t prev_end = k > 0 ? a.nal_end[k - 1] : 0;
+        const int64_t gap = a.nal_start[k] > prev_end ? a.nal_start[k] - prev_end : 0;
+        out_start[k] = out_off[k] + gap;
+        out_end[k] = out_off[k + 1];
+        rew = a.wlen[k] > 0 ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, rew != 0);
+    if ((threadIdx.x & 31) == 0 && m) { atomicAdd(n_rewritten, (unsigned long long)__popc(m)); }
+}
+
 } // namespace
+
+int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                         const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* parsed,
+                         const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap, int64_t* d_out_start, int64_t* d_out_end,
+                         hevcb_rewrite_summary* d_summary, cudaStream_t stream)
+{
+    if (n < 0 || size < 0 || !parsed || !d_summary || !d_out || out_cap < 0 || (edits && (edits->n < 0 || edits->n > HEVCB_MAX_EDITS)) ||
+        (n > 0 && (!d_buf || !d_nal_start || !d_nal_end || !d_rbsp || !d_rbsp_off || !d_rbsp_end || !d_out_start || !d_out_end))) {
+        HEVCB_SET_ERR(ctx, "hevcb_rewrite: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    if (ctx->last_parse.n != n) {
+        HEVCB_SET_ERR(ctx, "hevcb_rewrite: must follow hevcb_parse_device of the same %lld NALs on this context", (long long)n);
+        return HEVCB_E_ARG;
+    }
+    const int64_t m = n + 1; // + the bytes that follow the last NAL
+    const int64_t nb = (m + kScanTile - 1) / kScanTile;
+    size_t need = 0;
+    auto take = [&](size_t bytes) { size_t o = need; need += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_wlen = take((size_t)m * 4), o_woff = take((size_t)(m + 1) * 8), o_parts = take((size_t)m * 8 * 6), o_ooff = take((size_t)(m + 1) * 8);
+    const size_t o_bs = take((size_t)(nb + 1) * 8), o_isum = take(sizeof(hevcb_insert_summary)), o_cnt = take(64);
+    int rcx = hevcb_reserve(ctx, &ctx->rewrite_scratch, need);
+    if (rcx != HEVCB_OK) { return rcx; }
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->rewrite_scratch.p);
+    RewriteArgs a;
+    a.nal_start = d_nal_start; a.nal_end = d_nal_end; a.rbsp_off = d_rbsp_off; a.rbsp_end = d_rbsp_end; a.n = n; a.size = size;
+    a.cls = reinterpret_cast<const uint8_t*>(ctx->last_parse.cls);
+    a.sps_ord = reinterpret_cast<const int32_t*>(ctx->last_parse.sps_ord);
+    a.pps_ord = reinterpret_cast<const int32_t*>(ctx->last_parse.pps_ord);
+    a.sps_tab = reinterpret_cast<const hevcb_sps_ctx*>(ctx->last_parse.sps_tab);
+    a.pps_tab = reinterpret_cast<const hevcb_pps_ctx*>(ctx->last_parse.pps_tab);
+    a.sps_scratch = reinterpret_cast<hevcb_sps_ctx*>(ctx->last_parse.sps_scratch);
+    a.rc = parsed->rc; a.nal_hdr = parsed->nal_hdr; a.ubflag = parsed->ubflag; a.hdr_end = parsed->hdr_end;
+    a.pair_off = parsed->pair_off; a.pair_field = parsed->pair_field; a.pair_value = parsed->pair_value; a.cap_pairs = parsed->cap_pairs;
+    a.wlen = reinterpret_cast<int32_t*>(base + o_wlen);
+    int64_t* woff = reinterpret_cast<int64_t*>(base + o_woff);
+    a.woff = woff;
+    a.staging = nullptr;
+    int64_t* parts = reinterpret_cast<int64_t*>(base + o_parts);
+    a.raw_off = parts; a.raw_end = parts + m; a.a_off = parts + 2 * m; a.a_end = parts + 3 * m; a.b_off = parts + 4 * m; a.b_end = parts + 5 * m;
+    if (edits) { a.edits = *edits; } else { a.edits.n = 0; }
+    int64_t* out_off = reinterpret_cast<int64_t*>(base + o_ooff);
+    long long* bsums = reinterpret_cast<long long*>(base + o_bs);
+    hevcb_insert_summary* isum = reinterpret_cast<hevcb_insert_summary*>(base + o_isum);
+    unsigned long long* n_rew = reinterpret_cast<unsigned long long*>(base + o_cnt);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(n_rew, 0, 8, stream));
+    HEVCB_CUDA(ctx, cudaMemsetAsync(a.wlen, 0, (size_t)m * 4, stream));
+
+    const unsigned g128 = (unsigned)((m + 127) / 128);
+    long long h_total = 0;
+    if (n > 0) {
+        write_kernel<false><<<g128, 128, 0, stream>>>(a);
+        ctx->launches++;
+        HEVCB_CUDA(ctx, cudaGetLastError());
+        int rcs = run_scan<CntVal, int64_t, false>(ctx, CntVal{a.wlen}, m, woff, bsums, stream);
+        if (rcs != HEVCB_OK) { return rcs; }
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_total, bsums + nb, 8, cudaMemcpyDeviceToHost, stream));
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(stream)); // the staging size depends on the total header bytes
+    }
+    if ((rcx = hevcb_reserve(ctx, &ctx->rewrite_staging, (size_t)h_total + 64)) != HEVCB_OK) { return rcx; }
+    a.staging = reinterpret_cast<uint8_t*>(ctx->rewrite_staging.p);
+    if (n > 0) {
+        write_kernel<true><<<g128, 128, 0, stream>>>(a);
+        ctx->launches++;
+    }
+    compose_parts_kernel<<<g128, 128, 0, stream>>>(a);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    int rca = hevcb_launch_assemble3(ctx, d_buf, a.raw_off, a.raw_end, a.staging, a.a_off, a.a_end, d_rbsp, a.b_off, a.b_end, m, d_out, out_cap, out_off,
+                                     isum, stream);
+    if (rca != HEVCB_OK) { return rca; }
+    if (n > 0) {
+        rewrite_finish_kernel<<<g128, 128, 0, stream>>>(a, out_off, isum, d_out_start, d_out_end, n_rew, d_summary, 0);
+        ctx->launches++;
+    }
+    rewrite_finish_kernel<<<1, 32, 0, stream>>>(a, out_off, isum, d_out_start, d_out_end, n_rew, d_summary, 1);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
 
 int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
                        const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
@@ -293,7 +489,8 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
         return HEVCB_E_ARG;
     }
     HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_parse_summary), stream));
-    if (n == 0) { return HEVCB_OK; }
+    ctx->last_parse.n = -1;
+    if (n == 0) { ctx->last_parse.n = 0; return HEVCB_OK; }
     const int64_t nb = (n + kScanTile - 1) / kScanTile;
     // scratch: cls (n), cnt (n x4), sps_ord (n x4), pps_ord (n x4), block sums (nb + 1) x3, pair total
     size_t need = 0;
@@ -340,6 +537,9 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     a.rc = out->rc; a.kind = out->kind; a.ubflag = out->ubflag; a.cnt = cnt; a.hdr_end = out->hdr_end; a.cols = out->cols;
     a.pair_off = out->pair_off; a.pair_field = out->pair_field; a.pair_value = out->pair_value; a.cap_pairs = out->cap_pairs;
 
+    ctx->last_parse.n = n;
+    ctx->last_parse.cls = cls; ctx->last_parse.sps_ord = sps_ord; ctx->last_parse.pps_ord = pps_ord; ctx->last_parse.cnt = cnt;
+    ctx->last_parse.sps_tab = a.sps_tab; ctx->last_parse.pps_tab = a.pps_tab; ctx->last_parse.sps_scratch = a.sps_scratch;
     parse_kernel<false, false><<<g128, 128, 0, stream>>>(a); // parameter sets first
     parse_kernel<false, true><<<g128, 128, 0, stream>>>(a);  // then the slices that depend on them
     ctx->launches += 2;
