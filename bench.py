@@ -418,6 +418,72 @@ def run_ours(args):
         except Exception as ex:
             parse = {"error": repr(ex)}
 
+    # ---- BASELINE config[3]: round-trip rewrite (parse, edit slice_qp_delta + a VUI flag, write_hevc_nal_unit, rbsp_to_nal) on a
+    # stream of reference-written headers carrying 16 KiB payloads.  The unit is built on the device with the product's own
+    # kernels (headers of tests/golden/headers_unit.bin + random payload -> hevcb_insert_device), then tiled.
+    rewrite = None
+    if not args.no_rewrite:
+        try:
+            unit_h = np.fromfile(os.path.join(ROOT, "tests", "golden", "headers_unit.bin"), dtype=np.uint8)
+            dh = torch.zeros(unit_h.size + 32, dtype=torch.uint8, device=dev)
+            dh[: unit_h.size] = torch.from_numpy(unit_h).to(dev)
+            sc = ctx.scan_strip_device(dh, size=unit_h.size)
+            pr = ctx.parse_device(dh, sc)
+            nh = int(sc.n_nals)
+            ro, re_ = sc.rbsp_off[:nh], sc.rbsp_end[:nh]
+            is_slice = (pr["kind"][:nh] == 4) & (pr["rc"][:nh] >= 0) & (re_ >= 0)
+            keep = torch.where(is_slice, pr["hdr_end"][:nh].to(torch.int64), torch.clamp(re_ - ro, min=0))  # header bytes / whole RBSP
+            pay = args.rewrite_payload
+            seg = keep + torch.where(is_slice, torch.full_like(keep, pay + 1), torch.zeros_like(keep))
+            seg_end = torch.cumsum(seg, 0)
+            seg_off = seg_end - seg
+            total = int(seg_end[-1])
+            g = torch.Generator(device=dev).manual_seed(4242 + rank)
+            nr = torch.randint(0, 256, (total + 32,), dtype=torch.uint8, device=dev, generator=g)
+            dst = torch.repeat_interleave(seg_off, keep) + (torch.arange(int(keep.sum()), device=dev) - torch.repeat_interleave(torch.cumsum(keep, 0) - keep, keep))
+            src = torch.repeat_interleave(ro, keep) + (torch.arange(int(keep.sum()), device=dev) - torch.repeat_interleave(torch.cumsum(keep, 0) - keep, keep))
+            nr[dst] = sc.rbsp[src]
+            nr[(seg_end - 1)[is_slice]] = 0x80  # rbsp_trailing_bits
+            live = seg > 0  # a zero-length NAL would end the reference loop
+            unit_ins = ctx.insert_device(nr, seg_off[live].contiguous(), seg_end[live].contiguous(), start_code_len=4)
+            ub = int(unit_ins["out_bytes"])
+            reps = max(1, int(args.rewrite_gib * (1 << 30)) // ub)
+            dr = torch.zeros(ub * reps + 32, dtype=torch.uint8, device=dev)
+            dr[: ub * reps].view(reps, ub).copy_(unit_ins["out"][:ub].unsqueeze(0).expand(reps, -1))
+            rsize = ub * reps
+            del nr, unit_ins, src, dst
+            cap = nh * reps + 1024
+            edits = [(4, "slice_qp_delta", 0, 2), (2, "vui.video_full_range_flag", 2, 1)]
+
+            def pipeline():
+                scan = ctx.scan_strip_device(dr, size=rsize, cap_nals=cap)
+                parsed = ctx.parse_device(dr, scan, cap_pairs=80 * scan.n_nals)
+                return scan, parsed, ctx.rewrite_device(dr, scan, parsed, edits, size=rsize)
+
+            for _ in range(2):
+                scan, parsed, out = pipeline()
+            del scan, parsed, out
+            barrier()
+            l0 = ctx.launch_count
+            k = max(3, args.steps // 4)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                scan, parsed, out = pipeline()
+            e1.record()
+            barrier()
+            rms = e0.elapsed_time(e1) / k
+            rewrite = {"bytes_in": rsize, "n_nals": int(scan.n_nals), "n_rewritten": int(out["n_rewritten"]), "bytes_out": int(out["out_bytes"]),
+                       "epb_inserted": int(out["n_inserted"]), "ms_pipeline": rms, "input_GBps": rsize / (rms * 1e-3) / 1e9,
+                       "nals_per_s": int(scan.n_nals) / (rms * 1e-3), "launches_per_pipeline": int((ctx.launch_count - l0) // k),
+                       "workload": f"scan + strip + parse + rewrite (slice_qp_delta += 2, vui.video_full_range_flag ^= 1) of reference-written headers "
+                                   f"with {pay} B random payloads, {rsize / 2**30:.2f} GiB per rank; byte-exactness vs the reference writer is asserted in tests/test_rewrite_gpu.py"}
+            del dr, scan, parsed, out
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            rewrite = {"error": repr(ex)}
+
     # ---- CPU baseline: the unmodified reference on rank 0's host cores, bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 or (rank == 0 and args.cpu_baseline_multi):
@@ -462,6 +528,8 @@ def run_ours(args):
             line["sweep"] = sweep
         if parse:
             line["parse"] = parse
+        if rewrite:
+            line["rewrite"] = rewrite
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -480,6 +548,9 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-parse", action="store_true")
     ap.add_argument("--parse-nals", type=int, default=1_000_000)
+    ap.add_argument("--no-rewrite", action="store_true")
+    ap.add_argument("--rewrite-gib", type=float, default=4.0)
+    ap.add_argument("--rewrite-payload", type=int, default=16384)
     ap.add_argument("--ref-sample-mib", type=int, default=64)
     ap.add_argument("--cpu-baseline-multi", action="store_true")
     args = ap.parse_args()
