@@ -19,6 +19,7 @@
 // nothing here is a contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "hevcb_internal.h"
 #include "hevcb_scan_core.h"
@@ -59,25 +60,26 @@ struct WarpAgg {
     uint32_t kind;  // ordered carry summary of the warp's rows
     uint32_t err;
     uint32_t del;   // some row has removed bytes or is partially valid
-    uint32_t pad[3];
+    uint32_t rows;  // bit i: row i of the warp needs exact treatment
+    uint32_t pad[2];
 };
 
-// ordered summary of one warp's slice of the look-back window (slice 0 is the nearest)
-struct LookPart {
-    unsigned long long n;  // start codes in the slice up to and including its nearest prefix tile
-    unsigned long long k;  // kept bytes, same extent
-    uint32_t kind;         // carry summary of that extent (PASS when it saw no event)
+// what a writer CTA needs to know about a tile before it touches it
+struct TilePrefix {
+    unsigned long long n;    // start codes before the tile
+    unsigned long long k;    // kept bytes before the tile
+    unsigned long long mask; // bit r: row r of the tile needs exact treatment (two adjacent zero bytes nearby, or a stream edge)
+    uint32_t kind;           // ordered carry entering the tile
     uint32_t err;
-    uint32_t has_prefix;   // the slice contains a tile whose inclusive prefix is published
-    uint32_t pad;
 };
 
 // dynamic shared memory layout
 struct __align__(16) SmemLayout {
     uint8_t stage[kStages][kStageBytes];
     unsigned long long mbar[kStages];
-    WarpAgg wagg[2][kWorkers]; // per-warp aggregates of the tile analysed in iteration i (index i & 1)
-    LookPart pref[2];          // exclusive prefix of this CTA's i-th tile (index i & 1), written by the look-back warp
+    unsigned long long done[kStages]; // analyser: the workers are through with the stage (one arrival per warp)
+    WarpAgg wagg[kStages][kWorkers];  // per-warp aggregates of the tile in a stage (writer: index i & 1)
+    TilePrefix pref[2];        // writer: prefix + row mask of this CTA's i-th tile (index i & 1)
 };
 
 // ---- tile state for the decoupled look-back: one 16-byte word, read/written with single 128-bit accesses
@@ -90,6 +92,19 @@ __device__ __forceinline__ ulonglong2 pack_state(unsigned long long status, unsi
     s.y = k;
     return s;
 }
+// aggregate of one tile: x = status | kind | err | start codes (14 bits) | kept bytes (16 bits), y = row mask
+__device__ __forceinline__ ulonglong2 pack_agg(uint32_t n, uint32_t k, uint32_t kind, uint32_t err, unsigned long long mask)
+{
+    ulonglong2 s;
+    s.x = (kStatusAgg << 62) | ((unsigned long long)kind << 60) | ((unsigned long long)(err & 1u) << 59) | ((unsigned long long)(k & 0xFFFFFu) << 20) |
+          (unsigned long long)(n & 0xFFFFFu);
+    s.y = mask;
+    return s;
+}
+__device__ __forceinline__ uint32_t agg_n(const ulonglong2& s) { return (uint32_t)(s.x & 0xFFFFFull); }
+__device__ __forceinline__ uint32_t agg_k(const ulonglong2& s) { return (uint32_t)((s.x >> 20) & 0xFFFFFull); }
+__device__ __forceinline__ uint32_t agg_kind(const ulonglong2& s) { return (uint32_t)(s.x >> 60) & 3u; }
+__device__ __forceinline__ uint32_t agg_err(const ulonglong2& s) { return (uint32_t)(s.x >> 59) & 1u; }
 __device__ __forceinline__ ulonglong2 ld_state(const ulonglong2* p)
 {
     ulonglong2 v;
@@ -110,6 +125,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)
 {
@@ -135,7 +154,7 @@ __device__ __forceinline__ void fence_proxy_async()
 }
 
 // named barriers: 0 is __syncthreads; kBarWork = the worker warps only; kBarS1 / kBarE = workers + look-back warp
-constexpr int kBarWork = 1, kBarS1 = 2, kBarE = 3;
+constexpr int kBarWork = 1, kBarS1 = 2, kBarE = 3, kBarP = 4;
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -304,46 +323,42 @@ __device__ __forceinline__ void copy_row_clean(uint8_t* __restrict__ dst, const 
 }
 
 // Scanner warp (one per grid): the chained scan over the tile aggregates.  Batch by batch (320 tiles, 10 per lane, in
-// stream order) it waits for the aggregates, combines them with shuffles / ballots and publishes every tile's
-// EXCLUSIVE prefix (start codes, kept bytes, ordered carry) into tile_excl[].  One reader per aggregate and one
-// 16-byte poll per CTA and tile replace the all-to-all look-back, whose polling traffic on a few cache lines was
-// measured to cost ~14k cycles per wave of 296 tiles.
-// A batch is exactly one wave of the grid (tiles w*G .. w*G+G-1, G <= 320): the prefixes of wave w must not wait for
-// aggregates of wave w+1, which the CTAs only publish after they have received their wave-w prefix.
+// stream order) it waits for the aggregates the analyser CTAs publish, combines them with shuffles / ballots and
+// publishes every tile's EXCLUSIVE prefix (start codes, kept bytes, ordered carry) into tile_excl[].  One reader per
+// aggregate and one 16-byte poll per tile replace an all-to-all look-back, whose polling traffic on a few cache lines
+// was measured to cost ~14k cycles per wave of 296 tiles.
 __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl,
-                                             long long n_tiles, long long G, ScanHeader* __restrict__ hdr, int lane, uint32_t init_n,
-                                             uint32_t init_kind)
+                                             long long n_tiles, ScanHeader* __restrict__ hdr, int lane, uint32_t init_n, uint32_t init_kind)
 {
     unsigned long long runN = init_n, runK = 0;
     uint32_t runKind = init_kind, runErr = 0;
-    for (long long wbase = 0; wbase < n_tiles; wbase += G) {
-      const long long lim = (wbase + G < n_tiles) ? wbase + G : n_tiles; // end of this wave
-      for (long long base = wbase; base < lim; base += 32 * kScanPerLane) { // the wave in batches of 320 tiles
+    for (long long base = 0; base < n_tiles; base += 32 * kScanPerLane) {
         const long long first = base + (long long)lane * kScanPerLane;
         ulonglong2 sv[kScanPerLane];
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
             const long long idx = first + j;
-            if (idx < lim) { sv[j] = ld_state(&tile_state[idx]); }
-            else { sv[j] = pack_state(kStatusAgg, 0, 0, HEVCB_KIND_PASS, 0); } // past the wave: identity
+            if (idx < n_tiles) { sv[j] = ld_state(&tile_state[idx]); }
+            else { sv[j] = pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); } // past the end: identity
         }
         for (;;) { // re-poll, one batch per round trip, the aggregates that are not published yet
             bool missing = false;
 #pragma unroll
             for (int j = 0; j < kScanPerLane; j++) { missing = missing || ((sv[j].x >> 62) == 0ull); }
-            if (!missing) { break; }
+            if (!__any_sync(0xFFFFFFFFu, missing)) { break; }
 #pragma unroll
             for (int j = 0; j < kScanPerLane; j++) {
                 if ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[first + j]); }
             }
         }
+        __threadfence(); // the aggregates observed above happen before the prefixes published below (writers re-read them)
         // lane totals
         uint32_t ln = 0, lk = 0, lkind = HEVCB_KIND_PASS, lerr = 0;
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
-            ln += (uint32_t)(sv[j].x & ((1ull << 40) - 1));
-            lk += (uint32_t)sv[j].y;
-            hevcb_carry_combine(lkind, lerr, (uint32_t)(sv[j].x >> 60) & 3u, (uint32_t)(sv[j].x >> 59) & 1u);
+            ln += agg_n(sv[j]);
+            lk += agg_k(sv[j]);
+            hevcb_carry_combine(lkind, lerr, agg_kind(sv[j]), agg_err(sv[j]));
         }
         // exclusive scan over lanes (ascending lane = stream order)
         const uint32_t nin = warp_incl_scan(ln, lane), kin = warp_incl_scan(lk, lane);
@@ -358,23 +373,113 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
             const long long idx = first + j;
-            if (idx < lim) { st_state(&tile_excl[idx], pack_state(kStatusPrefix, cN, cK, cKind, cErr)); }
-            cN += (uint32_t)(sv[j].x & ((1ull << 40) - 1));
-            cK += (uint32_t)sv[j].y;
-            hevcb_carry_combine(cKind, cErr, (uint32_t)(sv[j].x >> 60) & 3u, (uint32_t)(sv[j].x >> 59) & 1u);
+            if (idx < n_tiles) { st_state(&tile_excl[idx], pack_state(kStatusPrefix, cN, cK, cKind, cErr)); }
+            cN += agg_n(sv[j]);
+            cK += agg_k(sv[j]);
+            hevcb_carry_combine(cKind, cErr, agg_kind(sv[j]), agg_err(sv[j]));
         }
         // running state after the batch = lane 31's state after its last tile
         runN = __shfl_sync(0xFFFFFFFFu, cN, 31);
         runK = __shfl_sync(0xFFFFFFFFu, cK, 31);
         runKind = __shfl_sync(0xFFFFFFFFu, cKind, 31);
         runErr = __shfl_sync(0xFFFFFFFFu, cErr, 31);
-      }
     }
     if (lane == 0) { hdr->final_state = pack_state(kStatusPrefix, runN, runK, runKind, runErr); }
 }
 
+// per-row analysis shared by both roles: exact masks of one 512-byte row (lanes without two adjacent zero bytes nearby take
+// the default), the warp's ballots, and the row's contribution to the warp aggregate
+struct RowMasks {
+    uint32_t evsc, deler, misc;
+    uint32_t Xb, Db; // some lane has an event / error position; some lane removes bytes or is partially owned
+};
+__device__ __forceinline__ RowMasks analyze_row(uint32_t wp, const uint4 v, uint32_t wn, bool slow, int64_t g0, const ScanGeom& geom,
+                                                uint32_t& wN, uint32_t& wK, uint32_t& wKind, uint32_t& wErr)
+{
+    const int64_t rem = geom.own - g0;
+    uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
+    if (slow) { m3 = analyze_cold(wp, v, wn, g0, geom.size, geom.own, geom.evl); }
+    const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
+    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
+    if (ev != 0u) {
+        const int tp = 31 - __clz((int)ev);
+        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+        le = ((er >> tp) >> 1) != 0u;
+    }
+    const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+    const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+    RowMasks r;
+    r.evsc = m3.x; r.deler = m3.y; r.misc = m3.z;
+    r.Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
+    r.Db = __ballot_sync(0xFFFFFFFFu, (del != 0u) || (valid != 0xFFFFu));
+    wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
+    wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid & ~del));
+    uint32_t rk, re;
+    warp_carry_total(Eb, Sb, Rb, rk, re);
+    hevcb_carry_combine(wKind, wErr, rk, re);
+    return r;
+}
+
+// writer: the same for row r of a staged tile, operands read from shared memory
+__device__ __forceinline__ RowMasks analyze_staged_row(const uint8_t* st, int r, int lane, int64_t t0, const ScanGeom& geom, uint32_t& wN,
+                                                       uint32_t& wK, uint32_t& wKind, uint32_t& wErr)
+{
+    const uint8_t* rp = st + kLead + r * kRowBytes + lane * 16;
+    const uint4 v = *reinterpret_cast<const uint4*>(rp);
+    const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
+    const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
+    const bool slow = zero_pair_any(wp, v.x, v.y, v.z, v.w, wn) != 0u;
+    const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
+    return analyze_row(wp, v, wn, slow, g0, geom, wN, wK, wKind, wErr);
+}
+
+// whole-tile copy of L bytes out of a stage: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
+__device__ __noinline__ void copy_tile(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int tid)
+{
+    const uint32_t head0 = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    const uint32_t head = head0 < L ? head0 : L;
+    if ((uint32_t)tid < head) { dst[tid] = src[tid]; }
+    const uint32_t nv = (L - head) >> 4;
+    const uint32_t sh = (head & 3u) * 8u; // source misalignment is tile-uniform
+    switch (head >> 2) {
+        case 0: copy_vectors<0>(dst + head, src, nv, sh, tid); break;
+        case 1: copy_vectors<1>(dst + head, src, nv, sh, tid); break;
+        case 2: copy_vectors<2>(dst + head, src, nv, sh, tid); break;
+        default: copy_vectors<3>(dst + head, src, nv, sh, tid); break;
+    }
+    const uint32_t done = head + (nv << 4);
+    if ((uint32_t)tid < L - done) { dst[done + tid] = src[done + tid]; }
+}
+
+// boundary fix-ups of a staged tile: positions < 0 read as non-zero, positions >= size read as zero
+__device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, int64_t size, int tid)
+{
+    const int64_t valid_end = (int64_t)kLead + (size - t0); // smem offset of position `size`
+    if (t == 0 || valid_end < kStageBytes) {
+        if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
+        if (valid_end < kStageBytes) {
+            for (int i = (int)valid_end + tid; i < kStageBytes; i += kWorkerThreads) { st[i] = 0; }
+        }
+        bar_sync(kBarWork, kWorkerThreads);
+    }
+}
+
+// ====================================================================================================================
+// The grid is split into two roles.
+//   ANALYSER CTAs walk the tiles (round-robin among themselves), build the exact predicates where two adjacent zero bytes
+//   occur, and publish one 16-byte aggregate per tile: start codes, kept bytes, ordered carry, and a 64-bit mask of the
+//   rows that need exact treatment.  They never wait for anything but their own TMA loads.
+//   The SCANNER warp turns aggregates into exclusive prefixes, in stream order.
+//   WRITER CTAs walk the same tiles some microseconds later (the second load of a tile is served by L2, so DRAM still sees
+//   every input byte once): they wait for the tile's prefix, redo the exact analysis of the flagged rows only, emit the
+//   NAL boundaries and write the EPB-free image.
+// The dependency analyser -> scanner -> writer is one-directional: no CTA ever waits on a CTA of its own kind, which is
+// what removes the wave-by-wave lock-step a single-role pipeline suffers from (its prefix round trip through L2 is as
+// long as the work on a tile).
+// ====================================================================================================================
 __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_kernel(
-    const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, ScanHeader* __restrict__ hdr,
+    const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, long long n_analysers, ScanHeader* __restrict__ hdr,
     ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, int64_t* __restrict__ nal_start,
     int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off,
     int64_t* __restrict__ rbsp_end, long long debug_flags)
@@ -384,122 +489,80 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const long long G = gridDim.x;
     const unsigned dbg = (unsigned)debug_flags; // experiment switches, 0 in production
     const int64_t size = geom.size;
+    const bool analyser = (long long)blockIdx.x < n_analysers;
+    const long long G = analyser ? n_analysers : (long long)gridDim.x - n_analysers; // CTAs of this role
+    const long long first_tile = analyser ? (long long)blockIdx.x : (long long)blockIdx.x - n_analysers;
 
     if (tid == kWorkerThreads) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); mbar_init(&sm.done[s], kWorkers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        for (int s = 0; s < kStages; s++) { // this CTA's first three tiles
-            const long long t = (long long)blockIdx.x + (long long)s * G;
+        for (int s = 0; s < kStages; s++) { // this CTA's first tiles
+            const long long t = first_tile + (long long)s * G;
             if (t < n_tiles) { issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, t); }
         }
     }
     __syncthreads();
 
     if (warp == kWorkers + 1) { // scanner warp: one per grid, never joins the CTA's barriers
-        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, G, hdr, lane, geom.init_n, geom.init_kind); }
+        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, hdr, lane, geom.init_n, geom.init_kind); }
         return;
     }
 
-    // Iteration i of a CTA: its i-th tile t_i = blockIdx.x + i * grid (stage i mod 3).
-    //   workers  : analyse t_i -> per-warp aggregates -> [S1] -> emit + write out t_(i-1) with the prefix the look-back
-    //              warp produced during the previous iteration -> arrive on [E] (no wait) -> next iteration
-    //   look-back: [S1] -> publish aggregate(t_i) -> look-back(t_i) (hidden behind the workers' write-out of t_(i-1) and
-    //              analysis of t_(i+1)) -> publish prefix(t_i) -> [E] wait -> TMA load of t_(i+2) into the freed stage
-    if (warp == kWorkers) {
-        // =================================== look-back / TMA warp ===================================
-        int s = 0;
-        long long prev_t = -1;
-        for (long long t = blockIdx.x, it = 0;; t += G, it++) {
-            const bool have_cur = t < n_tiles;
-            if (!have_cur && prev_t < 0) { break; }
-            bar_sync(kBarS1, kSyncThreads);
-            if (have_cur) {
+    if (!analyser && (dbg & 32u)) { return; } // experiment: writers off
+    if (analyser) {
+        // ============================================ ANALYSER ============================================
+        if (warp == kWorkers) {
+            // control warp: all workers are done with the stage -> publish the tile's aggregate, reload the stage
+            int s = 0;
+            uint32_t done_bits = 0;
+            for (long long t = first_tile; t < n_tiles; t += G) {
+                while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
+                done_bits ^= (1u << s);
                 uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0;
+                unsigned long long mask = 0ull;
 #pragma unroll
                 for (int w = 0; w < kWorkers; w++) {
-                    const WarpAgg a = sm.wagg[it & 1][w];
+                    const WarpAgg a = sm.wagg[s][w];
                     tile_n += a.n;
                     tile_k += a.k;
                     hevcb_carry_combine(ak, ae, a.kind, a.err);
+                    mask |= (unsigned long long)(a.rows & 0xFFu) << (w * kRowsPerWarp);
                 }
                 if (lane == 0) {
-                    if (!(dbg & 16u)) { st_state(&tile_state[t], pack_state(kStatusAgg, tile_n, tile_k, ak, ae)); }
-                    // fetch this tile's exclusive prefix from the scanner: needed only after the next [S1]
-                    ulonglong2 ex;
-                    if (dbg & 1u) { ex = pack_state(kStatusPrefix, 0, (unsigned long long)t * kTileBytes, HEVCB_KIND_Z3, 0); }
-                    else {
-                        ex = ld_state(&tile_excl[t]);
-                        while ((ex.x >> 62) == 0ull) { __nanosleep(64); ex = ld_state(&tile_excl[t]); }
+                    st_state(&tile_state[t], pack_agg(tile_n, tile_k, ak, ae, mask));
+                    const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
+                    if (nt < n_tiles) {
+                        fence_proxy_async();
+                        issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, nt);
                     }
-                    LookPart lp;
-                    lp.n = ex.x & ((1ull << 40) - 1); lp.k = ex.y; lp.kind = (uint32_t)(ex.x >> 60) & 3u; lp.err = (uint32_t)(ex.x >> 59) & 1u;
-                    lp.has_prefix = 1; lp.pad = 0;
-                    sm.pref[it & 1] = lp;
                 }
                 __syncwarp();
+                s = (s + 1 == kStages) ? 0 : s + 1;
             }
-            if (prev_t >= 0) {
-                bar_sync(kBarE, kSyncThreads); // every worker finished reading the stage of the previous tile
-                const int ps = (s == 0) ? kStages - 1 : s - 1;
-                const long long nt = prev_t + (long long)kStages * G; // the tile that reuses this stage
-                if (lane == 0 && nt < n_tiles) {
-                    fence_proxy_async();
-                    issue_tile_load(sm.stage[ps], &sm.mbar[ps], buf, size, nt);
-                }
-            }
-            prev_t = have_cur ? t : -1;
-            s = (s + 1 == kStages) ? 0 : s + 1;
+            return;
         }
-        return;
-    }
-
-    // ========================================= worker warps =========================================
-    DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
-    uint32_t phase_bits = 0;
-    int s = 0;
-    // state of the previous tile between its analysis and its write-out
-    long long prev_t = -1;
-    uint32_t p_evsc[kRowsPerWarp], p_deler[kRowsPerWarp], p_misc[kRowsPerWarp];
-    uint32_t p_rowflags = 0, p_rN = 0, p_rK = 0, p_rKind = HEVCB_KIND_PASS, p_rErr = 0, p_tile_k = 0, p_compact = 0;
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; i++) { p_evsc[i] = p_deler[i] = p_misc[i] = 0; }
-
-    for (long long t = blockIdx.x, it = 0;; t += G, it++) {
-        const bool have_cur = t < n_tiles;
-        if (!have_cur && prev_t < 0) { break; }
-        uint32_t c_evsc[kRowsPerWarp], c_deler[kRowsPerWarp], c_misc[kRowsPerWarp];
-        uint32_t c_rowflags = 0;
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; i++) { c_evsc[i] = c_deler[i] = 0; c_misc[i] = 0xFFFFu; }
-
-        if (have_cur) {
+        // workers: wait for the tile, analyse their rows, hand the warp aggregate to the control warp; they never wait for
+        // it (the stage they move on to was loaded three tiles ago; a stage is only reloaded after its aggregate was read)
+        uint32_t phase_bits = 0;
+        int s = 0;
+        for (long long t = first_tile; t < n_tiles; t += G) {
             const int64_t t0 = (int64_t)t * kTileBytes;
             uint8_t* st = sm.stage[s];
             while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
             phase_bits ^= (1u << s);
-            // ---- boundary fix-ups: positions < 0 read as non-zero, positions >= size read as zero
-            const int64_t valid_end = (int64_t)kLead + (size - t0); // smem offset of position `size`
-            // interior tile: every byte (and its halo) is owned and below the event limit
-            const bool interior = geom.evl - t0 >= (int64_t)kTileBytes + 32;
-            if (t == 0 || valid_end < kStageBytes) {
-                if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
-                if (valid_end < kStageBytes) {
-                    for (int i = (int)valid_end + tid; i < kStageBytes; i += kWorkerThreads) { st[i] = 0; }
-                }
-                bar_sync(kBarWork, kWorkerThreads);
-            }
-
-            // ---- phase 1: per-lane masks; the warp walks its rows in order and keeps the carries in registers.
+            fix_stage(st, t, t0, size, tid);
+            const bool interior = geom.evl - t0 >= (int64_t)kTileBytes + 32; // every byte (and its halo) owned and below the event limit
+            uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, rows = 0, anydel = 0;
+            if (dbg & 64u) { wK = kRowsPerWarp * kRowBytes; rows = (dbg >> 8) & 0xFFu; } // experiment: analysis off, rows flagged as told
+            else
             // Rows are taken four at a time: the four loads, halo exchanges and zero-pair tests are independent
             // instruction chains, and one vote sends the common "no two adjacent zero bytes anywhere" case on.
-            uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
-#pragma unroll
+            // (Loops over rows are kept rolled on purpose: two roles share the SM's instruction cache.)
+#pragma unroll 1
             for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
-                if (dbg & 2u) { wK += 4 * kRowBytes; continue; }
                 const int rbase = warp * kRowsPerWarp + i0;
                 const uint8_t* rp = st + kLead + rbase * kRowBytes + lane * 16;
                 uint4 v[4];
@@ -530,18 +593,173 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const int i = i0 + k;
                     const bool slow = ((slowmask >> k) & 1u) != 0u;
                     if (!__any_sync(0xFFFFFFFFu, slow) && interior) { wK += kRowBytes; continue; }
                     const int64_t g0 = t0 + (int64_t)(rbase + k) * kRowBytes + lane * 16;
-                    const int64_t rem = geom.own - g0;
-                    uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
-                    if (slow) { m3 = analyze_cold(wp[k], v[k], wn[k], g0, size, geom.own, geom.evl); }
-                    c_evsc[i] = m3.x;
-                    c_deler[i] = m3.y;
-                    c_misc[i] = m3.z;
-                    const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
-                    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
+                    const RowMasks r = analyze_row(wp[k], v[k], wn[k], slow, g0, geom, wN, wK, wKind, wErr);
+                    rows |= 1u << (i0 + k);
+                    anydel |= (r.Db != 0u) ? 1u : 0u;
+                }
+            }
+            if (lane == 0) {
+                WarpAgg a;
+                a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = anydel; a.rows = rows;
+                a.pad[0] = a.pad[1] = 0;
+                sm.wagg[s][warp] = a;
+                mbar_arrive(&sm.done[s]);
+            }
+            __syncwarp();
+            s = (s + 1 == kStages) ? 0 : s + 1;
+        }
+        return;
+    }
+
+    // ================================================ WRITER ================================================
+    if (warp == kWorkers) {
+        // control warp: lane j polls the prefix and the aggregate (row mask) of this CTA's tile number q + j, kAhead tiles
+        // ahead of the workers, so that the two L2 round trips never sit between two tiles.  Per tile: wait until lane 0 has
+        // both words -> shared memory -> [E] the workers are done with the previous stage -> reload it -> [P] release the
+        // workers into the tile -> every lane hands its words down by one lane.
+        constexpr int kAhead = 4;
+        if (first_tile >= n_tiles) { return; }
+        long long tq = first_tile + (long long)lane * G; // tile polled by this lane
+        ulonglong2 ex = make_ulonglong2(0ull, 0ull), ag = make_ulonglong2(0ull, 0ull);
+        int s = 0;
+        for (long long t = first_tile, it = 0; t < n_tiles; t += G, it++) {
+            for (;;) {
+                if (lane < kAhead && tq < n_tiles) {
+                    if (dbg & 1u) {
+                        ex = pack_state(kStatusPrefix, 0, (unsigned long long)tq * kTileBytes, HEVCB_KIND_Z3, 0);
+                        ag = pack_agg(0, 0, 0, 0, ~0ull);
+                    } else {
+                        if (dbg & 128u) { ex = pack_state(kStatusPrefix, 0, (unsigned long long)tq * kTileBytes, HEVCB_KIND_Z3, 0); } // experiment: scanner off the path
+                        else if ((ex.x >> 62) == 0ull) { ex = ld_state(&tile_excl[tq]); }
+                        if ((ag.x >> 62) == 0ull) { ag = ld_state(&tile_state[tq]); }
+                    }
+                }
+                const bool ready = (ex.x >> 62) != 0ull && (ag.x >> 62) != 0ull;
+                if (__shfl_sync(0xFFFFFFFFu, ready ? 1 : 0, 0)) { break; }
+                __nanosleep(20);
+            }
+            if (lane == 0) {
+                TilePrefix tp;
+                tp.n = ex.x & ((1ull << 40) - 1); tp.k = ex.y; tp.kind = (uint32_t)(ex.x >> 60) & 3u; tp.err = (uint32_t)(ex.x >> 59) & 1u;
+                tp.mask = ag.y;
+                sm.pref[it & 1] = tp;
+            }
+            __syncwarp();
+            if (it > 0) {
+                bar_sync(kBarE, kSyncThreads); // every worker finished reading the stage of the previous tile
+                const int ps = (s == 0) ? kStages - 1 : s - 1;
+                const long long nt = (t - G) + (long long)kStages * G;
+                if (lane == 0 && nt < n_tiles) {
+                    fence_proxy_async();
+                    issue_tile_load(sm.stage[ps], &sm.mbar[ps], buf, size, nt);
+                }
+            }
+            bar_arrive(kBarP, kSyncThreads);
+            // hand down: lane j takes over what lane j + 1 has polled so far; the last polling lane starts a new tile
+            ex.x = __shfl_down_sync(0xFFFFFFFFu, ex.x, 1); ex.y = __shfl_down_sync(0xFFFFFFFFu, ex.y, 1);
+            ag.x = __shfl_down_sync(0xFFFFFFFFu, ag.x, 1); ag.y = __shfl_down_sync(0xFFFFFFFFu, ag.y, 1);
+            tq += G;
+            if (lane >= kAhead - 1) { ex = make_ulonglong2(0ull, 0ull); ag = make_ulonglong2(0ull, 0ull); }
+            s = (s + 1 == kStages) ? 0 : s + 1;
+        }
+        bar_sync(kBarE, kSyncThreads); // the last tile
+        return;
+    }
+
+    DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
+    uint32_t phase_bits = 0;
+    int s = 0;
+    for (long long t = first_tile, it = 0; t < n_tiles; t += G, it++) {
+        const int64_t t0 = (int64_t)t * kTileBytes;
+        uint8_t* st = sm.stage[s];
+        bar_sync(kBarP, kSyncThreads); // the tile's prefix and row mask are in shared memory
+        const TilePrefix pref = sm.pref[it & 1];
+        while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
+        phase_bits ^= (1u << s);
+        const long long tileN = (long long)pref.n;
+        const long long tileK = (long long)pref.k;
+
+        if (pref.mask == 0ull) {
+            // ---- clean interior tile: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
+            if (rbsp != nullptr && !(dbg & 4u)) { copy_tile(rbsp + tileK, st + kLead, kTileBytes, tid); }
+            bar_arrive(kBarE, kSyncThreads);
+            s = (s + 1 == kStages) ? 0 : s + 1;
+            continue;
+        }
+
+        // ---- tile with flagged rows: exact masks of those rows, warp aggregates, ordered emission, row-wise write-out
+        fix_stage(st, t, t0, size, tid);
+        const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kRowsPerWarp)) & 0xFFu;
+        // pass 1: aggregates of this warp's flagged rows
+        uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, anyD = 0;
+#pragma unroll 1
+        for (int i = 0; i < kRowsPerWarp; i++) {
+            if (!((myrows >> i) & 1u)) { wK += kRowBytes; continue; }
+            const RowMasks m = analyze_staged_row(st, warp * kRowsPerWarp + i, lane, t0, geom, wN, wK, wKind, wErr);
+            anyD |= (m.Db != 0u) ? 1u : 0u;
+        }
+        if (lane == 0) {
+            WarpAgg a;
+            a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = anyD; a.rows = myrows;
+            a.pad[0] = a.pad[1] = 0;
+            sm.wagg[it & 1][warp] = a;
+        }
+        bar_sync(kBarWork, kWorkerThreads);
+        // aggregate of the warps before this one, tile totals
+        uint32_t rN = 0, rK = 0, rKind = HEVCB_KIND_PASS, rErr = 0, compact = 0, tile_k = 0;
+        {
+            uint32_t tn = 0, ak = HEVCB_KIND_PASS, ae = 0;
+#pragma unroll
+            for (int w = 0; w < kWorkers; w++) {
+                const WarpAgg a = sm.wagg[it & 1][w];
+                if (w == warp) { rN = tn; rK = tile_k; rKind = ak; rErr = ae; }
+                tn += a.n;
+                tile_k += a.k;
+                hevcb_carry_combine(ak, ae, a.kind, a.err);
+                compact |= a.del;
+            }
+        }
+        const bool write_rows = (rbsp != nullptr) && !(dbg & 4u);
+        const bool dirty_out = (compact != 0u) && write_rows;
+        // pass 2: ordered emission of NAL boundaries (the masks of the few flagged rows are rebuilt instead of being kept in
+        // registers across the barrier); tiles with removed bytes are also written out here, row by row
+        {
+            uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
+            hevcb_carry_combine(cKind, cErr, rKind, rErr);
+#pragma unroll 1
+            for (int i = 0; i < kRowsPerWarp; i++) {
+                const int r = warp * kRowsPerWarp + i;
+                if (!((myrows >> i) & 1u)) {
+                    if (dirty_out) { copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane); }
+                    rK += kRowBytes;
+                    continue;
+                }
+                uint32_t dN = 0, dK = 0, dKind = HEVCB_KIND_PASS, dErr = 0;
+                const RowMasks m = analyze_staged_row(st, r, lane, t0, geom, dN, dK, dKind, dErr);
+                const bool rowX = m.Xb != 0u, rowD = m.Db != 0u;
+                if (!rowD) {
+                    if (dirty_out) { copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane); }
+                    if (!rowX) { rK += kRowBytes; continue; } // nothing to emit
+                }
+                const uint32_t evsc = m.evsc, deler = m.deler, misc = m.misc;
+                const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16, valid = misc & 0xFFFFu;
+                const uint32_t keep = valid & ~del;
+                uint32_t klane, rowKept;
+                if (rowD) {
+                    const uint32_t c = (uint32_t)__popc(keep);
+                    const uint32_t inc = warp_incl_scan(c, lane);
+                    klane = inc - c;
+                    rowKept = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                } else {
+                    klane = (uint32_t)lane * 16u;
+                    rowKept = kRowBytes;
+                }
+                klane += rK;
+                if (rowX) {
+                    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
                     if (ev != 0u) {
                         const int tp = 31 - __clz((int)ev);
                         lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
@@ -550,148 +768,35 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
                     const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
                     const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-                    const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
-                    const uint32_t Db = __ballot_sync(0xFFFFFFFFu, (del != 0u) || (valid != 0xFFFFu));
-                    wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
-                    wK += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid & ~del));
+                    uint32_t ck, ce;
+                    warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+                    if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the row
+                    const uint32_t c = (uint32_t)__popc(sc);
+                    const uint32_t ninc = warp_incl_scan(c, lane);
+                    if ((ev | er) != 0u) {
+                        const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
+                        emit_cold(evsc, deler, misc, g0, (int64_t)(tileN + rN + (ninc - c)), (int64_t)(tileK + klane), ck, ce, sink);
+                    }
                     uint32_t rk, re;
                     warp_carry_total(Eb, Sb, Rb, rk, re);
-                    hevcb_carry_combine(wKind, wErr, rk, re);
-                    c_rowflags |= 1u << i;
-                    c_rowflags |= (Xb != 0u ? 1u : 0u) << (8 + i);
-                    c_rowflags |= (Db != 0u ? 1u : 0u) << (16 + i);
+                    hevcb_carry_combine(cKind, cErr, rk, re);
+                    rN += __shfl_sync(0xFFFFFFFFu, ninc, 31);
                 }
-            }
-            if (lane == 0) {
-                WarpAgg a;
-                a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = (c_rowflags >> 16) != 0u;
-                a.pad[0] = a.pad[1] = a.pad[2] = 0;
-                sm.wagg[it & 1][warp] = a;
+                if (rowD && dirty_out) { // row with removed / out-of-range bytes: byte-granular stores of the kept bytes
+                    const uint4 v = *reinterpret_cast<const uint4*>(st + kLead + r * kRowBytes + lane * 16);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    uint8_t* o = rbsp + tileK + klane;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if ((keep >> j) & 1u) { *o++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3))); }
+                    }
+                }
+                rK += rowKept;
             }
         }
-        bar_sync(kBarS1, kSyncThreads);
-
-        // tile aggregate and the aggregate of the warps before this one
-        uint32_t c_rN = 0, c_rK = 0, c_rKind = HEVCB_KIND_PASS, c_rErr = 0, c_tile_k = 0, c_compact = 0;
-        if (have_cur) {
-            uint32_t tn = 0, ak = HEVCB_KIND_PASS, ae = 0;
-#pragma unroll
-            for (int w = 0; w < kWorkers; w++) {
-                const WarpAgg a = sm.wagg[it & 1][w];
-                if (w == warp) { c_rN = tn; c_rK = c_tile_k; c_rKind = ak; c_rErr = ae; }
-                tn += a.n;
-                c_tile_k += a.k;
-                hevcb_carry_combine(ak, ae, a.kind, a.err);
-                c_compact |= a.del;
-            }
-        }
-
-        if (prev_t >= 0) {
-            const long long pt = prev_t;
-            const int ps = (s == 0) ? kStages - 1 : s - 1; // stage holding the previous tile
-            uint8_t* st = sm.stage[ps];
-            const int64_t t0 = (int64_t)pt * kTileBytes;
-            const LookPart pref = sm.pref[(it - 1) & 1];
-            const long long tileN = (long long)pref.n;
-            const long long tileK = (long long)pref.k;
-            const bool do_compact = (p_compact != 0u) && (rbsp != nullptr);
-
-            // ---- phase 2: ordered emission of NAL boundaries; tiles with removed bytes are also written out here, row by row
-            const bool dirty_out = do_compact && !(dbg & 4u);
-            if ((p_rowflags >> 8) != 0u || dirty_out) { // warp-uniform: something to emit, or a dirty tile to write
-                uint32_t rN = p_rN, rK = p_rK;
-                uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
-                hevcb_carry_combine(cKind, cErr, p_rKind, p_rErr);
-#pragma unroll
-                for (int i = 0; i < kRowsPerWarp; i++) {
-                    const bool rowS = ((p_rowflags >> i) & 1u) != 0u;
-                    const bool rowX = ((p_rowflags >> (8 + i)) & 1u) != 0u;
-                    const bool rowD = ((p_rowflags >> (16 + i)) & 1u) != 0u;
-                    const int r = warp * kRowsPerWarp + i;
-                    if (!rowD) {
-                        if (dirty_out) { // clean row of a dirty tile: shifted 16-byte vector copy by this warp
-                            copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane);
-                        }
-                        if (!rowX) { rK += kRowBytes; continue; } // nothing to emit
-                    }
-                    const uint32_t evsc = rowS ? p_evsc[i] : 0u, deler = rowS ? p_deler[i] : 0u, misc = rowS ? p_misc[i] : 0xFFFFu;
-                    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16, valid = misc & 0xFFFFu;
-                    const uint32_t keep = valid & ~del;
-                    uint32_t klane, rowKept;
-                    if (rowD) {
-                        const uint32_t c = (uint32_t)__popc(keep);
-                        const uint32_t inc = warp_incl_scan(c, lane);
-                        klane = inc - c;
-                        rowKept = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                    } else {
-                        klane = (uint32_t)lane * 16u;
-                        rowKept = kRowBytes;
-                    }
-                    klane += rK;
-                    if (rowX) {
-                        uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
-                        if (ev != 0u) {
-                            const int tp = 31 - __clz((int)ev);
-                            lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
-                            le = ((er >> tp) >> 1) != 0u;
-                        }
-                        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
-                        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-                        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-                        uint32_t ck, ce;
-                        warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
-                        if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the row
-                        const uint32_t c = (uint32_t)__popc(sc);
-                        const uint32_t ninc = warp_incl_scan(c, lane);
-                        if ((ev | er) != 0u) {
-                            const int64_t g0 = t0 + (int64_t)r * kRowBytes + lane * 16;
-                            emit_cold(evsc, deler, misc, g0, (int64_t)(tileN + rN + (ninc - c)), (int64_t)(tileK + klane), ck, ce, sink);
-                        }
-                        uint32_t rk, re;
-                        warp_carry_total(Eb, Sb, Rb, rk, re);
-                        hevcb_carry_combine(cKind, cErr, rk, re);
-                        rN += __shfl_sync(0xFFFFFFFFu, ninc, 31);
-                    }
-                    if (rowD && dirty_out) { // row with removed / out-of-range bytes: byte-granular stores of the kept bytes
-                        const uint4 v = *reinterpret_cast<const uint4*>(st + kLead + r * kRowBytes + lane * 16);
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        uint8_t* o = rbsp + tileK + klane;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            if ((keep >> j) & 1u) { *o++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3))); }
-                        }
-                    }
-                    rK += rowKept;
-                }
-            }
-
-            // ---- copy-out of a clean tile: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
-            if (rbsp != nullptr && !do_compact && !(dbg & 4u)) {
-                const uint8_t* src = st + kLead;
-                const uint32_t L = p_tile_k;
-                uint8_t* dst = rbsp + tileK;
-                const uint32_t head0 = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-                const uint32_t head = head0 < L ? head0 : L;
-                if ((uint32_t)tid < head) { dst[tid] = src[tid]; }
-                const uint32_t nv = (L - head) >> 4;
-                const uint32_t sh = (head & 3u) * 8u; // source misalignment is tile-uniform
-                switch (head >> 2) {
-                    case 0: copy_vectors<0>(dst + head, src, nv, sh, tid); break;
-                    case 1: copy_vectors<1>(dst + head, src, nv, sh, tid); break;
-                    case 2: copy_vectors<2>(dst + head, src, nv, sh, tid); break;
-                    default: copy_vectors<3>(dst + head, src, nv, sh, tid); break;
-                }
-                const uint32_t done = head + (nv << 4);
-                if ((uint32_t)tid < L - done) { dst[done + tid] = src[done + tid]; }
-            }
-            bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
-        }
-
-        // the tile analysed in this iteration becomes the one to write out in the next
-        prev_t = have_cur ? t : -1;
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; i++) { p_evsc[i] = c_evsc[i]; p_deler[i] = c_deler[i]; p_misc[i] = c_misc[i]; }
-        p_rowflags = c_rowflags; p_rN = c_rN; p_rK = c_rK; p_rKind = c_rKind; p_rErr = c_rErr; p_tile_k = c_tile_k; p_compact = c_compact;
+        // ---- tile without removed bytes: one shifted vector copy of the whole tile by all workers
+        if (write_rows && !dirty_out) { copy_tile(rbsp + tileK, st + kLead, tile_k, tid); }
+        bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
         s = (s + 1 == kStages) ? 0 : s + 1;
     }
 }
@@ -792,12 +897,15 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
             ctx->scan_blocks_per_sm = nb;
         }
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
-        if (grid > n_tiles) { grid = n_tiles; }
-        // cooperative launch: the chained scan needs every CTA of the grid to be resident
+        if (grid > 2 * n_tiles) { grid = 2 * n_tiles; }
+        if (grid < 2) { grid = 2; }
+        long long n_an = grid / 2; // analyser CTAs (the rest are writers); with 2 CTAs per SM every SM gets one of each
+        if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
+        // cooperative launch: writers wait on the scanner, the scanner on the analysers: every CTA must be resident
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
-        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
+        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
         ctx->launches++;
