@@ -78,6 +78,7 @@ struct __align__(16) SmemLayout {
     uint8_t stage[kStages][kStageBytes];
     unsigned long long mbar[kStages];
     unsigned long long done[kStages]; // analyser: the workers are through with the stage (one arrival per warp)
+    uint32_t evcount[kStages];        // analyser: event records written for the tile in the stage
     WarpAgg wagg[kStages][kWorkers];  // per-warp aggregates of the tile in a stage (writer: index i & 1)
     TilePrefix pref[2];        // writer: prefix + row mask of this CTA's i-th tile (index i & 1)
 };
@@ -93,10 +94,13 @@ __device__ __forceinline__ ulonglong2 pack_state(unsigned long long status, unsi
     return s;
 }
 // aggregate of one tile: x = status | kind | err | start codes (14 bits) | kept bytes (16 bits), y = row mask
-__device__ __forceinline__ ulonglong2 pack_agg(uint32_t n, uint32_t k, uint32_t kind, uint32_t err, unsigned long long mask)
+constexpr uint32_t kEvCap = 32;       // event records an analyser may leave per tile (one per lane of the emit pass)
+constexpr uint32_t kEvByWriter = 0xFFu; // "records" value: the writer CTA emits this tile's NAL boundaries itself
+__device__ __forceinline__ ulonglong2 pack_agg(uint32_t n, uint32_t k, uint32_t kind, uint32_t err, unsigned long long mask, uint32_t records = kEvByWriter)
 {
     ulonglong2 s;
-    s.x = (kStatusAgg << 62) | ((unsigned long long)kind << 60) | ((unsigned long long)(err & 1u) << 59) | ((unsigned long long)(k & 0xFFFFFu) << 20) |
+    s.x = (kStatusAgg << 62) | ((unsigned long long)kind << 60) | ((unsigned long long)(err & 1u) << 59) | ((unsigned long long)(records & 0xFFu) << 40) |
+          ((unsigned long long)(k & 0xFFFFFu) << 20) |
           (unsigned long long)(n & 0xFFFFFu);
     s.y = mask;
     return s;
@@ -105,6 +109,7 @@ __device__ __forceinline__ uint32_t agg_n(const ulonglong2& s) { return (uint32_
 __device__ __forceinline__ uint32_t agg_k(const ulonglong2& s) { return (uint32_t)((s.x >> 20) & 0xFFFFFull); }
 __device__ __forceinline__ uint32_t agg_kind(const ulonglong2& s) { return (uint32_t)(s.x >> 60) & 3u; }
 __device__ __forceinline__ uint32_t agg_err(const ulonglong2& s) { return (uint32_t)(s.x >> 59) & 1u; }
+__device__ __forceinline__ uint32_t agg_records(const ulonglong2& s) { return (uint32_t)(s.x >> 40) & 0xFFu; }
 __device__ __forceinline__ ulonglong2 ld_state(const ulonglong2* p)
 {
     ulonglong2 v;
@@ -480,9 +485,9 @@ __device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, 
 // ====================================================================================================================
 __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_kernel(
     const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, long long n_analysers, ScanHeader* __restrict__ hdr,
-    ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, int64_t* __restrict__ nal_start,
-    int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp, int64_t* __restrict__ rbsp_off,
-    int64_t* __restrict__ rbsp_end, long long debug_flags)
+    ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, uint4* __restrict__ tile_events,
+    int64_t* __restrict__ nal_start, int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp,
+    int64_t* __restrict__ rbsp_off, int64_t* __restrict__ rbsp_end, long long debug_flags)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     const long long first_tile = analyser ? (long long)blockIdx.x : (long long)blockIdx.x - n_analysers;
 
     if (tid == kWorkerThreads) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); mbar_init(&sm.done[s], kWorkers); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); mbar_init(&sm.done[s], kWorkers); sm.evcount[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
         for (int s = 0; s < kStages; s++) { // this CTA's first tiles
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             for (long long t = first_tile; t < n_tiles; t += G) {
                 while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
                 done_bits ^= (1u << s);
-                uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0;
+                uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0, adel = 0;
                 unsigned long long mask = 0ull;
 #pragma unroll
                 for (int w = 0; w < kWorkers; w++) {
@@ -530,9 +535,15 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     tile_k += a.k;
                     hevcb_carry_combine(ak, ae, a.kind, a.err);
                     mask |= (unsigned long long)(a.rows & 0xFFu) << (w * kRowsPerWarp);
+                    adel |= a.del;
                 }
                 if (lane == 0) {
-                    st_state(&tile_state[t], pack_agg(tile_n, tile_k, ak, ae, mask));
+                    // A tile whose bytes are all kept and whose event chunks fit into the record list looks CLEAN to the
+                    // writer (mask 0): its NAL boundaries are emitted from the records by hevcb_scan_emit_kernel.
+                    const uint32_t nrec = sm.evcount[s];
+                    sm.evcount[s] = 0;
+                    const bool light = (adel == 0u) && (nrec <= kEvCap) && (tile_k == (uint32_t)kTileBytes) && !(dbg & 1024u);
+                    st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
                     const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
                     if (nt < n_tiles) {
                         fence_proxy_async();
@@ -599,6 +610,12 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const RowMasks r = analyze_row(wp[k], v[k], wn[k], slow, g0, geom, wN, wK, wKind, wErr);
                     rows |= 1u << (i0 + k);
                     anydel |= (r.Db != 0u) ? 1u : 0u;
+                    if (((r.evsc & 0xFFFFu) | (r.deler >> 16)) != 0u) { // chunk with an event or an error position: leave a record
+                        const uint32_t slot = atomicAdd(&sm.evcount[s], 1u);
+                        if (slot < kEvCap) {
+                            tile_events[(size_t)t * kEvCap + slot] = make_uint4((uint32_t)((rbase + k) * 32 + lane), r.evsc, r.deler, r.misc);
+                        }
+                    }
                 }
             }
             if (lane == 0) {
@@ -801,6 +818,60 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     }
 }
 
+// Emit pass: NAL boundaries of the tiles whose event chunks the analysers left as records (one warp per tile, one lane per
+// record).  Records are in arrival order: they are ranked by chunk index, then the lanes run the same ordered-carry logic
+// a row of the writer runs.  Tiles of that kind keep all their bytes, so a chunk's image offset is prefix + chunk * 16.
+__global__ void __launch_bounds__(256) hevcb_scan_emit_kernel(long long n_tiles, ScanHeader* __restrict__ hdr, const ulonglong2* __restrict__ tile_state,
+                                                              const ulonglong2* __restrict__ tile_excl, const uint4* __restrict__ tile_events,
+                                                              int64_t* __restrict__ nal_start, int64_t* __restrict__ nal_end, int64_t cap_nals,
+                                                              int64_t* __restrict__ rbsp_off, int64_t* __restrict__ rbsp_end)
+{
+    __shared__ uint4 sorted[8][kEvCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * 8 + warp;
+    if (t >= n_tiles) { return; }
+    const ulonglong2 ag = tile_state[t];
+    const uint32_t nrec = agg_records(ag);
+    if (nrec == 0u || nrec == kEvByWriter) { return; }
+    const ulonglong2 ex = tile_excl[t];
+    const long long tileN = (long long)(ex.x & ((1ull << 40) - 1)), tileK = (long long)ex.y;
+    const uint32_t pKind = (uint32_t)(ex.x >> 60) & 3u, pErr = (uint32_t)(ex.x >> 59) & 1u;
+    uint4 rec = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu);
+    if ((uint32_t)lane < nrec) { rec = tile_events[(size_t)t * kEvCap + lane]; }
+    // rank by chunk index (distinct per record)
+    uint32_t rank = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        const uint32_t other = __shfl_sync(0xFFFFFFFFu, rec.x, i);
+        rank += (other < rec.x) ? 1u : 0u;
+    }
+    if ((uint32_t)lane < nrec) { sorted[warp][rank] = rec; }
+    __syncwarp();
+    rec = make_uint4(0u, 0u, 0u, 0xFFFFu);
+    if ((uint32_t)lane < nrec) { rec = sorted[warp][lane]; }
+    const uint32_t evsc = rec.y, deler = rec.z, misc = rec.w;
+    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
+    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+    if (ev != 0u) {
+        const int tp = 31 - __clz((int)ev);
+        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+        le = ((er >> tp) >> 1) != 0u;
+    }
+    const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+    const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+    uint32_t ck, ce;
+    warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+    if (ck == HEVCB_KIND_PASS) { ck = pKind; ce |= pErr; } // inherit the carry entering the tile
+    const uint32_t c = (uint32_t)__popc(sc);
+    const uint32_t ninc = warp_incl_scan(c, lane);
+    if ((ev | er) != 0u) {
+        DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
+        const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec.x * 16;
+        emit_cold(evsc, deler, misc, g0, (int64_t)(tileN + (ninc - c)), (int64_t)(tileK + (long long)rec.x * 16), ck, ce, sink);
+    }
+}
+
 // single-thread epilogue: reference end-of-buffer rules over the last 8 bytes + summary
 __global__ void hevcb_scan_finalize_kernel(const uint8_t* __restrict__ buf, int64_t size, long long n_tiles,
                                            const ScanHeader* __restrict__ hdr, const ulonglong2* __restrict__ tile_state,
@@ -875,14 +946,16 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
     }
     const long long n_tiles = (long long)((geom.own + kTileBytes - 1) / kTileBytes);
     const size_t n_states = (size_t)(n_tiles > 0 ? n_tiles : 1);
-    const size_t need = sizeof(ScanHeader) + 2 * n_states * sizeof(ulonglong2);
+    const size_t need_states = sizeof(ScanHeader) + 2 * n_states * sizeof(ulonglong2);
+    const size_t need = need_states + n_states * kEvCap * sizeof(uint4); // + the event records of the tiles (not cleared)
     int rc = hevcb_reserve(ctx, &ctx->scan_scratch, need);
     if (rc != HEVCB_OK) { return rc; }
     ScanHeader* hdr = reinterpret_cast<ScanHeader*>(ctx->scan_scratch.p);
     ulonglong2* states = reinterpret_cast<ulonglong2*>(reinterpret_cast<uint8_t*>(ctx->scan_scratch.p) + sizeof(ScanHeader));
     ulonglong2* excl = states + n_states;
+    uint4* events = reinterpret_cast<uint4*>(excl + n_states);
 
-    HEVCB_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch.p, 0, need, stream));
+    HEVCB_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch.p, 0, need_states, stream));
     hevcb_scan_init_kernel<<<1, 32, 0, stream>>>(hdr, geom.init_n, d_nal_start, d_rbsp_off, cap_nals);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
@@ -905,10 +978,13 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
-        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&d_nal_start, (void*)&d_nal_end,
+        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
-        ctx->launches++;
+        hevcb_scan_emit_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, stream>>>(n_tiles, hdr, states, excl, events, d_nal_start, d_nal_end, cap_nals,
+                                                                                 d_rbsp_off, d_rbsp_end);
+        ctx->launches += 2;
+        HEVCB_CUDA(ctx, cudaGetLastError());
     }
     *hdr_out = hdr;
     *n_tiles_out = n_tiles;
