@@ -94,7 +94,7 @@ __device__ __forceinline__ ulonglong2 pack_state(unsigned long long status, unsi
     return s;
 }
 // aggregate of one tile: x = status | kind | err | start codes (14 bits) | kept bytes (16 bits), y = row mask
-constexpr uint32_t kEvCap = 32;       // event records an analyser may leave per tile (one per lane of the emit pass)
+constexpr uint32_t kEvCap = 64;       // event records an analyser may leave per tile (two per lane of the emit pass)
 constexpr uint32_t kEvByWriter = 0xFFu; // "records" value: the writer CTA emits this tile's NAL boundaries itself
 __device__ __forceinline__ ulonglong2 pack_agg(uint32_t n, uint32_t k, uint32_t kind, uint32_t err, unsigned long long mask, uint32_t records = kEvByWriter)
 {
@@ -836,39 +836,50 @@ __global__ void __launch_bounds__(256) hevcb_scan_emit_kernel(long long n_tiles,
     const ulonglong2 ex = tile_excl[t];
     const long long tileN = (long long)(ex.x & ((1ull << 40) - 1)), tileK = (long long)ex.y;
     const uint32_t pKind = (uint32_t)(ex.x >> 60) & 3u, pErr = (uint32_t)(ex.x >> 59) & 1u;
-    uint4 rec = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu);
-    if ((uint32_t)lane < nrec) { rec = tile_events[(size_t)t * kEvCap + lane]; }
-    // rank by chunk index (distinct per record)
-    uint32_t rank = 0;
+    // rank by chunk index (distinct per record); lane l holds records l and l + 32
+    uint4 ra = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu), rb = ra;
+    if ((uint32_t)lane < nrec) { ra = tile_events[(size_t)t * kEvCap + lane]; }
+    if ((uint32_t)lane + 32u < nrec) { rb = tile_events[(size_t)t * kEvCap + 32 + lane]; }
+    uint32_t rank_a = 0, rank_b = 0;
 #pragma unroll 4
     for (int i = 0; i < 32; i++) {
-        const uint32_t other = __shfl_sync(0xFFFFFFFFu, rec.x, i);
-        rank += (other < rec.x) ? 1u : 0u;
+        const uint32_t oa = __shfl_sync(0xFFFFFFFFu, ra.x, i), ob = __shfl_sync(0xFFFFFFFFu, rb.x, i);
+        rank_a += ((oa < ra.x) ? 1u : 0u) + ((ob < ra.x) ? 1u : 0u);
+        rank_b += ((oa < rb.x) ? 1u : 0u) + ((ob < rb.x) ? 1u : 0u);
     }
-    if ((uint32_t)lane < nrec) { sorted[warp][rank] = rec; }
+    if ((uint32_t)lane < nrec) { sorted[warp][rank_a] = ra; }
+    if ((uint32_t)lane + 32u < nrec) { sorted[warp][rank_b] = rb; }
     __syncwarp();
-    rec = make_uint4(0u, 0u, 0u, 0xFFFFu);
-    if ((uint32_t)lane < nrec) { rec = sorted[warp][lane]; }
-    const uint32_t evsc = rec.y, deler = rec.z, misc = rec.w;
-    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
-    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
-    if (ev != 0u) {
-        const int tp = 31 - __clz((int)ev);
-        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
-        le = ((er >> tp) >> 1) != 0u;
-    }
-    const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
-    const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-    uint32_t ck, ce;
-    warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
-    if (ck == HEVCB_KIND_PASS) { ck = pKind; ce |= pErr; } // inherit the carry entering the tile
-    const uint32_t c = (uint32_t)__popc(sc);
-    const uint32_t ninc = warp_incl_scan(c, lane);
-    if ((ev | er) != 0u) {
-        DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
-        const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec.x * 16;
-        emit_cold(evsc, deler, misc, g0, (int64_t)(tileN + (ninc - c)), (int64_t)(tileK + (long long)rec.x * 16), ck, ce, sink);
+    uint32_t cKind = pKind, cErr = pErr; // carry entering the round
+    long long nbase = tileN;
+    DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
+    for (uint32_t base = 0; base < nrec; base += 32) {
+        uint4 rec = make_uint4(0u, 0u, 0u, 0xFFFFu);
+        if (base + (uint32_t)lane < nrec) { rec = sorted[warp][base + lane]; }
+        const uint32_t evsc = rec.y, deler = rec.z, misc = rec.w;
+        const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
+        uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+        if (ev != 0u) {
+            const int tp = 31 - __clz((int)ev);
+            lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+            le = ((er >> tp) >> 1) != 0u;
+        }
+        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+        uint32_t ck, ce;
+        warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+        if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the round
+        const uint32_t c = (uint32_t)__popc(sc);
+        const uint32_t ninc = warp_incl_scan(c, lane);
+        if ((ev | er) != 0u) {
+            const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec.x * 16;
+            emit_cold(evsc, deler, misc, g0, (int64_t)(nbase + (ninc - c)), (int64_t)(tileK + (long long)rec.x * 16), ck, ce, sink);
+        }
+        uint32_t rk, re;
+        warp_carry_total(Eb, Sb, Rb, rk, re);
+        hevcb_carry_combine(cKind, cErr, rk, re);
+        nbase += __shfl_sync(0xFFFFFFFFu, ninc, 31);
     }
 }
 
@@ -972,7 +983,9 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
         if (grid > 2 * n_tiles) { grid = 2 * n_tiles; }
         if (grid < 2) { grid = 2; }
-        long long n_an = grid / 2; // analyser CTAs (the rest are writers); with 2 CTAs per SM every SM gets one of each
+        long long n_an = (grid * 3 + 2) / 5; // analyser CTAs (the rest are writers): measured optimum for streams of NALs >= 4 KiB
+        if (n_an < 1) { n_an = 1; }
+        if (n_an > grid - 1) { n_an = grid - 1; }
         if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
         // cooperative launch: writers wait on the scanner, the scanner on the analysers: every CTA must be resident
         long long nt = n_tiles;
