@@ -42,7 +42,10 @@ constexpr int kRows = kWorkers * kRowsPerWarp;
 constexpr int kTileBytes = kRows * kRowBytes; // 32 KiB
 constexpr int kLead = 128;                    // leading halo: a whole 128-byte line so that every bulk copy starts line-aligned
 constexpr int kStageBytes = kLead + kTileBytes + 16;
-constexpr int kStages = 3;       // tile i-1 being written out, tile i being analysed, tile i+1 in flight
+#ifndef HEVCB_SCAN_STAGES
+#define HEVCB_SCAN_STAGES 3
+#endif
+constexpr int kStages = HEVCB_SCAN_STAGES;       // tile i-1 being written out, tile i being analysed, tile i+1 in flight
 constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
@@ -52,6 +55,7 @@ struct ScanGeom {
     int64_t evl;        // events / error positions honoured below this
     uint32_t init_n;    // 1: a NAL is considered open at position 0 (local index 0: the piece of a NAL begun in an earlier shard)
     uint32_t init_kind; // carry entering the range
+    long long window;   // analysers load at most this many tiles ahead of the writers' progress
 };
 
 struct WarpAgg {
@@ -198,7 +202,7 @@ struct DevSink {
 
 // scratch header (device): [1] first zero-length NAL index
 struct ScanHeader {
-    unsigned long long reserved;
+    unsigned long long tiles_written; // writer progress (analysers stay within a window of it so that a tile's second load hits L2)
     long long first_empty;
     ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
     unsigned long long pad[4];
@@ -523,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             // control warp: all workers are done with the stage -> publish the tile's aggregate, reload the stage
             int s = 0;
             uint32_t done_bits = 0;
+            long long seen_written = 0;
             for (long long t = first_tile; t < n_tiles; t += G) {
                 while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
                 done_bits ^= (1u << s);
@@ -546,6 +551,13 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
                     const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
                     if (nt < n_tiles) {
+                        // stay within `window` tiles of the writers: what they load a second time is then still in L2
+                        while (nt > seen_written + geom.window) {
+                            unsigned long long w;
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&hdr->tiles_written) : "memory");
+                            seen_written = (long long)w;
+                            if (nt > seen_written + geom.window) { __nanosleep(200); }
+                        }
                         fence_proxy_async();
                         issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, nt);
                     }
@@ -667,6 +679,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             __syncwarp();
             if (it > 0) {
                 bar_sync(kBarE, kSyncThreads); // every worker finished reading the stage of the previous tile
+                if (lane == 0) { atomicAdd(&hdr->tiles_written, 1ull); }
                 const int ps = (s == 0) ? kStages - 1 : s - 1;
                 const long long nt = (t - G) + (long long)kStages * G;
                 if (lane == 0 && nt < n_tiles) {
@@ -683,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             s = (s + 1 == kStages) ? 0 : s + 1;
         }
         bar_sync(kBarE, kSyncThreads); // the last tile
+        if (lane == 0) { atomicAdd(&hdr->tiles_written, 1ull); }
         return;
     }
 
@@ -917,7 +931,7 @@ __global__ void hevcb_scan_finalize_kernel(const uint8_t* __restrict__ buf, int6
 __global__ void hevcb_scan_init_kernel(ScanHeader* hdr, uint32_t init_n, int64_t* nal_start, int64_t* rbsp_off, int64_t cap_nals)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        hdr->reserved = 0ull;
+        hdr->tiles_written = 0ull;
         hdr->first_empty = 0x7FFFFFFFFFFFFFFFll;
         if (init_n && cap_nals > 0) { nal_start[0] = 0; rbsp_off[0] = 0; } // the NAL piece that enters the shard
     }
@@ -991,6 +1005,10 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
+        g.window = 1536; // tiles (48 MiB): more than both roles keep in flight (3 stages x grid), well inside the 126 MB L2
+        if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= 3 * grid) { g.window = v; } }
+        if (g.window < 3 * grid) { g.window = 3 * grid; }
+        if (dbg & 32u) { g.window = 1ll << 40; } // experiment "writers off": nothing to wait for
         void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
@@ -1013,7 +1031,7 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
         return HEVCB_E_ARG;
     }
     ScanGeom geom;
-    geom.size = size; geom.own = size; geom.evl = size - HEVCB_TAIL_ZONE; geom.init_n = 0; geom.init_kind = HEVCB_KIND_Z3;
+    geom.size = size; geom.own = size; geom.evl = size - HEVCB_TAIL_ZONE; geom.init_n = 0; geom.init_kind = HEVCB_KIND_Z3; geom.window = 0;
     ScanHeader* hdr = nullptr;
     long long n_tiles = 0;
     int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);
@@ -1040,6 +1058,7 @@ int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t 
     geom.evl = is_last ? own - HEVCB_TAIL_ZONE : own;
     geom.init_n = is_first ? 0u : 1u;
     geom.init_kind = is_first ? HEVCB_KIND_Z3 : HEVCB_KIND_SC3;
+    geom.window = 0;
     ScanHeader* hdr = nullptr;
     long long n_tiles = 0;
     int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);

@@ -252,6 +252,13 @@ struct hevcb_replay {
         if (!multi && cur < n && field[cur] == f) {
             v = value[cur];
             cur++;
+        } else if (multi && cur < n && field[cur] == f) {
+            // a field the reader stored several times in a row: the struct holds the last value of the run; every call
+            // consumes one pair of the run and returns that last value
+            uint32_t e = cur;
+            while (e + 1 < n && field[e + 1] == f) { e++; }
+            v = value[e];
+            cur++;
         } else {
             for (int64_t i = (int64_t)n - 1; i >= 0; i--) {
                 if (field[i] == f) {
