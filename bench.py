@@ -347,7 +347,7 @@ def run_ours(args):
             allv = v.cpu().numpy()[None, :]
         e2e = {"value": float(allv[:, 1].sum() / allv[:, 0].max() / 1e9), "unit": UNIT, "h2d_bytes_per_step": int(size),
                "d2h_bytes_per_step": int(sm.rbsp_bytes + 4 * 8 * sm.n_nals + C.sizeof(ScanSummary)), "bytes_per_rank": int(size),
-               "note": "hevcb_scan_strip_host: pinned host buffers, copies inside the timed region; PCIe-bound"}
+               "note": "hevcb_scan_strip_host: pinned host buffers, copies inside the timed region (64 MiB shards pipelined over copy-in / scan / copy-out streams, stitched on the host); PCIe-bound"}
         del h_in, h_rbsp, h_arr
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)}

@@ -65,6 +65,7 @@ HEVCB_API int hevcb_create(int device, hevcb_ctx** out)
         return HEVCB_E_CUDA;
     }
     if (const char* e2 = getenv("HEVCB_SCAN_DEBUG")) { ctx->scan_debug_flags = atoll(e2); } // kernel experiment switches
+    if (const char* e3 = getenv("HEVCB_HOST_CHUNK")) { const long long v = atoll(e3); if (v >= 4096) { ctx->host_chunk = v; } }
     *out = ctx;
     return HEVCB_OK;
 }
@@ -79,6 +80,19 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
     }
+    hevcb_devbuf* pbufs[] = {&ctx->p_in[0], &ctx->p_in[1], &ctx->p_img[0], &ctx->p_img[1], &ctx->p_arr[0], &ctx->p_arr[1], &ctx->p_sum};
+    for (hevcb_devbuf* b : pbufs) {
+        if (b->p) { cudaFree(b->p); }
+    }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_in[i]) { cudaEventDestroy(ctx->ev_in[i]); }
+        if (ctx->ev_k[i]) { cudaEventDestroy(ctx->ev_k[i]); }
+        if (ctx->ev_fix[i]) { cudaEventDestroy(ctx->ev_fix[i]); }
+        if (ctx->ev_out[i]) { cudaEventDestroy(ctx->ev_out[i]); }
+    }
+    if (ctx->pinned_sums) { cudaFreeHost(ctx->pinned_sums); }
+    if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); }
+    if (ctx->s_out) { cudaStreamDestroy(ctx->s_out); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
     delete ctx;
@@ -98,6 +112,155 @@ HEVCB_API int hevcb_scan_strip_device(hevcb_ctx* ctx, const uint8_t* d_buf, int6
                                    (cudaStream_t)stream);
 }
 
+namespace {
+// local -> whole-stream coordinates for the NALs a shard owns (pipelined host path)
+__global__ void globalize_offsets_kernel(int64_t* ns, int64_t* ne, int64_t* ro, int64_t* re, int64_t first, int64_t n, int64_t byte_base,
+                                         int64_t rbsp_base)
+{
+    const int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        ns[i] += byte_base;
+        ne[i] += byte_base;
+        ro[i] += rbsp_base;
+        if (re[i] >= 0) { re[i] += rbsp_base; }
+    }
+}
+} // namespace
+
+// Large host buffers: the stream is cut into shards (hevcb_plan_shards) that are copied in, scanned and copied out on three
+// streams with two buffer slots, so that the PCIe link carries input and output at the same time; the shard records are
+// stitched on the host exactly as they are between GPUs.
+static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, int64_t* nal_start, int64_t* nal_end, int64_t cap_nals,
+                                     uint8_t* rbsp, int64_t* rbsp_off, int64_t* rbsp_end, hevcb_scan_summary* summary)
+{
+    int64_t chunk = ctx->host_chunk;
+    while ((size + chunk - 1) / chunk > HEVCB_MAX_SHARDS) { chunk *= 2; }
+    const int K = (int)((size + chunk - 1) / chunk);
+    int64_t bounds[HEVCB_MAX_SHARDS + 1];
+    int rc = hevcb_plan_shards(buf, size, K, bounds);
+    if (rc != HEVCB_OK) { return rc; }
+    int64_t max_own = 0;
+    for (int r = 0; r < K; r++) { if (bounds[r + 1] - bounds[r] > max_own) { max_own = bounds[r + 1] - bounds[r]; } }
+    int64_t capS = max_own / 3 + 8;
+    if (capS > cap_nals + 8) { capS = cap_nals + 8; }
+    if (capS < 8) { capS = 8; }
+    if (!ctx->s_in) {
+        HEVCB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        HEVCB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            HEVCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            HEVCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+            HEVCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fix[i], cudaEventDisableTiming));
+            HEVCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+        HEVCB_CUDA(ctx, cudaMallocHost(&ctx->pinned_sums, sizeof(hevcb_shard_summary) * HEVCB_MAX_SHARDS));
+    }
+    for (int i = 0; i < 2; i++) {
+        if ((rc = hevcb_reserve(ctx, &ctx->p_in[i], (size_t)max_own + 64)) != HEVCB_OK) { return rc; }
+        if (rbsp && (rc = hevcb_reserve(ctx, &ctx->p_img[i], (size_t)max_own + 64)) != HEVCB_OK) { return rc; }
+        if ((rc = hevcb_reserve(ctx, &ctx->p_arr[i], (size_t)capS * 8 * 4)) != HEVCB_OK) { return rc; }
+    }
+    if ((rc = hevcb_reserve(ctx, &ctx->p_sum, sizeof(hevcb_shard_summary) * 2)) != HEVCB_OK) { return rc; }
+    hevcb_shard_summary* h_sums = reinterpret_cast<hevcb_shard_summary*>(ctx->pinned_sums);
+    memset(h_sums, 0, sizeof(hevcb_shard_summary) * K);
+    cudaStream_t s_k = ctx->stream;
+    bool slot_used[2] = {false, false};
+    auto shard_geom = [&](int r, int64_t& lo, int64_t& own, int64_t& halo, int& first, int& last) {
+        lo = bounds[r];
+        own = bounds[r + 1] - bounds[r];
+        first = (own > 0 && lo == 0) ? 1 : 0;
+        last = (own > 0 && bounds[r + 1] == size) ? 1 : 0;
+        halo = last ? 0 : (size - bounds[r + 1] < 16 ? size - bounds[r + 1] : 16);
+    };
+    auto copy_in = [&](int r) -> int {
+        int64_t lo, own, halo; int first, last;
+        shard_geom(r, lo, own, halo, first, last);
+        if (own <= 0) { return HEVCB_OK; }
+        const int sl = r & 1;
+        if (slot_used[sl]) { HEVCB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[sl], 0)); } // the scan of shard r - 2 has read this slot
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->p_in[sl].p, buf + lo, (size_t)(own + halo), cudaMemcpyHostToDevice, ctx->s_in));
+        HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->s_in));
+        return HEVCB_OK;
+    };
+    int64_t byte_base = 0, rbsp_base = 0, nal_base = 0;
+    bool overflow = false;
+    if ((rc = copy_in(0)) != HEVCB_OK) { return rc; }
+    for (int r = 0; r < K; r++) {
+        int64_t lo, own, halo; int first, last;
+        shard_geom(r, lo, own, halo, first, last);
+        if (r + 1 < K) { // the next shard's input travels while this one is scanned
+            // (its slot is free once the scan of shard r - 1 is done, which the stream order of s_k + ev_k guarantees)
+        }
+        if (own <= 0) { continue; }
+        const int sl = r & 1;
+        int64_t* arr = reinterpret_cast<int64_t*>(ctx->p_arr[sl].p);
+        int64_t *d_ns = arr, *d_ne = arr + capS, *d_ro = arr + 2 * capS, *d_re = arr + 3 * capS;
+        hevcb_shard_summary* d_sum = reinterpret_cast<hevcb_shard_summary*>(ctx->p_sum.p) + sl;
+        HEVCB_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev_in[sl], 0));
+        if (slot_used[sl]) { HEVCB_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev_out[sl], 0)); } // outputs of shard r - 2 have left the slot
+        rc = hevcb_launch_scan_strip_shard(ctx, reinterpret_cast<const uint8_t*>(ctx->p_in[sl].p), own, halo, first, last, d_ns, d_ne, capS,
+                                           rbsp ? reinterpret_cast<uint8_t*>(ctx->p_img[sl].p) : nullptr, d_ro, d_re, d_sum, s_k);
+        if (rc != HEVCB_OK) { return rc; }
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_sums[r], d_sum, sizeof(hevcb_shard_summary), cudaMemcpyDeviceToHost, s_k));
+        HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_k[sl], s_k));
+        slot_used[sl] = true;
+        if (r + 1 < K && (rc = copy_in(r + 1)) != HEVCB_OK) { return rc; }
+        HEVCB_CUDA(ctx, cudaEventSynchronize(ctx->ev_k[sl])); // record of shard r: where its outputs go
+        const hevcb_shard_summary& S = h_sums[r];
+        if (S.overflow) { overflow = true; }
+        const int64_t fl = first ? 0 : 1;
+        int64_t n_local = S.n_nals < capS ? S.n_nals : capS;
+        const int64_t cnt = n_local > fl ? n_local - fl : 0;
+        if (cnt > 0) {
+            globalize_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s_k>>>(d_ns, d_ne, d_ro, d_re, fl, n_local, byte_base, rbsp_base);
+            ctx->launches++;
+        }
+        HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_fix[sl], s_k));
+        HEVCB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_fix[sl], 0));
+        if (rbsp && S.rbsp_bytes > 0) {
+            HEVCB_CUDA(ctx, cudaMemcpyAsync(rbsp + rbsp_base, ctx->p_img[sl].p, (size_t)S.rbsp_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        int64_t fit = cnt;
+        if (nal_base + fit > cap_nals) { fit = cap_nals > nal_base ? cap_nals - nal_base : 0; overflow = true; }
+        if (fit > 0) {
+            HEVCB_CUDA(ctx, cudaMemcpyAsync(nal_start + nal_base, d_ns + fl, (size_t)fit * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+            HEVCB_CUDA(ctx, cudaMemcpyAsync(nal_end + nal_base, d_ne + fl, (size_t)fit * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+            if (rbsp_off) { HEVCB_CUDA(ctx, cudaMemcpyAsync(rbsp_off + nal_base, d_ro + fl, (size_t)fit * 8, cudaMemcpyDeviceToHost, ctx->s_out)); }
+            if (rbsp_end) { HEVCB_CUDA(ctx, cudaMemcpyAsync(rbsp_end + nal_base, d_re + fl, (size_t)fit * 8, cudaMemcpyDeviceToHost, ctx->s_out)); }
+        }
+        HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->s_out));
+        byte_base += own;
+        rbsp_base += S.rbsp_bytes;
+        nal_base += cnt;
+    }
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(s_k));
+    // join the shards (same code as between GPUs) and patch the entries that depend on a neighbour
+    hevcb_stitch_result* res = new (std::nothrow) hevcb_stitch_result();
+    if (!res) { return HEVCB_E_NOMEM; }
+    rc = hevcb_stitch(h_sums, K, res);
+    if (rc != HEVCB_OK) { delete res; HEVCB_SET_ERR(ctx, "hevcb_scan_strip_host: inconsistent shard records"); return rc; }
+    for (int i = 0; i < res->n_patches; i++) {
+        const hevcb_stitch_patch& p = res->patches[i];
+        const int64_t g = res->nal_base[p.shard] + p.index - res->first_local[p.shard];
+        if (g < 0 || g >= cap_nals) { if (g >= cap_nals) { overflow = true; } continue; }
+        if (p.set_start) {
+            nal_start[g] = res->byte_base[p.shard] + p.nal_start;
+            if (rbsp_off) { rbsp_off[g] = res->rbsp_base[p.shard] + p.rbsp_off; }
+        }
+        nal_end[g] = res->byte_base[p.shard] + p.nal_end;
+        if (rbsp_end) { rbsp_end[g] = p.rbsp_end < 0 ? -1 : res->rbsp_base[p.shard] + p.rbsp_end; }
+    }
+    *summary = res->global;
+    if (summary->n_nals > cap_nals || overflow) { summary->overflow = 1; }
+    delete res;
+    if (summary->overflow) {
+        HEVCB_SET_ERR(ctx, "hevcb_scan_strip_host: %lld NALs exceed cap_nals %lld", (long long)summary->n_nals, (long long)cap_nals);
+        return HEVCB_E_CAPACITY;
+    }
+    return HEVCB_OK;
+}
+
 HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, int64_t* nal_start, int64_t* nal_end,
                                     int64_t cap_nals, uint8_t* rbsp, int64_t* rbsp_off, int64_t* rbsp_end, hevcb_scan_summary* summary)
 {
@@ -106,6 +269,7 @@ HEVCB_API int hevcb_scan_strip_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t 
         return HEVCB_E_ARG;
     }
     HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (size >= 2 * ctx->host_chunk) { return scan_strip_host_pipelined(ctx, buf, size, nal_start, nal_end, cap_nals, rbsp, rbsp_off, rbsp_end, summary); }
     cudaStream_t st = ctx->stream;
     const size_t in_bytes = ((size_t)size + 15u) & ~(size_t)15u;
     const size_t arr_bytes = (size_t)(cap_nals > 0 ? cap_nals : 1) * sizeof(int64_t);

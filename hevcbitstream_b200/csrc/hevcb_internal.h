@@ -34,6 +34,12 @@ struct hevcb_ctx {
     void* pinned = nullptr; // small pinned block for summaries
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr; // stream used by *_host entry points
+    // pipelined host path (hevcb_scan_strip_host on large buffers): copy-in / kernel / copy-out streams, two slots
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_fix[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    hevcb_devbuf p_in[2], p_img[2], p_arr[2], p_sum;
+    void* pinned_sums = nullptr;   // HEVCB_MAX_SHARDS shard records
+    int64_t host_chunk = 64ll << 20; // bytes per shard of the pipelined host path (HEVCB_HOST_CHUNK); 64 MiB measured best
     int scan_blocks_per_sm = 0;
     long long scan_debug_flags = 0; // experiment switches of the scan kernel (HEVCB_SCAN_DEBUG); 0 in production
 };

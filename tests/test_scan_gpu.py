@@ -120,3 +120,28 @@ def test_capacity_overflow_is_reported(ctx):
     size = s.size - ref.PAD
     with pytest.raises(hb.HevcbError):
         ctx.scan_strip_host(s[:size], size=size, cap_nals=10)
+
+
+def test_pipelined_host_path_matches_oracle(monkeypatch):
+    """hevcb_scan_strip_host on 'large' buffers cuts the stream into shards that are copied, scanned and copied back on three
+    streams; forced here with a tiny shard size so that every boundary rule is exercised"""
+    import hevcbitstream_b200 as hb
+
+    monkeypatch.setenv("HEVCB_HOST_CHUNK", "4096")
+    c = hb.Context(0)
+    try:
+        rng = np.random.default_rng(21)
+        for it in range(30):
+            size = int(rng.integers(9000, 200_000))
+            buf = util.adversarial(rng, size, it, density=[1.0, 0.3, 0.01][it % 3])
+            res = c.scan_strip_host(buf[:size], size=size)
+            util.compare_scan(buf, size, res, res.rbsp, tag=f"pipe{it}")
+        s = ref.gen_stream(seed=6, profile=1, n_slices=5000, payload_min=1, payload_max=600, zero_heavy_pct=30, extra_zero_pct=20, ps_period=40,
+                           unsupported_pct=5)
+        size = s.size - ref.PAD
+        for cut in (0, 5):
+            res = c.scan_strip_host(s[: size - cut], size=size - cut)
+            n = util.compare_scan(util.padded(s[: size - cut]), size - cut, res, res.rbsp, tag=f"pipegen{cut}")
+            assert n > 5000
+    finally:
+        c.close()
