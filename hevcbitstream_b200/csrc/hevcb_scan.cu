@@ -402,12 +402,21 @@ struct RowMasks {
     uint32_t evsc, deler, misc;
     uint32_t Xb, Db; // some lane has an event / error position; some lane removes bytes or is partially owned
 };
+__device__ __forceinline__ uint3 default_masks(int64_t g0, const ScanGeom& geom)
+{
+    const int64_t rem = geom.own - g0;
+    return make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
+}
+__device__ __forceinline__ RowMasks summarize_row(const uint3 m3, uint32_t& wN, uint32_t& wK, uint32_t& wKind, uint32_t& wErr);
 __device__ __forceinline__ RowMasks analyze_row(uint32_t wp, const uint4 v, uint32_t wn, bool slow, int64_t g0, const ScanGeom& geom,
                                                 uint32_t& wN, uint32_t& wK, uint32_t& wKind, uint32_t& wErr)
 {
-    const int64_t rem = geom.own - g0;
-    uint3 m3 = make_uint3(0u, 0u, rem >= 16 ? 0xFFFFu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u)));
+    uint3 m3 = default_masks(g0, geom);
     if (slow) { m3 = analyze_cold(wp, v, wn, g0, geom.size, geom.own, geom.evl); }
+    return summarize_row(m3, wN, wK, wKind, wErr);
+}
+__device__ __forceinline__ RowMasks summarize_row(const uint3 m3, uint32_t& wN, uint32_t& wK, uint32_t& wKind, uint32_t& wErr)
+{
     const uint32_t ev = m3.x & 0xFFFFu, sc = m3.x >> 16, del = m3.y & 0xFFFFu, er = m3.y >> 16, valid = m3.z & 0xFFFFu;
     uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
     if (ev != 0u) {
@@ -1006,8 +1015,8 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
         g.window = 1536; // tiles (48 MiB): more than both roles keep in flight (3 stages x grid), well inside the 126 MB L2
-        if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= 3 * grid) { g.window = v; } }
-        if (g.window < 3 * grid) { g.window = 3 * grid; }
+        if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= kStages * grid) { g.window = v; } }
+        if (g.window < kStages * grid) { g.window = kStages * grid; }
         if (dbg & 32u) { g.window = 1ll << 40; } // experiment "writers off": nothing to wait for
         void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
