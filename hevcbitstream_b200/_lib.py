@@ -74,7 +74,7 @@ class ShardSummary(C.Structure):
         ("n_epb", C.c_int64), ("head_end", C.c_int64), ("head_rbsp_end", C.c_int64), ("last_nal_start", C.c_int64),
         ("last_rbsp_off", C.c_int64), ("last_nal_end", C.c_int64), ("is_first", C.c_int32), ("is_last", C.c_int32),
         ("open_at_end", C.c_int32), ("open_err", C.c_int32), ("overflow", C.c_int32), ("tail_len", C.c_int32), ("tail", C.c_uint8 * 32),
-        ("pad", C.c_int32),
+        ("head_last3", C.c_uint8 * 3), ("pad", C.c_uint8),
     ]
 
 
@@ -83,7 +83,11 @@ MAX_SHARDS = 64
 
 class StitchPatch(C.Structure):
     _fields_ = [("shard", C.c_int32), ("set_start", C.c_int32), ("index", C.c_int64), ("nal_start", C.c_int64), ("rbsp_off", C.c_int64),
-                ("nal_end", C.c_int64), ("rbsp_end", C.c_int64)]
+                ("nal_end", C.c_int64), ("rbsp_end", C.c_int64), ("ends_003", C.c_int32), ("pad", C.c_int32)]
+
+
+class ParseChain(C.Structure):
+    _fields_ = [("sps_in", C.c_void_p), ("pps_in", C.c_void_p), ("sps_out", C.c_void_p), ("pps_out", C.c_void_p), ("buf_size", C.c_int64)]
 
 
 class StitchResult(C.Structure):
@@ -150,6 +154,10 @@ def load_library() -> C.CDLL:
     L.hevcb_insert_host.argtypes = [vp, vp, i64, vp, vp, i64, C.c_int, vp, i64, vp, C.POINTER(InsertSummary)]
     L.hevcb_parse_device.restype = C.c_int
     L.hevcb_parse_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), vp, vp]
+    L.hevcb_parse_shard_device.restype = C.c_int
+    L.hevcb_parse_shard_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), vp, C.POINTER(ParseChain), vp]
+    L.hevcb_ps_context_bytes.restype = C.c_int
+    L.hevcb_ps_context_bytes.argtypes = [C.POINTER(i64), C.POINTER(i64)]
     L.hevcb_index_host.restype = C.c_int
     L.hevcb_index_host.argtypes = [vp, vp, i64, C.POINTER(StreamIndex)]
     L.hevcb_materialize.restype = C.c_int

@@ -428,7 +428,16 @@ HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int
 {
     if (!ctx) { return HEVCB_E_ARG; }
     HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    return hevcb_launch_parse(ctx, d_buf, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, out, d_summary, (cudaStream_t)stream);
+    return hevcb_launch_parse(ctx, d_buf, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, out, d_summary, nullptr, (cudaStream_t)stream);
+}
+
+HEVCB_API int hevcb_parse_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
+                                       const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals, const hevcb_parse_buffers* out,
+                                       hevcb_parse_summary* d_summary, const hevcb_parse_chain* chain, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_parse(ctx, d_buf, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, out, d_summary, chain, (cudaStream_t)stream);
 }
 
 HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx)
@@ -490,7 +499,7 @@ HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size,
     d.pair_field = reinterpret_cast<uint32_t*>(ctx->h_p[7].p);
     d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
     d.cap_pairs = idx->p.cap_pairs;
-    rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, st);
+    rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, nullptr, st);
     if (rc != HEVCB_OK) { return rc; }
     HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
     if (n > 0) {

@@ -83,7 +83,7 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
 
 int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
                        const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
-                       hevcb_parse_summary* d_summary, cudaStream_t stream);
+                       hevcb_parse_summary* d_summary, const hevcb_parse_chain* chain, cudaStream_t stream);
 
 int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,
                         int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream);

@@ -157,9 +157,10 @@ __global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t*
 }
 
 // consumed bytes reported by read_hevc_nal_unit: nal_size, minus one when a trailing 00 00 03 was dropped (h264_nal.c:170-173,197)
-__device__ __forceinline__ int32_t consumed_bytes(const uint8_t* __restrict__ buf, int64_t start, int64_t end)
+__device__ __forceinline__ int32_t consumed_bytes(const uint8_t* __restrict__ buf, int64_t start, int64_t end, int64_t buf_size)
 {
     const int64_t size = end - start;
+    if (end > buf_size) { return (int32_t)size; } // ends in a later shard: corrected by the caller (hevcb_stitch_patch.ends_003)
     if (size >= 3 && buf[end - 1] == 3 && buf[end - 2] == 0 && buf[end - 3] == 0) { return (int32_t)(size - 1); }
     return (int32_t)size;
 }
@@ -167,6 +168,7 @@ __device__ __forceinline__ int32_t consumed_bytes(const uint8_t* __restrict__ bu
 // ---- passes 3/4/6: parse (count or emit) ------------------------------------------------------------------------
 struct ParseArgs {
     const uint8_t* buf;
+    int64_t buf_size;
     const int64_t* nal_start;
     const int64_t* nal_end;
     const uint8_t* rbsp;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
         a.cnt[k] = (int32_t)sink.n;
         a.kind[k] = (uint8_t)r.kind;
         a.ubflag[k] = (uint8_t)(r.flags & 0xFFu);
-        a.rc[k] = r.ok ? consumed_bytes(a.buf, a.nal_start[k], a.nal_end[k]) : -1;
+        a.rc[k] = r.ok ? consumed_bytes(a.buf, a.nal_start[k], a.nal_end[k], a.buf_size) : -1;
         a.hdr_end[k] = kSlices ? r.hdr_end : (int32_t)r.end_bits;
         if (kSlices) {
             a.cols[0 * a.n + k] = r.cols.slice_type;
@@ -477,7 +479,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
 
 int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, const uint8_t* d_rbsp,
                        const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* out,
-                       hevcb_parse_summary* d_summary, cudaStream_t stream)
+                       hevcb_parse_summary* d_summary, const hevcb_parse_chain* chain, cudaStream_t stream)
 {
     if (n < 0 || !out || !d_summary || (n > 0 && (!d_buf || !d_nal_start || !d_nal_end || !d_rbsp || !d_rbsp_off || !d_rbsp_end))) {
         HEVCB_SET_ERR(ctx, "hevcb_parse: invalid argument");
@@ -490,7 +492,14 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     }
     HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_parse_summary), stream));
     ctx->last_parse.n = -1;
-    if (n == 0) { ctx->last_parse.n = 0; return HEVCB_OK; }
+    if (n == 0) {
+        ctx->last_parse.n = 0;
+        if (chain) { // nothing in the shard changes the state
+            if (chain->sps_out) { if (chain->sps_in) { memcpy(chain->sps_out, chain->sps_in, sizeof(hevcb_sps_ctx)); } else { memset(chain->sps_out, 0, sizeof(hevcb_sps_ctx)); } }
+            if (chain->pps_out) { if (chain->pps_in) { memcpy(chain->pps_out, chain->pps_in, sizeof(hevcb_pps_ctx)); } else { memset(chain->pps_out, 0, sizeof(hevcb_pps_ctx)); } }
+        }
+        return HEVCB_OK;
+    }
     const int64_t nb = (n + kScanTile - 1) / kScanTile;
     // scratch: cls (n), cnt (n x4), sps_ord (n x4), pps_ord (n x4), block sums (nb + 1) x3, pair total
     size_t need = 0;
@@ -527,7 +536,10 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     if ((rcx = hevcb_reserve(ctx, &ctx->parse_ps, 2 * sps_bytes + 2 * pps_bytes + 1024)) != HEVCB_OK) { return rcx; }
     uint8_t* pb = reinterpret_cast<uint8_t*>(ctx->parse_ps.p);
     HEVCB_CUDA(ctx, cudaMemsetAsync(pb, 0, 2 * sps_bytes + 2 * pps_bytes, stream));
+    if (chain && chain->sps_in) { HEVCB_CUDA(ctx, cudaMemcpyAsync(pb, chain->sps_in, sizeof(hevcb_sps_ctx), cudaMemcpyHostToDevice, stream)); }
+    if (chain && chain->pps_in) { HEVCB_CUDA(ctx, cudaMemcpyAsync(pb + 2 * sps_bytes, chain->pps_in, sizeof(hevcb_pps_ctx), cudaMemcpyHostToDevice, stream)); }
     ParseArgs a;
+    a.buf_size = (chain && chain->buf_size > 0) ? chain->buf_size : 0x7FFFFFFFFFFFFFFFll;
     a.buf = d_buf; a.nal_start = d_nal_start; a.nal_end = d_nal_end; a.rbsp = d_rbsp; a.rbsp_off = d_rbsp_off; a.rbsp_end = d_rbsp_end;
     a.n = n; a.cls = cls; a.sps_ord = sps_ord; a.pps_ord = pps_ord;
     a.sps_tab = reinterpret_cast<hevcb_sps_ctx*>(pb);
@@ -552,5 +564,17 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     parse_summary_kernel<<<148, 256, 0, stream>>>(cls, out->rc, n, pair_total, out->cap_pairs, d_summary);
     ctx->launches += 2;
     HEVCB_CUDA(ctx, cudaGetLastError());
+    if (chain && (chain->sps_out || chain->pps_out)) { // state after the shard's last SPS / PPS (entry 0 = the entering state)
+        if (chain->sps_out) { HEVCB_CUDA(ctx, cudaMemcpyAsync(chain->sps_out, a.sps_tab + n_sps, sizeof(hevcb_sps_ctx), cudaMemcpyDeviceToHost, stream)); }
+        if (chain->pps_out) { HEVCB_CUDA(ctx, cudaMemcpyAsync(chain->pps_out, a.pps_tab + n_pps, sizeof(hevcb_pps_ctx), cudaMemcpyDeviceToHost, stream)); }
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(stream));
+    }
+    return HEVCB_OK;
+}
+
+extern "C" HEVCB_API int hevcb_ps_context_bytes(int64_t* sps_bytes, int64_t* pps_bytes)
+{
+    if (sps_bytes) { *sps_bytes = (int64_t)sizeof(hevcb_sps_ctx); }
+    if (pps_bytes) { *pps_bytes = (int64_t)sizeof(hevcb_pps_ctx); }
     return HEVCB_OK;
 }

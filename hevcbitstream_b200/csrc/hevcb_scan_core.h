@@ -475,6 +475,10 @@ HEVCB_HD void hevcb_shard_finalize(int64_t own, int64_t N, uint32_t kind, uint32
     const bool closed0 = have0 && (N > 1 || kind != HEVCB_KIND_SC3);
     out->head_end = closed0 ? nal_end[0] : -1;
     out->head_rbsp_end = closed0 ? rbsp_end[0] : -1;
+    for (int i = 0; i < 3; i++) {
+        const int64_t pos = out->head_end - 3 + i;
+        out->head_last3[i] = (closed0 && pos >= 0 && pos < own) ? (uint8_t)fetch(pos) : (uint8_t)0xFF;
+    }
     const bool havel = N > 0 && N <= cap;
     out->last_nal_start = havel ? nal_start[N - 1] : -1;
     out->last_nal_end = (havel && kind != HEVCB_KIND_SC3) ? nal_end[N - 1] : -1;

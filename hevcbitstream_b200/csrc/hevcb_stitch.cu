@@ -72,6 +72,27 @@ extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shard
     auto add_patch = [&](int shard, int64_t index, bool set_start, int64_t ns, int64_t ro, int64_t ne, int64_t re) {
         hevcb_stitch_patch& p = out->patches[out->n_patches++];
         p.shard = shard; p.set_start = set_start ? 1 : 0; p.index = index; p.nal_start = ns; p.rbsp_off = ro; p.nal_end = ne; p.rbsp_end = re;
+        p.ends_003 = 0; p.pad = 0;
+    };
+    // raw byte at a global position close to a shard boundary: the end of a NAL closed in shard q (its last three bytes) or
+    // in the last bytes of the stream; served from the records (head_last3 of q, tail[] of the shards)
+    auto raw_near = [&](int q, int64_t gpos, int64_t gend_in_q) -> int {
+        for (int r = q; r >= 0; r--) {
+            if (sh[r].own <= 0) { continue; }
+            const int64_t b = out->byte_base[r];
+            if (gpos < b) { continue; }
+            const int64_t local = gpos - b;
+            if (r == q && gend_in_q >= 0 && local >= gend_in_q - 3 && local < gend_in_q) { return sh[r].head_last3[local - (gend_in_q - 3)]; }
+            const int64_t tfirst = sh[r].own - sh[r].tail_len;
+            if (local >= tfirst && local < sh[r].own) { return sh[r].tail[local - tfirst]; }
+            return -1;
+        }
+        return -1;
+    };
+    auto ends_003 = [&](int q, int64_t gstart, int64_t gend, int64_t end_local_in_q) -> int {
+        if (gend - gstart < 3) { return 0; }
+        const int b1 = raw_near(q, gend - 1, end_local_in_q), b2 = raw_near(q, gend - 2, end_local_in_q), b3 = raw_near(q, gend - 3, end_local_in_q);
+        return (b1 == 3 && b2 == 0 && b3 == 0) ? 1 : 0;
     };
 
     for (int r = 0; r < n_shards && !stopped; r++) {
@@ -89,6 +110,7 @@ extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shard
                     const bool err = open_err || S.head_rbsp_end < 0;
                     const int64_t cont = err ? 0 : cont_mid + S.head_rbsp_end;
                     add_patch(owner, owner_idx, false, 0, 0, base + S.head_end - out->byte_base[owner], err ? -1 : sh[owner].rbsp_bytes + cont);
+                    out->patches[out->n_patches - 1].ends_003 = ends_003(r, open_start, base + S.head_end, S.head_end);
                     out->cont_last_shard[owner] = err ? -1 : r;
                     out->cont_last_bytes[owner] = err ? 0 : S.head_rbsp_end;
                     out->cont_bytes[owner] = cont;
@@ -158,6 +180,7 @@ extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shard
                 re = sh[owner].rbsp_bytes + cont_mid + re;
             }
             add_patch(owner, owner_idx, false, 0, 0, base + t.nal[0].end - out->byte_base[owner], re);
+            out->patches[out->n_patches - 1].ends_003 = ends_003(last, open_start, base + t.nal[0].end, -1);
         } else {
             add_patch(last, local_next + (i - (t.closes_open ? 1 : 0)), true, t.nal[i].start, t.nal[i].rbsp_off, t.nal[i].end, t.nal[i].rbsp_end);
         }

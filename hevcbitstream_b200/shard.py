@@ -154,3 +154,141 @@ def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw)
     res = stitch(records)
     apply_patches_device(ctx, res, rank, sc)
     return sc, res
+
+
+# ---- sharded header parse: parameter-set hand-over between ranks -------------------------------------------------------
+HEAD_BYTES = 65536  # bytes of every shard's image that are all-gathered so that a NAL crossing into the next shard can be parsed
+
+
+def ps_context_bytes():
+    from ._lib import load_library
+    a, b = C.c_int64(0), C.c_int64(0)
+    load_library().hevcb_ps_context_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def _parse_call(ctx, buf, ns, ne, rbsp, ro, re, n, cap_pairs, chain):
+    """hevcb_parse_shard_device on already sliced device arrays; returns the dict api.Context.parse_device returns."""
+    import torch
+
+    from ._lib import ParseBuffers
+
+    dev = buf.device
+    m = max(n, 1)
+    out = dict(rc=torch.empty(m, dtype=torch.int32, device=dev), nal_hdr=torch.empty(m, dtype=torch.int32, device=dev),
+               kind=torch.empty(m, dtype=torch.uint8, device=dev), ubflag=torch.empty(m, dtype=torch.uint8, device=dev),
+               hdr_end=torch.empty(m, dtype=torch.int32, device=dev), cols=torch.empty((8, m), dtype=torch.int32, device=dev),
+               pair_off=torch.empty(n + 1, dtype=torch.int64, device=dev), pair_field=torch.empty(cap_pairs, dtype=torch.int32, device=dev),
+               pair_value=torch.empty(cap_pairs, dtype=torch.int32, device=dev), summary=torch.zeros(8, dtype=torch.int64, device=dev))
+    pb = ParseBuffers(out["rc"].data_ptr(), out["nal_hdr"].data_ptr(), out["kind"].data_ptr(), out["ubflag"].data_ptr(), out["hdr_end"].data_ptr(),
+                      out["cols"].data_ptr(), out["pair_off"].data_ptr(), out["pair_field"].data_ptr(), out["pair_value"].data_ptr(), cap_pairs)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ctx._check(ctx._L.hevcb_parse_shard_device(ctx._h, buf.data_ptr(), ns.data_ptr(), ne.data_ptr(), rbsp.data_ptr(), ro.data_ptr(), re.data_ptr(), n,
+                                               C.byref(pb), out["summary"].data_ptr(), C.byref(chain), stream))
+    s = out["summary"].cpu().numpy()
+    out["n"], out["cap_pairs"] = n, cap_pairs
+    out["n_ok"], out["n_pairs"], out["n_vps"], out["n_sps"], out["n_pps"], out["n_slices"] = (int(x) for x in s[1:7])
+    if int(s[7]) & 0xFFFFFFFF:
+        raise HevcbError(-104, f"{out['n_pairs']} syntax elements exceed cap_pairs {cap_pairs}")
+    return out
+
+
+def append_continuation(sc: ShardScan, res: StitchResult, rank: int, heads):
+    """Copies the continuation of this shard's last NAL (it ends in a later shard) behind the shard's image.
+    heads[q]: the first HEAD_BYTES image bytes of shard q.  Returns the number of bytes appended."""
+    q = int(res.cont_last_shard[rank])
+    if q < 0:
+        return 0
+    total = int(res.cont_bytes[rank])
+    last = int(res.cont_last_bytes[rank])
+    if total != last:
+        raise HevcbError(-102, "a NAL that spans whole shards cannot be parsed from the all-gathered heads")
+    take = min(last, int(heads[q].numel()))
+    base = int(sc.record.rbsp_bytes)
+    assert sc.rbsp.numel() >= base + take + 16, "scan_strip_shard(extra_rbsp=HEAD_BYTES) is required for the sharded parse"
+    sc.rbsp[base: base + take] = heads[q][:take]
+    return take
+
+
+def local_ps_contexts(ctx, buf, sc: ShardScan, first: int, n: int):
+    """State after this shard's last SPS / PPS NAL: (has_sps, sps_blob, has_pps, pps_blob) as numpy uint8 arrays."""
+    import torch
+
+    from ._lib import ParseChain
+
+    sps_b, pps_b = ps_context_bytes()
+    sps = np.zeros(sps_b, np.uint8)
+    pps = np.zeros(pps_b, np.uint8)
+    has = [0, 0]
+    if n > 0:
+        ns = sc.nal_start[first: first + n]
+        ok = sc.rbsp_end[first: first + n] >= 0
+        types = (buf[ns].to(torch.int32) >> 1) & 0x3F
+        for slot, (t, blob) in enumerate(((33, sps), (34, pps))):
+            idx = torch.nonzero((types == t) & ok).flatten()
+            if idx.numel() == 0:
+                continue
+            k = first + int(idx[-1])
+            chain = ParseChain(None, None, blob.ctypes.data if slot == 0 else None, blob.ctypes.data if slot == 1 else None, 0)
+            _parse_call(ctx, buf, sc.nal_start[k:k + 1], sc.nal_end[k:k + 1], sc.rbsp, sc.rbsp_off[k:k + 1], sc.rbsp_end[k:k + 1], 1, 1 << 16, chain)
+            has[slot] = 1
+    return has[0], sps, has[1], pps
+
+
+def pick_incoming(states, rank: int):
+    """states[r] = (has_sps, sps_blob, has_pps, pps_blob) of every rank; returns the (sps, pps) blobs entering `rank` (None = zero state)."""
+    sps = pps = None
+    for r in range(rank - 1, -1, -1):
+        if sps is None and states[r][0]:
+            sps = states[r][1]
+        if pps is None and states[r][2]:
+            pps = states[r][3]
+    return sps, pps
+
+
+def parse_shard(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResult, rank: int, sps_in, pps_in, cap_pairs=None):
+    """Header parse of the NALs this shard owns, with the parameter-set state that enters it."""
+    import torch
+
+    from ._lib import ParseChain
+
+    f, n = int(res.first_local[rank]), int(res.n_owned[rank])
+    if cap_pairs is None:
+        cap_pairs = 80 * n + 4096
+    chain = ParseChain(sps_in.ctypes.data if sps_in is not None else None, pps_in.ctypes.data if pps_in is not None else None, None, None, own + halo)
+    out = _parse_call(ctx, buf, sc.nal_start[f: f + n], sc.nal_end[f: f + n], sc.rbsp, sc.rbsp_off[f: f + n], sc.rbsp_end[f: f + n], n, cap_pairs, chain)
+    # read_hevc_nal_unit reports one byte less for a NAL that ends in 00 00 03; for a NAL that ends in a later shard only the
+    # stitch has seen those bytes
+    for p in patches_for(res, rank):
+        k = int(p.index) - f
+        if p.ends_003 and 0 <= k < n and int(p.nal_end) > own + halo and int(out["rc"][k]) >= 0:
+            out["rc"][k] -= 1
+    return out
+
+
+def parse_sharded(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResult, group=None, cap_pairs=None):
+    """The distributed header parse (after scan_strip_sharded with extra_rbsp=HEAD_BYTES): all_gather of the image heads (a NAL
+    that crosses into the next shard) and of each rank's last SPS / PPS state (~9 KB), then a local parse."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = buf.device
+    head = torch.zeros(HEAD_BYTES, dtype=torch.uint8, device=dev)
+    nb = min(HEAD_BYTES, int(sc.record.rbsp_bytes))
+    head[:nb] = sc.rbsp[:nb]
+    heads = [torch.empty_like(head) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    append_continuation(sc, res, rank, heads)
+    f, n = int(res.first_local[rank]), int(res.n_owned[rank])
+    hs_, sps, hp_, pps = local_ps_contexts(ctx, buf, sc, f, n)
+    blob = torch.from_numpy(np.concatenate([np.array([hs_, hp_], np.uint8), sps, pps])).to(dev)
+    blobs = [torch.empty_like(blob) for _ in range(world)]
+    dist.all_gather(blobs, blob, group=group)
+    sps_b, _ = ps_context_bytes()
+    states = []
+    for b in blobs:
+        h = b.cpu().numpy()
+        states.append((int(h[0]), h[2: 2 + sps_b].copy(), int(h[1]), h[2 + sps_b:].copy()))
+    sps_in, pps_in = pick_incoming(states, rank)
+    return parse_shard(ctx, buf, own, halo, sc, res, rank, sps_in, pps_in, cap_pairs)

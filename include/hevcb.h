@@ -135,7 +135,8 @@ typedef struct hevcb_shard_summary {
     int32_t overflow;       /* n_nals > cap_nals */
     int32_t tail_len;       /* the last min(32, own) bytes of the shard: the last shard's end-of-stream rules are */
     uint8_t tail[32];       /* applied to them by hevcb_stitch (h264_nal.c:46-72 at the end of the buffer) */
-    int32_t pad;
+    uint8_t head_last3[3];  /* the three bytes in front of head_end (0xFF where they lie before the shard) */
+    uint8_t pad;
 } hevcb_shard_summary;
 
 /* Scan + strip of one shard.  d_buf holds own + halo bytes (halo: the bytes that follow the shard in the stream, 3..16;
@@ -159,6 +160,8 @@ typedef struct hevcb_stitch_patch { /* overwrite entry `index` of shard `shard`'
     int64_t nal_start, rbsp_off;
     int64_t nal_end;   /* may exceed the shard's own size: the NAL ends in a later shard */
     int64_t rbsp_end;  /* -1, or the end in the shard's image extended by the continuation bytes (cont_bytes) */
+    int32_t ends_003;  /* the NAL's last three bytes are 00 00 03: read_hevc_nal_unit reports one byte less (h264_nal.c:170) */
+    int32_t pad;
 } hevcb_stitch_patch;
 
 typedef struct hevcb_stitch_result {
@@ -264,6 +267,24 @@ typedef struct hevcb_parse_summary {
 HEVCB_API int hevcb_parse_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end,
                                  const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
                                  const hevcb_parse_buffers* out, hevcb_parse_summary* d_summary, void* stream);
+
+/* Parsing a shard of a stream (byte-range sharding): slices at the start of a shard depend on the last SPS / PPS
+ * NAL of an EARLIER shard.  That state travels as two opaque blobs (hevcb_ps_context_bytes: the handful of SPS / PPS fields
+ * slices need + the derived RPS tables that are file-static in the reference, hevc_stream.in.c:26-32; ~9 KB + 80 B) which
+ * the ranks exchange with one all_gather.  All pointers of the chain are HOST pointers. */
+typedef struct hevcb_parse_chain {
+    const void* sps_in; /* state entering the shard; NULL = the zeroed state of hevc_new() */
+    const void* pps_in;
+    void* sps_out;      /* state after the shard's last SPS / PPS NAL (= the entering state when it has none); may be NULL */
+    void* pps_out;
+    int64_t buf_size;   /* bytes readable at d_buf (owned + halo).  A NAL that ends beyond it gets rc = its size; the caller
+                           corrects it with hevcb_stitch_patch.ends_003 */
+} hevcb_parse_chain;
+HEVCB_API int hevcb_ps_context_bytes(int64_t* sps_bytes, int64_t* pps_bytes);
+HEVCB_API int hevcb_parse_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end,
+                                       const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
+                                       const hevcb_parse_buffers* out, hevcb_parse_summary* d_summary, const hevcb_parse_chain* chain,
+                                       void* stream);
 
 /* ---- header rewrite ------------------------------------------------------------------------------
  *

@@ -95,3 +95,71 @@ def test_apply_patches_device_matches_host_patching(ctx):
         n = int(res.first_local[r] + res.n_owned[r])
         for h, t in zip(host, (sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)):
             assert np.array_equal(h[:n], t.cpu().numpy()[:n])
+
+
+def _pairs(p, k):
+    a, b = int(p["pair_off"][k]), int(p["pair_off"][k + 1])
+    return p["pair_field"][a:b], p["pair_value"][a:b]
+
+
+@pytest.mark.parametrize("n_shards", [2, 5])
+def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards):
+    """parameter-set hand-over: every shard parses the NALs it owns with the last SPS / PPS state of the earlier shards and the
+    continuation of its last NAL; rc, NAL header, kind, header end and every syntax element must equal the unsharded parse
+    (which the other tests pin against the reference)"""
+    import torch
+
+    from hevcbitstream_b200 import shard as hs
+
+    s = ref.gen_stream(seed=8, profile=1, n_slices=6000, payload_min=1, payload_max=900, zero_heavy_pct=20, extra_zero_pct=10, ps_period=300,
+                       unsupported_pct=3)
+    size = s.size - ref.PAD
+    d = torch.zeros(size + 32, dtype=torch.uint8, device="cuda")
+    d[:size] = torch.from_numpy(s[:size].copy())
+    whole = ctx.scan_strip_device(d, size=size)
+    pw = ctx.parse_device(d, whole)
+    pw = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in pw.items()}
+    bounds = hs.plan_shards(s, n_shards, size)
+    bufs, scans = [], []
+    for r in range(n_shards):
+        own, halo, first, last = hs.shard_flags(bounds, r)
+        lo = int(bounds[r])
+        b = torch.zeros(own + halo + 32, dtype=torch.uint8, device="cuda")
+        b[: own + halo] = torch.from_numpy(s[lo: lo + own + halo].copy())
+        bufs.append(b)
+        scans.append(hs.scan_strip_shard(ctx, b, own, halo, first, last, extra_rbsp=hs.HEAD_BYTES))
+    res = hs.stitch([sc.record for sc in scans])
+    heads = []
+    for r, sc in enumerate(scans):
+        hs.apply_patches_device(ctx, res, r, sc)
+        h = torch.zeros(hs.HEAD_BYTES, dtype=torch.uint8, device="cuda")
+        nb = min(hs.HEAD_BYTES, int(sc.record.rbsp_bytes))
+        h[:nb] = sc.rbsp[:nb]
+        heads.append(h)
+    states = []
+    for r, sc in enumerate(scans):
+        hs.append_continuation(sc, res, r, heads)
+        states.append(hs.local_ps_contexts(ctx, bufs[r], sc, int(res.first_local[r]), int(res.n_owned[r])))
+    g = 0
+    crossing = 0
+    for r, sc in enumerate(scans):
+        own, halo, first, last = hs.shard_flags(bounds, r)
+        sps_in, pps_in = hs.pick_incoming(states, r)
+        ps = hs.parse_shard(ctx, bufs[r], own, halo, sc, res, r, sps_in, pps_in)
+        n = int(res.n_owned[r])
+        ps = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in ps.items()}
+        crossing += int(res.cont_last_shard[r] >= 0)
+        assert np.array_equal(ps["rc"][:n], pw["rc"][g:g + n]), f"rc differs in shard {r}"
+        assert np.array_equal(ps["nal_hdr"][:n], pw["nal_hdr"][g:g + n])
+        assert np.array_equal(ps["kind"][:n], pw["kind"][g:g + n])
+        sl = ps["kind"][:n] == 4
+        assert np.array_equal(ps["hdr_end"][:n][sl], pw["hdr_end"][g:g + n][sl])
+        cnt_s = np.diff(ps["pair_off"][: n + 1])
+        cnt_w = np.diff(pw["pair_off"][g: g + n + 1])
+        assert np.array_equal(cnt_s, cnt_w), f"element counts differ in shard {r}"
+        a0, a1 = int(pw["pair_off"][g]), int(pw["pair_off"][g + n])
+        assert np.array_equal(ps["pair_field"][: a1 - a0], pw["pair_field"][a0:a1])
+        assert np.array_equal(ps["pair_value"][: a1 - a0], pw["pair_value"][a0:a1]), f"values differ in shard {r}"
+        g += n
+    assert g == whole.n_nals
+    assert crossing >= n_shards - 1
