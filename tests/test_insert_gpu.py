@@ -142,3 +142,26 @@ def test_capacity_overflow_is_reported(ctx):
 def test_empty_batch(ctx):
     out, out_off, n_ins = ctx.insert_host(np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int64), start_code_len=4)
     assert out.size == 0 and out_off.tolist() == [0] and n_ins == 0
+
+
+def test_full_size_strip_insert_round_trip(ctx):
+    """BASELINE config-1 size (4 GiB, 16 KiB NALs, built like bench.py builds it): insert(strip(x)) re-creates x byte for byte,
+    n_epb == n_inserted, every NAL found -- the size-independent properties at the full benchmark size"""
+    import torch
+
+    import bench
+
+    unit = bench.make_unit(16384, 64 << 20, 99, False)
+    reps = (4 << 30) // unit.size
+    d = torch.from_numpy(unit).cuda().repeat(reps)
+    size = d.numel()
+    d = torch.cat([d, torch.zeros(32, dtype=torch.uint8, device="cuda")])
+    res = ctx.scan_strip_device(d, size=size, cap_nals=size // 8192 + 65536)
+    n = res.n_nals
+    assert n == reps * (unit.size // 16384 if unit.size % 16384 == 0 else n // reps)
+    assert res.rbsp_bytes == size - res.n_epb and res.last_rc == -1
+    assert bool((res.rbsp_end[:n] >= 0).all())
+    ins = ctx.insert_device(res.rbsp, res.rbsp_off[:n].contiguous(), res.rbsp_end[:n].contiguous(), n_nals=n, start_code_len=3,
+                            out_cap=size + size // 64 + 4096)
+    assert ins["out_bytes"] == size and ins["n_inserted"] == res.n_epb
+    assert torch.equal(ins["out"][:size], d[:size])
