@@ -64,6 +64,7 @@ HEVCB_API int hevcb_create(int device, hevcb_ctx** out)
         delete ctx;
         return HEVCB_E_CUDA;
     }
+    cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming);
     if (const char* e2 = getenv("HEVCB_SCAN_DEBUG")) { ctx->scan_debug_flags = atoll(e2); } // kernel experiment switches
     if (const char* e3 = getenv("HEVCB_HOST_CHUNK")) { const long long v = atoll(e3); if (v >= 4096) { ctx->host_chunk = v; } }
     *out = ctx;
@@ -90,6 +91,7 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
         if (ctx->ev_fix[i]) { cudaEventDestroy(ctx->ev_fix[i]); }
         if (ctx->ev_out[i]) { cudaEventDestroy(ctx->ev_out[i]); }
     }
+    if (ctx->ev_stats) { cudaEventDestroy(ctx->ev_stats); }
     if (ctx->pinned_sums) { cudaFreeHost(ctx->pinned_sums); }
     if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); }
     if (ctx->s_out) { cudaStreamDestroy(ctx->s_out); }

@@ -41,6 +41,9 @@ struct hevcb_ctx {
     void* pinned_sums = nullptr;   // HEVCB_MAX_SHARDS shard records
     int64_t host_chunk = 64ll << 20; // bytes per shard of the pipelined host path (HEVCB_HOST_CHUNK); 64 MiB measured best
     int scan_blocks_per_sm = 0;
+    cudaEvent_t ev_stats = nullptr; // scan kernel: heavy-tile count of the last launch has arrived in the pinned block
+    bool stats_pending = false;
+    double last_heavy_frac = 0.0;
     long long scan_debug_flags = 0; // experiment switches of the scan kernel (HEVCB_SCAN_DEBUG); 0 in production
 };
 

@@ -205,7 +205,8 @@ struct ScanHeader {
     unsigned long long tiles_written; // writer progress (analysers stay within a window of it so that a tile's second load hits L2)
     long long first_empty;
     ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
-    unsigned long long pad[4];
+    unsigned long long heavy_tiles; // tiles the writers had to analyse themselves (feeds the role split of the next launch)
+    unsigned long long pad[3];
 };
 
 // ordered-carry resolution inside a warp: lane l receives the (kind, err) state produced by lanes < l.
@@ -537,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             int s = 0;
             uint32_t done_bits = 0;
             long long seen_written = 0;
+            unsigned long long heavy_local = 0;
             for (long long t = first_tile; t < n_tiles; t += G) {
                 while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
                 done_bits ^= (1u << s);
@@ -558,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     sm.evcount[s] = 0;
                     const bool light = (adel == 0u) && (nrec <= kEvCap) && (tile_k == (uint32_t)kTileBytes) && !(dbg & 1024u);
                     st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
+                    if (!light && mask != 0ull) { heavy_local++; }
                     const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
                     if (nt < n_tiles) {
                         // stay within `window` tiles of the writers: what they load a second time is then still in L2
@@ -574,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 __syncwarp();
                 s = (s + 1 == kStages) ? 0 : s + 1;
             }
+            if (lane == 0 && heavy_local) { atomicAdd(&hdr->heavy_tiles, heavy_local); }
             return;
         }
         // workers: wait for the tile, analyse their rows, hand the warp aggregate to the control warp; they never wait for
@@ -733,13 +737,17 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         // ---- tile with flagged rows: exact masks of those rows, warp aggregates, ordered emission, row-wise write-out
         fix_stage(st, t, t0, size, tid);
         const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kRowsPerWarp)) & 0xFFu;
-        // pass 1: aggregates of this warp's flagged rows
+        // pass 1: aggregates of this warp's flagged rows; their masks are parked (thread-local memory) for pass 2
         uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, anyD = 0;
+        uint32_t k_evsc[kRowsPerWarp], k_deler[kRowsPerWarp], k_misc[kRowsPerWarp], k_flags = 0;
 #pragma unroll 1
         for (int i = 0; i < kRowsPerWarp; i++) {
             if (!((myrows >> i) & 1u)) { wK += kRowBytes; continue; }
             const RowMasks m = analyze_staged_row(st, warp * kRowsPerWarp + i, lane, t0, geom, wN, wK, wKind, wErr);
             anyD |= (m.Db != 0u) ? 1u : 0u;
+            k_evsc[i] = m.evsc; k_deler[i] = m.deler; k_misc[i] = m.misc;
+            k_flags |= ((m.Xb != 0u) ? 1u : 0u) << i;
+            k_flags |= ((m.Db != 0u) ? 1u : 0u) << (8 + i);
         }
         if (lane == 0) {
             WarpAgg a;
@@ -777,14 +785,12 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     rK += kRowBytes;
                     continue;
                 }
-                uint32_t dN = 0, dK = 0, dKind = HEVCB_KIND_PASS, dErr = 0;
-                const RowMasks m = analyze_staged_row(st, r, lane, t0, geom, dN, dK, dKind, dErr);
-                const bool rowX = m.Xb != 0u, rowD = m.Db != 0u;
+                const bool rowX = ((k_flags >> i) & 1u) != 0u, rowD = ((k_flags >> (8 + i)) & 1u) != 0u;
                 if (!rowD) {
                     if (dirty_out) { copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane); }
                     if (!rowX) { rK += kRowBytes; continue; } // nothing to emit
                 }
-                const uint32_t evsc = m.evsc, deler = m.deler, misc = m.misc;
+                const uint32_t evsc = k_evsc[i], deler = k_deler[i], misc = k_misc[i];
                 const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16, valid = misc & 0xFFFFu;
                 const uint32_t keep = valid & ~del;
                 uint32_t klane, rowKept;
@@ -941,6 +947,7 @@ __global__ void hevcb_scan_init_kernel(ScanHeader* hdr, uint32_t init_n, int64_t
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         hdr->tiles_written = 0ull;
+        hdr->heavy_tiles = 0ull;
         hdr->first_empty = 0x7FFFFFFFFFFFFFFFll;
         if (init_n && cap_nals > 0) { nal_start[0] = 0; rbsp_off[0] = 0; } // the NAL piece that enters the shard
     }
@@ -1006,7 +1013,15 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
         if (grid > 2 * n_tiles) { grid = 2 * n_tiles; }
         if (grid < 2) { grid = 2; }
-        long long n_an = (grid * 3 + 2) / 5; // analyser CTAs (the rest are writers): measured optimum for streams of NALs >= 4 KiB
+        // analyser CTAs (the rest are writers): 60 % is the measured optimum when the writers mostly copy (NALs >= 4 KiB); when
+        // the previous launch on this context found that the writers had to analyse most tiles themselves (tiny NALs,
+        // EPB-dense payloads) they get the larger share.  Results do not depend on the split.
+        if (ctx->ev_stats && ctx->stats_pending && cudaEventQuery(ctx->ev_stats) == cudaSuccess) {
+            const unsigned long long* st = reinterpret_cast<const unsigned long long*>(ctx->pinned) + 64;
+            ctx->last_heavy_frac = st[1] ? (double)st[0] / (double)st[1] : 0.0;
+            ctx->stats_pending = false;
+        }
+        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 7 + 10) / 20 : (grid * 3 + 2) / 5;
         if (n_an < 1) { n_an = 1; }
         if (n_an > grid - 1) { n_an = grid - 1; }
         if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
@@ -1025,6 +1040,13 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
                                                                                  d_rbsp_off, d_rbsp_end);
         ctx->launches += 2;
         HEVCB_CUDA(ctx, cudaGetLastError());
+        if (ctx->ev_stats && !ctx->stats_pending) { // heavy-tile count of this launch, read back without ever waiting for it
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(ctx->pinned) + 64;
+            st[1] = (unsigned long long)n_tiles;
+            HEVCB_CUDA(ctx, cudaMemcpyAsync(&st[0], &hdr->heavy_tiles, 8, cudaMemcpyDeviceToHost, stream));
+            HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_stats, stream));
+            ctx->stats_pending = true;
+        }
     }
     *hdr_out = hdr;
     *n_tiles_out = n_tiles;
