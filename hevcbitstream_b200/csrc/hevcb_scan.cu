@@ -1,22 +1,29 @@
 // hevcb_scan.cu -- fused Annex-B start-code scan + emulation-prevention strip for sm_100a.
 //
 // Replaces the reference's per-NAL loop  find_nal_unit (h264_nal.c:38-76) -> nal_to_rbsp
-// (h264_nal.c:147-200, called at hevc_stream.c:165)  by ONE pass over the byte range:
+// (h264_nal.c:147-200, called at hevc_stream.c:165)  by one pass over the byte range (a whole stream, or one shard of a
+// byte-range partition, see ScanGeom):
 //
-//   * persistent CTAs (cooperative launch: all co-resident) walk 32 KiB tiles round-robin, tile t -> CTA t mod grid,
-//     so that the predecessor tiles of a tile are always being processed at the same time by the neighbouring CTAs;
-//   * each tile (+16 B halo on either side) is staged into shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier), double buffered so the next tile is in flight while this one is processed;
-//   * every lane owns 16 bytes: a conservative "two adjacent zero bytes?" SWAR test sends the common
-//     case down a fast path, exact predicate bit-masks (hevcb_chunk_analyze) are built otherwise;
-//   * counts (start codes, kept bytes) and the ordered (last-event-kind, error) carry are combined with
-//     warp ballots / redux at lane -> row -> tile level and across tiles with a single-pass decoupled
-//     look-back over a 16-byte tile-state word;
-//   * NAL offsets are written by the lanes that own the events (ordered compaction), the EPB-free image
-//     is written as an aligned, funnel-shifted 16-byte-vector copy out of shared memory.
+//   * a persistent cooperative grid (2 CTAs / SM) is split into ANALYSER and WRITER CTAs plus one SCANNER warp; the
+//     dependency analyser -> scanner -> writer is one-directional (see the comment in front of the kernel);
+//   * 32 KiB tiles (+128 B leading / 16 B trailing halo) are staged into shared memory with TMA bulk copies
+//     (cp.async.bulk + mbarrier), three stages per CTA; a tile is loaded by one analyser and, a few microseconds later,
+//     by one writer -- out of L2, the analysers stay within a window of the writers' progress;
+//   * every lane owns 16 bytes: an exact "two adjacent zero bytes?" SWAR test sends the common case down a fast path,
+//     exact predicate bit masks (hevcb_chunk_analyze) are built otherwise;
+//   * counts (start codes, kept bytes) go through redux, the ordered (last-event-kind, error) carry through warp ballots,
+//     lane -> row -> warp -> tile; across tiles one warp scans the 16-byte tile aggregates in stream order;
+//   * the EPB-free image is written as aligned 16-byte vectors, funnel-shifted by the tile-uniform misalignment; NAL
+//     offsets are written by the lanes that own the events (hevcb_scan_emit_kernel for tiles handed over as event
+//     records, the writer itself for tiles with removed bytes or very many events).
 //
-// HBM traffic: input read once, image written once, 32 B of metadata per NAL.  Tensor cores unused:
+// HBM traffic: input read once (second load from L2), image written once, 32 B of metadata per NAL.  Tensor cores unused:
 // nothing here is a contraction.
+//
+// HEVCB_SCAN_DEBUG (context creation) is a bit mask of measurement switches used to attribute time to the parts of the
+// kernel (results are wrong with any of them set): 1 no scanner / fake prefixes, 4 no image write, 32 writers off,
+// 64 analysis off (bits 8..15: rows to flag), 128 writers do not wait for the scanner, 512 every tile takes the clean
+// path, 1024 no event records.  HEVCB_SCAN_ANALYSERS / HEVCB_SCAN_WINDOW override the role split and the L2 window.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -45,7 +52,7 @@ constexpr int kStageBytes = kLead + kTileBytes + 16;
 #ifndef HEVCB_SCAN_STAGES
 #define HEVCB_SCAN_STAGES 3
 #endif
-constexpr int kStages = HEVCB_SCAN_STAGES;       // tile i-1 being written out, tile i being analysed, tile i+1 in flight
+constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memory (one being worked on, the others in flight)
 constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
@@ -162,8 +169,8 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// named barriers: 0 is __syncthreads; kBarWork = the worker warps only; kBarS1 / kBarE = workers + look-back warp
-constexpr int kBarWork = 1, kBarS1 = 2, kBarE = 3, kBarP = 4;
+// named barriers: 0 is __syncthreads; kBarWork = the worker warps only; kBarE / kBarP = workers + control warp (writer role)
+constexpr int kBarWork = 1, kBarE = 3, kBarP = 4;
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
