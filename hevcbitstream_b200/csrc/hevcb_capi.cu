@@ -444,6 +444,11 @@ HEVCB_API int hevcb_parse_shard_device(hevcb_ctx* ctx, const uint8_t* d_buf, con
 
 HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx)
 {
+    return hevcb_index_host_chain(ctx, buf, size, idx, nullptr);
+}
+
+HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx, const hevcb_parse_chain* chain)
+{
     if (!ctx || !idx || size < 0 || (size > 0 && !buf) || idx->cap_nals < 0 || !idx->nal_start || !idx->nal_end || !idx->rbsp_off || !idx->rbsp_end ||
         !idx->p.rc || !idx->p.nal_hdr || !idx->p.kind || !idx->p.ubflag || !idx->p.hdr_end || !idx->p.cols || !idx->p.pair_off) {
         HEVCB_SET_ERR(ctx, "hevcb_index_host: invalid argument");
@@ -501,7 +506,7 @@ HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size,
     d.pair_field = reinterpret_cast<uint32_t*>(ctx->h_p[7].p);
     d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
     d.cap_pairs = idx->p.cap_pairs;
-    rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, nullptr, st);
+    rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, chain, st);
     if (rc != HEVCB_OK) { return rc; }
     HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
     if (n > 0) {

@@ -349,6 +349,10 @@ typedef struct hevcb_stream_index {
 /* Annex-B bytes in host memory -> complete index (scan + strip + parse on the device, results copied back). */
 HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx);
 
+/* Same, continuing from / handing on the parameter-set state of an earlier call (hevcb_parse_chain, all host pointers):
+ * what lets a caller feed a stream piece by piece, like the reference's one-NAL-at-a-time read_hevc_nal_unit. */
+HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx, const hevcb_parse_chain* chain);
+
 /* Applies NAL k of an index to caller-owned structs the way read_hevc_nal_unit updates hevc_stream_t: h->nal always
  * (unless nal_to_rbsp failed), and the struct selected by kind[k] is zeroed and refilled.  The struct pointers are the
  * reference-layout types of hevcb_layout.h passed as void* (any of them may be NULL).  Calling it for k = 0, 1, 2, ...

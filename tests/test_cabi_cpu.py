@@ -46,3 +46,27 @@ def test_layout_header_compiles_as_c():
     exe = p[:-2]
     subprocess.check_call(["gcc", "-std=gnu99", "-Wall", "-I" + ROOT, "-o", exe, p])
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_compat_library_exports_the_reference_api_and_fails_loudly_without_a_device():
+    """include/hevcb_compat.h: the reference's own function names; without a GPU hevc_new() returns NULL (no CPU fallback)"""
+    import ctypes as C
+
+    import torch
+
+    path = os.path.join(ROOT, "hevcbitstream_b200", "libhevcb200_compat.so")
+    hb.load_library()
+    L = C.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "hevcb_compat.h")).read()
+    names = re.findall(r"HEVCB_COMPAT_API\s+[\w\s\*]+?\b(\w+)\s*\(", hdr)
+    assert set(names) == {"hevc_new", "hevc_free", "find_nal_unit", "nal_to_rbsp", "rbsp_to_nal", "read_hevc_nal_unit", "peek_hevc_nal_unit"}
+    for name in names:
+        assert getattr(L, name) is not None, name
+    out = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+    assert "libhevcb200.so" in out and "hevcref" not in out
+    if not torch.cuda.is_available():
+        L.hevc_new.restype = C.c_void_p
+        assert L.hevc_new() is None
+        s, e = C.c_int(0), C.c_int(0)
+        buf = (C.c_uint8 * 16)(0, 0, 1, 0x40, 1, 2, 3)
+        assert L.find_nal_unit(buf, 7, C.byref(s), C.byref(e)) == -1
