@@ -76,7 +76,7 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
     hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
-                            &ctx->insert_scratch, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
+                            &ctx->insert_scratch, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->wstruct, &ctx->parse_scratch, &ctx->parse_ps, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
                             &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
@@ -367,6 +367,60 @@ HEVCB_API int hevcb_rewrite_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t
     HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
     return hevcb_launch_rewrite(ctx, d_buf, size, d_nal_start, d_nal_end, d_rbsp, d_rbsp_off, d_rbsp_end, n_nals, parsed, edits, d_out, out_cap,
                                 d_out_start, d_out_end, d_summary, (cudaStream_t)stream);
+}
+
+HEVCB_API int hevcb_write_nal_host(hevcb_ctx* ctx, int nal_unit_type, int nal_layer_id, int nal_temporal_id_plus1, const void* vps, const void* sps,
+                                   const void* pps, const void* sh, uint8_t* nal_out, int64_t size, int64_t* nal_bytes)
+{
+    if (!ctx || !vps || !sps || !pps || !sh || !nal_out || !nal_bytes || size < 0) {
+        HEVCB_SET_ERR(ctx, "hevcb_write_nal_host: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *nal_bytes = -1;
+    const bool slice = (nal_unit_type >= 0 && nal_unit_type <= 9) || (nal_unit_type >= 16 && nal_unit_type <= 21);
+    if (!slice && nal_unit_type != 32 && nal_unit_type != 33 && nal_unit_type != 34) { return HEVCB_OK; } // default: return -1 (hevc_stream.c:1313)
+    cudaStream_t st = ctx->stream;
+    const int64_t rcap = size * 3 / 4; // hevc_stream.c:1266
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_vps = 0, o_sps = o_vps + up(sizeof(hevc_vps_t)), o_pps = o_sps + up(sizeof(hevc_sps_t)), o_sh = o_pps + up(sizeof(hevc_pps_t));
+    const size_t o_ctx = o_sh + up(sizeof(hevc_slice_header_t)), o_res = o_ctx + up(hevcb_write_struct_scratch_bytes()), o_off = o_res + 256;
+    const size_t o_rbsp = o_off + 256, o_nal = o_rbsp + up((size_t)rcap + 64), total = o_nal + up((size_t)rcap * 3 / 2 + 128);
+    int rc = hevcb_reserve(ctx, &ctx->wstruct, total);
+    if (rc != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_misc, 256)) != HEVCB_OK) { return rc; }
+    uint8_t* b = reinterpret_cast<uint8_t*>(ctx->wstruct.p);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(b + o_vps, vps, sizeof(hevc_vps_t), cudaMemcpyHostToDevice, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(b + o_sps, sps, sizeof(hevc_sps_t), cudaMemcpyHostToDevice, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(b + o_pps, pps, sizeof(hevc_pps_t), cudaMemcpyHostToDevice, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(b + o_sh, sh, sizeof(hevc_slice_header_t), cudaMemcpyHostToDevice, st));
+    HEVCB_CUDA(ctx, cudaMemsetAsync(b + o_rbsp, 0, (size_t)rcap + 64, st)); // the reference writes into a calloc'ed buffer
+    const int32_t hdr = (nal_unit_type & 0xFF) | ((nal_layer_id & 0xFF) << 8) | ((nal_temporal_id_plus1 & 0xFF) << 16);
+    int64_t* d_res = reinterpret_cast<int64_t*>(b + o_res);
+    rc = hevcb_launch_write_struct(ctx, hdr, reinterpret_cast<const int32_t*>(b + o_vps), reinterpret_cast<const int32_t*>(b + o_sps),
+                                   reinterpret_cast<const int32_t*>(b + o_pps), reinterpret_cast<const int32_t*>(b + o_sh), b + o_ctx, b + o_rbsp, rcap, d_res,
+                                   st);
+    if (rc != HEVCB_OK) { return rc; }
+    int64_t* p_res = reinterpret_cast<int64_t*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 1024);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_res, d_res, 16, cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!p_res[1]) { return HEVCB_OK; } // overrun: -1 (hevc_stream.c:1317)
+    // rbsp_to_nal of what was written (hevc_stream.c:1324-1326)
+    int64_t* d_off = reinterpret_cast<int64_t*>(b + o_off);
+    const int64_t seg[2] = {0, p_res[0]};
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(d_off, seg, 16, cudaMemcpyHostToDevice, st));
+    hevcb_insert_summary* d_sum = reinterpret_cast<hevcb_insert_summary*>(ctx->h_misc.p);
+    rc = hevcb_launch_insert(ctx, b + o_rbsp, d_off, d_off + 1, 1, 0, b + o_nal, (int64_t)((size_t)rcap * 3 / 2 + 64), d_off + 2, d_sum, st);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_insert_summary* p_sum = reinterpret_cast<hevcb_insert_summary*>(ctx->pinned);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_sum, d_sum, sizeof(hevcb_insert_summary), cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (p_sum->out_bytes > 0) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(nal_out, b + o_nal, (size_t)p_sum->out_bytes, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    *nal_bytes = p_sum->out_bytes;
+    return HEVCB_OK;
 }
 
 HEVCB_API int hevcb_insert_device(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,

@@ -264,4 +264,18 @@ int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.
     return ret;
 }
 
+int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.c:1249-1335
+{
+    hevcb_ctx* ctx = context();
+    if (!ctx || !h || size < 0) { return -1; }
+    int64_t n = -1;
+    const int rc = hevcb_write_nal_host(ctx, h->nal->nal_unit_type, h->nal->nal_layer_id, h->nal->nal_temporal_id_plus1, h->vps, h->sps, h->pps, h->sh, buf,
+                                        size, &n);
+    if (rc != HEVCB_OK) {
+        fprintf(stderr, "!! libhevcb200: %s\n", hevcb_last_error(ctx));
+        return -1;
+    }
+    return (int)n;
+}
+
 } // extern "C"

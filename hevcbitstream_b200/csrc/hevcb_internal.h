@@ -21,6 +21,7 @@ struct hevcb_ctx {
     hevcb_devbuf scan_scratch;
     hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
     hevcb_devbuf rewrite_scratch, rewrite_staging; // rewrite: part arrays, written headers
+    hevcb_devbuf wstruct;                 // hevcb_write_nal_host: uploaded structs, contexts, RBSP, NAL
     // what the last hevcb_parse_* left on the device (consumed by hevcb_rewrite_*)
     struct {
         int64_t n = -1;
@@ -103,3 +104,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
                          const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* parsed,
                          const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap, int64_t* d_out_start, int64_t* d_out_end,
                          hevcb_rewrite_summary* d_summary, cudaStream_t stream);
+
+int hevcb_launch_write_struct(hevcb_ctx* ctx, int32_t nal_hdr, const int32_t* d_vps, const int32_t* d_sps, const int32_t* d_pps, const int32_t* d_sh,
+                              void* d_ctx_scratch, uint8_t* d_out, int64_t cap, int64_t* d_result, cudaStream_t stream);
+size_t hevcb_write_struct_scratch_bytes();

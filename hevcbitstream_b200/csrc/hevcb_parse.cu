@@ -395,7 +395,72 @@ __global__ void rewrite_finish_kernel(RewriteArgs a, const int64_t* __restrict__
     if ((threadIdx.x & 31) == 0 && m) { atomicAdd(n_rewritten, (unsigned long long)__popc(m)); }
 }
 
+// ---- write_hevc_nal_unit from caller-owned structs (one NAL, one thread): the compatibility path ------------------------
+struct WriteStructArgs {
+    const int32_t* vps;
+    const int32_t* sps;
+    const int32_t* pps;
+    const int32_t* sh;
+    int32_t nal_hdr;
+    hevcb_sps_ctx* sps_ctx; // derived from the SPS struct the way the writer walks it
+    hevcb_sps_ctx* sps_scr;
+    uint8_t* out;
+    int64_t cap;            // RBSP room: size * 3 / 4 of the caller's buffer (hevc_stream.c:1266)
+    int64_t* result;        // [0] RBSP bytes, [1] ok
+};
+
+__global__ void write_struct_kernel(WriteStructArgs a)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+    int32_t* z = reinterpret_cast<int32_t*>(a.sps_ctx);
+    for (size_t i = 0; i < sizeof(hevcb_sps_ctx) / 4; i++) { z[i] = 0; }
+    z = reinterpret_cast<int32_t*>(a.sps_scr);
+    for (size_t i = 0; i < sizeof(hevcb_sps_ctx) / 4; i++) { z[i] = 0; }
+    hevcb_bits nob;
+    nob.init(nullptr, 0);
+    hevcb_sink nos{nullptr, nullptr, 0};
+    hevcb_pps_ctx pc;
+    { // what a slice needs from the current SPS / PPS: walk the structs like the writer does, writing nowhere
+        hevcb_replay rp{nullptr, nullptr, 0u, 0u, HEVCB_KIND_SPS, nullptr, a.sps};
+        hevcb_bitwriter bw;
+        bw.init(nullptr, (int64_t)1 << 40);
+        hevcb_walker<hevcb_sink, true> w(nob, nos, &bw, &rp);
+        w.seq_parameter_set(*a.sps_ctx);
+        hevcb_replay rq{nullptr, nullptr, 0u, 0u, HEVCB_KIND_PPS, nullptr, a.pps};
+        hevcb_bitwriter bq;
+        bq.init(nullptr, (int64_t)1 << 40);
+        hevcb_walker<hevcb_sink, true> wq(nob, nos, &bq, &rq);
+        wq.pic_parameter_set(pc);
+    }
+    const int t = a.nal_hdr & 0xFF;
+    const int32_t* dense = hevcb_is_slice_type(t) ? a.sh : (t == 32 ? a.vps : (t == 33 ? a.sps : a.pps));
+    const int kind = hevcb_is_slice_type(t) ? HEVCB_KIND_SLICE : (t == 32 ? HEVCB_KIND_VPS : (t == 33 ? HEVCB_KIND_SPS : HEVCB_KIND_PPS));
+    hevcb_replay rp{nullptr, nullptr, 0u, 0u, kind, nullptr, dense};
+    hevcb_bitwriter bw;
+    bw.init(a.out, a.cap);
+    hevcb_write_result wr;
+    hevcb_write_nal(rp, bw, a.nal_hdr, a.sps_ctx, &pc, a.sps_scr, wr);
+    a.result[0] = wr.bytes;
+    a.result[1] = wr.ok;
+}
+
 } // namespace
+
+int hevcb_launch_write_struct(hevcb_ctx* ctx, int32_t nal_hdr, const int32_t* d_vps, const int32_t* d_sps, const int32_t* d_pps, const int32_t* d_sh,
+                              void* d_ctx_scratch, uint8_t* d_out, int64_t cap, int64_t* d_result, cudaStream_t stream)
+{
+    WriteStructArgs a;
+    a.vps = d_vps; a.sps = d_sps; a.pps = d_pps; a.sh = d_sh; a.nal_hdr = nal_hdr;
+    a.sps_ctx = reinterpret_cast<hevcb_sps_ctx*>(d_ctx_scratch);
+    a.sps_scr = a.sps_ctx + 1;
+    a.out = d_out; a.cap = cap; a.result = d_result;
+    write_struct_kernel<<<1, 32, 0, stream>>>(a);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
+
+size_t hevcb_write_struct_scratch_bytes() { return 2 * sizeof(hevcb_sps_ctx); }
 
 int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
                          const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n, const hevcb_parse_buffers* parsed,

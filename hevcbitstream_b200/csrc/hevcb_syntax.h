@@ -245,11 +245,14 @@ struct hevcb_replay {
     uint32_t n, cur;
     int32_t kind;
     const hevcb_edit_set* edits;
+    const int32_t* dense; // alternative source: the struct itself as an int array (write_hevc_nal_unit from caller-owned structs)
 
     HEVCB_SHD int32_t load(uint32_t f, bool multi)
     {
         int32_t v = 0;
-        if (!multi && cur < n && field[cur] == f) {
+        if (dense) {
+            v = dense[f];
+        } else if (!multi && cur < n && field[cur] == f) {
             v = value[cur];
             cur++;
         } else if (multi && cur < n && field[cur] == f) {

@@ -329,6 +329,14 @@ HEVCB_API int hevcb_rewrite_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t
                                    const hevcb_parse_buffers* parsed, const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap,
                                    int64_t* d_out_start, int64_t* d_out_end, hevcb_rewrite_summary* d_summary, void* stream);
 
+/* write_hevc_nal_unit (hevc_stream.c:1249-1335) for ONE NAL from caller-owned structs (host pointers to hevc_vps_t / hevc_sps_t /
+ * hevc_pps_t / hevc_slice_header_t, hevcb_layout.h): the struct selected by nal_unit_type is written, a slice against the given
+ * SPS and PPS; then rbsp_to_nal.  `size` is the caller's buffer size as in the reference (the writer gets size * 3 / 4 bytes of
+ * RBSP room).  *nal_bytes: NAL size, or -1 where the reference returns -1 (unsupported type, overrun).  The compatibility layer's
+ * write_hevc_nal_unit is this call; batches should use hevcb_rewrite_device. */
+HEVCB_API int hevcb_write_nal_host(hevcb_ctx* ctx, int nal_unit_type, int nal_layer_id, int nal_temporal_id_plus1, const void* vps, const void* sps,
+                                   const void* pps, const void* sh, uint8_t* nal_out, int64_t size, int64_t* nal_bytes);
+
 /* Field index (offset in ints) of a member of the struct of `kind`, by name: "slice_qp_delta", "vui.video_full_range_flag",
  * "pwt.luma_offset_l0[3]", "st_ref_pic_set[2].delta_poc_s0_minus1[0]".  -1 when the path does not exist. */
 HEVCB_API int64_t hevcb_field_index(int kind, const char* path);

@@ -3,7 +3,7 @@
  * served by the B200 library.  A program written against leslie-wang/hevcbitstream's headers
  *     find_nal_unit / nal_to_rbsp / rbsp_to_nal          h264_stream.h:54-57  (h264_nal.c:38-200)
  *     hevc_new / hevc_free / peek_hevc_nal_unit           hevc_stream.h:571-572, hevc_nal.c:34,64,97
- *     read_hevc_nal_unit                                  hevc_stream.c:155-241
+ *     read_hevc_nal_unit / write_hevc_nal_unit            hevc_stream.c:155-241 / :1249-1335
  * links against libhevcb200_compat.so + libhevcb200.so instead of libhevcbitstream and behaves the same.  Every call is
  * executed by the CUDA kernels of libhevcb200 (there is no CPU implementation: without a usable B200 hevc_new() returns
  * NULL and the byte-layer calls return -1 after printing the reason to stderr).
@@ -55,6 +55,7 @@ HEVCB_COMPAT_API int find_nal_unit(uint8_t* buf, int size, int* nal_start, int* 
 HEVCB_COMPAT_API int nal_to_rbsp(const uint8_t* nal_buf, int* nal_size, uint8_t* rbsp_buf, int* rbsp_size);
 HEVCB_COMPAT_API int rbsp_to_nal(const uint8_t* rbsp_buf, const int* rbsp_size, uint8_t* nal_buf, int* nal_size);
 HEVCB_COMPAT_API int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
+HEVCB_COMPAT_API int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
 HEVCB_COMPAT_API int peek_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
 
 #ifdef __cplusplus

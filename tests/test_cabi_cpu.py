@@ -59,7 +59,8 @@ def test_compat_library_exports_the_reference_api_and_fails_loudly_without_a_dev
     L = C.CDLL(path)
     hdr = open(os.path.join(ROOT, "include", "hevcb_compat.h")).read()
     names = re.findall(r"HEVCB_COMPAT_API\s+[\w\s\*]+?\b(\w+)\s*\(", hdr)
-    assert set(names) == {"hevc_new", "hevc_free", "find_nal_unit", "nal_to_rbsp", "rbsp_to_nal", "read_hevc_nal_unit", "peek_hevc_nal_unit"}
+    assert set(names) == {"hevc_new", "hevc_free", "find_nal_unit", "nal_to_rbsp", "rbsp_to_nal", "read_hevc_nal_unit", "write_hevc_nal_unit",
+                          "peek_hevc_nal_unit"}
     for name in names:
         assert getattr(L, name) is not None, name
     out = subprocess.run(["ldd", path], capture_output=True, text=True).stdout

@@ -120,3 +120,52 @@ def test_read_hevc_nal_unit_matches_reference(compat):
             n_checked += 1
     compat.hevc_free(h)
     assert n_checked > 400
+
+
+def test_write_hevc_nal_unit_matches_reference(compat):
+    """read every NAL with both libraries, edit slice_qp_delta / a VUI flag in both hevc_stream_t, write with both:
+    return values and bytes must be equal (write_hevc_nal_unit from caller-owned, edited structs)"""
+    Lr = ref.lib()
+    Lr.ref_writer_struct.restype = C.c_void_p
+    Lr.ref_writer_read.argtypes = [C.c_void_p, C.c_int]
+    Lr.ref_writer_write.argtypes = [C.c_void_p, C.c_int]
+    compat.write_hevc_nal_unit.argtypes = [C.POINTER(Stream), C.c_void_p, C.c_int]
+    from tests import rewrite_check as rcx
+
+    f_qp = rcx.field_index(rcx.KIND_SLICE, "slice_qp_delta")
+    f_fr = rcx.field_index(rcx.KIND_SPS, "vui.video_full_range_flag")
+    for profile in (0, 1):
+        s = ref.gen_stream(seed=11 + profile, profile=profile, n_slices=250, payload_min=1, payload_max=200, zero_heavy_pct=20, ps_period=30,
+                           unsupported_pct=5)
+        size = s.size - ref.PAD
+        st, en, _ = ref.scan_all_with_tail(s, size)
+        Lr.ref_writer_reset()
+        h = compat.hevc_new()
+        n_written = 0
+        for k in range(len(st)):
+            nal = np.ascontiguousarray(s[st[k]: en[k]])
+            r_ref = Lr.ref_writer_read(nal.ctypes.data, nal.size)
+            r_c = compat.read_hevc_nal_unit(h, nal.ctypes.data, nal.size)
+            assert r_ref == r_c
+            if r_ref < 0:
+                continue
+            typ = int(np.ctypeslib.as_array(h.contents.nal, shape=(4,))[1])
+            if typ <= 21:  # edit the slice header in both objects
+                for ptr in (Lr.ref_writer_struct(3), h.contents.sh):
+                    C.cast(ptr, C.POINTER(C.c_int32))[f_qp] += 3
+            elif typ == 33:
+                for ptr in (Lr.ref_writer_struct(1), h.contents.sps):
+                    C.cast(ptr, C.POINTER(C.c_int32))[f_fr] ^= 1
+            cap = nal.size * 2 + 64
+            o_ref, o_c = np.zeros(cap + 16, np.uint8), np.zeros(cap + 16, np.uint8)
+            w_ref = Lr.ref_writer_write(o_ref.ctypes.data, cap)
+            w_c = compat.write_hevc_nal_unit(h, o_c.ctypes.data, cap)
+            assert w_ref == w_c, f"profile {profile} NAL {k} type {typ}: write rc {w_c} != {w_ref}"
+            if w_ref > 0:
+                assert np.array_equal(o_ref[:w_ref], o_c[:w_ref]), f"profile {profile} NAL {k} type {typ}: written bytes differ"
+                n_written += 1
+            if typ == 33:  # keep both objects in the state a real tool would have: re-read what was written (App. A-1)
+                Lr.ref_writer_read(o_ref.ctypes.data, w_ref)
+                compat.read_hevc_nal_unit(h, o_c.ctypes.data, w_c)
+        compat.hevc_free(h)
+        assert n_written > 250
