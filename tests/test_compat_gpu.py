@@ -169,3 +169,38 @@ def test_write_hevc_nal_unit_matches_reference(compat):
                 compat.read_hevc_nal_unit(h, o_c.ctypes.data, w_c)
         compat.hevc_free(h)
         assert n_written > 250
+
+
+def test_analyze_tool_on_the_compat_api(tmp_path):
+    """tools/hevcb_analyze.c (a reader in the shape of hevc_analyze.c, plain C against hevcb_compat.h): its '!! Found NAL' lines
+    must be the reference CLI loop's, and its per-NAL summaries must agree with the reference parse"""
+    import re
+    import subprocess
+
+    exe = str(tmp_path / "hevcb_analyze")
+    libdir = os.path.join(ROOT, "hevcbitstream_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "hevcb_analyze.c"), "-L" + libdir,
+                           "-lhevcb200_compat", "-lhevcb200", "-Wl,-rpath," + libdir, "-o", exe])
+    s = ref.gen_stream(seed=21, profile=1, n_slices=300, payload_min=1, payload_max=400, zero_heavy_pct=20, extra_zero_pct=20, ps_period=40,
+                       unsupported_pct=5)
+    size = s.size - ref.PAD
+    path = str(tmp_path / "s.h265")
+    s[:size].tofile(path)
+    out = subprocess.run([exe, "-v", path], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = [l for l in out.stdout.splitlines() if l.startswith("!! Found NAL")]
+    refpath = str(tmp_path / "ref.txt")
+    assert ref.lib().ref_analyze_to_file(s.ctypes.data_as(C.c_void_p), C.c_int64(size), refpath.encode(), 1) == 0
+    want = [l.rstrip("\n") for l in open(refpath, errors="replace") if l.startswith("!! Found NAL")]
+    assert len(want) > 300 and got == want
+    st, en, _ = ref.scan_all_with_tail(s, size)
+    rec = ref.parse_all(s, st, en)["rec"]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("nal_unit_type")]
+    assert len(lines) == len(st)
+    for k, l in enumerate(lines):
+        if rec["strip_rc"][k] >= 0:
+            assert int(re.match(r"nal_unit_type (\d+)", l).group(1)) == rec["nal_unit_type"][k]
+        assert ("not parsed" in l) == (rec["rc"][k] < 0)
+        m = re.search(r"slice_data (-?\d+) bytes", l)
+        if m:
+            assert int(m.group(1)) == rec["slice_data_size"][k]
