@@ -611,19 +611,13 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 uint4 v[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) { v[k] = *reinterpret_cast<const uint4*>(rp + k * kRowBytes); }
+                // the four bytes in front of and behind every chunk straight from shared memory (two narrow loads per chunk
+                // instead of shuffles + divergent edge fix-ups for lanes 0 / 31)
                 uint32_t wp[4], wn[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    wp[k] = __shfl_up_sync(0xFFFFFFFFu, v[k].w, 1);
-                    wn[k] = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
-                }
-                // lane 0 / lane 31 take the neighbouring row's edge words (from registers inside the group of four)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t prev_last = (k > 0) ? __shfl_sync(0xFFFFFFFFu, v[k > 0 ? k - 1 : 0].w, 31) : 0u;
-                    const uint32_t next_first = (k < 3) ? __shfl_sync(0xFFFFFFFFu, v[k < 3 ? k + 1 : 3].x, 0) : 0u;
-                    if (lane == 0) { wp[k] = (k > 0) ? prev_last : *reinterpret_cast<const uint32_t*>(rp - 4); }
-                    if (lane == 31) { wn[k] = (k < 3) ? next_first : *reinterpret_cast<const uint32_t*>(rp + 3 * kRowBytes + 16); }
+                    wp[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes - 4);
+                    wn[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes + 16);
                 }
                 uint32_t slowmask = 0;
 #pragma unroll
