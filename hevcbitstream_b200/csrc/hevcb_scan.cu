@@ -53,6 +53,10 @@ constexpr int kStageBytes = kLead + kTileBytes + 16;
 #define HEVCB_SCAN_STAGES 3
 #endif
 constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memory (one being worked on, the others in flight)
+#ifndef HEVCB_SCAN_AUNROLL
+#define HEVCB_SCAN_AUNROLL 1
+#endif
+constexpr int kAnalyserUnroll = HEVCB_SCAN_AUNROLL; // the analyser's loop over groups of four rows stays rolled (two roles share the instruction cache)
 constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             // Rows are taken four at a time: the four loads, halo exchanges and zero-pair tests are independent
             // instruction chains, and one vote sends the common "no two adjacent zero bytes anywhere" case on.
             // (Loops over rows are kept rolled on purpose: two roles share the SM's instruction cache.)
-#pragma unroll 1
+#pragma unroll kAnalyserUnroll
             for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
                 const int rbase = warp * kRowsPerWarp + i0;
                 const uint8_t* rp = st + kLead + rbase * kRowBytes + lane * 16;
