@@ -418,6 +418,36 @@ def run_ours(args):
         except Exception as ex:
             parse = {"error": repr(ex)}
 
+    # ---- rbsp_to_nal on the headline stream: re-insert the emulation prevention bytes of every NAL of the image just produced
+    insert = None
+    if not args.no_insert and world == 1:
+        try:
+            sres = ctx.scan_strip_device(head["d"], size=head["size_local"], cap_nals=head["cap"], out=head["outs"])
+            nn = int(sres.n_nals)
+            roff, rend = sres.rbsp_off[:nn].contiguous(), sres.rbsp_end[:nn].contiguous()
+            ocap = int(head["size_local"]) + int(head["size_local"]) // 32 + 4096
+            for _ in range(2):
+                ins = ctx.insert_device(sres.rbsp, roff, rend, n_nals=nn, start_code_len=3, out_cap=ocap)
+            barrier()
+            k = max(3, args.steps // 4)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                ins = ctx.insert_device(sres.rbsp, roff, rend, n_nals=nn, start_code_len=3, out_cap=ocap, sync=False)
+            e1.record()
+            barrier()
+            ims = e0.elapsed_time(e1) / k
+            s_ = ins["summary"].cpu().numpy()
+            alg_i = 2.0 * int(sres.rbsp_bytes) + float(s_[1]) + 24.0 * nn  # payload read by the count and the write pass, output written, offsets
+            insert = {"ms": ims, "n_nals": nn, "out_bytes": int(s_[1]), "epb_inserted": int(s_[2]), "input_GBps": int(sres.rbsp_bytes) / (ims * 1e-3) / 1e9,
+                      "algorithmic_GBps": alg_i / (ims * 1e-3) / 1e9, "frac_of_peak": alg_i / (ims * 1e-3) / 1e9 / peak,
+                      "round_trip_identical": bool(int(s_[1]) == int(head["size_local"]) and torch.equal(ins["out"][: int(s_[1])], head["d"][: int(s_[1])])),
+                      "workload": "hevcb_insert_device (start codes + rbsp_to_nal) over the image and extents of the headline stream; output must equal the input stream"}
+            del ins
+        except Exception as ex:
+            insert = {"error": repr(ex)}
+
     # ---- BASELINE config[3]: round-trip rewrite (parse, edit slice_qp_delta + a VUI flag, write_hevc_nal_unit, rbsp_to_nal) on a
     # stream of reference-written headers carrying 16 KiB payloads.  The unit is built on the device with the product's own
     # kernels (headers of tests/golden/headers_unit.bin + random payload -> hevcb_insert_device), then tiled.
@@ -528,6 +558,8 @@ def run_ours(args):
             line["sweep"] = sweep
         if parse:
             line["parse"] = parse
+        if insert:
+            line["insert"] = insert
         if rewrite:
             line["rewrite"] = rewrite
         sys.stdout.flush()
@@ -549,6 +581,7 @@ def main():
     ap.add_argument("--no-parse", action="store_true")
     ap.add_argument("--parse-nals", type=int, default=1_000_000)
     ap.add_argument("--no-rewrite", action="store_true")
+    ap.add_argument("--no-insert", action="store_true")
     ap.add_argument("--rewrite-gib", type=float, default=4.0)
     ap.add_argument("--rewrite-payload", type=int, default=16384)
     ap.add_argument("--ref-sample-mib", type=int, default=64)

@@ -25,10 +25,11 @@ struct hevcb_ctx {
     // what the last hevcb_parse_* left on the device (consumed by hevcb_rewrite_*)
     struct {
         int64_t n = -1;
-        const void *cls = nullptr, *sps_ord = nullptr, *pps_ord = nullptr, *cnt = nullptr;
+        const void *cls = nullptr, *sps_ord = nullptr, *pps_ord = nullptr, *cnt = nullptr, *perm = nullptr;
         void *sps_tab = nullptr, *pps_tab = nullptr, *sps_scratch = nullptr;
     } last_parse;
     hevcb_devbuf parse_scratch, parse_ps; // parser: per-NAL scratch arrays, parameter-set context tables
+    hevcb_devbuf parse_sort;              // parser: radix sort workspace
     hevcb_devbuf h_p[9];                  // staging of the parse outputs for the *_host entry points
     // staging used by the *_host entry points
     hevcb_devbuf h_in, h_rbsp, h_a0, h_a1, h_a2, h_a3, h_misc;
@@ -108,3 +109,5 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
 int hevcb_launch_write_struct(hevcb_ctx* ctx, int32_t nal_hdr, const int32_t* d_vps, const int32_t* d_sps, const int32_t* d_pps, const int32_t* d_sh,
                               void* d_ctx_scratch, uint8_t* d_out, int64_t cap, int64_t* d_result, cudaStream_t stream);
 size_t hevcb_write_struct_scratch_bytes();
+
+int hevcb_sort_perm(hevcb_ctx* ctx, const uint32_t* d_keys, int64_t n, int32_t* d_perm, cudaStream_t stream);

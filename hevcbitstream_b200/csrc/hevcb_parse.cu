@@ -127,11 +127,13 @@ int run_scan(hevcb_ctx* ctx, F f, int64_t n, TOut* out, long long* block_sums /*
 // ---- pass 1: classify ----------------------------------------------------------------------------------------
 __global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t* __restrict__ rbsp_off, const int64_t* __restrict__ rbsp_end,
                                 int64_t n, uint8_t* __restrict__ cls, int32_t* __restrict__ nal_hdr, int32_t* __restrict__ rc,
-                                uint8_t* __restrict__ kind, uint8_t* __restrict__ ubflag, int32_t* __restrict__ cnt, int32_t* __restrict__ hdr_end)
+                                uint8_t* __restrict__ kind, uint8_t* __restrict__ ubflag, int32_t* __restrict__ cnt, int32_t* __restrict__ hdr_end,
+                                uint32_t* __restrict__ sortkey)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) { return; }
     const int64_t off = rbsp_off[k], end = rbsp_end[k];
+    sortkey[k] = 0xFFFFFFFFu; // NALs the parser does not walk go last
     cnt[k] = 0;
     kind[k] = HEVCB_KIND_NONE;
     ubflag[k] = 0;
@@ -154,6 +156,12 @@ __global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t*
     else if (type == 33u) { c = (uint8_t)kCls_Sps; }
     else if (type == 34u) { c = (uint8_t)kCls_Pps; }
     cls[k] = c;
+    if (c != (uint8_t)kCls_Other) {
+        // shape key: NAL type, then the first payload bytes (first_slice_segment_in_pic_flag, ids, slice_type, ... live there):
+        // NALs with equal keys take the same branches for most of the header
+        const uint32_t b2 = size > 2 ? rbsp[off + 2] : 0u, b3 = size > 3 ? rbsp[off + 3] : 0u, b4 = size > 4 ? rbsp[off + 4] : 0u;
+        sortkey[k] = (type << 24) | (b2 << 16) | (b3 << 8) | b4;
+    }
 }
 
 // consumed bytes reported by read_hevc_nal_unit: nal_size, minus one when a trailing 00 00 03 was dropped (h264_nal.c:170-173,197)
@@ -178,6 +186,7 @@ struct ParseArgs {
     const uint8_t* cls;
     const int32_t* sps_ord; // inclusive count of SPS NALs up to and including k
     const int32_t* pps_ord;
+    const int32_t* perm;    // thread i takes NAL perm[i]: NALs of the same shape side by side (hevcb_sort.cu)
     hevcb_sps_ctx* sps_tab;  // [n_sps + 1]; entry 0 = the zeroed state before any SPS (calloc in hevc_new)
     hevcb_pps_ctx* pps_tab;  // [n_pps + 1]
     hevcb_sps_ctx* sps_scratch; // emit pass: where re-parsed SPS contexts go (same shape as sps_tab)
@@ -197,8 +206,9 @@ struct ParseArgs {
 template <bool kEmit, bool kSlices>
 __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) { return; }
+    const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= a.n) { return; }
+    const int64_t k = a.perm[ti];
     const int c = a.cls[k];
     const bool is_ps = (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps);
     const bool is_slice = (c == kCls_Slice);
@@ -300,6 +310,7 @@ struct RewriteArgs {
     const uint32_t* pair_field;
     const int32_t* pair_value;
     int64_t cap_pairs;
+    const int32_t* perm; // thread order of the parse (same-shape NALs side by side)
     int32_t* wlen;       // [n] bytes of the written header part (0: the NAL is copied through)
     const int64_t* woff; // exclusive scan of wlen
     uint8_t* staging;
@@ -310,8 +321,9 @@ struct RewriteArgs {
 template <bool kEmit>
 __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) { return; }
+    const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= a.n) { return; }
+    const int64_t k = a.perm[ti];
     const int c = a.cls[k];
     const bool is_slice = (c == kCls_Slice);
     if (!kEmit) { a.wlen[k] = 0; }
@@ -493,6 +505,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     a.sps_tab = reinterpret_cast<const hevcb_sps_ctx*>(ctx->last_parse.sps_tab);
     a.pps_tab = reinterpret_cast<const hevcb_pps_ctx*>(ctx->last_parse.pps_tab);
     a.sps_scratch = reinterpret_cast<hevcb_sps_ctx*>(ctx->last_parse.sps_scratch);
+    a.perm = reinterpret_cast<const int32_t*>(ctx->last_parse.perm);
     a.rc = parsed->rc; a.nal_hdr = parsed->nal_hdr; a.ubflag = parsed->ubflag; a.hdr_end = parsed->hdr_end;
     a.pair_off = parsed->pair_off; a.pair_field = parsed->pair_field; a.pair_value = parsed->pair_value; a.cap_pairs = parsed->cap_pairs;
     a.wlen = reinterpret_cast<int32_t*>(base + o_wlen);
@@ -570,6 +583,7 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     size_t need = 0;
     auto take = [&](size_t bytes) { size_t o = need; need += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_cls = take((size_t)n), o_cnt = take((size_t)n * 4), o_so = take((size_t)n * 4), o_po = take((size_t)n * 4);
+    const size_t o_key = take((size_t)n * 4), o_perm = take((size_t)n * 4);
     const size_t o_bs = take((size_t)(nb + 1) * 8), o_tot = take(64);
     int rcx = hevcb_reserve(ctx, &ctx->parse_scratch, need);
     if (rcx != HEVCB_OK) { return rcx; }
@@ -580,12 +594,16 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     int32_t* pps_ord = reinterpret_cast<int32_t*>(base + o_po);
     long long* bsums = reinterpret_cast<long long*>(base + o_bs);
     long long* pair_total = reinterpret_cast<long long*>(base + o_tot);
+    uint32_t* sortkey = reinterpret_cast<uint32_t*>(base + o_key);
+    int32_t* perm = reinterpret_cast<int32_t*>(base + o_perm);
 
     const unsigned g128 = (unsigned)((n + 127) / 128);
     classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rbsp, d_rbsp_off, d_rbsp_end, n, cls, out->nal_hdr, out->rc, out->kind,
-                                                                    out->ubflag, cnt, out->hdr_end);
+                                                                    out->ubflag, cnt, out->hdr_end, sortkey);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
+    int rcp = hevcb_sort_perm(ctx, sortkey, n, perm, stream);
+    if (rcp != HEVCB_OK) { return rcp; }
     int rcs = run_scan<ClsIsSps, int32_t, true>(ctx, ClsIsSps{cls}, n, sps_ord, bsums, stream);
     if (rcs != HEVCB_OK) { return rcs; }
     long long h_counts[2] = {0, 0};
@@ -606,7 +624,7 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     ParseArgs a;
     a.buf_size = (chain && chain->buf_size > 0) ? chain->buf_size : 0x7FFFFFFFFFFFFFFFll;
     a.buf = d_buf; a.nal_start = d_nal_start; a.nal_end = d_nal_end; a.rbsp = d_rbsp; a.rbsp_off = d_rbsp_off; a.rbsp_end = d_rbsp_end;
-    a.n = n; a.cls = cls; a.sps_ord = sps_ord; a.pps_ord = pps_ord;
+    a.n = n; a.cls = cls; a.sps_ord = sps_ord; a.pps_ord = pps_ord; a.perm = perm;
     a.sps_tab = reinterpret_cast<hevcb_sps_ctx*>(pb);
     a.sps_scratch = reinterpret_cast<hevcb_sps_ctx*>(pb + sps_bytes);
     a.pps_tab = reinterpret_cast<hevcb_pps_ctx*>(pb + 2 * sps_bytes);
@@ -616,6 +634,7 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
 
     ctx->last_parse.n = n;
     ctx->last_parse.cls = cls; ctx->last_parse.sps_ord = sps_ord; ctx->last_parse.pps_ord = pps_ord; ctx->last_parse.cnt = cnt;
+    ctx->last_parse.perm = perm;
     ctx->last_parse.sps_tab = a.sps_tab; ctx->last_parse.pps_tab = a.pps_tab; ctx->last_parse.sps_scratch = a.sps_scratch;
     parse_kernel<false, false><<<g128, 128, 0, stream>>>(a); // parameter sets first
     parse_kernel<false, true><<<g128, 128, 0, stream>>>(a);  // then the slices that depend on them
