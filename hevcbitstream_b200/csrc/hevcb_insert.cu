@@ -173,8 +173,15 @@ __device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, 
         if (clean) {
             // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
             const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-            if ((uint32_t)lane == 0u) {
-                for (uint32_t j = 0; j < head; j++) { dst[j] = (uint8_t)byte_of(r.v, (int)j); }
+            if (head != 0u) { // the bytes in front of the first / behind the last aligned vector, one per lane
+                // lanes 0..15 look at lane 0's chunk (head bytes), lanes 16..31 at lane 31's chunk (tail bytes)
+                const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, r.v.x, lane < 16 ? 0 : 31), w1 = __shfl_sync(0xFFFFFFFFu, r.v.y, lane < 16 ? 0 : 31);
+                const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, r.v.z, lane < 16 ? 0 : 31), w3 = __shfl_sync(0xFFFFFFFFu, r.v.w, lane < 16 ? 0 : 31);
+                const uint32_t j = (uint32_t)lane & 15u;
+                const uint32_t w = (j < 4u) ? w0 : (j < 8u) ? w1 : (j < 12u) ? w2 : w3;
+                const uint8_t bv = (uint8_t)(w >> (8u * (j & 3u)));
+                if (lane < 16) { if (j < head) { dst[j] = bv; } }
+                else { if (j >= head) { dst[496u + j] = bv; } }
             }
             // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
             uint4 nx;
@@ -195,11 +202,7 @@ __device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, 
                 o4.y = __funnelshift_r(x[1], x[2], sh);
                 o4.z = __funnelshift_r(x[2], x[3], sh);
                 o4.w = __funnelshift_r(x[3], x[4], sh);
-                if (lane < 31) {
-                    *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4;
-                } else { // last lane: only 16 - head bytes remain
-                    for (uint32_t j = head; j < 16u; j++) { dst[496 + j] = (uint8_t)byte_of(r.v, (int)j); }
-                }
+                if (lane < 31) { *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4; } // lane 31's 16 - head bytes were stored above
             }
         } else {
             uint8_t* p = dst + (inc - cnt);
