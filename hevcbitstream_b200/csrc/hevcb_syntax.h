@@ -47,14 +47,27 @@ struct hevcb_bits {
         wbyte = -16;
         win = 0;
     }
+    // Loads bytes [byte, byte + 8) as a big-endian window, bytes at or beyond `size` read as 0.  Two aligned 8-byte loads
+    // instead of eight byte loads: the buffer must be readable up to the next 8-byte boundary behind its last byte (every
+    // image buffer of this library is; hevcb.h).
     HEVCB_SHD void refill(int64_t byte)
     {
         uint64_t v = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int64_t b = byte + i;
-            const uint32_t x = (b < size) ? (uint32_t)base[b] : 0u;
-            v = (v << 8) | x;
+        const int64_t valid = size - byte; // bytes of the window that exist
+        if (byte >= 0 && valid > 0) {
+            const uintptr_t p = (uintptr_t)(base + byte);
+            const uintptr_t a = p & ~(uintptr_t)7;
+            const uint32_t o = (uint32_t)(p - a) * 8u;
+            const uint64_t lo = *reinterpret_cast<const uint64_t*>(a);
+            uint64_t le = lo >> o;
+            if (o != 0u && (int64_t)(8u - o / 8u) < valid) { le |= *reinterpret_cast<const uint64_t*>(a + 8) << (64u - o); }
+#if defined(__CUDA_ARCH__)
+            const uint32_t l32 = (uint32_t)le, h32 = (uint32_t)(le >> 32);
+            v = ((uint64_t)__byte_perm(l32, 0u, 0x0123) << 32) | (uint64_t)__byte_perm(h32, 0u, 0x0123);
+#else
+            v = __builtin_bswap64(le);
+#endif
+            if (valid < 8) { v &= ~0ull << (8 * (8 - (int)valid)); }
         }
         win = v;
         wbyte = byte;

@@ -86,7 +86,8 @@ HEVCB_API int hevcb_sm_count(const hevcb_ctx* ctx);
  *                              rbsp[rbsp_off[k] .. rbsp_end[k]); start codes stay in between.
  *   rbsp_off[k], rbsp_end[k]   extent of NAL k's RBSP inside `rbsp`; rbsp_end[k] == -1 when nal_to_rbsp
  *                              returns -1 for that NAL (00 00 0{0,1,2} inside, or 00 00 03 followed by > 3).
- * `rbsp` may be NULL (scan only; rbsp_off / rbsp_end are still produced).  `rbsp` needs `size` bytes.
+ * `rbsp` may be NULL (scan only; rbsp_off / rbsp_end are still produced).  `rbsp` needs `size` bytes, rounded up to a multiple
+ * of 16 (the parser and the insert kernels read it with aligned vector loads).
  * All arrays hold cap_nals entries.  `summary` is written on the device for the _device variant (read it
  * after synchronising the stream).  Device pointers `buf` and `rbsp` must be 16-byte aligned.
  */
