@@ -190,9 +190,6 @@ static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     for (int r = 0; r < K; r++) {
         int64_t lo, own, halo; int first, last;
         shard_geom(r, lo, own, halo, first, last);
-        if (r + 1 < K) { // the next shard's input travels while this one is scanned
-            // (its slot is free once the scan of shard r - 1 is done, which the stream order of s_k + ev_k guarantees)
-        }
         if (own <= 0) { continue; }
         const int sl = r & 1;
         int64_t* arr = reinterpret_cast<int64_t*>(ctx->p_arr[sl].p);
@@ -206,6 +203,7 @@ static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t
         HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_sums[r], d_sum, sizeof(hevcb_shard_summary), cudaMemcpyDeviceToHost, s_k));
         HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_k[sl], s_k));
         slot_used[sl] = true;
+        // the next shard's input travels while this one is scanned (its slot is free once the scan of shard r - 1 is done)
         if (r + 1 < K && (rc = copy_in(r + 1)) != HEVCB_OK) { return rc; }
         HEVCB_CUDA(ctx, cudaEventSynchronize(ctx->ev_k[sl])); // record of shard r: where its outputs go
         const hevcb_shard_summary& S = h_sums[r];
