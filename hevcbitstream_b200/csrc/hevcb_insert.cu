@@ -62,6 +62,24 @@ __device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, i
     const int64_t cpos = row + lane * 16;
     r.v = make_uint4(0, 0, 0, 0);
     if (cpos < end && cpos + 16 > off) { r.v = *reinterpret_cast<const uint4*>(img + cpos); }
+    if (row >= off && row + 512 <= end) {
+        // Interior row, the common case: no insertion is possible when the row holds no two adjacent zero bytes and the run
+        // that enters it cannot complete one with the row's first byte.  One SWAR test + one vote instead of the exact masks.
+        uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
+        if (lane == 31) { nx = 0xFFFFFFFFu; } // a pair that straddles the row end is seen by the next row through run_m
+        const uint32_t m0 = r.v.x | __funnelshift_r(r.v.x, r.v.y, 8), m1 = r.v.y | __funnelshift_r(r.v.y, r.v.z, 8);
+        const uint32_t m2 = r.v.z | __funnelshift_r(r.v.z, r.v.w, 8), m3 = r.v.w | __funnelshift_r(r.v.w, nx, 8);
+        const uint32_t c = 0x01010101u, h = 0x80808080u;
+        const uint32_t pair = (((m0 - c) & ~m0) | ((m1 - c) & ~m1) | ((m2 - c) & ~m2) | ((m3 - c) & ~m3)) & h; // exact: some byte of m is zero
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, r.v.x, 0) & 0xFFu, bl = __shfl_sync(0xFFFFFFFFu, r.v.w, 31) >> 24;
+        const bool entering = (run_m >= 1u && b0 == 0u) || (run_m >= 2u && b0 <= 3u);
+        if (!__any_sync(0xFFFFFFFFu, pair != 0u) && !entering) {
+            r.valid = 0xFFFFu;
+            r.ins = 0u;
+            run_m = (bl == 0u) ? 1u : 0u;
+            return r;
+        }
+    }
     // validity of the 16 positions
     const int64_t lo = off - cpos, hi = end - cpos; // valid j in [lo, hi)
     uint32_t valid = 0xFFFFu;
@@ -165,10 +183,13 @@ __device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, 
     int64_t row = off & ~(int64_t)15;
     for (; row < end; row += 512) {
         const RowInfo r = insert_row(base, row, off, end, lane, run_m);
-        const uint32_t cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
-        const uint32_t inc = warp_incl_scan_u32(cnt, lane);
-        const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
         const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
+        uint32_t cnt = 16u, inc = ((uint32_t)lane + 1u) * 16u, row_total = 512u;
+        if (!clean) { // output offsets of the lanes: only rows with insertions or partial chunks need the scan
+            cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
+            inc = warp_incl_scan_u32(cnt, lane);
+            row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
         uint8_t* dst = out + o;
         if (clean) {
             // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
