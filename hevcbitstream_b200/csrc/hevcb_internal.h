@@ -45,7 +45,7 @@ struct hevcb_ctx {
     int scan_blocks_per_sm = 0;
     cudaEvent_t ev_stats = nullptr; // scan kernel: heavy-tile count of the last launch has arrived in the pinned block
     bool stats_pending = false;
-    double last_heavy_frac = 0.0;
+    double last_heavy_frac = 0.0, last_flagged_frac = 0.0;
     long long scan_debug_flags = 0; // experiment switches of the scan kernel (HEVCB_SCAN_DEBUG); 0 in production
 };
 

@@ -216,8 +216,9 @@ struct ScanHeader {
     unsigned long long tiles_written; // writer progress (analysers stay within a window of it so that a tile's second load hits L2)
     long long first_empty;
     ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
-    unsigned long long heavy_tiles; // tiles the writers had to analyse themselves (feeds the role split of the next launch)
-    unsigned long long pad[3];
+    unsigned long long heavy_tiles;  // tiles the writers had to analyse themselves (feeds the role split of the next launch)
+    unsigned long long flagged_rows; // rows the analysers had to analyse exactly
+    unsigned long long pad[2];
 };
 
 // ordered-carry resolution inside a warp: lane l receives the (kind, err) state produced by lanes < l.
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             int s = 0;
             uint32_t done_bits = 0;
             long long seen_written = 0;
-            unsigned long long heavy_local = 0;
+            unsigned long long heavy_local = 0, flagged_local = 0;
             for (long long t = first_tile; t < n_tiles; t += G) {
                 while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
                 done_bits ^= (1u << s);
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const bool light = (adel == 0u) && (nrec <= kEvCap) && (tile_k == (uint32_t)kTileBytes) && !(dbg & 1024u);
                     st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
                     if (!light && mask != 0ull) { heavy_local++; }
+                    flagged_local += (unsigned long long)__popcll(mask);
                     const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
                     if (nt < n_tiles) {
                         // stay within `window` tiles of the writers: what they load a second time is then still in L2
@@ -589,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 s = (s + 1 == kStages) ? 0 : s + 1;
             }
             if (lane == 0 && heavy_local) { atomicAdd(&hdr->heavy_tiles, heavy_local); }
+            if (lane == 0 && flagged_local) { atomicAdd(&hdr->flagged_rows, flagged_local); }
             return;
         }
         // workers: wait for the tile, analyse their rows, hand the warp aggregate to the control warp; they never wait for
@@ -953,6 +956,7 @@ __global__ void hevcb_scan_init_kernel(ScanHeader* hdr, uint32_t init_n, int64_t
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         hdr->tiles_written = 0ull;
         hdr->heavy_tiles = 0ull;
+        hdr->flagged_rows = 0ull;
         hdr->first_empty = 0x7FFFFFFFFFFFFFFFll;
         if (init_n && cap_nals > 0) { nal_start[0] = 0; rbsp_off[0] = 0; } // the NAL piece that enters the shard
     }
@@ -1023,10 +1027,13 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         // EPB-dense payloads) they get the larger share.  Results do not depend on the split.
         if (ctx->ev_stats && ctx->stats_pending && cudaEventQuery(ctx->ev_stats) == cudaSuccess) {
             const unsigned long long* st = reinterpret_cast<const unsigned long long*>(ctx->pinned) + 64;
-            ctx->last_heavy_frac = st[1] ? (double)st[0] / (double)st[1] : 0.0;
+            ctx->last_heavy_frac = st[2] ? (double)st[0] / (double)st[2] : 0.0;
+            ctx->last_flagged_frac = st[2] ? (double)st[1] / ((double)st[2] * kRows) : 0.0;
             ctx->stats_pending = false;
         }
-        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 7 + 10) / 20 : (grid * 3 + 2) / 5;
+        // 35 % analysers when the writers analyse most tiles themselves, 70 % when the tiles are handed over as records but most
+        // rows need exact analysis (NALs of ~1 KiB: the analysers are the bottleneck), 60 % otherwise
+        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 7 + 10) / 20 : (ctx->last_flagged_frac > 0.5 ? (grid * 7 + 5) / 10 : (grid * 3 + 2) / 5);
         if (n_an < 1) { n_an = 1; }
         if (n_an > grid - 1) { n_an = grid - 1; }
         if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
@@ -1047,8 +1054,8 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         HEVCB_CUDA(ctx, cudaGetLastError());
         if (ctx->ev_stats && !ctx->stats_pending) { // heavy-tile count of this launch, read back without ever waiting for it
             unsigned long long* st = reinterpret_cast<unsigned long long*>(ctx->pinned) + 64;
-            st[1] = (unsigned long long)n_tiles;
-            HEVCB_CUDA(ctx, cudaMemcpyAsync(&st[0], &hdr->heavy_tiles, 8, cudaMemcpyDeviceToHost, stream));
+            st[2] = (unsigned long long)n_tiles;
+            HEVCB_CUDA(ctx, cudaMemcpyAsync(&st[0], &hdr->heavy_tiles, 16, cudaMemcpyDeviceToHost, stream)); // heavy_tiles, flagged_rows
             HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_stats, stream));
             ctx->stats_pending = true;
         }
