@@ -109,7 +109,7 @@ __device__ __forceinline__ ulonglong2 pack_state(unsigned long long status, unsi
     return s;
 }
 // aggregate of one tile: x = status | kind | err | start codes (14 bits) | kept bytes (16 bits), y = row mask
-constexpr uint32_t kEvCap = 64;       // event records an analyser may leave per tile (two per lane of the emit pass)
+constexpr uint32_t kEvCap = 128;      // event records an analyser may leave per tile (four per lane of the emit pass)
 constexpr uint32_t kEvByWriter = 0xFFu; // "records" value: the writer CTA emits this tile's NAL boundaries itself
 __device__ __forceinline__ ulonglong2 pack_agg(uint32_t n, uint32_t k, uint32_t kind, uint32_t err, unsigned long long mask, uint32_t records = kEvByWriter)
 {
@@ -873,19 +873,31 @@ __global__ void __launch_bounds__(256) hevcb_scan_emit_kernel(long long n_tiles,
     const ulonglong2 ex = tile_excl[t];
     const long long tileN = (long long)(ex.x & ((1ull << 40) - 1)), tileK = (long long)ex.y;
     const uint32_t pKind = (uint32_t)(ex.x >> 60) & 3u, pErr = (uint32_t)(ex.x >> 59) & 1u;
-    // rank by chunk index (distinct per record); lane l holds records l and l + 32
-    uint4 ra = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu), rb = ra;
-    if ((uint32_t)lane < nrec) { ra = tile_events[(size_t)t * kEvCap + lane]; }
-    if ((uint32_t)lane + 32u < nrec) { rb = tile_events[(size_t)t * kEvCap + 32 + lane]; }
-    uint32_t rank_a = 0, rank_b = 0;
-#pragma unroll 4
-    for (int i = 0; i < 32; i++) {
-        const uint32_t oa = __shfl_sync(0xFFFFFFFFu, ra.x, i), ob = __shfl_sync(0xFFFFFFFFu, rb.x, i);
-        rank_a += ((oa < ra.x) ? 1u : 0u) + ((ob < ra.x) ? 1u : 0u);
-        rank_b += ((oa < rb.x) ? 1u : 0u) + ((ob < rb.x) ? 1u : 0u);
+    // rank by chunk index (distinct per record); lane l holds records l, l + 32, l + 64, ...
+    constexpr int kPerLane = (int)(kEvCap / 32);
+    uint4 rec_[kPerLane];
+    uint32_t rank_[kPerLane];
+#pragma unroll
+    for (int q = 0; q < kPerLane; q++) {
+        rec_[q] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu);
+        rank_[q] = 0;
+        if ((uint32_t)(q * 32 + lane) < nrec) { rec_[q] = tile_events[(size_t)t * kEvCap + q * 32 + lane]; }
     }
-    if ((uint32_t)lane < nrec) { sorted[warp][rank_a] = ra; }
-    if ((uint32_t)lane + 32u < nrec) { sorted[warp][rank_b] = rb; }
+#pragma unroll
+    for (int p = 0; p < kPerLane; p++) {
+        if ((uint32_t)(p * 32) < nrec) { // warp-uniform: slots beyond the record count hold nothing
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                const uint32_t other = __shfl_sync(0xFFFFFFFFu, rec_[p].x, i);
+#pragma unroll
+                for (int q = 0; q < kPerLane; q++) { rank_[q] += (other < rec_[q].x) ? 1u : 0u; }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kPerLane; q++) {
+        if ((uint32_t)(q * 32 + lane) < nrec) { sorted[warp][rank_[q]] = rec_[q]; }
+    }
     __syncwarp();
     uint32_t cKind = pKind, cErr = pErr; // carry entering the round
     long long nbase = tileN;
