@@ -96,6 +96,8 @@ struct __align__(16) SmemLayout {
     uint32_t evcount[kStages];        // analyser: event records written for the tile in the stage
     WarpAgg wagg[kStages][kWorkers];  // per-warp aggregates of the tile in a stage (writer: index i & 1)
     TilePrefix pref[2];        // writer: prefix + row mask of this CTA's i-th tile (index i & 1)
+    uint8_t slowmap[kWorkers][kRowsPerWarp * 32]; // the warp's chunks that need exact analysis, in stream order
+    alignas(16) uint16_t delmask[kWorkers][kRowsPerWarp * 32]; // writer: removed bytes of every chunk of the warp's rows (tiles with removed bytes)
 };
 
 // ---- tile state for the decoupled look-back: one 16-byte word, read/written with single 128-bit accesses
@@ -295,9 +297,10 @@ __device__ __noinline__ void emit_cold(uint32_t evsc, uint32_t deler, uint32_t m
 // copy `nv` 16-byte vectors from shared memory (16-byte aligned `src16`, byte offset Q*4 + sh/8 into it) to the
 // 16-byte aligned global destination; Q selects the word offset at compile time, sh is the byte shift in bits.
 template <int Q>
-__device__ __forceinline__ void copy_vectors(uint8_t* __restrict__ dst16, const uint8_t* __restrict__ src16, uint32_t nv, uint32_t sh, int tid)
+__device__ __forceinline__ void copy_vectors(uint8_t* __restrict__ dst16, const uint8_t* __restrict__ src16, uint32_t nv, uint32_t sh, int tid,
+                                             uint32_t nthreads = kWorkerThreads)
 {
-    for (uint32_t vi = tid; vi < nv; vi += kWorkerThreads) {
+    for (uint32_t vi = tid; vi < nv; vi += nthreads) {
         const uint4 lo = *reinterpret_cast<const uint4*>(src16 + (vi << 4));
         const uint4 hi = *reinterpret_cast<const uint4*>(src16 + (vi << 4) + 16);
         const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -465,22 +468,27 @@ __device__ __forceinline__ RowMasks analyze_staged_row(const uint8_t* st, int r,
     return analyze_row(wp, v, wn, slow, g0, geom, wN, wK, wKind, wErr);
 }
 
-// whole-tile copy of L bytes out of a stage: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
-__device__ __noinline__ void copy_tile(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int tid)
+// copy of L bytes out of a stage (16-byte aligned source) by a group of `nthreads` threads (the CTA's workers for a whole tile, one
+// warp for its own rows): aligned 16-byte vectors, funnel-shifted by the (copy-uniform) misalignment of the destination
+__device__ __forceinline__ void copy_span(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int tid, uint32_t nthreads)
 {
     const uint32_t head0 = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
     const uint32_t head = head0 < L ? head0 : L;
     if ((uint32_t)tid < head) { dst[tid] = src[tid]; }
     const uint32_t nv = (L - head) >> 4;
-    const uint32_t sh = (head & 3u) * 8u; // source misalignment is tile-uniform
+    const uint32_t sh = (head & 3u) * 8u; // source misalignment is uniform
     switch (head >> 2) {
-        case 0: copy_vectors<0>(dst + head, src, nv, sh, tid); break;
-        case 1: copy_vectors<1>(dst + head, src, nv, sh, tid); break;
-        case 2: copy_vectors<2>(dst + head, src, nv, sh, tid); break;
-        default: copy_vectors<3>(dst + head, src, nv, sh, tid); break;
+        case 0: copy_vectors<0>(dst + head, src, nv, sh, tid, nthreads); break;
+        case 1: copy_vectors<1>(dst + head, src, nv, sh, tid, nthreads); break;
+        case 2: copy_vectors<2>(dst + head, src, nv, sh, tid, nthreads); break;
+        default: copy_vectors<3>(dst + head, src, nv, sh, tid, nthreads); break;
     }
     const uint32_t done = head + (nv << 4);
     if ((uint32_t)tid < L - done) { dst[done + tid] = src[done + tid]; }
+}
+__device__ __noinline__ void copy_tile(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int tid)
+{
+    copy_span(dst, src, L, tid, kWorkerThreads);
 }
 
 // boundary fix-ups of a staged tile: positions < 0 read as non-zero, positions >= size read as zero
@@ -494,6 +502,65 @@ __device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, 
         }
         bar_sync(kBarWork, kWorkerThreads);
     }
+}
+
+// Analyser, interior tile: exact analysis of the warp's "slow" chunks (two adjacent zero bytes nearby) only.  The slow chunks of
+// the warp's eight rows are ranked in stream order (ballots), their indices parked in shared memory, and the lanes then take
+// them 32 at a time: one pass of the exact masks with every lane busy instead of one pass per flagged row with a few lanes
+// busy.  The ordered carry, the counts and the event records follow from ballots over the ranked chunks (the combine is
+// associative, chunks without a zero pair contribute nothing).  slow8 bit i: this lane's chunk of row i is slow.
+__device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st, uint8_t* __restrict__ slowmap, int warp, int lane, uint32_t slow8,
+                                                 int64_t t0, long long t, const ScanGeom& geom, uint32_t* evcount, uint4* __restrict__ tile_events,
+                                                 uint32_t& wN, uint32_t& wDel, uint32_t& wKind, uint32_t& wErr, uint32_t& rows)
+{
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t total = 0;
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; i++) {
+        const bool mine = ((slow8 >> i) & 1u) != 0u;
+        const uint32_t sb = __ballot_sync(0xFFFFFFFFu, mine);
+        if (mine) { slowmap[total + (uint32_t)__popc(sb & below)] = (uint8_t)(i * 32 + lane); }
+        rows |= (sb != 0u ? 1u : 0u) << i;
+        total += (uint32_t)__popc(sb);
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t slot = base + (uint32_t)lane;
+        uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu, chunk = 0u;
+        if (slot < total) {
+            chunk = (uint32_t)(warp * kRowsPerWarp * 32) + slowmap[slot];
+            const uint8_t* rp = st + kLead + chunk * 16u;
+            const uint4 v = *reinterpret_cast<const uint4*>(rp);
+            const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
+            const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
+            const hevcb_chunk_masks m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, t0 + (int64_t)chunk * 16, geom.size, geom.own, geom.evl);
+            evsc = m.ev | (m.sc << 16); deler = m.del | (m.err << 16); misc = m.valid | (m.scb << 16);
+        }
+        const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
+        uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+        if (ev != 0u) {
+            const int tp = 31 - __clz((int)ev);
+            lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+            le = ((er >> tp) >> 1) != 0u;
+        }
+        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+        const uint32_t Xb = __ballot_sync(0xFFFFFFFFu, (ev | er) != 0u);
+        wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
+        wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(del));
+        uint32_t rk, re;
+        warp_carry_total(Eb, Sb, Rb, rk, re);
+        hevcb_carry_combine(wKind, wErr, rk, re);
+        if (Xb != 0u) { // chunks with an event or an error position leave a record (one shared-memory atomic per batch)
+            uint32_t first = 0u;
+            if (lane == 0) { first = atomicAdd(evcount, (uint32_t)__popc(Xb)); }
+            first = __shfl_sync(0xFFFFFFFFu, first, 0);
+            const uint32_t rslot = first + (uint32_t)__popc(Xb & below);
+            if (((ev | er) != 0u) && rslot < kEvCap) { tile_events[(size_t)t * kEvCap + rslot] = make_uint4(chunk, evsc, deler, misc); }
+        }
+    }
+    __syncwarp(); // the map is rewritten for the warp's next tile
 }
 
 // ====================================================================================================================
@@ -607,6 +674,54 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             const bool interior = geom.evl - t0 >= (int64_t)kTileBytes + 32; // every byte (and its halo) owned and below the event limit
             uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, rows = 0, anydel = 0;
             if (dbg & 64u) { wK = kRowsPerWarp * kRowBytes; rows = (dbg >> 8) & 0xFFu; } // experiment: analysis off, rows flagged as told
+            else if (interior && !(dbg & 2048u)) {
+                // interior tile: SWAR zero-pair test of the warp's eight rows, four rows (independent instruction chains) at a
+                // time; one vote sends the common "no two adjacent zero bytes anywhere" case on, otherwise the slow chunks are
+                // analysed exactly, ranked in stream order (analyse_slow_chunks)
+                uint32_t slow8 = 0;
+#pragma unroll kAnalyserUnroll
+                for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
+                    const uint8_t* rp = st + kLead + (warp * kRowsPerWarp + i0) * kRowBytes + lane * 16;
+                    uint4 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { v[k] = *reinterpret_cast<const uint4*>(rp + k * kRowBytes); }
+                    uint32_t wp[4], wn[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        wp[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes - 4);
+                        wn[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes + 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        slow8 |= (zero_pair_any(wp[k], v[k].x, v[k].y, v[k].z, v[k].w, wn[k]) != 0u ? 1u : 0u) << (i0 + k);
+                    }
+                }
+                uint32_t wDel = 0;
+                const uint32_t rowany = __reduce_or_sync(0xFFFFFFFFu, slow8); // bit i: row i has a slow chunk
+                if (rowany != 0u) {
+                    const uint32_t thr = (dbg & 0xF000u) ? ((dbg >> 12) & 15u) - 1u : 1u; // experiment switch; production: 1
+                    if ((uint32_t)__popc(rowany) <= thr) {
+                        // a single flagged row: row by row (measured: shorter dependency chain than ranking the chunks first)
+                        uint32_t dummyK = 0;
+                        for (uint32_t rm = rowany; rm != 0u; rm &= rm - 1u) {
+                            const int i = __ffs((int)rm) - 1;
+                            const RowMasks r = analyze_staged_row(st, warp * kRowsPerWarp + i, lane, t0, geom, wN, dummyK, wKind, wErr);
+                            rows |= 1u << i;
+                            wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.deler & 0xFFFFu));
+                            if (((r.evsc & 0xFFFFu) | (r.deler >> 16)) != 0u) {
+                                const uint32_t slot = atomicAdd(&sm.evcount[s], 1u);
+                                if (slot < kEvCap) {
+                                    tile_events[(size_t)t * kEvCap + slot] = make_uint4((uint32_t)((warp * kRowsPerWarp + i) * 32 + lane), r.evsc, r.deler, r.misc);
+                                }
+                            }
+                        }
+                    } else {
+                        analyse_slow_chunks(st, sm.slowmap[warp], warp, lane, slow8, t0, t, geom, &sm.evcount[s], tile_events, wN, wDel, wKind, wErr, rows);
+                    }
+                }
+                wK = kRowsPerWarp * kRowBytes - wDel;
+                anydel = wDel;
+            }
             else
             // Rows are taken four at a time: the four loads, halo exchanges and zero-pair tests are independent
             // instruction chains, and one vote sends the common "no two adjacent zero bytes anywhere" case on.
@@ -744,6 +859,169 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
 
         // ---- tile with flagged rows: exact masks of those rows, warp aggregates, ordered emission, row-wise write-out
         fix_stage(st, t, t0, size, tid);
+        if (geom.evl - t0 >= (int64_t)kTileBytes + 32 && !(dbg & 65536u)) {
+            // Interior tile.  The warp ranks the slow chunks of its eight rows in stream order and takes them 32 at a time
+            // (every lane busy, see analyse_slow_chunks); pass 1 parks the masks and builds the warp aggregate, pass 2 emits.
+            uint8_t* const map = sm.slowmap[warp];
+            const uint32_t below = (1u << lane) - 1u;
+            uint32_t total = 0;
+#pragma unroll 1
+            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
+                const uint8_t* rp = st + kLead + (warp * kRowsPerWarp + i0) * kRowBytes + lane * 16;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + k * kRowBytes);
+                    const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes - 4);
+                    const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes + 16);
+                    const bool mine = zero_pair_any(wp, v.x, v.y, v.z, v.w, wn) != 0u;
+                    const uint32_t sb = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (mine) { map[total + (uint32_t)__popc(sb & below)] = (uint8_t)((i0 + k) * 32 + lane); }
+                    total += (uint32_t)__popc(sb);
+                }
+            }
+            __syncwarp();
+            constexpr int kBatches = kRowsPerWarp;
+            uint32_t p_evsc[kBatches], p_deler[kBatches], p_misc[kBatches];
+            uint32_t wN = 0, wDel = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
+#pragma unroll 1
+            for (int b = 0; b < kBatches; b++) {
+                const uint32_t slot = (uint32_t)b * 32u + (uint32_t)lane;
+                if ((uint32_t)b * 32u >= total) { break; }
+                uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu;
+                if (slot < total) {
+                    const uint32_t chunk = (uint32_t)(warp * kRowsPerWarp * 32) + map[slot];
+                    const uint8_t* rp = st + kLead + chunk * 16u;
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp);
+                    const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
+                    const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
+                    const uint3 m3 = analyze_cold(wp, v, wn, t0 + (int64_t)chunk * 16, geom.size, geom.own, geom.evl);
+                    evsc = m3.x; deler = m3.y; misc = m3.z;
+                }
+                p_evsc[b] = evsc; p_deler[b] = deler; p_misc[b] = misc;
+                const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
+                uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+                if (ev != 0u) {
+                    const int tp = 31 - __clz((int)ev);
+                    lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                    le = ((er >> tp) >> 1) != 0u;
+                }
+                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
+                wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(del));
+                uint32_t rk, re;
+                warp_carry_total(Eb, Sb, Rb, rk, re);
+                hevcb_carry_combine(wKind, wErr, rk, re);
+            }
+            if (lane == 0) {
+                WarpAgg a;
+                a.n = wN; a.k = kRowsPerWarp * kRowBytes - wDel; a.kind = wKind; a.err = wErr; a.del = wDel; a.rows = 0;
+                a.pad[0] = a.pad[1] = 0;
+                sm.wagg[it & 1][warp] = a;
+            }
+            bar_sync(kBarWork, kWorkerThreads);
+            uint32_t rN = 0, rK = 0, rKind = HEVCB_KIND_PASS, rErr = 0, tileDel = 0;
+            {
+                uint32_t tn = 0, tk = 0, ak = HEVCB_KIND_PASS, ae = 0;
+#pragma unroll
+                for (int w = 0; w < kWorkers; w++) {
+                    const WarpAgg a = sm.wagg[it & 1][w];
+                    if (w == warp) { rN = tn; rK = tk; rKind = ak; rErr = ae; }
+                    tn += a.n;
+                    tk += a.k;
+                    hevcb_carry_combine(ak, ae, a.kind, a.err);
+                    tileDel += a.del;
+                }
+            }
+            const bool write_img = (rbsp != nullptr) && !(dbg & 4u);
+            const bool compacting = write_img && tileDel != 0u && wDel != 0u; // this warp's rows lose bytes
+            uint16_t* const dm = sm.delmask[warp];
+            if (compacting) {
+                *reinterpret_cast<uint4*>(dm + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+            }
+            // pass 2: ordered emission over the ranked chunks
+            {
+                uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
+                hevcb_carry_combine(cKind, cErr, rKind, rErr);
+                uint32_t nrun = rN, drun = (uint32_t)(warp * kRowsPerWarp * kRowBytes) - rK; // start codes / removed bytes before, within the tile
+#pragma unroll 1
+                for (int b = 0; b < kBatches; b++) {
+                    const uint32_t slot = (uint32_t)b * 32u + (uint32_t)lane;
+                    if ((uint32_t)b * 32u >= total) { break; }
+                    const uint32_t evsc = p_evsc[b], deler = p_deler[b], misc = p_misc[b];
+                    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
+                    const uint32_t local = (slot < total) ? (uint32_t)map[slot] : 0u;
+                    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+                    if (ev != 0u) {
+                        const int tp = 31 - __clz((int)ev);
+                        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                        le = ((er >> tp) >> 1) != 0u;
+                    }
+                    const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                    const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                    const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                    uint32_t ck, ce;
+                    warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+                    if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the batch
+                    const uint32_t c = (uint32_t)__popc(sc);
+                    const uint32_t ninc = warp_incl_scan(c, lane);
+                    uint32_t dinc = 0, d = 0;
+                    if (tileDel != 0u) { // (uniform) tiles that keep every byte need no removed-byte ranks
+                        d = (uint32_t)__popc(del);
+                        dinc = warp_incl_scan(d, lane);
+                        if (compacting && del != 0u) { dm[local] = (uint16_t)del; }
+                    }
+                    if ((ev | er) != 0u) {
+                        const uint32_t chunk = (uint32_t)(warp * kRowsPerWarp * 32) + local;
+                        emit_cold(evsc, deler, misc, t0 + (int64_t)chunk * 16, (int64_t)(tileN + nrun + (ninc - c)),
+                                  (int64_t)(tileK + (long long)chunk * 16 - (long long)(drun + dinc - d)), ck, ce, sink);
+                    }
+                    uint32_t rk, re;
+                    warp_carry_total(Eb, Sb, Rb, rk, re);
+                    hevcb_carry_combine(cKind, cErr, rk, re);
+                    nrun += __shfl_sync(0xFFFFFFFFu, ninc, 31);
+                    if (tileDel != 0u) { drun += __shfl_sync(0xFFFFFFFFu, dinc, 31); }
+                }
+            }
+            if (write_img) {
+                if (tileDel == 0u) {
+                    copy_tile(rbsp + tileK, st + kLead, kTileBytes, tid); // every byte kept: one shifted vector copy by all workers
+                } else {
+                    // tile with removed bytes: every warp closes the gaps of its own rows in place (shared memory), then copies
+                    // its kept bytes out as one span
+                    uint8_t* const wb = st + kLead + warp * (kRowsPerWarp * kRowBytes);
+                    uint32_t out = kRowsPerWarp * kRowBytes;
+                    if (compacting) {
+                        __syncwarp();
+                        out = 0;
+#pragma unroll 1
+                        for (int i = 0; i < kRowsPerWarp; i++) {
+                            const uint32_t del = dm[i * 32 + lane];
+                            if (out == (uint32_t)(i * kRowBytes) && !__any_sync(0xFFFFFFFFu, del != 0u)) { out += kRowBytes; continue; } // still in place
+                            const uint4 v = *reinterpret_cast<const uint4*>(wb + i * kRowBytes + lane * 16);
+                            const uint32_t keep = 0xFFFFu & ~del;
+                            const uint32_t c = (uint32_t)__popc(keep);
+                            const uint32_t inc = warp_incl_scan(c, lane);
+                            __syncwarp(); // every lane holds its chunk before bytes move
+                            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                            uint8_t* o = wb + out + (inc - c);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                if ((keep >> j) & 1u) { *o++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3))); }
+                            }
+                            __syncwarp();
+                            out += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                        }
+                    }
+                    copy_span(rbsp + tileK + rK, wb, out, lane, 32u);
+                }
+            }
+            bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
+            s = (s + 1 == kStages) ? 0 : s + 1;
+            continue;
+        }
         const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kRowsPerWarp)) & 0xFFu;
         // pass 1: aggregates of this warp's flagged rows; their masks are parked (thread-local memory) for pass 2
         uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, anyD = 0;

@@ -92,7 +92,7 @@ def test_config1_stream_device_api(ctx):
     assert np.array_equal(res2.rbsp_end.cpu().numpy()[:10003], res.rbsp_end[:10003])
 
 
-@pytest.mark.parametrize("nal_size,dense", [(64, False), (4096, False), (1 << 20, False), (4096, True), (67, True)])
+@pytest.mark.parametrize("nal_size,dense", [(64, False), (256, False), (1000, False), (4096, False), (1 << 20, False), (4096, True), (67, True), (300, True)])
 def test_config2_shapes(ctx, nal_size, dense):
     """BASELINE config 2 shapes at 96 MiB: fixed-size NALs with escaped random payload, and the EPB-dense worst case"""
     import torch
