@@ -44,13 +44,16 @@ constexpr int kSyncThreads = (kWorkers + 1) * 32; // workers + the control warp 
 constexpr int kThreads = (kWorkers + 2) * 32;     // + the scanner warp (only active in CTA 0)
 constexpr int kWorkerThreads = kWorkers * 32;
 constexpr int kRowBytes = 512;  // one warp-row: 32 lanes x 16 B
-constexpr int kRowsPerWarp = 8; // rows a warp walks in order (its carries stay in registers)
+#ifndef HEVCB_SCAN_ROWS
+#define HEVCB_SCAN_ROWS 8
+#endif
+constexpr int kRowsPerWarp = HEVCB_SCAN_ROWS; // rows a warp walks in order (its carries stay in registers); 4 or 8
 constexpr int kRows = kWorkers * kRowsPerWarp;
 constexpr int kTileBytes = kRows * kRowBytes; // 32 KiB
 constexpr int kLead = 128;                    // leading halo: a whole 128-byte line so that every bulk copy starts line-aligned
 constexpr int kStageBytes = kLead + kTileBytes + 16;
 #ifndef HEVCB_SCAN_STAGES
-#define HEVCB_SCAN_STAGES 3
+#define HEVCB_SCAN_STAGES 2
 #endif
 constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memory (one being worked on, the others in flight)
 #ifndef HEVCB_SCAN_AUNROLL
@@ -938,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             const bool compacting = write_img && tileDel != 0u && wDel != 0u; // this warp's rows lose bytes
             uint16_t* const dm = sm.delmask[warp];
             if (compacting) {
-                *reinterpret_cast<uint4*>(dm + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+                for (int e = lane * 8; e < kRowsPerWarp * 32; e += 256) { *reinterpret_cast<uint4*>(dm + e) = make_uint4(0u, 0u, 0u, 0u); }
                 __syncwarp();
             }
             // pass 2: ordered emission over the ranked chunks
@@ -1321,9 +1324,10 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
             ctx->last_flagged_frac = st[2] ? (double)st[1] / ((double)st[2] * kRows) : 0.0;
             ctx->stats_pending = false;
         }
-        // 35 % analysers when the writers analyse most tiles themselves, 70 % when the tiles are handed over as records but most
-        // rows need exact analysis (NALs of ~1 KiB: the analysers are the bottleneck), 60 % otherwise
-        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 7 + 10) / 20 : (ctx->last_flagged_frac > 0.5 ? (grid * 7 + 5) / 10 : (grid * 3 + 2) / 5);
+        // 3/8 analysers when the writers analyse most tiles themselves (tiny NALs, EPB-dense payloads); 65 % when more than a fifth
+        // of the rows needed exact analysis (NALs <= 2 KiB: the analysers are the bottleneck); 60 % otherwise (measured optima, 4 GiB)
+        const double ff = ctx->last_flagged_frac;
+        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 3 + 4) / 8 : (ff > 0.2 ? (grid * 13 + 10) / 20 : (grid * 3 + 2) / 5);
         if (n_an < 1) { n_an = 1; }
         if (n_an > grid - 1) { n_an = grid - 1; }
         if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
