@@ -284,6 +284,12 @@ __device__ __noinline__ uint3 analyze_cold(uint32_t wp, uint4 v, uint32_t wn, in
     return make_uint3(m.ev | (m.sc << 16), m.del | (m.err << 16), m.valid | (m.scb << 16));
 }
 
+__device__ __noinline__ uint3 analyze_interior_cold(uint32_t wp, uint4 v, uint32_t wn)
+{
+    const hevcb_chunk_masks m = hevcb_chunk_analyze_interior(wp, v.x, v.y, v.z, v.w, wn);
+    return make_uint3(m.ev | (m.sc << 16), m.del | (m.err << 16), m.valid | (m.scb << 16));
+}
+
 __device__ __noinline__ void emit_cold(uint32_t evsc, uint32_t deler, uint32_t misc, int64_t g0, int64_t nbase, int64_t kbase, uint32_t ck,
                                        uint32_t ce, DevSink sink)
 {
@@ -536,7 +542,7 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
             const uint4 v = *reinterpret_cast<const uint4*>(rp);
             const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
             const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
-            const hevcb_chunk_masks m = hevcb_chunk_analyze(wp, v.x, v.y, v.z, v.w, wn, t0 + (int64_t)chunk * 16, geom.size, geom.own, geom.evl);
+            const hevcb_chunk_masks m = hevcb_chunk_analyze_interior(wp, v.x, v.y, v.z, v.w, wn); // interior tile: no position limits
             evsc = m.ev | (m.sc << 16); deler = m.del | (m.err << 16); misc = m.valid | (m.scb << 16);
         }
         const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
@@ -897,7 +903,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const uint4 v = *reinterpret_cast<const uint4*>(rp);
                     const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
                     const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
-                    const uint3 m3 = analyze_cold(wp, v, wn, t0 + (int64_t)chunk * 16, geom.size, geom.own, geom.evl);
+                    const uint3 m3 = analyze_interior_cold(wp, v, wn); // interior tile: no position limits
                     evsc = m3.x; deler = m3.y; misc = m3.z;
                 }
                 p_evsc[b] = evsc; p_deler[b] = deler; p_misc[b] = misc;
@@ -956,6 +962,14 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     const uint32_t evsc = p_evsc[b], deler = p_deler[b], misc = p_misc[b];
                     const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
                     const uint32_t local = (slot < total) ? (uint32_t)map[slot] : 0u;
+                    if (!__any_sync(0xFFFFFFFFu, (ev | er) != 0u)) {
+                        // nothing to emit and no carry change in this batch (EPB-dense payload): only the removed bytes count
+                        if (tileDel != 0u) {
+                            if (compacting && del != 0u) { dm[local] = (uint16_t)del; }
+                            drun += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(del));
+                        }
+                        continue;
+                    }
                     uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
                     if (ev != 0u) {
                         const int tp = 31 - __clz((int)ev);

@@ -79,23 +79,59 @@ struct hevcb_chunk_masks {
 //   own   bytes that are kept / reported by this pass (image, removal and error masks stop here)
 //   evl   events and error positions are honoured below evl (whole stream and last shard: own - HEVCB_TAIL_ZONE, the rest
 //         is resolved by hevcb_scan_tail; inner shard: own, the patterns read on into the halo)
+// The three per-byte facts every predicate is built from, as 21-bit masks (bit (j+3) <-> position g0+j, j in [-3, 17]):
+// LE: byte <= 3, B0 / B1: bit 0 / bit 1 of the byte.  Then  == 0: LE & ~B0 & ~B1,  == 1: LE & B0 & ~B1,  == 3: LE & B0 & B1.
+struct hevcb_chunk_bits {
+    uint32_t LE, B0, B1;
+};
+HEVCB_HD uint32_t hevcb_gather_bit0(uint32_t w) { return (((w & 0x01010101u) * 0x00204081u) >> 21) & 0xFu; }
+HEVCB_HD hevcb_chunk_bits hevcb_chunk_classify(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn)
+{
+    const uint32_t cfc = 0xFCFCFCFCu;
+    hevcb_chunk_bits b;
+    b.LE = (hevcb_gather4(hevcb_zero_flags(wp & cfc)) >> 1) | (hevcb_gather4(hevcb_zero_flags(w0 & cfc)) << 3) |
+           (hevcb_gather4(hevcb_zero_flags(w1 & cfc)) << 7) | (hevcb_gather4(hevcb_zero_flags(w2 & cfc)) << 11) |
+           (hevcb_gather4(hevcb_zero_flags(w3 & cfc)) << 15) | ((hevcb_gather4(hevcb_zero_flags(wn & cfc)) & 3u) << 19);
+    b.B0 = (hevcb_gather_bit0(wp) >> 1) | (hevcb_gather_bit0(w0) << 3) | (hevcb_gather_bit0(w1) << 7) | (hevcb_gather_bit0(w2) << 11) |
+           (hevcb_gather_bit0(w3) << 15) | ((hevcb_gather_bit0(wn) & 3u) << 19);
+    b.B1 = (hevcb_gather_bit0(wp >> 1) >> 1) | (hevcb_gather_bit0(w0 >> 1) << 3) | (hevcb_gather_bit0(w1 >> 1) << 7) |
+           (hevcb_gather_bit0(w2 >> 1) << 11) | (hevcb_gather_bit0(w3 >> 1) << 15) | ((hevcb_gather_bit0(wn >> 1) & 3u) << 19);
+    return b;
+}
+
+// Exact masks of a chunk whose 16 bytes and the 3 bytes behind them are all owned, below the event limit and inside the data
+// (every chunk of an interior tile): no position limits apply.
+HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze_interior(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn)
+{
+    hevcb_chunk_masks m;
+    const hevcb_chunk_bits b = hevcb_chunk_classify(wp, w0, w1, w2, w3, wn);
+    const uint32_t Z = b.LE & ~(b.B0 | b.B1), O = b.LE & b.B0 & ~b.B1, T3 = b.LE & b.B0 & b.B1;
+    const uint32_t P = Z & (Z >> 1);                       // bit (j+3): b[j]==0 && b[j+1]==0
+    const uint32_t EV = P & ((b.LE & ~b.B1) >> 2) & 0x7FFFFu; // third byte <= 1; events at j in [-3, 15]
+    const uint32_t SC = P & (O >> 2) & 0x7FFFFu;
+    const uint32_t PP = P << 2;                            // bit (j+3): b[j-2]==0 && b[j-1]==0
+    const uint32_t DEL = T3 & PP;
+    const uint32_t ERR1 = b.LE & ~T3 & PP & ~(EV << 2);    // third byte of an honoured event is not an error
+    const uint32_t ERR2 = DEL & ((~b.LE) >> 1);            // EPB followed by > 3
+    m.ev = (EV >> 3) & 0xFFFFu;
+    m.sc = (SC >> 3) & 0xFFFFu;
+    m.scb = SC & 7u;
+    m.del = (DEL >> 3) & 0xFFFFu;
+    m.err = ((ERR1 | ERR2) >> 3) & 0xFFFFu;
+    m.valid = 0xFFFFu;
+    return m;
+}
+
 HEVCB_HD hevcb_chunk_masks hevcb_chunk_analyze(uint32_t wp, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn,
                                                int64_t g0, int64_t size, int64_t own, int64_t evl)
 {
+    if (own - g0 >= 16 && evl - g0 >= 16 && size - 1 - g0 >= 16) { return hevcb_chunk_analyze_interior(wp, w0, w1, w2, w3, wn); }
     hevcb_chunk_masks m;
     // 21-bit masks, bit (j+3) <-> position g0+j, j in [-3, 17]
-    uint32_t Z = (hevcb_gather4(hevcb_zero_flags(wp)) >> 1) | (hevcb_gather4(hevcb_zero_flags(w0)) << 3) |
-                 (hevcb_gather4(hevcb_zero_flags(w1)) << 7) | (hevcb_gather4(hevcb_zero_flags(w2)) << 11) |
-                 (hevcb_gather4(hevcb_zero_flags(w3)) << 15) | ((hevcb_gather4(hevcb_zero_flags(wn)) & 3u) << 19);
-    const uint32_t c1 = 0x01010101u, c3 = 0x03030303u, cfc = 0xFCFCFCFCu;
-    uint32_t O = (hevcb_gather4(hevcb_zero_flags(wp ^ c1)) >> 1) | (hevcb_gather4(hevcb_zero_flags(w0 ^ c1)) << 3) |
-                 (hevcb_gather4(hevcb_zero_flags(w1 ^ c1)) << 7) | (hevcb_gather4(hevcb_zero_flags(w2 ^ c1)) << 11) |
-                 (hevcb_gather4(hevcb_zero_flags(w3 ^ c1)) << 15) | ((hevcb_gather4(hevcb_zero_flags(wn ^ c1)) & 3u) << 19);
-    uint32_t T3 = (hevcb_gather4(hevcb_zero_flags(w0 ^ c3)) << 3) | (hevcb_gather4(hevcb_zero_flags(w1 ^ c3)) << 7) |
-                  (hevcb_gather4(hevcb_zero_flags(w2 ^ c3)) << 11) | (hevcb_gather4(hevcb_zero_flags(w3 ^ c3)) << 15);
-    uint32_t LE3 = (hevcb_gather4(hevcb_zero_flags(w0 & cfc)) << 3) | (hevcb_gather4(hevcb_zero_flags(w1 & cfc)) << 7) |
-                   (hevcb_gather4(hevcb_zero_flags(w2 & cfc)) << 11) | (hevcb_gather4(hevcb_zero_flags(w3 & cfc)) << 15) |
-                   ((hevcb_gather4(hevcb_zero_flags(wn & cfc)) & 1u) << 19);
+    const hevcb_chunk_bits b = hevcb_chunk_classify(wp, w0, w1, w2, w3, wn);
+    const uint32_t Z = b.LE & ~(b.B0 | b.B1), O = b.LE & b.B0 & ~b.B1;
+    const uint32_t T3 = b.LE & b.B0 & b.B1 & 0x7FFF8u;    // positions 0..15
+    const uint32_t LE3 = b.LE & 0xFFFF8u;                  // positions 0..16
 
     // position limits
     int64_t rem = own - g0;                      // positions j < rem are owned
