@@ -7,15 +7,17 @@
 //   * a persistent cooperative grid (2 CTAs / SM) is split into ANALYSER and WRITER CTAs plus one SCANNER warp; the
 //     dependency analyser -> scanner -> writer is one-directional (see the comment in front of the kernel);
 //   * 32 KiB tiles (+128 B leading / 16 B trailing halo) are staged into shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier), three stages per CTA; a tile is loaded by one analyser and, a few microseconds later,
+//     (cp.async.bulk + mbarrier), two stages per CTA; a tile is loaded by one analyser and, a few microseconds later,
 //     by one writer -- out of L2, the analysers stay within a window of the writers' progress;
-//   * every lane owns 16 bytes: an exact "two adjacent zero bytes?" SWAR test sends the common case down a fast path,
-//     exact predicate bit masks (hevcb_chunk_analyze) are built otherwise;
+//   * every lane owns 16 bytes: an exact "two adjacent zero bytes?" SWAR test sends the common case down a fast path;
+//     the chunks that fail it are ranked in stream order and their exact predicate bit masks (hevcb_chunk_analyze) are
+//     built 32 at a time, every lane busy;
 //   * counts (start codes, kept bytes) go through redux, the ordered (last-event-kind, error) carry through warp ballots,
 //     lane -> row -> warp -> tile; across tiles one warp scans the 16-byte tile aggregates in stream order;
 //   * the EPB-free image is written as aligned 16-byte vectors, funnel-shifted by the tile-uniform misalignment; NAL
 //     offsets are written by the lanes that own the events (hevcb_scan_emit_kernel for tiles handed over as event
-//     records, the writer itself for tiles with removed bytes or very many events).
+//     records, the writer itself for tiles with removed bytes or very many events); tiles with removed bytes are
+//     compacted in shared memory first, so the image never sees byte-granular stores.
 //
 // HBM traffic: input read once (second load from L2), image written once, 32 B of metadata per NAL.  Tensor cores unused:
 // nothing here is a contraction.
@@ -23,7 +25,8 @@
 // HEVCB_SCAN_DEBUG (context creation) is a bit mask of measurement switches used to attribute time to the parts of the
 // kernel (results are wrong with any of them set): 1 no scanner / fake prefixes, 4 no image write, 32 writers off,
 // 64 analysis off (bits 8..15: rows to flag), 128 writers do not wait for the scanner, 512 every tile takes the clean
-// path, 1024 no event records.  HEVCB_SCAN_ANALYSERS / HEVCB_SCAN_WINDOW override the role split and the L2 window.
+// path, 1024 no event records, 2048 / 65536 the row-by-row analysis / writer paths of interior tiles, bits 12..15 rows up to
+// which the analyser stays row-wise (+1).  HEVCB_SCAN_ANALYSERS / HEVCB_SCAN_WINDOW override the role split and the L2 window.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -60,7 +63,10 @@ constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memo
 #define HEVCB_SCAN_AUNROLL 1
 #endif
 constexpr int kAnalyserUnroll = HEVCB_SCAN_AUNROLL; // the analyser's loop over groups of four rows stays rolled (two roles share the instruction cache)
-constexpr int kScanPerLane = 10; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
+#ifndef HEVCB_SCAN_PERLANE
+#define HEVCB_SCAN_PERLANE 5
+#endif
+constexpr int kScanPerLane = HEVCB_SCAN_PERLANE; // tile aggregates per lane and batch of the scanner warp (160 tiles per batch)
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
 struct ScanGeom {
@@ -366,15 +372,19 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 {
     unsigned long long runN = init_n, runK = 0;
     uint32_t runKind = init_kind, runErr = 0;
+    // the aggregates of the next batch are requested before the current batch is combined and published (the round trip to L2
+    // is the scanner's cycle time), so a batch can be short: the writers follow the analysers more closely
+    ulonglong2 nx[kScanPerLane];
+#pragma unroll
+    for (int j = 0; j < kScanPerLane; j++) {
+        const long long idx = (long long)lane * kScanPerLane + j;
+        nx[j] = (idx < n_tiles) ? ld_state(&tile_state[idx]) : pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); // past the end: identity
+    }
     for (long long base = 0; base < n_tiles; base += 32 * kScanPerLane) {
         const long long first = base + (long long)lane * kScanPerLane;
         ulonglong2 sv[kScanPerLane];
 #pragma unroll
-        for (int j = 0; j < kScanPerLane; j++) {
-            const long long idx = first + j;
-            if (idx < n_tiles) { sv[j] = ld_state(&tile_state[idx]); }
-            else { sv[j] = pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); } // past the end: identity
-        }
+        for (int j = 0; j < kScanPerLane; j++) { sv[j] = nx[j]; }
         for (;;) { // re-poll, one batch per round trip, the aggregates that are not published yet
             bool missing = false;
 #pragma unroll
@@ -384,6 +394,11 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
             for (int j = 0; j < kScanPerLane; j++) {
                 if ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[first + j]); }
             }
+        }
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; j++) {
+            const long long idx = first + 32 * kScanPerLane + j;
+            nx[j] = (idx < n_tiles) ? ld_state(&tile_state[idx]) : pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull);
         }
         __threadfence(); // the aggregates observed above happen before the prefixes published below (writers re-read them)
         // lane totals
@@ -1349,7 +1364,7 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
-        g.window = 1200; // tiles (37.5 MiB): more than both roles keep in flight (3 stages x grid); measured: DRAM reads 1.08x the input (1536: 1.7x) at the same speed
+        g.window = 1000; // tiles (31 MiB): more than both roles keep in flight (2 stages x grid) plus a scanner batch; measured: DRAM reads 1.02x the input (1200: 1.24x, 1536: 1.7x) at the same speed
         if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= kStages * grid) { g.window = v; } }
         if (g.window < kStages * grid) { g.window = kStages * grid; }
         if (dbg & 32u) { g.window = 1ll << 40; } // experiment "writers off": nothing to wait for
