@@ -45,7 +45,7 @@ Report file: `gpurun_out/scan_r1_aw_final.ncu-rep` (scratch; numbers copied here
 DRAM traffic per launch = read + write = {rd / 1e9:.3f} + {wr / 1e9:.3f} = **{(rd + wr) / 1e9:.3f} GB**; algorithmic bytes (N_in + N_rbsp + 24*NALs) = {alg / 1e9:.3f} GB -> traffic / algorithmic = {(rd + wr) / alg:.3f}.
 The image is written once.  The input is loaded twice (once by an analyser CTA, once by a writer CTA) but the second load is served by L2: the analysers stay within a 1000-tile (31 MiB) window of the writers' progress counter.  Measured sensitivity (same command, `HEVCB_SCAN_WINDOW`, 2 stages per CTA, scanner batches of 160 tiles): 1200 tiles -> DRAM reads 1.24x the input, 1100 -> 1.10x, 1000 -> 1.03x, all at the same speed (the kernel is not DRAM-bound); at 900 and below the pipeline (2 tiles in flight per CTA in both roles = 592 tiles, plus one scanner batch) is throttled.
 
-Where the time goes now (warp-state sampling of this capture): the largest single item is the writers' control warp polling for prefixes (long scoreboard on one branch: by design, it is the one warp per CTA that waits), then writers' workers at the "prefix ready" barrier, i.e. the writers run slightly ahead of the analysers at the 60/40 split; issue slots are ~40 % used.  The previous single-role pipeline spent 38 % of all warp samples at one CTA barrier in lock-step with the scanner (`profiles/r1_scan_strip_ncu_v1.md`).
+Where the time goes now (warp-state sampling of this capture, `--page source`): 31 % of all samples are the analysers' worker warps waiting for their bulk copies (`mbarrier.try_wait` loop), 15 % the writers' workers at the \"prefix ready\" barrier, 2 % the analysers' control warps polling the writers' progress (the L2 window); no single arithmetic instruction holds more than 1.5 %.  Issue slots are ~37 % used: the pass is bound by the latency of the memory system under the mixed load (the bare load pipeline alone sustains 4.0 TB/s, see DESIGN 4.1), not by DRAM bandwidth or instruction issue.  The previous single-role pipeline spent 38 % of all warp samples at one CTA barrier in lock-step with the scanner (`profiles/r1_scan_strip_ncu_v1.md`).
 
 SASS evidence of the async-copy path: `UBLKCP.S.G` (cp.async.bulk), `SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `REDUX`, `VOTE`, `LDG.E.128.STRONG.GPU` (tile-state polls) in `cuobjdump -sass hevcbitstream_b200/libhevcb200.so`.
 """
