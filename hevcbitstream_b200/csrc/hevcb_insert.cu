@@ -56,12 +56,20 @@ struct RowInfo {
 
 // One 512-byte row of a part: loads, zero-run carry, insertion mask.  run_m = length of the zero run that ends right in
 // front of the row's first byte of the part (warp uniform), updated to the run that reaches the end of the row.
-__device__ __forceinline__ RowInfo insert_row(const uint8_t* __restrict__ img, int64_t row, int64_t off, int64_t end, int lane, uint32_t& run_m)
+// Rows whose loads are issued together (template parameter kInsAhead of the part walkers): one row per round trip leaves the
+// warp latency bound on long parts (16 KiB NALs: 1073 -> 1317 GB/s with four), short parts keep the short loop.
+__device__ __forceinline__ uint4 load_row_chunk(const uint8_t* __restrict__ img, int64_t row, int64_t off, int64_t end, int lane)
+{
+    const int64_t cpos = row + lane * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (cpos < end && cpos + 16 > off) { v = *reinterpret_cast<const uint4*>(img + cpos); }
+    return v;
+}
+__device__ __forceinline__ RowInfo insert_row(const uint4 v, int64_t row, int64_t off, int64_t end, int lane, uint32_t& run_m)
 {
     RowInfo r;
     const int64_t cpos = row + lane * 16;
-    r.v = make_uint4(0, 0, 0, 0);
-    if (cpos < end && cpos + 16 > off) { r.v = *reinterpret_cast<const uint4*>(img + cpos); }
+    r.v = v;
     if (row >= off && row + 512 <= end) {
         // Interior row, the common case: no insertion is possible when the row holds no two adjacent zero bytes and the run
         // that enters it cannot complete one with the row's first byte.  One SWAR test + one vote instead of the exact masks.
@@ -133,17 +141,38 @@ struct AssembleParts {
 };
 
 // insertions of one escaped part (count pass)
+template <int kInsAhead>
+__device__ __forceinline__ uint32_t count_part_n(const uint8_t* __restrict__ base, int64_t off, int64_t end, int lane, uint32_t& run_m)
+{
+    uint32_t total = 0;
+    int64_t row = off & ~(int64_t)15;
+    for (; row < end; row += 512 * kInsAhead) {
+        uint4 v[kInsAhead];
+#pragma unroll
+        for (int k = 0; k < kInsAhead; k++) { v[k] = load_row_chunk(base, row + 512 * k, off, end, lane); }
+#pragma unroll
+        for (int k = 0; k < kInsAhead; k++) {
+            if (row + 512 * k < end) {
+                const RowInfo r = insert_row(v[k], row + 512 * k, off, end, lane, run_m);
+                total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
+            }
+        }
+    }
+    {
+        const int64_t row0 = off & ~(int64_t)15;
+        const int64_t after = row0 + ((end - row0 + 511) / 512) * 512; // end of the last row
+        run_m -= (uint32_t)(after - end); // bytes of the last row behind the part
+    }
+    return total;
+}
+
 __device__ __forceinline__ uint32_t count_part(const uint8_t* __restrict__ base, int64_t off, int64_t end, int lane, uint32_t& run_m)
 {
     if (end <= off) { return 0u; }
-    uint32_t total = 0;
-    int64_t row = off & ~(int64_t)15;
-    for (; row < end; row += 512) {
-        const RowInfo r = insert_row(base, row, off, end, lane, run_m);
-        total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
-    }
-    run_m -= (uint32_t)(row - end); // bytes of the last row behind the part
-    return total;
+    const int64_t len = end - off;
+    if (len > 2048) { return count_part_n<4>(base, off, end, lane, run_m); }
+    if (len > 512) { return count_part_n<2>(base, off, end, lane, run_m); }
+    return count_part_n<1>(base, off, end, lane, run_m);
 }
 
 // pass 1: output size of every NAL (start code + verbatim bytes + escaped bytes)
@@ -175,14 +204,21 @@ __global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const Assembl
 }
 
 // writes one escaped part at out + o; returns the bytes written (warp uniform)
-__device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, int64_t off, int64_t end, uint8_t* __restrict__ out, int64_t o, int lane,
-                                              uint32_t& run_m)
+template <int kInsAhead>
+__device__ __forceinline__ int64_t write_part_n(const uint8_t* __restrict__ base, int64_t off, int64_t end, uint8_t* __restrict__ out, int64_t o, int lane,
+                                                uint32_t& run_m)
 {
-    if (end <= off) { return 0; }
     const int64_t o0 = o;
-    int64_t row = off & ~(int64_t)15;
-    for (; row < end; row += 512) {
-        const RowInfo r = insert_row(base, row, off, end, lane, run_m);
+    const int64_t row0 = off & ~(int64_t)15;
+    for (int64_t rowq = row0; rowq < end; rowq += 512 * kInsAhead) {
+      uint4 vq[kInsAhead];
+#pragma unroll
+      for (int k = 0; k < kInsAhead; k++) { vq[k] = load_row_chunk(base, rowq + 512 * k, off, end, lane); }
+#pragma unroll
+      for (int k = 0; k < kInsAhead; k++) {
+        const int64_t row = rowq + 512 * k;
+        if (row >= end) { break; }
+        const RowInfo r = insert_row(vq[k], row, off, end, lane, run_m);
         const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
         uint32_t cnt = 16u, inc = ((uint32_t)lane + 1u) * 16u, row_total = 512u;
         if (!clean) { // output offsets of the lanes: only rows with insertions or partial chunks need the scan
@@ -236,9 +272,20 @@ __device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, 
             }
         }
         o += row_total;
+      }
     }
-    run_m -= (uint32_t)(row - end);
+    run_m -= (uint32_t)(row0 + ((end - row0 + 511) / 512) * 512 - end);
     return o - o0;
+}
+
+__device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, int64_t off, int64_t end, uint8_t* __restrict__ out, int64_t o, int lane,
+                                              uint32_t& run_m)
+{
+    if (end <= off) { return 0; }
+    const int64_t len = end - off;
+    if (len > 2048) { return write_part_n<4>(base, off, end, out, o, lane, run_m); }
+    if (len > 512) { return write_part_n<2>(base, off, end, out, o, lane, run_m); }
+    return write_part_n<1>(base, off, end, out, o, lane, run_m);
 }
 
 // pass 2: write start code, verbatim bytes and escaped bytes of every NAL at out_off[k]
