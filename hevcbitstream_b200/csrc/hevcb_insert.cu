@@ -176,8 +176,109 @@ __device__ __forceinline__ uint32_t count_part(const uint8_t* __restrict__ base,
 }
 
 // pass 1: output size of every NAL (start code + verbatim bytes + escaped bytes)
+// ---- long escaped parts are cut into pieces that are walked by different warps --------------------------------------------
+// rbsp_to_nal's state is 0 behind every non-zero byte, so a part B of at least kSplitMin bytes is cut at positions whose
+// preceding byte is non-zero (searched forward from every nominal cut; a cut that finds none within kSplitSearch bytes is
+// dropped): the pieces are independent sub-problems.  The NAL's own entry keeps the start code, the verbatim bytes and part
+// A; the pieces of B go to a side list ("extras") that a second pair of launches walks, one warp per piece.
+constexpr int64_t kSplitSeg = 32 << 10, kSplitMin = 64 << 10, kSplitSearch = 4096;
+constexpr int kSplitMaxPieces = 4096;
+struct SplitList {
+    uint8_t* flag;        // per NAL: 1 = part B is walked through the side list
+    int64_t* e_off;       // per piece: extent of the piece in part B's source
+    int64_t* e_end;
+    int64_t* e_k;         // NAL the piece belongs to
+    int32_t* e_j;         // index of the piece inside its NAL
+    int32_t* e_np;        // pieces of that NAL
+    int64_t* e_size;      // output bytes of the piece (count pass)
+    int64_t* e_prefix;    // output offset of the piece inside its NAL
+    unsigned long long* n_extras;
+    int64_t cap;
+};
+__device__ __forceinline__ int64_t split_pieces(int64_t boff, int64_t bend, int64_t& seg)
+{
+    seg = kSplitSeg;
+    if (bend < 0 || bend - boff < kSplitMin) { return 1; }
+    const int64_t len = bend - boff;
+    int64_t np = len / seg;
+    if (np > kSplitMaxPieces) {
+        seg = ((len / kSplitMaxPieces) + 511) & ~(int64_t)511;
+        np = len / seg;
+    }
+    return np;
+}
+__global__ void __launch_bounds__(256) split_kernel(const AssembleParts P, int64_t n, SplitList L)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || !P.b_off) { return; }
+    const int64_t boff = P.b_off[k], bend = P.b_end[k];
+    int64_t seg;
+    const int64_t np = split_pieces(boff, bend, seg);
+    if (np < 2) { return; }
+    const int64_t base = (int64_t)atomicAdd(L.n_extras, (unsigned long long)np);
+    if (base + np > L.cap) { // no room in the side list: the NAL stays with its own warp; the slots it was handed are marked unused
+        for (int64_t j = 0; base + j < L.cap && j < np; j++) { L.e_k[base + j] = -1; }
+        return;
+    }
+    L.flag[k] = 1;
+    int64_t cut = boff;
+    for (int64_t j = 0; j < np; j++) {
+        int64_t next = bend;
+        if (j + 1 < np) {
+            int64_t q = boff + (j + 1) * seg;
+            const int64_t lim = q + kSplitSearch;
+            while (q < lim && P.b_base[q - 1] == 0) { q++; }
+            next = (q < lim) ? q : cut; // no usable cut: this piece is empty, the next one starts where this one did
+        }
+        L.e_off[base + j] = cut;
+        L.e_end[base + j] = next;
+        L.e_k[base + j] = k;
+        L.e_j[base + j] = (int32_t)j;
+        L.e_np[base + j] = (int32_t)np;
+        cut = next;
+    }
+}
+// count pass over the pieces: output bytes of every piece (piece 0 continues the state part A leaves behind)
+__global__ void __launch_bounds__(kInsThreads) extras_count_kernel(const AssembleParts P, SplitList L, unsigned long long* __restrict__ n_ins_total)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * kInsWarps;
+    int64_t ne = (int64_t)*L.n_extras;
+    if (ne > L.cap) { ne = L.cap; }
+    unsigned long long local_ins = 0;
+    for (int64_t e = wid; e < ne; e += nw) {
+        const int64_t k = L.e_k[e];
+        if (k < 0) { continue; } // slot of a NAL that found no room in the list
+        uint32_t run_m = 0;
+        if (L.e_j[e] == 0 && P.a_off) { (void)count_part(P.a_base, P.a_off[k], P.a_end[k], lane, run_m); }
+        const int64_t off = L.e_off[e], end = L.e_end[e];
+        const uint32_t ins = count_part(P.b_base, off, end, lane, run_m);
+        if (lane == 0) { L.e_size[e] = (end > off ? end - off : 0) + (int64_t)ins; }
+        local_ins += ins;
+    }
+    if (lane == 0 && local_ins) { atomicAdd(n_ins_total, local_ins); }
+}
+// output offsets of the pieces inside their NAL; the NAL's size becomes head + all pieces
+__global__ void __launch_bounds__(256) extras_prefix_kernel(SplitList L, int64_t* __restrict__ out_size)
+{
+    int64_t ne = (int64_t)*L.n_extras;
+    if (ne > L.cap) { ne = L.cap; }
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = L.e_k[e];
+        if (k < 0 || L.e_j[e] != 0) { continue; }
+        int64_t run = out_size[k]; // start code + verbatim bytes + part A, written by the NAL's own warp
+        const int np = L.e_np[e];
+        for (int j = 0; j < np; j++) {
+            L.e_prefix[e + j] = run;
+            run += L.e_size[e + j];
+        }
+        out_size[k] = run;
+    }
+}
+
 __global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const AssembleParts P, int64_t n, int64_t* __restrict__ out_size,
-                                                                   unsigned long long* __restrict__ n_ins_total)
+                                                                   unsigned long long* __restrict__ n_ins_total, const uint8_t* __restrict__ split_flag)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
@@ -193,10 +294,11 @@ __global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const Assembl
         const int64_t aoff = P.a_off ? P.a_off[k] : 0, aend = P.a_off ? P.a_end[k] : 0;
         uint32_t run_m = 0;
         uint32_t total = count_part(P.a_base, aoff, aend, lane, run_m);
-        total += count_part(P.b_base, boff, bend, lane, run_m);
+        const bool split = (bend - boff >= kSplitMin) && split_flag[k] != 0; // part B is counted piece by piece (extras_count_kernel)
+        if (!split) { total += count_part(P.b_base, boff, bend, lane, run_m); }
         if (lane == 0) {
-            out_size[k] = (int64_t)P.sc_len + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) + (bend > boff ? bend - boff : 0) +
-                          (int64_t)total;
+            out_size[k] = (int64_t)P.sc_len + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) +
+                          ((bend > boff && !split) ? bend - boff : 0) + (int64_t)total;
         }
         local_ins += total;
     }
@@ -290,7 +392,7 @@ __device__ __forceinline__ int64_t write_part(const uint8_t* __restrict__ base, 
 
 // pass 2: write start code, verbatim bytes and escaped bytes of every NAL at out_off[k]
 __global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const AssembleParts P, int64_t n, const int64_t* __restrict__ out_off,
-                                                                   uint8_t* __restrict__ out, int64_t out_cap)
+                                                                   uint8_t* __restrict__ out, int64_t out_cap, const uint8_t* __restrict__ split_flag)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
@@ -309,7 +411,26 @@ __global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const Assembl
         }
         uint32_t run_m = 0;
         if (P.a_off) { o += write_part(P.a_base, P.a_off[k], P.a_end[k], out, o, lane, run_m); }
-        o += write_part(P.b_base, boff, bend, out, o, lane, run_m);
+        if (bend - boff < kSplitMin || !split_flag[k]) { o += write_part(P.b_base, boff, bend, out, o, lane, run_m); }
+    }
+}
+
+// pass 2 over the pieces of the long parts
+__global__ void __launch_bounds__(kInsThreads) extras_write_kernel(const AssembleParts P, SplitList L, const int64_t* __restrict__ out_off,
+                                                                   uint8_t* __restrict__ out, int64_t out_cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * kInsWarps + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * kInsWarps;
+    int64_t ne = (int64_t)*L.n_extras;
+    if (ne > L.cap) { ne = L.cap; }
+    for (int64_t e = wid; e < ne; e += nw) {
+        const int64_t k = L.e_k[e];
+        if (k < 0) { continue; }
+        if (out_off[k + 1] > out_cap) { continue; } // capacity overflow is reported by the summary
+        uint32_t run_m = 0;
+        if (L.e_j[e] == 0 && P.a_off) { (void)count_part(P.a_base, P.a_off[k], P.a_end[k], lane, run_m); }
+        (void)write_part(P.b_base, L.e_off[e], L.e_end[e], out, out_off[k] + L.e_prefix[e], lane, run_m);
     }
 }
 
@@ -403,28 +524,52 @@ static int launch_assemble(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, ui
                            hevcb_insert_summary* d_summary, cudaStream_t stream)
 {
     const int64_t nb = (n + kSTile - 1) / kSTile;
-    const size_t need = (size_t)(n > 0 ? n : 1) * 8 + (size_t)(nb + 2) * 8 + 64;
+    const int64_t n1 = n > 0 ? n : 1;
+    const int64_t capE = out_cap / kSplitSeg + 1024; // pieces of long parts (a piece is at least kSplitSeg bytes of output)
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_sizes = 0, o_bs = up((size_t)n1 * 8), o_misc = o_bs + up((size_t)(nb + 2) * 8), o_flag = o_misc + 256;
+    const size_t o_e64 = o_flag + up((size_t)n1), o_e32 = o_e64 + up((size_t)capE * 8) * 5, need = o_e32 + up((size_t)capE * 4) * 2;
     int rc = hevcb_reserve(ctx, &ctx->insert_scratch, need);
     if (rc != HEVCB_OK) { return rc; }
-    int64_t* sizes = reinterpret_cast<int64_t*>(ctx->insert_scratch.p);
-    long long* bs = reinterpret_cast<long long*>(sizes + (n > 0 ? n : 1));
-    unsigned long long* n_ins = reinterpret_cast<unsigned long long*>(bs + nb + 1);
-    HEVCB_CUDA(ctx, cudaMemsetAsync(n_ins, 0, 8, stream));
+    uint8_t* sb = reinterpret_cast<uint8_t*>(ctx->insert_scratch.p);
+    int64_t* sizes = reinterpret_cast<int64_t*>(sb + o_sizes);
+    long long* bs = reinterpret_cast<long long*>(sb + o_bs);
+    unsigned long long* n_ins = reinterpret_cast<unsigned long long*>(sb + o_misc);
+    SplitList L;
+    L.n_extras = n_ins + 1;
+    L.flag = sb + o_flag;
+    L.e_off = reinterpret_cast<int64_t*>(sb + o_e64);
+    L.e_end = reinterpret_cast<int64_t*>(sb + o_e64 + up((size_t)capE * 8));
+    L.e_k = reinterpret_cast<int64_t*>(sb + o_e64 + up((size_t)capE * 8) * 2);
+    L.e_size = reinterpret_cast<int64_t*>(sb + o_e64 + up((size_t)capE * 8) * 3);
+    L.e_prefix = reinterpret_cast<int64_t*>(sb + o_e64 + up((size_t)capE * 8) * 4);
+    L.e_j = reinterpret_cast<int32_t*>(sb + o_e32);
+    L.e_np = reinterpret_cast<int32_t*>(sb + o_e32 + up((size_t)capE * 4));
+    L.cap = capE;
+    HEVCB_CUDA(ctx, cudaMemsetAsync(n_ins, 0, 16, stream));
     if (n == 0) {
         HEVCB_CUDA(ctx, cudaMemsetAsync(d_out_off, 0, 8, stream));
         HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_insert_summary), stream));
         return HEVCB_OK;
     }
+    HEVCB_CUDA(ctx, cudaMemsetAsync(L.flag, 0, (size_t)n, stream));
     long long grid = (long long)ctx->sm_count * 8;
+    long long egrid = grid; // the side list's length is only known on the device: a full grid, idle when the list is empty
     const long long max_grid = (n + kInsWarps - 1) / kInsWarps;
     if (grid > max_grid) { grid = max_grid; }
-    insert_count_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, sizes, n_ins);
+    const long long max_egrid = (capE + kInsWarps - 1) / kInsWarps;
+    if (egrid > max_egrid) { egrid = max_egrid; }
+    split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P, n, L);
+    insert_count_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, sizes, n_ins, L.flag);
+    extras_count_kernel<<<(unsigned)egrid, kInsThreads, 0, stream>>>(P, L, n_ins);
+    extras_prefix_kernel<<<(unsigned)((capE + 255) / 256 < 1024 ? (capE + 255) / 256 : 1024), 256, 0, stream>>>(L, sizes);
     sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs);
     sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
     sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(sizes, n, bs, nb, d_out_off);
-    insert_write_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, d_out_off, d_out, out_cap);
+    insert_write_kernel<<<(unsigned)grid, kInsThreads, 0, stream>>>(P, n, d_out_off, d_out, out_cap, L.flag);
+    extras_write_kernel<<<(unsigned)egrid, kInsThreads, 0, stream>>>(P, L, d_out_off, d_out, out_cap);
     insert_summary_kernel<<<1, 32, 0, stream>>>(d_out_off, n, out_cap, n_ins, d_summary);
-    ctx->launches += 6;
+    ctx->launches += 10;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
 }

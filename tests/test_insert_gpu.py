@@ -165,3 +165,30 @@ def test_full_size_strip_insert_round_trip(ctx):
                             out_cap=size + size // 64 + 4096)
     assert ins["out_bytes"] == size and ins["n_inserted"] == res.n_epb
     assert torch.equal(ins["out"][:size], d[:size])
+
+
+@pytest.mark.parametrize("alphabet", [0, 1, 3])
+def test_long_parts_are_split(ctx, alphabet):
+    """NALs of 64 KiB and more are cut into pieces walked by different warps (cuts only behind non-zero bytes): zero runs
+    around every nominal cut, an all-zero NAL (no usable cut), long and short NALs mixed, every start alignment"""
+    rng = np.random.default_rng(77 + alphabet)
+    n_bytes = 3 << 20
+    rbsp = zero_heavy(rng, n_bytes, alphabet)
+    for c in range(32 << 10, n_bytes, 32 << 10):  # zero runs of various lengths across the nominal cut positions
+        run = int(rng.integers(0, 6000))
+        lo = max(0, c - int(rng.integers(0, run + 1)))
+        rbsp[lo:lo + run] = 0
+    rbsp[(1 << 20) + 1000:(1 << 20) + 200000] = 0  # a long all-zero stretch
+    off, end = [], []
+    p = int(rng.integers(0, 16))
+    while p < n_bytes - 10:
+        ln = int(rng.choice([50, 3000, 65535, 65536, 65537, 100000, 300001, 700000]))
+        e = min(n_bytes, p + ln)
+        off.append(p)
+        end.append(e)
+        p = e + int(rng.integers(0, 3))
+    check(ctx, rbsp, np.array(off, np.int64), np.array(end, np.int64), 3, f"split-a{alphabet}", use_ref=True)
+    # one NAL over the whole buffer, and an all-zero NAL
+    check(ctx, rbsp, np.array([5], np.int64), np.array([n_bytes - 3], np.int64), 4, f"split-one-a{alphabet}")
+    z = np.zeros(200000, np.uint8)
+    check(ctx, z, np.array([0, 7], np.int64), np.array([200000, 150000], np.int64), 0, f"split-zero-a{alphabet}")
