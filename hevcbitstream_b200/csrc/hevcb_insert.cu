@@ -52,6 +52,7 @@ struct RowInfo {
     uint4 v;        // this lane's 16 bytes (aligned chunk of the image)
     uint32_t valid; // bit j: byte belongs to the NAL
     uint32_t ins;   // bit j: 03 is inserted before byte j
+    bool fast;      // (warp uniform) interior row that cannot take an insertion: every byte valid, nothing inserted
 };
 
 // One 512-byte row of a part: loads, zero-run carry, insertion mask.  run_m = length of the zero run that ends right in
@@ -84,6 +85,7 @@ __device__ __forceinline__ RowInfo insert_row(const uint4 v, int64_t row, int64_
         if (!__any_sync(0xFFFFFFFFu, pair != 0u) && !entering) {
             r.valid = 0xFFFFu;
             r.ins = 0u;
+            r.fast = true;
             run_m = (bl == 0u) ? 1u : 0u;
             return r;
         }
@@ -128,6 +130,7 @@ __device__ __forceinline__ RowInfo insert_row(const uint4 v, int64_t row, int64_
         }
     }
     r.ins = ins;
+    r.fast = false;
     return r;
 }
 
@@ -154,7 +157,7 @@ __device__ __forceinline__ uint32_t count_part_n(const uint8_t* __restrict__ bas
         for (int k = 0; k < kInsAhead; k++) {
             if (row + 512 * k < end) {
                 const RowInfo r = insert_row(v[k], row + 512 * k, off, end, lane, run_m);
-                total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins));
+                if (!r.fast) { total += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.ins)); }
             }
         }
     }
@@ -321,7 +324,7 @@ __device__ __forceinline__ int64_t write_part_n(const uint8_t* __restrict__ base
         const int64_t row = rowq + 512 * k;
         if (row >= end) { break; }
         const RowInfo r = insert_row(vq[k], row, off, end, lane, run_m);
-        const bool clean = (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
+        const bool clean = r.fast || (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
         uint32_t cnt = 16u, inc = ((uint32_t)lane + 1u) * 16u, row_total = 512u;
         if (!clean) { // output offsets of the lanes: only rows with insertions or partial chunks need the scan
             cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
