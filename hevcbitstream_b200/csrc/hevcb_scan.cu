@@ -64,9 +64,9 @@ constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memo
 #endif
 constexpr int kAnalyserUnroll = HEVCB_SCAN_AUNROLL; // the analyser's loop over groups of four rows stays rolled (two roles share the instruction cache)
 #ifndef HEVCB_SCAN_PERLANE
-#define HEVCB_SCAN_PERLANE 5
+#define HEVCB_SCAN_PERLANE 10
 #endif
-constexpr int kScanPerLane = HEVCB_SCAN_PERLANE; // tile aggregates per lane and batch of the scanner warp (160 tiles per batch)
+constexpr int kScanPerLane = HEVCB_SCAN_PERLANE; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
 struct ScanGeom {
@@ -372,19 +372,15 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 {
     unsigned long long runN = init_n, runK = 0;
     uint32_t runKind = init_kind, runErr = 0;
-    // the aggregates of the next batch are requested before the current batch is combined and published (the round trip to L2
-    // is the scanner's cycle time), so a batch can be short: the writers follow the analysers more closely
-    ulonglong2 nx[kScanPerLane];
-#pragma unroll
-    for (int j = 0; j < kScanPerLane; j++) {
-        const long long idx = (long long)lane * kScanPerLane + j;
-        nx[j] = (idx < n_tiles) ? ld_state(&tile_state[idx]) : pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); // past the end: identity
-    }
     for (long long base = 0; base < n_tiles; base += 32 * kScanPerLane) {
         const long long first = base + (long long)lane * kScanPerLane;
         ulonglong2 sv[kScanPerLane];
 #pragma unroll
-        for (int j = 0; j < kScanPerLane; j++) { sv[j] = nx[j]; }
+        for (int j = 0; j < kScanPerLane; j++) {
+            const long long idx = first + j;
+            if (idx < n_tiles) { sv[j] = ld_state(&tile_state[idx]); }
+            else { sv[j] = pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); } // past the end: identity
+        }
         for (;;) { // re-poll, one batch per round trip, the aggregates that are not published yet
             bool missing = false;
 #pragma unroll
@@ -394,11 +390,6 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
             for (int j = 0; j < kScanPerLane; j++) {
                 if ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[first + j]); }
             }
-        }
-#pragma unroll
-        for (int j = 0; j < kScanPerLane; j++) {
-            const long long idx = first + 32 * kScanPerLane + j;
-            nx[j] = (idx < n_tiles) ? ld_state(&tile_state[idx]) : pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull);
         }
         __threadfence(); // the aggregates observed above happen before the prefixes published below (writers re-read them)
         // lane totals
@@ -1364,7 +1355,7 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
-        g.window = 1000; // tiles (31 MiB): more than both roles keep in flight (2 stages x grid) plus a scanner batch; measured: DRAM reads 1.02x the input (1200: 1.24x, 1536: 1.7x) at the same speed
+        g.window = 1100; // tiles (34 MiB): more than both roles keep in flight (2 stages x grid) plus a scanner batch (measured, bench.py on one box: 1200 tiles 2259 GB/s, 1100 2241, below 1050 the analysers are throttled)
         if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= kStages * grid) { g.window = v; } }
         if (g.window < kStages * grid) { g.window = kStages * grid; }
         if (dbg & 32u) { g.window = 1ll << 40; } // experiment "writers off": nothing to wait for

@@ -43,7 +43,7 @@ Report file: `gpurun_out/scan_r1_aw_final.ncu-rep` (scratch; numbers copied here
 {tab}
 
 DRAM traffic per launch = read + write = {rd / 1e9:.3f} + {wr / 1e9:.3f} = **{(rd + wr) / 1e9:.3f} GB**; algorithmic bytes (N_in + N_rbsp + 24*NALs) = {alg / 1e9:.3f} GB -> traffic / algorithmic = {(rd + wr) / alg:.3f}.
-The image is written once.  The input is loaded twice (once by an analyser CTA, once by a writer CTA) but the second load is served by L2: the analysers stay within a 1000-tile (31 MiB) window of the writers' progress counter.  Measured sensitivity (same command, `HEVCB_SCAN_WINDOW`, 2 stages per CTA, scanner batches of 160 tiles): 1200 tiles -> DRAM reads 1.24x the input, 1100 -> 1.10x, 1000 -> 1.03x, all at the same speed (the kernel is not DRAM-bound); at 900 and below the pipeline (2 tiles in flight per CTA in both roles = 592 tiles, plus one scanner batch) is throttled.
+The image is written once.  The input is loaded twice (once by an analyser CTA, once by a writer CTA) but the second load is served by L2: the analysers stay within a 1100-tile (34 MiB) window of the writers' progress counter.  Measured sensitivity (same command, `HEVCB_SCAN_WINDOW`, 2 stages per CTA): 1200 tiles -> DRAM reads 1.27x the input, 1100 -> 1.11x, both at the same speed within 1 % (the kernel is not DRAM-bound); at 1050 and below the pipeline (2 tiles in flight per CTA in both roles = 592 tiles, plus one scanner batch of 320) is throttled.
 
 Where the time goes now (warp-state sampling of this capture, `--page source`): 31 % of all samples are the analysers' worker warps waiting for their bulk copies (`mbarrier.try_wait` loop), 15 % the writers' workers at the \"prefix ready\" barrier, 2 % the analysers' control warps polling the writers' progress (the L2 window); no single arithmetic instruction holds more than 1.5 %.  Issue slots are ~37 % used: the pass is bound by the latency of the memory system under the mixed load (the bare load pipeline alone sustains 4.0 TB/s, see DESIGN 4.1), not by DRAM bandwidth or instruction issue.  The previous single-role pipeline spent 38 % of all warp samples at one CTA barrier in lock-step with the scanner (`profiles/r1_scan_strip_ncu_v1.md`).
 
