@@ -76,7 +76,7 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
     hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
-                            &ctx->insert_scratch, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->wstruct, &ctx->parse_scratch, &ctx->parse_ps, &ctx->parse_sort, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
+                            &ctx->insert_scratch, &ctx->rewrite_slots, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->wstruct, &ctx->parse_scratch, &ctx->parse_ps, &ctx->parse_sort, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
                             &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }

@@ -19,6 +19,7 @@ struct hevcb_ctx {
     char err[512] = {0};
     // scan scratch: [0,64) counters, then one 16-byte state word per tile
     hevcb_devbuf scan_scratch;
+    hevcb_devbuf rewrite_slots;           // rewrite: per-NAL header slots of the first write pass
     hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
     hevcb_devbuf rewrite_scratch, rewrite_staging; // rewrite: part arrays, written headers
     hevcb_devbuf wstruct;                 // hevcb_write_nal_host: uploaded structs, contexts, RBSP, NAL

@@ -56,6 +56,9 @@ __device__ __forceinline__ T block_incl_scan(T v, T* warp_sums, T& block_total)
 struct ClsIsSps { const uint8_t* cls; __device__ long long operator()(int64_t i) const { return cls[i] == kCls_Sps ? 1 : 0; } };
 struct ClsIsPps { const uint8_t* cls; __device__ long long operator()(int64_t i) const { return cls[i] == kCls_Pps ? 1 : 0; } };
 struct CntVal { const int32_t* cnt; __device__ long long operator()(int64_t i) const { return (long long)cnt[i]; } };
+// header bytes that do not fit the per-NAL slot of the first write pass (they are written again, compactly, by the second)
+constexpr int kHdrSlot = 128;
+struct CntBig { const int32_t* cnt; __device__ long long operator()(int64_t i) const { return cnt[i] > kHdrSlot ? (long long)cnt[i] : 0ll; } };
 
 template <class F>
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(F f, int64_t n, long long* block_sums)
@@ -312,8 +315,9 @@ struct RewriteArgs {
     int64_t cap_pairs;
     const int32_t* perm; // thread order of the parse (same-shape NALs side by side)
     int32_t* wlen;       // [n] bytes of the written header part (0: the NAL is copied through)
-    const int64_t* woff; // exclusive scan of wlen
-    uint8_t* staging;
+    const int64_t* woff; // exclusive scan of the header lengths beyond kHdrSlot
+    uint8_t* staging;    // headers longer than kHdrSlot, compact (second write pass)
+    uint8_t* slots;      // [n][kHdrSlot]: the first write pass keeps the first kHdrSlot bytes of every header here
     int64_t *raw_off, *raw_end, *a_off, *a_end, *b_off, *b_end; // [n + 1]
     hevcb_edit_set edits;
 };
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
     const bool is_slice = (c == kCls_Slice);
     if (!kEmit) { a.wlen[k] = 0; }
     if (!(is_slice || c == kCls_Vps || c == kCls_Sps || c == kCls_Pps)) { return; }
-    if (kEmit && a.wlen[k] == 0) { return; }
+    if (kEmit && a.wlen[k] <= kHdrSlot) { return; } // not rewritten, or complete in its slot
     const int64_t po = a.pair_off[k];
     const int64_t pn = a.pair_off[k + 1] - po;
     if (!kEmit) {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
     const int kind = is_slice ? HEVCB_KIND_SLICE : (c == kCls_Vps ? HEVCB_KIND_VPS : (c == kCls_Sps ? HEVCB_KIND_SPS : HEVCB_KIND_PPS));
     hevcb_replay rp{a.pair_field + po, a.pair_value + po, (uint32_t)pn, 0u, kind, &a.edits};
     hevcb_bitwriter bw;
-    if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(nullptr, wcap); }
+    if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(a.slots + k * kHdrSlot, wcap, kHdrSlot); }
     hevcb_write_result wr;
     hevcb_write_nal(rp, bw, a.nal_hdr[k], sps_in, pps_in, scr, wr);
     if (!kEmit) {
@@ -368,7 +372,8 @@ __global__ void compose_parts_kernel(RewriteArgs a)
         re = a.size; // what follows the last NAL
     } else if (a.wlen[k] > 0) {
         re = a.nal_start[k];
-        ao = a.woff[k];
+        // absolute addresses (the assembly is given a null base): the slot of the first write pass, or the compact staging
+        ao = (int64_t)(uintptr_t)(a.wlen[k] <= kHdrSlot ? a.slots + k * kHdrSlot : a.staging + a.woff[k]);
         ae = ao + a.wlen[k];
         if (a.cls[k] == kCls_Slice) { bo = a.rbsp_off[k] + a.hdr_end[k]; be = a.rbsp_end[k]; }
     } else {
@@ -512,6 +517,8 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     int64_t* woff = reinterpret_cast<int64_t*>(base + o_woff);
     a.woff = woff;
     a.staging = nullptr;
+    if ((rcx = hevcb_reserve(ctx, &ctx->rewrite_slots, (size_t)m * kHdrSlot + 64)) != HEVCB_OK) { return rcx; }
+    a.slots = reinterpret_cast<uint8_t*>(ctx->rewrite_slots.p);
     int64_t* parts = reinterpret_cast<int64_t*>(base + o_parts);
     a.raw_off = parts; a.raw_end = parts + m; a.a_off = parts + 2 * m; a.a_end = parts + 3 * m; a.b_off = parts + 4 * m; a.b_end = parts + 5 * m;
     if (edits) { a.edits = *edits; } else { a.edits.n = 0; }
@@ -528,7 +535,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
         write_kernel<false><<<g128, 128, 0, stream>>>(a);
         ctx->launches++;
         HEVCB_CUDA(ctx, cudaGetLastError());
-        int rcs = run_scan<CntVal, int64_t, false>(ctx, CntVal{a.wlen}, m, woff, bsums, stream);
+        int rcs = run_scan<CntBig, int64_t, false>(ctx, CntBig{a.wlen}, m, woff, bsums, stream);
         if (rcs != HEVCB_OK) { return rcs; }
         HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_total, bsums + nb, 8, cudaMemcpyDeviceToHost, stream));
         HEVCB_CUDA(ctx, cudaStreamSynchronize(stream)); // the staging size depends on the total header bytes
@@ -542,7 +549,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     compose_parts_kernel<<<g128, 128, 0, stream>>>(a);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
-    int rca = hevcb_launch_assemble3(ctx, d_buf, a.raw_off, a.raw_end, a.staging, a.a_off, a.a_end, d_rbsp, a.b_off, a.b_end, m, d_out, out_cap, out_off,
+    int rca = hevcb_launch_assemble3(ctx, d_buf, a.raw_off, a.raw_end, nullptr, a.a_off, a.a_end, d_rbsp, a.b_off, a.b_end, m, d_out, out_cap, out_off,
                                      isum, stream);
     if (rca != HEVCB_OK) { return rca; }
     if (n > 0) {

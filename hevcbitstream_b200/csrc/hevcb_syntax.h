@@ -199,11 +199,13 @@ HEVCB_SHD inline int hevcb_ceil_log2(int64_t n) // ceil(log2(n)) as the referenc
 struct hevcb_bitwriter {
     uint8_t* dst;  // null: count only
     int64_t cap;   // bytes that may be stored (bits beyond are dropped like bs_write_u1 past the end, bs.h:228)
+    int64_t room;  // bytes of dst that exist (<= cap): a count pass may keep the first bytes in a small slot
     int64_t pos;   // bits written
     uint64_t acc;  // pending bits of the current byte (nacc < 8 between calls)
     int nacc;
 
-    HEVCB_SHD void init(uint8_t* d, int64_t c) { dst = d; cap = c; pos = 0; acc = 0; nacc = 0; }
+    HEVCB_SHD void init(uint8_t* d, int64_t c) { dst = d; cap = c; room = c; pos = 0; acc = 0; nacc = 0; }
+    HEVCB_SHD void init(uint8_t* d, int64_t c, int64_t r) { dst = d; cap = c; room = r < c ? r : c; pos = 0; acc = 0; nacc = 0; }
     HEVCB_SHD void put_bits(int n, uint32_t v) // 0 <= n <= 32: low n bits of v, MSB first
     {
         if (n <= 0) { return; }
@@ -214,7 +216,7 @@ struct hevcb_bitwriter {
         while (nacc >= 8) {
             const int64_t byte = ((pos - nacc) >> 3);
             const uint8_t x = (uint8_t)(acc >> (nacc - 8));
-            if (dst && byte < cap) { dst[byte] = x; }
+            if (dst && byte < room) { dst[byte] = x; }
             nacc -= 8;
         }
         acc &= 0xFFull;
