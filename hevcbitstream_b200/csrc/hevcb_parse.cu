@@ -58,7 +58,26 @@ struct ClsIsPps { const uint8_t* cls; __device__ long long operator()(int64_t i)
 struct CntVal { const int32_t* cnt; __device__ long long operator()(int64_t i) const { return (long long)cnt[i]; } };
 // header bytes that do not fit the per-NAL slot of the first write pass (they are written again, compactly, by the second)
 constexpr int kHdrSlot = 128;
-struct CntBig { const int32_t* cnt; __device__ long long operator()(int64_t i) const { return cnt[i] > kHdrSlot ? (long long)cnt[i] : 0ll; } };
+struct CntBig {
+    const int32_t* cnt; const int64_t* slot_off;
+    __device__ long long operator()(int64_t i) const { return (long long)cnt[i] > slot_off[i + 1] - slot_off[i] ? (long long)cnt[i] : 0ll; }
+};
+// room of a NAL's slot: kHdrSlot bytes for a slice header, the writer's whole capacity for a parameter set (their walk is the
+// longest single thread of the pass, so it should not be repeated)
+struct SlotCap {
+    const uint8_t* cls; const int64_t* nal_start; const int64_t* nal_end; int64_t n;
+    __device__ long long operator()(int64_t i) const
+    {
+        if (i >= n) { return 0; }
+        const int c = cls[i];
+        if (c == kCls_Slice) { return kHdrSlot; }
+        if (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps) {
+            const long long nsz = nal_end[i] - nal_start[i];
+            return ((((nsz * 2 + 64) * 3) / 4) + 31) & ~15ll;
+        }
+        return 0;
+    }
+};
 
 template <class F>
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(F f, int64_t n, long long* block_sums)
@@ -317,7 +336,8 @@ struct RewriteArgs {
     int32_t* wlen;       // [n] bytes of the written header part (0: the NAL is copied through)
     const int64_t* woff; // exclusive scan of the header lengths beyond kHdrSlot
     uint8_t* staging;    // headers longer than kHdrSlot, compact (second write pass)
-    uint8_t* slots;      // [n][kHdrSlot]: the first write pass keeps the first kHdrSlot bytes of every header here
+    uint8_t* slots;      // the first write pass keeps the first bytes of every header in the NAL's slot
+    const int64_t* slot_off; // [n + 2] exclusive scan of the slot sizes (SlotCap)
     int64_t *raw_off, *raw_end, *a_off, *a_end, *b_off, *b_end; // [n + 1]
     hevcb_edit_set edits;
 };
@@ -332,7 +352,8 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
     const bool is_slice = (c == kCls_Slice);
     if (!kEmit) { a.wlen[k] = 0; }
     if (!(is_slice || c == kCls_Vps || c == kCls_Sps || c == kCls_Pps)) { return; }
-    if (kEmit && a.wlen[k] <= kHdrSlot) { return; } // not rewritten, or complete in its slot
+    const int64_t room = a.slot_off[k + 1] - a.slot_off[k];
+    if (kEmit && (int64_t)a.wlen[k] <= room) { return; } // not rewritten, or complete in its slot
     const int64_t po = a.pair_off[k];
     const int64_t pn = a.pair_off[k + 1] - po;
     if (!kEmit) {
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
     const int kind = is_slice ? HEVCB_KIND_SLICE : (c == kCls_Vps ? HEVCB_KIND_VPS : (c == kCls_Sps ? HEVCB_KIND_SPS : HEVCB_KIND_PPS));
     hevcb_replay rp{a.pair_field + po, a.pair_value + po, (uint32_t)pn, 0u, kind, &a.edits};
     hevcb_bitwriter bw;
-    if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(a.slots + k * kHdrSlot, wcap, kHdrSlot); }
+    if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(a.slots + a.slot_off[k], wcap, room); }
     hevcb_write_result wr;
     hevcb_write_nal(rp, bw, a.nal_hdr[k], sps_in, pps_in, scr, wr);
     if (!kEmit) {
@@ -373,7 +394,7 @@ __global__ void compose_parts_kernel(RewriteArgs a)
     } else if (a.wlen[k] > 0) {
         re = a.nal_start[k];
         // absolute addresses (the assembly is given a null base): the slot of the first write pass, or the compact staging
-        ao = (int64_t)(uintptr_t)(a.wlen[k] <= kHdrSlot ? a.slots + k * kHdrSlot : a.staging + a.woff[k]);
+        ao = (int64_t)(uintptr_t)((int64_t)a.wlen[k] <= a.slot_off[k + 1] - a.slot_off[k] ? a.slots + a.slot_off[k] : a.staging + a.woff[k]);
         ae = ao + a.wlen[k];
         if (a.cls[k] == kCls_Slice) { bo = a.rbsp_off[k] + a.hdr_end[k]; be = a.rbsp_end[k]; }
     } else {
@@ -498,7 +519,8 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     size_t need = 0;
     auto take = [&](size_t bytes) { size_t o = need; need += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_wlen = take((size_t)m * 4), o_woff = take((size_t)(m + 1) * 8), o_parts = take((size_t)m * 8 * 6), o_ooff = take((size_t)(m + 1) * 8);
-    const size_t o_bs = take((size_t)(nb + 1) * 8), o_isum = take(sizeof(hevcb_insert_summary)), o_cnt = take(64);
+    const size_t o_soff = take((size_t)(m + 2) * 8);
+    const size_t o_bs = take((size_t)(nb + 3) * 8), o_isum = take(sizeof(hevcb_insert_summary)), o_cnt = take(64);
     int rcx = hevcb_reserve(ctx, &ctx->rewrite_scratch, need);
     if (rcx != HEVCB_OK) { return rcx; }
     uint8_t* base = reinterpret_cast<uint8_t*>(ctx->rewrite_scratch.p);
@@ -517,8 +539,8 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     int64_t* woff = reinterpret_cast<int64_t*>(base + o_woff);
     a.woff = woff;
     a.staging = nullptr;
-    if ((rcx = hevcb_reserve(ctx, &ctx->rewrite_slots, (size_t)m * kHdrSlot + 64)) != HEVCB_OK) { return rcx; }
-    a.slots = reinterpret_cast<uint8_t*>(ctx->rewrite_slots.p);
+    a.slots = nullptr;
+    a.slot_off = reinterpret_cast<const int64_t*>(base + o_soff);
     int64_t* parts = reinterpret_cast<int64_t*>(base + o_parts);
     a.raw_off = parts; a.raw_end = parts + m; a.a_off = parts + 2 * m; a.a_end = parts + 3 * m; a.b_off = parts + 4 * m; a.b_end = parts + 5 * m;
     if (edits) { a.edits = *edits; } else { a.edits.n = 0; }
@@ -531,11 +553,22 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
 
     const unsigned g128 = (unsigned)((m + 127) / 128);
     long long h_total = 0;
+    {
+        // slot sizes -> offsets; the slot buffer's size is known after the scan
+        long long h_slots = 0;
+        const int64_t ns = m + 1, nbs = (ns + kScanTile - 1) / kScanTile;
+        int rcs = run_scan<SlotCap, int64_t, false>(ctx, SlotCap{a.cls, d_nal_start, d_nal_end, n}, ns, reinterpret_cast<int64_t*>(base + o_soff), bsums, stream);
+        if (rcs != HEVCB_OK) { return rcs; }
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_slots, bsums + nbs, 8, cudaMemcpyDeviceToHost, stream));
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(stream));
+        if ((rcx = hevcb_reserve(ctx, &ctx->rewrite_slots, (size_t)h_slots + 64)) != HEVCB_OK) { return rcx; }
+        a.slots = reinterpret_cast<uint8_t*>(ctx->rewrite_slots.p);
+    }
     if (n > 0) {
         write_kernel<false><<<g128, 128, 0, stream>>>(a);
         ctx->launches++;
         HEVCB_CUDA(ctx, cudaGetLastError());
-        int rcs = run_scan<CntBig, int64_t, false>(ctx, CntBig{a.wlen}, m, woff, bsums, stream);
+        int rcs = run_scan<CntBig, int64_t, false>(ctx, CntBig{a.wlen, a.slot_off}, m, woff, bsums, stream);
         if (rcs != HEVCB_OK) { return rcs; }
         HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_total, bsums + nb, 8, cudaMemcpyDeviceToHost, stream));
         HEVCB_CUDA(ctx, cudaStreamSynchronize(stream)); // the staging size depends on the total header bytes

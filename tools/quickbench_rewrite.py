@@ -16,7 +16,7 @@ size = d.numel()
 d = torch.cat([d, torch.zeros(32, dtype=torch.uint8, device="cuda")])
 def ev():
     return torch.cuda.Event(enable_timing=True)
-for it in range(3):
+for it in range(6):
     e = [ev() for _ in range(4)]
     e[0].record()
     scan = ctx.scan_strip_device(d, size=size, cap_nals=size // 1000 + 1024)
