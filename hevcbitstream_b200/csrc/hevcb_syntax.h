@@ -261,6 +261,7 @@ struct hevcb_replay {
     int32_t kind;
     const hevcb_edit_set* edits;
     const int32_t* dense; // alternative source: the struct itself as an int array (write_hevc_nal_unit from caller-owned structs)
+    uint32_t run_f = 0xFFFFFFFFu, run_e = 0; // last run of a multiply-stored field: its field and the index of its last pair
 
     HEVCB_SHD int32_t load(uint32_t f, bool multi)
     {
@@ -273,8 +274,13 @@ struct hevcb_replay {
         } else if (multi && cur < n && field[cur] == f) {
             // a field the reader stored several times in a row: the struct holds the last value of the run; every call
             // consumes one pair of the run and returns that last value
-            uint32_t e = cur;
-            while (e + 1 < n && field[e + 1] == f) { e++; }
+            uint32_t e = run_e;
+            if (run_f != f || cur > run_e) { // the end of the run is looked up once per run, not once per call (runs of 64 coefficients)
+                e = cur;
+                while (e + 1 < n && field[e + 1] == f) { e++; }
+                run_f = f;
+                run_e = e;
+            }
             v = value[e];
             cur++;
         } else {
