@@ -347,7 +347,9 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
 {
     const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= a.n) { return; }
-    const int64_t k = a.perm[ti];
+    // shape order, last shape first: the parameter sets (highest keys) are the longest single-thread walks of the pass and
+    // start with the first blocks instead of forming its tail
+    const int64_t k = a.perm[a.n - 1 - ti];
     const int c = a.cls[k];
     const bool is_slice = (c == kCls_Slice);
     if (!kEmit) { a.wlen[k] = 0; }
