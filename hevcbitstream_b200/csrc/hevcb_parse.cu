@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
 {
     const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= a.n) { return; }
-    const int64_t k = a.perm[ti];
+    const int64_t k = a.perm[a.n - 1 - ti]; // shape order, last shape first: the long parameter-set walks start with the first blocks
     const int c = a.cls[k];
     const bool is_ps = (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps);
     const bool is_slice = (c == kCls_Slice);
