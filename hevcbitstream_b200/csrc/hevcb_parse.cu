@@ -12,6 +12,7 @@
 //   6. emit          every parsed NAL walks its syntax once more and writes its (field, value) pairs at pair_off[k]
 // The walker itself (bit reader with 64-bit window and clz exp-Golomb, all syntax structures) is hevcb_syntax.h.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "hevcb_internal.h"
@@ -65,12 +66,12 @@ struct CntBig {
 // room of a NAL's slot: kHdrSlot bytes for a slice header, the writer's whole capacity for a parameter set (their walk is the
 // longest single thread of the pass, so it should not be repeated)
 struct SlotCap {
-    const uint8_t* cls; const int64_t* nal_start; const int64_t* nal_end; int64_t n;
+    const uint8_t* cls; const int64_t* nal_start; const int64_t* nal_end; int64_t n; int slice_slot;
     __device__ long long operator()(int64_t i) const
     {
         if (i >= n) { return 0; }
         const int c = cls[i];
-        if (c == kCls_Slice) { return kHdrSlot; }
+        if (c == kCls_Slice) { return slice_slot; }
         if (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps) {
             const long long nsz = nal_end[i] - nal_start[i];
             return ((((nsz * 2 + 64) * 3) / 4) + 31) & ~15ll;
@@ -559,7 +560,9 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
         // slot sizes -> offsets; the slot buffer's size is known after the scan
         long long h_slots = 0;
         const int64_t ns = m + 1, nbs = (ns + kScanTile - 1) / kScanTile;
-        int rcs = run_scan<SlotCap, int64_t, false>(ctx, SlotCap{a.cls, d_nal_start, d_nal_end, n}, ns, reinterpret_cast<int64_t*>(base + o_soff), bsums, stream);
+        int slice_slot = kHdrSlot; // HEVCB_HDR_SLOT: test switch (small slots send the slice headers through the second pass)
+        if (const char* e = getenv("HEVCB_HDR_SLOT")) { const int v = atoi(e); if (v >= 0 && v <= 4096) { slice_slot = v & ~15; } }
+        int rcs = run_scan<SlotCap, int64_t, false>(ctx, SlotCap{a.cls, d_nal_start, d_nal_end, n, slice_slot}, ns, reinterpret_cast<int64_t*>(base + o_soff), bsums, stream);
         if (rcs != HEVCB_OK) { return rcs; }
         HEVCB_CUDA(ctx, cudaMemcpyAsync(&h_slots, bsums + nbs, 8, cudaMemcpyDeviceToHost, stream));
         HEVCB_CUDA(ctx, cudaStreamSynchronize(stream));

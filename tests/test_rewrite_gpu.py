@@ -102,3 +102,25 @@ def test_rewrite_requires_matching_parse(ctx):
     scan2 = ctx.scan_strip_device(d2, size=s2.size - ref.PAD)
     with pytest.raises(HevcbError):
         ctx.rewrite_device(d2, scan2, parsed, [], size=s2.size - ref.PAD)
+
+
+@pytest.mark.parametrize("slot", ["0", "16", "48"])
+def test_second_header_pass_with_small_slots(ctx, monkeypatch, slot):
+    """HEVCB_HDR_SLOT shrinks the per-slice slot of the first header pass, so that (nearly) every slice header is written by
+    the second pass into the compact staging: both routes must give the reference's bytes"""
+    monkeypatch.setenv("HEVCB_HDR_SLOT", slot)
+    s = ref.gen_stream(seed=11, profile=1, n_slices=300, payload_min=1, payload_max=400, zero_heavy_pct=20, ps_period=40, unsupported_pct=3)
+    size = s.size - ref.PAD
+    got, os_, oe, out, st, en = device_rewrite(ctx, s, size, 2, 1)
+    want = ref.rewrite_all(s, size, st, en, qp_delta_add=2, vui_flip=1)
+    assert out["n_rewritten"] > 300
+    rc.compare_rewrite(got, os_, oe, want, tag=f"slot{slot}")
+
+
+def test_rewrite_of_a_buffer_without_nals(ctx):
+    """no start code at all: nothing to parse, every byte is copied through"""
+    rng = np.random.default_rng(3)
+    s = np.concatenate([rng.integers(2, 256, 5000, dtype=np.uint8), np.zeros(ref.PAD, np.uint8)])
+    size = s.size - ref.PAD
+    got, os_, oe, out, st, en = device_rewrite(ctx, s, size, 1, 0)
+    assert len(st) == 0 and np.array_equal(got, s[:size])
