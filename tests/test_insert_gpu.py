@@ -192,3 +192,20 @@ def test_long_parts_are_split(ctx, alphabet):
     check(ctx, rbsp, np.array([5], np.int64), np.array([n_bytes - 3], np.int64), 4, f"split-one-a{alphabet}")
     z = np.zeros(200000, np.uint8)
     check(ctx, z, np.array([0, 7], np.int64), np.array([200000, 150000], np.int64), 0, f"split-zero-a{alphabet}")
+
+
+def test_side_list_of_pieces_can_fill_up(ctx):
+    """more pieces than the side list holds (only possible when the output does not fit either): the NALs that find no room
+    stay with their own warp, sizes are still exact and the overflow is reported; with room for the output the same extents
+    (overlapping on purpose) come out right"""
+    from hevcbitstream_b200 import HevcbError
+
+    rng = np.random.default_rng(9)
+    rbsp = zero_heavy(rng, 1 << 20, 0)
+    n = 40
+    off = np.arange(n, dtype=np.int64) * 3
+    end = np.full(n, (1 << 20) - 5, np.int64)
+    with pytest.raises(HevcbError) as e:
+        ctx.insert_host(rbsp, off, end, start_code_len=3, out_cap=2 << 20)
+    assert e.value.code == -104
+    check(ctx, rbsp, off[:6], end[:6], 3, "overlap-6")
