@@ -80,8 +80,11 @@ class Context:
 
         assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
         size = int(buf.numel() if size is None else size)
+        auto_cap = cap_nals is None and out is None and sync
         if cap_nals is None:
-            cap_nals = size // 3 + 8
+            # a realistic bound (one NAL per 64 bytes: 0.5 bytes of arrays per input byte); when a stream holds more NALs the
+            # summary reports the true count and the call is repeated with it (only when the arrays are ours and we synchronise)
+            cap_nals = size // 64 + 1024
         dev = buf.device
         if out is None:
             out = dict(
@@ -105,6 +108,8 @@ class Context:
         last_rc = int(np.int32(s[2] & 0xFFFFFFFF))
         overflow = int(s[2] >> 32)
         if overflow:
+            if auto_cap:
+                return self.scan_strip_device(buf, size=size, cap_nals=max(n_nals + 8, min(size // 3 + 8, 2 * cap_nals)), want_rbsp=want_rbsp)
             raise HevcbError(-104, f"{n_nals} NALs exceed cap_nals {cap_nals}")
         return ScanResult(n_nals, n_term, last_rc, int(s[3]), int(s[4]), int(s[5]), int(s[6]),
                           out["nal_start"], out["nal_end"], out["rbsp_off"], out["rbsp_end"], out.get("rbsp"))
@@ -113,16 +118,20 @@ class Context:
         """buf: numpy uint8 array (host).  Includes H2D/D2H copies (hevcb_scan_strip_host)."""
         assert buf.dtype == np.uint8
         size = int(buf.size if size is None else size)
+        auto_cap = cap_nals is None
         if cap_nals is None:
-            cap_nals = size // 3 + 8
+            cap_nals = size // 64 + 1024  # see scan_strip_device
         ns = np.empty(cap_nals, dtype=np.int64)
         ne = np.empty(cap_nals, dtype=np.int64)
         ro = np.empty(cap_nals, dtype=np.int64)
         re = np.empty(cap_nals, dtype=np.int64)
         rb = np.empty(size + 16, dtype=np.uint8) if want_rbsp else None
         sm = ScanSummary()
-        self._check(self._L.hevcb_scan_strip_host(self._h, _np_ptr(buf), size, _np_ptr(ns), _np_ptr(ne), cap_nals,
-                                                 _np_ptr(rb), _np_ptr(ro), _np_ptr(re), C.byref(sm)))
+        rc = self._L.hevcb_scan_strip_host(self._h, _np_ptr(buf), size, _np_ptr(ns), _np_ptr(ne), cap_nals,
+                                           _np_ptr(rb), _np_ptr(ro), _np_ptr(re), C.byref(sm))
+        if rc == -104 and auto_cap:  # HEVCB_E_CAPACITY: the summary holds the true NAL count
+            return self.scan_strip_host(buf, size=size, cap_nals=max(int(sm.n_nals) + 8, min(size // 3 + 8, 2 * cap_nals)), want_rbsp=want_rbsp)
+        self._check(rc)
         n = sm.n_nals
         return ScanResult(n, sm.n_terminated, sm.last_rc, sm.last_start, sm.last_end, sm.rbsp_bytes, sm.n_epb,
                           ns[:n], ne[:n], ro[:n], re[:n], rb[: sm.rbsp_bytes] if rb is not None else None)

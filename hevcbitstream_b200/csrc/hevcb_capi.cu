@@ -174,11 +174,15 @@ static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t
         last = (own > 0 && bounds[r + 1] == size) ? 1 : 0;
         halo = last ? 0 : (size - bounds[r + 1] < 16 ? size - bounds[r + 1] : 16);
     };
-    auto copy_in = [&](int r) -> int {
+    // Shards without bytes (a run of bytes < 2 can swallow a whole nominal chunk, hevcb_plan_shards) take no slot and no
+    // launch: the pipeline walks the non-empty shards, slot = position in that list, and their zeroed records reach the stitch.
+    int live[HEVCB_MAX_SHARDS];
+    int n_live = 0;
+    for (int r = 0; r < K; r++) { if (bounds[r + 1] - bounds[r] > 0) { live[n_live++] = r; } }
+    auto copy_in = [&](int j) -> int {
         int64_t lo, own, halo; int first, last;
-        shard_geom(r, lo, own, halo, first, last);
-        if (own <= 0) { return HEVCB_OK; }
-        const int sl = r & 1;
+        shard_geom(live[j], lo, own, halo, first, last);
+        const int sl = j & 1;
         if (slot_used[sl]) { HEVCB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[sl], 0)); } // the scan of shard r - 2 has read this slot
         HEVCB_CUDA(ctx, cudaMemcpyAsync(ctx->p_in[sl].p, buf + lo, (size_t)(own + halo), cudaMemcpyHostToDevice, ctx->s_in));
         HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->s_in));
@@ -186,12 +190,12 @@ static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     };
     int64_t byte_base = 0, rbsp_base = 0, nal_base = 0;
     bool overflow = false;
-    if ((rc = copy_in(0)) != HEVCB_OK) { return rc; }
-    for (int r = 0; r < K; r++) {
+    if (n_live > 0 && (rc = copy_in(0)) != HEVCB_OK) { return rc; }
+    for (int j = 0; j < n_live; j++) {
+        const int r = live[j];
         int64_t lo, own, halo; int first, last;
         shard_geom(r, lo, own, halo, first, last);
-        if (own <= 0) { continue; }
-        const int sl = r & 1;
+        const int sl = j & 1;
         int64_t* arr = reinterpret_cast<int64_t*>(ctx->p_arr[sl].p);
         int64_t *d_ns = arr, *d_ne = arr + capS, *d_ro = arr + 2 * capS, *d_re = arr + 3 * capS;
         hevcb_shard_summary* d_sum = reinterpret_cast<hevcb_shard_summary*>(ctx->p_sum.p) + sl;
@@ -204,7 +208,7 @@ static int scan_strip_host_pipelined(hevcb_ctx* ctx, const uint8_t* buf, int64_t
         HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_k[sl], s_k));
         slot_used[sl] = true;
         // the next shard's input travels while this one is scanned (its slot is free once the scan of shard r - 1 is done)
-        if (r + 1 < K && (rc = copy_in(r + 1)) != HEVCB_OK) { return rc; }
+        if (j + 1 < n_live && (rc = copy_in(j + 1)) != HEVCB_OK) { return rc; }
         HEVCB_CUDA(ctx, cudaEventSynchronize(ctx->ev_k[sl])); // record of shard r: where its outputs go
         const hevcb_shard_summary& S = h_sums[r];
         if (S.overflow) { overflow = true; }

@@ -108,8 +108,11 @@ def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: boo
     import torch
 
     assert buf.is_cuda and buf.dtype == torch.uint8 and buf.numel() >= own + halo
+    auto_cap = out is None and cap_nals is None and sync
     if out is None:
-        out = alloc_shard_outputs(buf, own, own // 3 + 8 if cap_nals is None else cap_nals, want_rbsp, extra_rbsp)
+        # default: one NAL per 64 bytes (0.5 bytes of arrays per input byte); a denser shard reports its true count in the
+        # record and the synchronous call repeats with it
+        out = alloc_shard_outputs(buf, own, own // 64 + 1024 if cap_nals is None else cap_nals, want_rbsp, extra_rbsp)
     a, rbsp, d_sum, cap_nals = out["arrays"], out["rbsp"], out["summary"], out["cap_nals"]
     stream = torch.cuda.current_stream(buf.device).cuda_stream
     rc = ctx._L.hevcb_scan_strip_shard_device(ctx._h, buf.data_ptr(), own, halo, int(is_first), int(is_last), a[0].data_ptr(), a[1].data_ptr(),
@@ -121,6 +124,9 @@ def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: boo
     if sync:
         sc.record = ShardSummary.from_buffer_copy(d_sum.cpu().numpy().tobytes())
         if sc.record.overflow:
+            if auto_cap:
+                return scan_strip_shard(ctx, buf, own, halo, is_first, is_last, cap_nals=int(sc.record.n_nals) + 8, want_rbsp=want_rbsp,
+                                        extra_rbsp=extra_rbsp)
             raise HevcbError(-104, f"{sc.record.n_nals} NALs exceed cap_nals {cap_nals}")
     return sc
 
@@ -149,8 +155,9 @@ def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw)
     n = C.sizeof(ShardSummary)
     records = [ShardSummary.from_buffer_copy(raw[i * n:(i + 1) * n]) for i in range(world)]
     sc.record = records[rank]
-    if sc.record.overflow:
-        raise HevcbError(-104, f"{sc.record.n_nals} NALs exceed cap_nals {sc.cap_nals}")
+    over = [r for r in range(world) if records[r].overflow]
+    if over:  # decided from the gathered records: every rank raises together, none is left waiting in a later collective
+        raise HevcbError(-104, f"shard(s) {over}: more NALs than cap_nals ({records[over[0]].n_nals} on shard {over[0]}, cap {sc.cap_nals})")
     res = stitch(records)
     apply_patches_device(ctx, res, rank, sc)
     return sc, res
@@ -194,20 +201,29 @@ def _parse_call(ctx, buf, ns, ne, rbsp, ro, re, n, cap_pairs, chain):
 
 
 def append_continuation(sc: ShardScan, res: StitchResult, rank: int, heads):
-    """Copies the continuation of this shard's last NAL (it ends in a later shard) behind the shard's image.
-    heads[q]: the first HEAD_BYTES image bytes of shard q.  Returns the number of bytes appended."""
+    """Copies the continuation of this shard's last NAL (it ends in a later shard) behind the shard's image, at most HEAD_BYTES of
+    it: header bytes are all the parser needs.  heads[q]: the first HEAD_BYTES image bytes of shard q.  A NAL that spans whole
+    shards takes the (complete) images of the shards in between from their heads as long as they fit.  Decided from the
+    StitchResult, which is identical on every rank, so no rank can raise alone between two collectives.
+    Returns (bytes appended, bytes of the continuation that were NOT appended)."""
     q = int(res.cont_last_shard[rank])
     if q < 0:
-        return 0
+        return 0, 0
     total = int(res.cont_bytes[rank])
     last = int(res.cont_last_bytes[rank])
-    if total != last:
-        raise HevcbError(-102, "a NAL that spans whole shards cannot be parsed from the all-gathered heads")
-    take = min(last, int(heads[q].numel()))
     base = int(sc.record.rbsp_bytes)
-    assert sc.rbsp.numel() >= base + take + 16, "scan_strip_shard(extra_rbsp=HEAD_BYTES) is required for the sharded parse"
-    sc.rbsp[base: base + take] = heads[q][:take]
-    return take
+    room = min(HEAD_BYTES, int(sc.rbsp.numel()) - base - 16)
+    assert room >= min(total, HEAD_BYTES), "scan_strip_shard(extra_rbsp=HEAD_BYTES) is required for the sharded parse"
+    take = 0
+    for r in range(rank + 1, q + 1):
+        avail = last if r == q else int(res.rbsp_base[r + 1] - res.rbsp_base[r])  # image bytes of shard r that belong to the NAL
+        use = min(avail, room - take, int(heads[r].numel()))
+        if use > 0:
+            sc.rbsp[base + take: base + take + use] = heads[r][:use]
+            take += use
+        if use < avail:
+            break
+    return take, total - take
 
 
 def local_ps_contexts(ctx, buf, sc: ShardScan, first: int, n: int):
@@ -246,8 +262,9 @@ def pick_incoming(states, rank: int):
     return sps, pps
 
 
-def parse_shard(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResult, rank: int, sps_in, pps_in, cap_pairs=None):
-    """Header parse of the NALs this shard owns, with the parameter-set state that enters it."""
+def parse_shard(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResult, rank: int, sps_in, pps_in, cap_pairs=None, missing=0):
+    """Header parse of the NALs this shard owns, with the parameter-set state that enters it.  missing: bytes at the end of the
+    last NAL's RBSP that are not present behind the local image (append_continuation): the bit reader is kept off them."""
     import torch
 
     from ._lib import ParseChain
@@ -256,7 +273,13 @@ def parse_shard(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResult,
     if cap_pairs is None:
         cap_pairs = 80 * n + 4096
     chain = ParseChain(sps_in.ctypes.data if sps_in is not None else None, pps_in.ctypes.data if pps_in is not None else None, None, None, own + halo)
-    out = _parse_call(ctx, buf, sc.nal_start[f: f + n], sc.nal_end[f: f + n], sc.rbsp, sc.rbsp_off[f: f + n], sc.rbsp_end[f: f + n], n, cap_pairs, chain)
+    rend = sc.rbsp_end[f: f + n]
+    if missing > 0 and n > 0 and int(rend[n - 1]) >= 0:
+        # the tail of the last NAL lives on another rank: a header never reaches that far (HEAD_BYTES of it are here), but a
+        # malformed one must not walk off the local image
+        rend = rend.clone()
+        rend[n - 1] -= missing
+    out = _parse_call(ctx, buf, sc.nal_start[f: f + n], sc.nal_end[f: f + n], sc.rbsp, sc.rbsp_off[f: f + n], rend, n, cap_pairs, chain)
     # read_hevc_nal_unit reports one byte less for a NAL that ends in 00 00 03; for a NAL that ends in a later shard only the
     # stitch has seen those bytes
     for p in patches_for(res, rank):
@@ -279,7 +302,7 @@ def parse_sharded(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResul
     head[:nb] = sc.rbsp[:nb]
     heads = [torch.empty_like(head) for _ in range(world)]
     dist.all_gather(heads, head, group=group)
-    append_continuation(sc, res, rank, heads)
+    _, missing = append_continuation(sc, res, rank, heads)
     f, n = int(res.first_local[rank]), int(res.n_owned[rank])
     hs_, sps, hp_, pps = local_ps_contexts(ctx, buf, sc, f, n)
     blob = torch.from_numpy(np.concatenate([np.array([hs_, hp_], np.uint8), sps, pps])).to(dev)
@@ -291,4 +314,4 @@ def parse_sharded(ctx, buf, own: int, halo: int, sc: ShardScan, res: StitchResul
         h = b.cpu().numpy()
         states.append((int(h[0]), h[2: 2 + sps_b].copy(), int(h[1]), h[2 + sps_b:].copy()))
     sps_in, pps_in = pick_incoming(states, rank)
-    return parse_shard(ctx, buf, own, halo, sc, res, rank, sps_in, pps_in, cap_pairs)
+    return parse_shard(ctx, buf, own, halo, sc, res, rank, sps_in, pps_in, cap_pairs, missing=missing)

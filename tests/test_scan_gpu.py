@@ -92,7 +92,8 @@ def test_config1_stream_device_api(ctx):
     assert np.array_equal(res2.rbsp_end.cpu().numpy()[:10003], res.rbsp_end[:10003])
 
 
-@pytest.mark.parametrize("nal_size,dense", [(64, False), (256, False), (1000, False), (4096, False), (1 << 20, False), (4096, True), (67, True), (300, True)])
+@pytest.mark.parametrize("nal_size,dense", [(64, False), (256, False), (1000, False), (4096, False), (16384, False), (65536, False), (262144, False),
+                                            (1 << 20, False), (4096, True), (67, True), (300, True)])
 def test_config2_shapes(ctx, nal_size, dense):
     """BASELINE config 2 shapes at 96 MiB: fixed-size NALs with escaped random payload, and the EPB-dense worst case"""
     import torch
@@ -143,5 +144,97 @@ def test_pipelined_host_path_matches_oracle(monkeypatch):
             res = c.scan_strip_host(s[: size - cut], size=size - cut)
             n = util.compare_scan(util.padded(s[: size - cut]), size - cut, res, res.rbsp, tag=f"pipegen{cut}")
             assert n > 5000
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("workload", ["nal16k", "epb_dense_4k"])
+def test_bench_inputs_4gib_vs_oracle(ctx, workload):
+    """The very buffers bench.py times (BASELINE config[1]: 4 GiB, 16 KiB NALs = the headline, and the EPB-dense worst case):
+    one hevcb_scan_strip_device call over the whole 4 GiB, compared with the unmodified reference fed in 512 MiB pieces cut
+    at NAL boundaries (its API takes `int` sizes): every NAL offset, every nal_to_rbsp status / size and every RBSP byte."""
+    import torch
+
+    import bench
+
+    name, nal_size, dense = next(w for w in bench.WORKLOADS if w[0] == workload)
+    unit = bench.make_unit(nal_size, bench.UNIT_BYTES, 1234, dense)  # rank 0's unit, as bench.py builds it
+    assert unit[0] == 0 and unit[1] == 0 and unit[2] == 1 and unit[-1] >= 2  # a unit starts with a start code and ends a NAL
+    reps = (4 << 30) // unit.size
+    size = unit.size * reps
+    ut = torch.from_numpy(unit).cuda()
+    d = torch.zeros(size + 32, dtype=torch.uint8, device="cuda")[: size + 16]
+    d[:size].view(reps, -1).copy_(ut.unsqueeze(0).expand(reps, -1))
+    cap = size // max(16, (nal_size if not dense else 4096) // 2) + (1 << 16)
+    res = ctx.scan_strip_device(d, size=size, cap_nals=cap)
+    n = res.n_nals
+    # the oracle on one piece of `upp` units (every piece holds the same bytes: the buffer is the unit tiled)
+    upp = max(1, (512 << 20) // unit.size)
+    piece = np.tile(unit, upp)
+    pbuf = util.padded(piece)
+    st, en, r = ref.scan_all_with_tail(pbuf, piece.size)
+    assert r["last_rc"] == -1  # the piece ends inside its last NAL, which the next piece's start code terminates
+    sr = ref.strip_all(pbuf, st, en)
+    npp = len(st)
+    rc_ref = torch.from_numpy(sr["rc"].astype(np.int64)).cuda()
+    st_t, en_t = torch.from_numpy(st).cuda(), torch.from_numpy(en).cuda()
+    want = torch.from_numpy(sr["rbsp"]).cuda()
+    lens = torch.clamp(rc_ref, min=0)
+    dense_off = torch.cumsum(lens, 0) - lens
+    n_pieces = -(-reps // upp)
+    assert res.n_terminated == n - 1 and res.last_rc == -1 and res.last_end == size
+    assert res.rbsp_bytes == size - res.n_epb
+    k0 = 0
+    for p in range(n_pieces):
+        units_here = min(upp, reps - p * upp)
+        if units_here != upp:  # the shorter last piece
+            piece = np.tile(unit, units_here)
+            pbuf = util.padded(piece)
+            st, en, r = ref.scan_all_with_tail(pbuf, piece.size)
+            sr = ref.strip_all(pbuf, st, en)
+            npp = len(st)
+            rc_ref = torch.from_numpy(sr["rc"].astype(np.int64)).cuda()
+            st_t, en_t = torch.from_numpy(st).cuda(), torch.from_numpy(en).cuda()
+            want = torch.from_numpy(sr["rbsp"]).cuda()
+            lens = torch.clamp(rc_ref, min=0)
+            dense_off = torch.cumsum(lens, 0) - lens
+        base = p * upp * unit.size
+        gs, ge = res.nal_start[k0: k0 + npp], res.nal_end[k0: k0 + npp]
+        go, gr = res.rbsp_off[k0: k0 + npp], res.rbsp_end[k0: k0 + npp]
+        assert torch.equal(gs - base, st_t), f"{workload}: nal_start differs in piece {p}"
+        assert torch.equal(ge - base, en_t), f"{workload}: nal_end differs in piece {p}"
+        assert torch.equal(gr == -1, rc_ref < 0), f"{workload}: nal_to_rbsp status differs in piece {p}"
+        assert torch.equal(torch.where(gr >= 0, gr - go, torch.full_like(gr, -1)), rc_ref), f"{workload}: RBSP sizes differ in piece {p}"
+        idx = torch.repeat_interleave(go - dense_off, lens) + torch.arange(int(lens.sum()), device="cuda")
+        assert torch.equal(res.rbsp[idx], want[: idx.numel()]), f"{workload}: RBSP bytes differ in piece {p}"
+        del idx
+        k0 += npp
+    assert k0 == n
+
+
+def test_pipelined_host_path_empty_shards(monkeypatch):
+    """A run of bytes < 2 that covers whole nominal chunks leaves shards without bytes (hevcb_plan_shards moves every cut forward to
+    a byte >= 2): the pipeline must skip them without losing the prefetch of the next non-empty shard."""
+    import hevcbitstream_b200 as hb
+
+    monkeypatch.setenv("HEVCB_HOST_CHUNK", "4096")
+    c = hb.Context(0)
+    try:
+        rng = np.random.default_rng(77)
+        for it, (runlen, fill) in enumerate([(4096 * 3 + 17, 0), (4096 * 5, 0), (4096 * 2 + 1, 1), (4096 * 7 + 5, 0)]):
+            parts = []
+            for blk in range(4):
+                s = util.c2_stream([64, 300, 1000, 4096][(it + blk) % 4], 20000, seed=it * 10 + blk)
+                parts.append(s[: s.size - ref.PAD])
+                if blk < 3:
+                    run = np.full(runlen, fill, np.uint8)
+                    if fill == 1:
+                        run[::2] = 0  # 00 01 00 01 ...: bytes < 2 without a start code
+                    parts.append(run)
+            a = np.concatenate(parts)
+            buf = util.padded(a)
+            res = c.scan_strip_host(buf[: a.size], size=a.size)
+            n = util.compare_scan(buf, a.size, res, res.rbsp, tag=f"emptyshard{it}")
+            assert n > 20
     finally:
         c.close()

@@ -102,8 +102,8 @@ def _pairs(p, k):
     return p["pair_field"][a:b], p["pair_value"][a:b]
 
 
-@pytest.mark.parametrize("n_shards", [2, 5])
-def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards):
+@pytest.mark.parametrize("n_shards,big", [(2, False), (5, False), (40, True), (23, True)])
+def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards, big):
     """parameter-set hand-over: every shard parses the NALs it owns with the last SPS / PPS state of the earlier shards and the
     continuation of its last NAL; rc, NAL header, kind, header end and every syntax element must equal the unsharded parse
     (which the other tests pin against the reference)"""
@@ -111,8 +111,12 @@ def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards):
 
     from hevcbitstream_b200 import shard as hs
 
-    s = ref.gen_stream(seed=8, profile=1, n_slices=6000, payload_min=1, payload_max=900, zero_heavy_pct=20, extra_zero_pct=10, ps_period=300,
-                       unsupported_pct=3)
+    if big:  # NALs larger than a shard: the continuation of a shard's last NAL then runs through whole shards
+        s = ref.gen_stream(seed=9, profile=1, n_slices=70, payload_min=1, payload_max=120000, zero_heavy_pct=20, extra_zero_pct=10, ps_period=9,
+                           unsupported_pct=3)
+    else:
+        s = ref.gen_stream(seed=8, profile=1, n_slices=6000, payload_min=1, payload_max=900, zero_heavy_pct=20, extra_zero_pct=10, ps_period=300,
+                           unsupported_pct=3)
     size = s.size - ref.PAD
     d = torch.zeros(size + 32, dtype=torch.uint8, device="cuda")
     d[:size] = torch.from_numpy(s[:size].copy())
@@ -136,16 +140,17 @@ def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards):
         nb = min(hs.HEAD_BYTES, int(sc.record.rbsp_bytes))
         h[:nb] = sc.rbsp[:nb]
         heads.append(h)
-    states = []
+    states, missing, spanning = [], [], 0
     for r, sc in enumerate(scans):
-        hs.append_continuation(sc, res, r, heads)
+        missing.append(hs.append_continuation(sc, res, r, heads)[1])
+        spanning += int(res.cont_last_shard[r] > r + 1)
         states.append(hs.local_ps_contexts(ctx, bufs[r], sc, int(res.first_local[r]), int(res.n_owned[r])))
     g = 0
     crossing = 0
     for r, sc in enumerate(scans):
         own, halo, first, last = hs.shard_flags(bounds, r)
         sps_in, pps_in = hs.pick_incoming(states, r)
-        ps = hs.parse_shard(ctx, bufs[r], own, halo, sc, res, r, sps_in, pps_in)
+        ps = hs.parse_shard(ctx, bufs[r], own, halo, sc, res, r, sps_in, pps_in, missing=missing[r])
         n = int(res.n_owned[r])
         ps = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in ps.items()}
         crossing += int(res.cont_last_shard[r] >= 0)
@@ -162,4 +167,7 @@ def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards):
         assert np.array_equal(ps["pair_value"][: a1 - a0], pw["pair_value"][a0:a1]), f"values differ in shard {r}"
         g += n
     assert g == whole.n_nals
-    assert crossing >= n_shards - 1
+    if big:
+        assert spanning >= 3, "the stream was meant to hold NALs that span whole shards"
+    else:
+        assert crossing >= n_shards - 1
