@@ -41,6 +41,7 @@ class ParseBuffers(C.Structure):
     _fields_ = [
         ("rc", C.c_void_p), ("nal_hdr", C.c_void_p), ("kind", C.c_void_p), ("ubflag", C.c_void_p), ("hdr_end", C.c_void_p),
         ("cols", C.c_void_p), ("pair_off", C.c_void_p), ("pair_field", C.c_void_p), ("pair_value", C.c_void_p), ("cap_pairs", C.c_int64),
+        ("pair_pos", C.c_void_p),  # None: plain parse; an array: the trace (read_debug) variant
     ]
 
 
@@ -148,6 +149,8 @@ def load_library() -> C.CDLL:
     L.hevcb_rewrite_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), C.POINTER(EditSet), vp, i64, vp, vp, vp, vp]
     L.hevcb_field_index.restype = i64
     L.hevcb_field_index.argtypes = [C.c_int, C.c_char_p]
+    L.hevcb_trace_name.restype = C.c_int
+    L.hevcb_trace_name.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.c_int]
     L.hevcb_insert_device.restype = C.c_int
     L.hevcb_insert_device.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp, i64, vp, vp, vp]
     L.hevcb_insert_host.restype = C.c_int

@@ -69,18 +69,26 @@ class Context:
     def sm_count(self) -> int:
         return int(self._L.hevcb_sm_count(self._h))
 
+    def trace_name(self, kind: int, code: int) -> str:
+        """Text the reference prints for a trace record (hevcb_trace_name)."""
+        b = C.create_string_buffer(160)
+        n = self._L.hevcb_trace_name(int(kind), int(code) & 0xFFFFFFFF, b, 160)
+        if n < 0:
+            raise HevcbError(-101, f"unknown trace code {code:#x} for kind {kind}")
+        return b.value.decode()
+
     # ---- scan + strip -----------------------------------------------------------------------
     def scan_strip_device_raw(self, d_buf, size, d_start, d_end, cap, d_rbsp, d_off, d_rend, d_summary, stream_ptr):
         """Direct call of hevcb_scan_strip_device with raw device pointers (ints)."""
         self._check(self._L.hevcb_scan_strip_device(self._h, d_buf, size, d_start, d_end, cap, d_rbsp, d_off, d_rend, d_summary, stream_ptr))
 
-    def scan_strip_device(self, buf, size=None, cap_nals=None, want_rbsp=True, out=None, sync=True):
+    def scan_strip_device(self, buf, size=None, cap_nals=None, want_rbsp=True, out=None, sync=True, _grow=False):
         """buf: torch.uint8 CUDA tensor.  Returns ScanResult with torch tensors (device resident)."""
         import torch
 
         assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
         size = int(buf.numel() if size is None else size)
-        auto_cap = cap_nals is None and out is None and sync
+        auto_cap = (cap_nals is None or _grow) and out is None and sync
         if cap_nals is None:
             # a realistic bound (one NAL per 64 bytes: 0.5 bytes of arrays per input byte); when a stream holds more NALs the
             # summary reports the true count and the call is repeated with it (only when the arrays are ours and we synchronise)
@@ -108,17 +116,18 @@ class Context:
         last_rc = int(np.int32(s[2] & 0xFFFFFFFF))
         overflow = int(s[2] >> 32)
         if overflow:
-            if auto_cap:
-                return self.scan_strip_device(buf, size=size, cap_nals=max(n_nals + 8, min(size // 3 + 8, 2 * cap_nals)), want_rbsp=want_rbsp)
+            if auto_cap and cap_nals < size // 3 + 8:
+                del out
+                return self.scan_strip_device(buf, size=size, cap_nals=min(size // 3 + 8, max(n_nals + 8, 4 * cap_nals)), want_rbsp=want_rbsp, _grow=True)
             raise HevcbError(-104, f"{n_nals} NALs exceed cap_nals {cap_nals}")
         return ScanResult(n_nals, n_term, last_rc, int(s[3]), int(s[4]), int(s[5]), int(s[6]),
                           out["nal_start"], out["nal_end"], out["rbsp_off"], out["rbsp_end"], out.get("rbsp"))
 
-    def scan_strip_host(self, buf: np.ndarray, size=None, cap_nals=None, want_rbsp=True) -> ScanResult:
+    def scan_strip_host(self, buf: np.ndarray, size=None, cap_nals=None, want_rbsp=True, _grow=False) -> ScanResult:
         """buf: numpy uint8 array (host).  Includes H2D/D2H copies (hevcb_scan_strip_host)."""
         assert buf.dtype == np.uint8
         size = int(buf.size if size is None else size)
-        auto_cap = cap_nals is None
+        auto_cap = cap_nals is None or _grow
         if cap_nals is None:
             cap_nals = size // 64 + 1024  # see scan_strip_device
         ns = np.empty(cap_nals, dtype=np.int64)
@@ -129,8 +138,9 @@ class Context:
         sm = ScanSummary()
         rc = self._L.hevcb_scan_strip_host(self._h, _np_ptr(buf), size, _np_ptr(ns), _np_ptr(ne), cap_nals,
                                            _np_ptr(rb), _np_ptr(ro), _np_ptr(re), C.byref(sm))
-        if rc == -104 and auto_cap:  # HEVCB_E_CAPACITY: the summary holds the true NAL count
-            return self.scan_strip_host(buf, size=size, cap_nals=max(int(sm.n_nals) + 8, min(size // 3 + 8, 2 * cap_nals)), want_rbsp=want_rbsp)
+        if rc == -104 and auto_cap and cap_nals < size // 3 + 8:  # HEVCB_E_CAPACITY: grow (the summary's count is a lower bound)
+            return self.scan_strip_host(buf, size=size, cap_nals=min(size // 3 + 8, max(int(sm.n_nals) + 8, 4 * cap_nals)), want_rbsp=want_rbsp,
+                                        _grow=True)
         self._check(rc)
         n = sm.n_nals
         return ScanResult(n, sm.n_terminated, sm.last_rc, sm.last_start, sm.last_end, sm.rbsp_bytes, sm.n_epb,
@@ -176,15 +186,17 @@ class Context:
         return out[: sm.out_bytes], out_off, int(sm.n_inserted)
 
     # ---- batched header parse -----------------------------------------------------------------
-    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True):
+    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False):
         """Header parse of every NAL found by scan_strip_device (device resident).  Returns a dict of torch tensors
-        (rc, nal_hdr, kind, ubflag, hdr_end, cols[8][n], pair_off[n+1], pair_field, pair_value) and `summary`."""
+        (rc, nal_hdr, kind, ubflag, hdr_end, cols[8][n], pair_off[n+1], pair_field, pair_value) and `summary`.
+        trace=True: the read_debug variant (include/hevcb.h): the lists hold what read_debug_hevc_nal_unit prints, with
+        `pair_pos` = bit position of every record."""
         import torch
 
         n = int(scan.n_nals)
         dev = buf.device
         if cap_pairs is None:
-            cap_pairs = 64 * n + 4096
+            cap_pairs = (96 if trace else 64) * n + 4096
         out = dict(
             rc=torch.empty(max(n, 1), dtype=torch.int32, device=dev), nal_hdr=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
             kind=torch.empty(max(n, 1), dtype=torch.uint8, device=dev), ubflag=torch.empty(max(n, 1), dtype=torch.uint8, device=dev),
@@ -195,6 +207,9 @@ class Context:
         pb = ParseBuffers(out["rc"].data_ptr(), out["nal_hdr"].data_ptr(), out["kind"].data_ptr(), out["ubflag"].data_ptr(),
                           out["hdr_end"].data_ptr(), out["cols"].data_ptr(), out["pair_off"].data_ptr(), out["pair_field"].data_ptr(),
                           out["pair_value"].data_ptr(), cap_pairs)
+        if trace:
+            out["pair_pos"] = torch.empty(cap_pairs, dtype=torch.int32, device=dev)
+            pb.pair_pos = out["pair_pos"].data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self._L.hevcb_parse_device(self._h, buf.data_ptr(), scan.nal_start.data_ptr(), scan.nal_end.data_ptr(), scan.rbsp.data_ptr(),
                                                scan.rbsp_off.data_ptr(), scan.rbsp_end.data_ptr(), n, C.byref(pb), out["summary"].data_ptr(), stream))

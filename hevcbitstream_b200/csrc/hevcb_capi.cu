@@ -75,9 +75,9 @@ HEVCB_API void hevcb_destroy(hevcb_ctx* ctx)
 {
     if (!ctx) { return; }
     cudaSetDevice(ctx->device);
-    hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
+    hevcb_devbuf* bufs[] = {&ctx->scan_scratch, &ctx->scan_timing, &ctx->h_in, &ctx->h_rbsp, &ctx->h_a0, &ctx->h_a1, &ctx->h_a2, &ctx->h_a3, &ctx->h_misc,
                             &ctx->insert_scratch, &ctx->rewrite_slots, &ctx->rewrite_scratch, &ctx->rewrite_staging, &ctx->wstruct, &ctx->parse_scratch, &ctx->parse_ps, &ctx->parse_sort, &ctx->h_p[0], &ctx->h_p[1], &ctx->h_p[2], &ctx->h_p[3], &ctx->h_p[4],
-                            &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8]};
+                            &ctx->h_p[5], &ctx->h_p[6], &ctx->h_p[7], &ctx->h_p[8], &ctx->h_p[9]};
     for (hevcb_devbuf* b : bufs) {
         if (b->p) { cudaFree(b->p); }
     }
@@ -546,9 +546,9 @@ HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     }
     const int64_t n = idx->scan.n_nals;
     // device staging of the parse outputs
-    const size_t sizes[9] = {(size_t)n * 4, (size_t)n * 4, (size_t)n, (size_t)n, (size_t)n * 4, (size_t)n * 32, (size_t)(n + 1) * 8,
-                             (size_t)idx->p.cap_pairs * 4, (size_t)idx->p.cap_pairs * 4};
-    for (int i = 0; i < 9; i++) {
+    const size_t sizes[10] = {(size_t)n * 4, (size_t)n * 4, (size_t)n, (size_t)n, (size_t)n * 4, (size_t)n * 32, (size_t)(n + 1) * 8,
+                              (size_t)idx->p.cap_pairs * 4, (size_t)idx->p.cap_pairs * 4, idx->p.pair_pos ? (size_t)idx->p.cap_pairs * 4 : 0};
+    for (int i = 0; i < 10; i++) {
         if ((rc = hevcb_reserve(ctx, &ctx->h_p[i], sizes[i] + 16)) != HEVCB_OK) { return rc; }
     }
     hevcb_parse_buffers d;
@@ -562,6 +562,7 @@ HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     d.pair_field = reinterpret_cast<uint32_t*>(ctx->h_p[7].p);
     d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
     d.cap_pairs = idx->p.cap_pairs;
+    d.pair_pos = idx->p.pair_pos ? reinterpret_cast<uint32_t*>(ctx->h_p[9].p) : nullptr; // host array given: the trace variant
     rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, chain, st);
     if (rc != HEVCB_OK) { return rc; }
     HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
@@ -587,10 +588,97 @@ HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     if (np > 0 && idx->p.pair_field && idx->p.pair_value) {
         HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_field, d.pair_field, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
         HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_value, d.pair_value, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        if (idx->p.pair_pos) { HEVCB_CUDA(ctx, cudaMemcpyAsync(idx->p.pair_pos, d.pair_pos, (size_t)np * 4, cudaMemcpyDeviceToHost, st)); }
         HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
     }
     if (idx->parse.overflow) {
         HEVCB_SET_ERR(ctx, "hevcb_index_host: %lld syntax elements exceed cap_pairs %lld", (long long)idx->parse.n_pairs, (long long)idx->p.cap_pairs);
+        return HEVCB_E_CAPACITY;
+    }
+    return HEVCB_OK;
+}
+
+// Header parse of RBSPs the caller already holds (no start codes, no emulation prevention bytes): n segments of one host buffer.
+HEVCB_API int hevcb_parse_rbsp_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t rbsp_bytes, const int64_t* rbsp_off, const int64_t* rbsp_end,
+                                    int64_t n, const hevcb_parse_buffers* out, hevcb_parse_summary* summary, const hevcb_parse_chain* chain)
+{
+    if (!ctx || !out || !summary || n < 0 || rbsp_bytes < 0 || (n > 0 && (!rbsp_off || !rbsp_end)) || (rbsp_bytes > 0 && !rbsp) || !out->rc ||
+        !out->nal_hdr || !out->kind || !out->ubflag || !out->hdr_end || !out->cols || !out->pair_off) {
+        HEVCB_SET_ERR(ctx, "hevcb_parse_rbsp_host: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    for (int64_t k = 0; k < n; k++) {
+        if (rbsp_end[k] >= 0 && (rbsp_off[k] < 0 || rbsp_end[k] < rbsp_off[k] || rbsp_end[k] > rbsp_bytes)) {
+            HEVCB_SET_ERR(ctx, "hevcb_parse_rbsp_host: segment %lld lies outside the buffer", (long long)k);
+            return HEVCB_E_ARG;
+        }
+    }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    memset(summary, 0, sizeof(*summary));
+    int rc;
+    if (n == 0) {
+        if ((rc = hevcb_reserve(ctx, &ctx->h_misc, 256)) != HEVCB_OK) { return rc; }
+        return hevcb_launch_parse(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, out, reinterpret_cast<hevcb_parse_summary*>(ctx->h_misc.p), chain, st);
+    }
+    const size_t img = ((size_t)rbsp_bytes + 31u) & ~(size_t)15u;
+    if ((rc = hevcb_reserve(ctx, &ctx->h_rbsp, img + 16)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a2, (size_t)n * 8)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_a3, (size_t)n * 8)) != HEVCB_OK) { return rc; }
+    if ((rc = hevcb_reserve(ctx, &ctx->h_misc, 256)) != HEVCB_OK) { return rc; }
+    uint8_t* d_rbsp = reinterpret_cast<uint8_t*>(ctx->h_rbsp.p);
+    int64_t* d_ro = reinterpret_cast<int64_t*>(ctx->h_a2.p);
+    int64_t* d_re = reinterpret_cast<int64_t*>(ctx->h_a3.p);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(d_rbsp + (img - 32), 0, 32, st)); // the bit reader's aligned 8-byte loads reach past the last byte
+    if (rbsp_bytes > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(d_rbsp, rbsp, (size_t)rbsp_bytes, cudaMemcpyHostToDevice, st)); }
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(d_ro, rbsp_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(d_re, rbsp_end, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const size_t sizes[10] = {(size_t)n * 4, (size_t)n * 4, (size_t)n, (size_t)n, (size_t)n * 4, (size_t)n * 32, (size_t)(n + 1) * 8,
+                              (size_t)out->cap_pairs * 4, (size_t)out->cap_pairs * 4, out->pair_pos ? (size_t)out->cap_pairs * 4 : 0};
+    for (int i = 0; i < 10; i++) {
+        if ((rc = hevcb_reserve(ctx, &ctx->h_p[i], sizes[i] + 16)) != HEVCB_OK) { return rc; }
+    }
+    hevcb_parse_buffers d;
+    d.rc = reinterpret_cast<int32_t*>(ctx->h_p[0].p);
+    d.nal_hdr = reinterpret_cast<int32_t*>(ctx->h_p[1].p);
+    d.kind = reinterpret_cast<uint8_t*>(ctx->h_p[2].p);
+    d.ubflag = reinterpret_cast<uint8_t*>(ctx->h_p[3].p);
+    d.hdr_end = reinterpret_cast<int32_t*>(ctx->h_p[4].p);
+    d.cols = reinterpret_cast<int32_t*>(ctx->h_p[5].p);
+    d.pair_off = reinterpret_cast<int64_t*>(ctx->h_p[6].p);
+    d.pair_field = reinterpret_cast<uint32_t*>(ctx->h_p[7].p);
+    d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
+    d.cap_pairs = out->cap_pairs;
+    d.pair_pos = out->pair_pos ? reinterpret_cast<uint32_t*>(ctx->h_p[9].p) : nullptr;
+    // the RBSP doubles as "the NAL bytes": rc[k] is then the RBSP size (buf_size 1 keeps the trailing-00-00-03 rule, which is about
+    // bytes the caller stripped, away from it)
+    hevcb_parse_chain ch;
+    ch.sps_in = chain ? chain->sps_in : nullptr; ch.pps_in = chain ? chain->pps_in : nullptr;
+    ch.sps_out = chain ? chain->sps_out : nullptr; ch.pps_out = chain ? chain->pps_out : nullptr;
+    ch.buf_size = 1;
+    hevcb_parse_summary* d_psum = reinterpret_cast<hevcb_parse_summary*>(reinterpret_cast<uint8_t*>(ctx->h_misc.p) + 128);
+    rc = hevcb_launch_parse(ctx, d_rbsp, d_ro, d_re, d_rbsp, d_ro, d_re, n, &d, d_psum, &ch, st);
+    if (rc != HEVCB_OK) { return rc; }
+    hevcb_parse_summary* p_psum = reinterpret_cast<hevcb_parse_summary*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 128);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->rc, d.rc, sizes[0], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->nal_hdr, d.nal_hdr, sizes[1], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->kind, d.kind, sizes[2], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->ubflag, d.ubflag, sizes[3], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->hdr_end, d.hdr_end, sizes[4], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->cols, d.cols, sizes[5], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_off, d.pair_off, sizes[6], cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    *summary = *p_psum;
+    const int64_t np = summary->n_pairs < out->cap_pairs ? summary->n_pairs : out->cap_pairs;
+    if (np > 0 && out->pair_field && out->pair_value) {
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_field, d.pair_field, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_value, d.pair_value, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        if (out->pair_pos) { HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_pos, d.pair_pos, (size_t)np * 4, cudaMemcpyDeviceToHost, st)); }
+        HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (summary->overflow) {
+        HEVCB_SET_ERR(ctx, "hevcb_parse_rbsp_host: %lld syntax elements exceed cap_pairs %lld", (long long)summary->n_pairs, (long long)out->cap_pairs);
         return HEVCB_E_CAPACITY;
     }
     return HEVCB_OK;
@@ -621,7 +709,9 @@ HEVCB_API int hevcb_materialize(const hevcb_stream_index* idx, int64_t k, void* 
         memset(dst, 0, words * 4);
         const int64_t a = idx->p.pair_off[k], b = idx->p.pair_off[k + 1];
         for (int64_t i = a; i < b && i < idx->p.cap_pairs; i++) {
-            const uint32_t f = idx->p.pair_field[i];
+            uint32_t f = idx->p.pair_field[i];
+            if (f & HEVCB_TRACE_SPECIAL) { continue; } // trace variant: a printed line that is not a struct member
+            f &= ~HEVCB_TRACE_SILENT;
             if (f < words) { dst[f] = idx->p.pair_value[i]; }
         }
     }

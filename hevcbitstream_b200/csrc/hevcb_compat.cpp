@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "../../include/hevcb.h"
+#include "../../include/compat/bs.h"
+#include "../../include/compat/h264_sei.h"
 #include "../../include/hevcb_compat.h"
 
 namespace {
@@ -69,7 +71,7 @@ struct IndexBuffers {
     std::vector<int64_t> a[4];
     std::vector<uint8_t> rbsp, kind, ubflag, stream;
     std::vector<int32_t> rc, hdr, hdr_end, cols, pval;
-    std::vector<uint32_t> pfield;
+    std::vector<uint32_t> pfield, ppos;
     std::vector<int64_t> pair_off;
 } g_ib;
 
@@ -202,7 +204,12 @@ int peek_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_nal.c:9
     return h->nal->nal_unit_type;
 }
 
-int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.c:155-241
+} // extern "C"
+
+namespace {
+// read_hevc_nal_unit (hevc_stream.c:155-241) and, with `debug`, read_debug_hevc_nal_unit (:2343-3436): the same call with the
+// parse run in its trace variant and one line printed per record
+int read_nal(hevc_stream_t* h, uint8_t* buf, int size, bool debug)
 {
     hevcb_ctx* ctx = context();
     std::map<hevc_stream_t*, StreamState>::iterator it = g_streams.find(h);
@@ -219,6 +226,7 @@ int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.
     g_ib.rc.assign((size_t)cap, 0); g_ib.hdr.assign((size_t)cap, 0); g_ib.kind.assign((size_t)cap, 0); g_ib.ubflag.assign((size_t)cap, 0);
     g_ib.hdr_end.assign((size_t)cap, 0); g_ib.cols.assign((size_t)cap * 8, 0); g_ib.pair_off.assign((size_t)cap + 1, 0);
     g_ib.pfield.resize((size_t)cap_pairs); g_ib.pval.resize((size_t)cap_pairs);
+    if (debug) { g_ib.ppos.resize((size_t)cap_pairs); }
     hevcb_stream_index idx;
     memset(&idx, 0, sizeof(idx));
     idx.cap_nals = cap;
@@ -227,15 +235,34 @@ int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.
     idx.p.rc = g_ib.rc.data(); idx.p.nal_hdr = g_ib.hdr.data(); idx.p.kind = g_ib.kind.data(); idx.p.ubflag = g_ib.ubflag.data();
     idx.p.hdr_end = g_ib.hdr_end.data(); idx.p.cols = g_ib.cols.data(); idx.p.pair_off = g_ib.pair_off.data();
     idx.p.pair_field = g_ib.pfield.data(); idx.p.pair_value = g_ib.pval.data(); idx.p.cap_pairs = cap_pairs;
+    idx.p.pair_pos = debug ? g_ib.ppos.data() : nullptr;
     std::vector<uint8_t> sps_out(st.sps.size()), pps_out(st.pps.size());
     hevcb_parse_chain chain;
     chain.sps_in = st.sps.data(); chain.pps_in = st.pps.data(); chain.sps_out = sps_out.data(); chain.pps_out = pps_out.data(); chain.buf_size = 0;
-    const int rc = hevcb_index_host_chain(ctx, s.data(), n + 3, &idx, &chain);
-    if (rc != HEVCB_OK) { return -1; }
-    // nal_to_rbsp fails on the NAL (start codes inside, 00 00 02, ...): -1 before h->nal is touched (hevc_stream.c:165-167)
-    if (idx.scan.n_nals != 1 || idx.nal_start[0] != 3 || idx.nal_end[0] != n + 3 || idx.rbsp_end[0] < 0) { return -1; }
+    if (n == 0) {
+        // a zero-length NAL (hevc_analyze hands one over when its loop ends on return code 0, hevc_analyze.c:190-205): nal_to_rbsp
+        // yields an empty RBSP and every read returns 0 bits; no start code can frame that for the scanner, so it is parsed as given
+        idx.rbsp_off[0] = 0; idx.rbsp_end[0] = 0; idx.nal_start[0] = 0; idx.nal_end[0] = 0;
+        if (hevcb_parse_rbsp_host(ctx, nullptr, 0, idx.rbsp_off, idx.rbsp_end, 1, &idx.p, &idx.parse, &chain) != HEVCB_OK) { return -1; }
+        idx.scan.n_nals = 1;
+    } else {
+        const int rc = hevcb_index_host_chain(ctx, s.data(), n + 3, &idx, &chain);
+        if (rc != HEVCB_OK) { return -1; }
+        // nal_to_rbsp fails on the NAL (start codes inside, 00 00 02, ...): -1 before h->nal is touched (hevc_stream.c:165-167)
+        if (idx.scan.n_nals != 1 || idx.nal_start[0] != 3 || idx.nal_end[0] != n + 3 || idx.rbsp_end[0] < 0) { return -1; }
+    }
     st.sps.swap(sps_out);
     st.pps.swap(pps_out);
+    if (debug) { // "%ld.%d: <expr>: %d \n" per element, always to stdout (the dbgfile redirect only exists in h264_stream.c)
+        char name[160];
+        for (int64_t i = idx.p.pair_off[0]; i < idx.p.pair_off[1]; i++) {
+            const uint32_t code = idx.p.pair_field[i], pos = idx.p.pair_pos[i];
+            if (!(code & HEVCB_TRACE_SPECIAL) && (code & HEVCB_TRACE_SILENT)) { continue; }
+            if (code == (HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TRACE_OPEN_LINE)) { printf("%ld.%d: ", (long)(pos >> 3), 8 - (int)(pos & 7u)); continue; }
+            if (hevcb_trace_name(idx.p.kind[0], code, name, (int)sizeof(name)) < 0) { snprintf(name, sizeof(name), "?%08x", code); }
+            printf("%ld.%d: %s: %d \n", (long)(pos >> 3), 8 - (int)(pos & 7u), name, idx.p.pair_value[i]);
+        }
+    }
     const int ret = hevcb_materialize(&idx, 0, h->nal, h->vps, h->sps, h->pps, h->sh);
     switch (idx.p.kind[0]) {
         case HEVCB_KIND_SPS: { // hevc_stream.c: memcpy(h->sps_table[sps->sps_seq_parameter_set_id], h->sps, ...)
@@ -264,6 +291,115 @@ int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.
     return ret;
 }
 
+} // namespace
+
+#pragma GCC visibility push(default) // everything below is API surface of the reference (include/compat/*.h declares it without attributes)
+extern "C" {
+
+FILE* h264_dbgfile = nullptr; // h264_stream.c:33
+
+int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) { return read_nal(h, buf, size, false); }       // hevc_stream.c:155
+int read_debug_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) { return read_nal(h, buf, size, true); } // hevc_stream.c:2343
+
+// ---- host-side helpers of the reference's API surface (plain formatting / bs_t arithmetic, nothing to accelerate) ----------------
+
+void debug_bytes(uint8_t* buf, int len) // h264_stream.c:117-126: every byte as "%02X ", a newline after every 16th and at the end
+{
+    FILE* f = h264_dbgfile ? h264_dbgfile : stdout;
+    for (int i = 0; i < len; i++) {
+        fprintf(f, "%02X ", buf[i]);
+        if ((i + 1) % 16 == 0) { fputc('\n', f); }
+    }
+    fputc('\n', f);
+}
+
+int intlog2(int x) // h264_stream.c:42-52: ceil(log2(x)), 0 for x <= 0
+{
+    if (x <= 1) { return 0; }
+    int bits = 0;
+    for (unsigned v = (unsigned)x - 1u; v; v >>= 1) { bits++; }
+    return bits;
+}
+
+int is_slice_type(int slice_type, int cmp_type) // h264_stream.c:54-60: types 5..9 alias 0..4
+{
+    return (slice_type >= 5 ? slice_type - 5 : slice_type) == (cmp_type >= 5 ? cmp_type - 5 : cmp_type);
+}
+
+int more_rbsp_data(bs_t* bs) // h264_stream.c:62-84: data follows unless the next 1 bit is the last 1 bit of the buffer
+{
+    if (bs_eof(bs)) { return 0; }
+    if (bs_peek_u1(bs) == 0) { return 1; }
+    bs_t t;
+    bs_clone(&t, bs);
+    bs_skip_u1(&t);
+    while (!bs_eof(&t)) {
+        if (bs_read_u1(&t)) { return 1; }
+    }
+    return 0;
+}
+
+int more_rbsp_trailing_data(bs_t* b) { return !bs_eof(b); } // h264_stream.c:86
+
+int _read_ff_coded_number(bs_t* b) // h264_stream.c:88-98: bytes are summed up to and including the first one below 0xff
+{
+    int sum = 0;
+    for (;;) {
+        const int byte = (int)bs_read_u8(b);
+        sum += byte;
+        if (byte != 0xff) { return sum; }
+    }
+}
+
+void _write_ff_coded_number(bs_t* b, int n) // h264_stream.c:100-115
+{
+    for (; n > 0xff; n -= 0xff) { bs_write_u8(b, 0xff); }
+    bs_write_u8(b, (uint32_t)n);
+}
+
+void read_rbsp_trailing_bits(bs_t* b) // h264_stream.c:129-137
+{
+    bs_skip_u(b, 1);
+    while (!bs_byte_aligned(b)) { bs_skip_u(b, 1); }
+}
+
+sei_t* sei_new() { return (sei_t*)calloc(1, sizeof(sei_t)); } // h264_sei.c:37-43
+void sei_free(sei_t* s) // h264_sei.c:45-52
+{
+    if (!s) { return; }
+    free(s->data);
+    free(s);
+}
+void read_sei_end_bits(bs_t* b) // h264_sei.c:54-67
+{
+    if (!bs_byte_aligned(b)) {
+        if (!bs_read_u1(b)) { fprintf(stderr, "WARNING: bit_equal_to_one is 0!!!!\n"); }
+        while (!bs_byte_aligned(b)) {
+            if (bs_read_u1(b)) { fprintf(stderr, "WARNING: bit_equal_to_zero is 1!!!!\n"); }
+        }
+    }
+    read_rbsp_trailing_bits(b);
+}
+void read_sei_payload(sei_t* s, bs_t* b) // h264_sei.c:75-92: payloadSize raw bytes
+{
+    s->data = (uint8_t*)calloc(1, (size_t)(s->payloadSize > 0 ? s->payloadSize : 1));
+    for (int i = 0; i < s->payloadSize; i++) { s->data[i] = (uint8_t)bs_read_u8(b); }
+}
+void write_sei_payload(sei_t* s, bs_t* b) // h264_sei.c:99-116
+{
+    for (int i = 0; i < s->payloadSize; i++) { bs_write_u8(b, s->data[i]); }
+}
+void read_debug_sei_payload(sei_t* s, bs_t* b) // h264_sei.c:123-140
+{
+    // As generated, only the position prefix sits inside the reference's loop; the read and the value line follow it once, with
+    // i == payloadSize (a write one past the array there).  The visible output is reproduced, the byte is stored when it fits.
+    s->data = (uint8_t*)calloc(1, (size_t)(s->payloadSize > 0 ? s->payloadSize : 0) + 1);
+    for (int i = 0; i < s->payloadSize; i++) { printf("%ld.%d: ", (long)(b->p - b->start), b->bits_left); }
+    const uint32_t v = bs_read_u8(b);
+    s->data[s->payloadSize > 0 ? s->payloadSize : 0] = (uint8_t)v;
+    printf("s->data[i]: %d \n", (int)(uint8_t)v);
+}
+
 int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.c:1249-1335
 {
     hevcb_ctx* ctx = context();
@@ -279,3 +415,4 @@ int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream
 }
 
 } // extern "C"
+#pragma GCC visibility pop

@@ -19,6 +19,8 @@ struct hevcb_ctx {
     char err[512] = {0};
     // scan scratch: [0,64) counters, then one 16-byte state word per tile
     hevcb_devbuf scan_scratch;
+    hevcb_devbuf scan_timing;             // HEVCB_SCAN_TIMING: event stamps of the scan pipeline (measurement aid)
+    int scan_timing_ctas = 0;
     hevcb_devbuf rewrite_slots;           // rewrite: per-NAL header slots of the first write pass
     hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
     hevcb_devbuf rewrite_scratch, rewrite_staging; // rewrite: part arrays, written headers
@@ -31,7 +33,7 @@ struct hevcb_ctx {
     } last_parse;
     hevcb_devbuf parse_scratch, parse_ps; // parser: per-NAL scratch arrays, parameter-set context tables
     hevcb_devbuf parse_sort;              // parser: radix sort workspace
-    hevcb_devbuf h_p[9];                  // staging of the parse outputs for the *_host entry points
+    hevcb_devbuf h_p[10];                 // staging of the parse outputs for the *_host entry points
     // staging used by the *_host entry points
     hevcb_devbuf h_in, h_rbsp, h_a0, h_a1, h_a2, h_a3, h_misc;
     void* pinned = nullptr; // small pinned block for summaries

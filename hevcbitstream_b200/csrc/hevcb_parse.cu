@@ -223,10 +223,13 @@ struct ParseArgs {
     const int64_t* pair_off;
     uint32_t* pair_field;
     int32_t* pair_value;
+    uint32_t* pair_pos; // trace mode (read_debug variant): bit position of every record
     int64_t cap_pairs;
 };
 
-template <bool kEmit, bool kSlices>
+// kTrace: the read_debug variant of the walk (hevcb_sink_t<true>): the lists hold what read_debug_hevc_nal_unit prints; NALs of
+// unsupported types then contribute their four NAL header lines (they are taken with the slices).
+template <bool kEmit, bool kSlices, bool kTrace>
 __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
 {
     const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
     const int64_t k = a.perm[a.n - 1 - ti]; // shape order, last shape first: the long parameter-set walks start with the first blocks
     const int c = a.cls[k];
     const bool is_ps = (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps);
-    const bool is_slice = (c == kCls_Slice);
+    const bool is_slice = (c == kCls_Slice) || (kTrace && c == kCls_Other);
     if (!kEmit) {
         if (kSlices ? !is_slice : !is_ps) { return; }
     } else {
@@ -251,8 +254,9 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
     if (c == kCls_Sps) { sps_out = kEmit ? &a.sps_scratch[sps_count] : &a.sps_tab[sps_count]; }
     if (c == kCls_Pps) { pps_out = kEmit ? &a.pps_scratch[pps_count] : &a.pps_tab[pps_count]; }
     hevcb_nal_result r;
+    typedef hevcb_sink_t<kTrace> SinkT;
     if (!kEmit) {
-        hevcb_sink sink{nullptr, nullptr, 0};
+        SinkT sink{nullptr, nullptr, 0, nullptr};
         hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
         a.cnt[k] = (int32_t)sink.n;
         a.kind[k] = (uint8_t)r.kind;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
         const int64_t po = a.pair_off[k];
         const int64_t pn = (int64_t)a.cnt[k];
         if (pn == 0 || po + pn > a.cap_pairs) { return; }
-        hevcb_sink sink{a.pair_field + po, a.pair_value + po, 0};
+        SinkT sink{a.pair_field + po, a.pair_value + po, 0, kTrace ? a.pair_pos + po : nullptr};
         hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
         if (sink.n != (uint32_t)pn) { a.ubflag[k] |= 0x80u; a.cols[k] = (int32_t)r.end_bits; a.cols[a.n + k] = (int32_t)sink.n; } // self-check
     }
@@ -681,15 +685,22 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     ctx->last_parse.cls = cls; ctx->last_parse.sps_ord = sps_ord; ctx->last_parse.pps_ord = pps_ord; ctx->last_parse.cnt = cnt;
     ctx->last_parse.perm = perm;
     ctx->last_parse.sps_tab = a.sps_tab; ctx->last_parse.pps_tab = a.pps_tab; ctx->last_parse.sps_scratch = a.sps_scratch;
-    parse_kernel<false, false><<<g128, 128, 0, stream>>>(a); // parameter sets first
-    parse_kernel<false, true><<<g128, 128, 0, stream>>>(a);  // then the slices that depend on them
+    const bool trace = out->pair_pos != nullptr;
+    a.pair_pos = out->pair_pos;
+    if (trace) {
+        parse_kernel<false, false, true><<<g128, 128, 0, stream>>>(a);
+        parse_kernel<false, true, true><<<g128, 128, 0, stream>>>(a);
+    } else {
+        parse_kernel<false, false, false><<<g128, 128, 0, stream>>>(a); // parameter sets first
+        parse_kernel<false, true, false><<<g128, 128, 0, stream>>>(a);  // then the slices that depend on them
+    }
     ctx->launches += 2;
     HEVCB_CUDA(ctx, cudaGetLastError());
     rcs = run_scan<CntVal, int64_t, false>(ctx, CntVal{cnt}, n, out->pair_off, bsums, stream);
     if (rcs != HEVCB_OK) { return rcs; }
     HEVCB_CUDA(ctx, cudaMemcpyAsync(pair_total, bsums + nb, 8, cudaMemcpyDeviceToDevice, stream));
     HEVCB_CUDA(ctx, cudaMemcpyAsync(out->pair_off + n, bsums + nb, 8, cudaMemcpyDeviceToDevice, stream));
-    parse_kernel<true, false><<<g128, 128, 0, stream>>>(a);
+    if (trace) { parse_kernel<true, false, true><<<g128, 128, 0, stream>>>(a); } else { parse_kernel<true, false, false><<<g128, 128, 0, stream>>>(a); }
     parse_summary_kernel<<<148, 256, 0, stream>>>(cls, out->rc, n, pair_total, out->cap_pairs, d_summary);
     ctx->launches += 2;
     HEVCB_CUDA(ctx, cudaGetLastError());

@@ -4,11 +4,11 @@
 // (h264_nal.c:147-200, called at hevc_stream.c:165)  by one pass over the byte range (a whole stream, or one shard of a
 // byte-range partition, see ScanGeom):
 //
-//   * a persistent cooperative grid (2 CTAs / SM) is split into ANALYSER and WRITER CTAs plus one SCANNER warp; the
-//     dependency analyser -> scanner -> writer is one-directional (see the comment in front of the kernel);
-//   * 32 KiB tiles (+128 B leading / 16 B trailing halo) are staged into shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier), two stages per CTA; a tile is loaded by one analyser and, a few microseconds later,
-//     by one writer -- out of L2, the analysers stay within a window of the writers' progress;
+//   * a persistent cooperative grid, one CTA per SM, every CTA a warp-specialised pipeline over a six-stage shared-memory
+//     ring: PRODUCER (TMA bulk copies) -> ANALYSER warps -> aggregate published -> [SCANNER warp: prefixes, across CTAs] ->
+//     WRITER warps -> stage free.  A tile is loaded ONCE and stays in shared memory until its prefix has arrived; nothing
+//     inside a CTA waits in lock-step (see the comment in front of the kernel);
+//   * 32 KiB tiles (+128 B leading / 16 B trailing halo) are staged with cp.async.bulk + mbarrier;
 //   * every lane owns 16 bytes: an exact "two adjacent zero bytes?" SWAR test sends the common case down a fast path;
 //     the chunks that fail it are ranked in stream order and their exact predicate bit masks (hevcb_chunk_analyze) are
 //     built 32 at a time, every lane busy;
@@ -16,17 +16,16 @@
 //     lane -> row -> warp -> tile; across tiles one warp scans the 16-byte tile aggregates in stream order;
 //   * the EPB-free image is written as aligned 16-byte vectors, funnel-shifted by the tile-uniform misalignment; NAL
 //     offsets are written by the lanes that own the events (hevcb_scan_emit_kernel for tiles handed over as event
-//     records, the writer itself for tiles with removed bytes or very many events); tiles with removed bytes are
+//     records, the writer warps for tiles with removed bytes or very many events); tiles with removed bytes are
 //     compacted in shared memory first, so the image never sees byte-granular stores.
 //
-// HBM traffic: input read once (second load from L2), image written once, 32 B of metadata per NAL.  Tensor cores unused:
-// nothing here is a contraction.
+// HBM traffic: input read once, image written once, 32 B of metadata per NAL.  Tensor cores unused: nothing here is a
+// contraction.
 //
 // HEVCB_SCAN_DEBUG (context creation) is a bit mask of measurement switches used to attribute time to the parts of the
-// kernel (results are wrong with any of them set): 1 no scanner / fake prefixes, 4 no image write, 32 writers off,
-// 64 analysis off (bits 8..15: rows to flag), 128 writers do not wait for the scanner, 512 every tile takes the clean
-// path, 1024 no event records, 2048 / 65536 the row-by-row analysis / writer paths of interior tiles, bits 12..15 rows up to
-// which the analyser stays row-wise (+1).  HEVCB_SCAN_ANALYSERS / HEVCB_SCAN_WINDOW override the role split and the L2 window.
+// kernel (results are wrong with any of them set): 4 no image write, 64 analysis off (bits 8..15: rows to flag),
+// 1024 no event records, 2048 / 65536 the row-by-row analysis / writer paths of interior tiles, bits 12..15 rows up to
+// which the analyser stays row-wise (+1).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -40,33 +39,38 @@ namespace {
 #define HEVCB_SCAN_WORKERS 8
 #endif
 #ifndef HEVCB_SCAN_CTAS
-#define HEVCB_SCAN_CTAS 2
+#define HEVCB_SCAN_CTAS 1
 #endif
-constexpr int kWorkers = HEVCB_SCAN_WORKERS;   // warps that analyse / write tiles
-constexpr int kSyncThreads = (kWorkers + 1) * 32; // workers + the control warp (publishes aggregates, fetches prefixes, issues TMA)
-constexpr int kThreads = (kWorkers + 2) * 32;     // + the scanner warp (only active in CTA 0)
-constexpr int kWorkerThreads = kWorkers * 32;
+// warp roles inside a CTA: kAWarps analysers (kARows rows of a tile each), kWWarps writers (kWRows rows each), then one warp each
+// for: analyser control (publishes tile aggregates), writer control (fetches tile prefixes), producer (TMA).  The last CTA of
+// the grid is the scanner.  Analysis is the longer job per row (and a tile's aggregate waits for its slowest warp), so it gets
+// twice the warps.
+constexpr int kAWarps = 16, kARows = 4;
+constexpr int kWWarps = 8, kWRows = 8;
+constexpr int kAThreads = kAWarps * 32, kWThreads = kWWarps * 32;
+constexpr int kWarpAC = kAWarps + kWWarps, kWarpWC = kWarpAC + 1, kWarpProd = kWarpAC + 2;
+constexpr int kThreads = (kAWarps + kWWarps + 3) * 32;
 constexpr int kRowBytes = 512;  // one warp-row: 32 lanes x 16 B
-#ifndef HEVCB_SCAN_ROWS
-#define HEVCB_SCAN_ROWS 8
-#endif
-constexpr int kRowsPerWarp = HEVCB_SCAN_ROWS; // rows a warp walks in order (its carries stay in registers); 4 or 8
-constexpr int kRows = kWorkers * kRowsPerWarp;
+constexpr int kRows = kAWarps * kARows;
+static_assert(kRows == kWWarps * kWRows && kRows == 64, "a tile is 64 rows: its row mask is one 64-bit word");
 constexpr int kTileBytes = kRows * kRowBytes; // 32 KiB
 constexpr int kLead = 128;                    // leading halo: a whole 128-byte line so that every bulk copy starts line-aligned
 constexpr int kStageBytes = kLead + kTileBytes + 16;
 #ifndef HEVCB_SCAN_STAGES
-#define HEVCB_SCAN_STAGES 2
+#define HEVCB_SCAN_STAGES 6
 #endif
-constexpr int kStages = HEVCB_SCAN_STAGES;       // tiles per CTA in shared memory (one being worked on, the others in flight)
+constexpr int kStages = HEVCB_SCAN_STAGES;       // ring of tiles per CTA: in flight / being analysed / waiting for their prefix / being written
 #ifndef HEVCB_SCAN_AUNROLL
 #define HEVCB_SCAN_AUNROLL 1
 #endif
 constexpr int kAnalyserUnroll = HEVCB_SCAN_AUNROLL; // the analyser's loop over groups of four rows stays rolled (two roles share the instruction cache)
 #ifndef HEVCB_SCAN_PERLANE
-#define HEVCB_SCAN_PERLANE 10
+#define HEVCB_SCAN_PERLANE 4
 #endif
-constexpr int kScanPerLane = HEVCB_SCAN_PERLANE; // tile aggregates per lane and batch of the scanner warp (320 tiles per batch)
+constexpr int kScanPerLane = HEVCB_SCAN_PERLANE; // most tile aggregates per lane and batch of a scanner warp
+#ifndef HEVCB_SCAN_BATCH_PER_LANE
+#define HEVCB_SCAN_BATCH_PER_LANE 2
+#endif
 
 // byte range handled by one launch (see hevcb_chunk_analyze): a whole stream or one shard of a byte-range partition
 struct ScanGeom {
@@ -75,7 +79,8 @@ struct ScanGeom {
     int64_t evl;        // events / error positions honoured below this
     uint32_t init_n;    // 1: a NAL is considered open at position 0 (local index 0: the piece of a NAL begun in an earlier shard)
     uint32_t init_kind; // carry entering the range
-    long long window;   // analysers load at most this many tiles ahead of the writers' progress
+    int scan_per_lane;  // scanner batch = 32 x this many tiles; a batch must fit into what the rings let the analysers run ahead
+    long long prefetch; // tiles between a claimed tile and the tile it prefetches into L2 (0: off)
 };
 
 struct WarpAgg {
@@ -100,13 +105,20 @@ struct TilePrefix {
 // dynamic shared memory layout
 struct __align__(16) SmemLayout {
     uint8_t stage[kStages][kStageBytes];
-    unsigned long long mbar[kStages];
-    unsigned long long done[kStages]; // analyser: the workers are through with the stage (one arrival per warp)
-    uint32_t evcount[kStages];        // analyser: event records written for the tile in the stage
-    WarpAgg wagg[kStages][kWorkers];  // per-warp aggregates of the tile in a stage (writer: index i & 1)
-    TilePrefix pref[2];        // writer: prefix + row mask of this CTA's i-th tile (index i & 1)
-    uint8_t slowmap[kWorkers][kRowsPerWarp * 32]; // the warp's chunks that need exact analysis, in stream order
-    alignas(16) uint16_t delmask[kWorkers][kRowsPerWarp * 32]; // writer: removed bytes of every chunk of the warp's rows (tiles with removed bytes)
+    unsigned long long full[kStages];  // the tile has landed (TMA transaction count)
+    unsigned long long done[kStages];  // the analyser warps are through with the stage (one arrival per warp)
+    unsigned long long ready[kStages]; // the tile's prefix and row mask are in pref[] (one arrival, writer control warp)
+    unsigned long long freeb[kStages]; // the writer warps are through with the stage (one arrival per warp): it may be reloaded
+    unsigned long long pub[kStages];   // the tile's aggregate is published and its row mask is in aggmask[] (one arrival, analyser control warp)
+    long long tile[kStages];           // tile in the stage (claimed by the producer from the grid-wide counter); -1: no more tiles
+    unsigned long long aggmask[kStages]; // rows of the tile that need exact treatment by the writers (0: clean or handed over as records)
+    uint32_t evcount[kStages];         // event records the analysers wrote for the tile in the stage
+    WarpAgg wagg[kStages][kAWarps];    // analysers: per-warp aggregates of the tile in a stage
+    WarpAgg waggW[kStages][kWWarps];   // writers: the same for tiles they analyse themselves
+    TilePrefix pref[kStages];          // prefix + row mask of the tile in a stage
+    uint8_t slowmapA[kAWarps][kARows * 32]; // analyser warp: its chunks that need exact analysis, in stream order
+    uint8_t slowmapW[kWWarps][kWRows * 32]; // writer warp: the same
+    alignas(16) uint16_t delmask[kWWarps][kWRows * 32]; // writer: removed bytes of every chunk of the warp's rows (tiles with removed bytes)
 };
 
 // ---- tile state for the decoupled look-back: one 16-byte word, read/written with single 128-bit accesses
@@ -173,19 +185,36 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, uint32_t parity) // never blocks
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// asks L2 to fetch a byte range from HBM (no destination on the SM): the tile's later bulk copy into shared memory then hits L2
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// named barriers: 0 is __syncthreads; kBarWork = the worker warps only; kBarE / kBarP = workers + control warp (writer role)
-constexpr int kBarWork = 1, kBarE = 3, kBarP = 4;
+// named barriers: 0 is __syncthreads; kBarWork = the analyser warps, kBarW = the writer warps
+constexpr int kBarWork = 1, kBarW = 2;
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -202,6 +231,13 @@ __device__ __forceinline__ void issue_tile_load(uint8_t* st, unsigned long long*
     uint32_t bytes = (uint32_t)(hi - lo);
     mbar_expect_tx(bar, bytes);
     tma_bulk_g2s(st + dst_off, buf + lo, bytes, bar);
+}
+
+// a worker warp is through with a stage: one arrival per warp
+__device__ __forceinline__ void release_stage(unsigned long long* bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(bar); }
 }
 
 struct DevSink {
@@ -224,7 +260,7 @@ struct DevSink {
 
 // scratch header (device): [1] first zero-length NAL index
 struct ScanHeader {
-    unsigned long long tiles_written; // writer progress (analysers stay within a window of it so that a tile's second load hits L2)
+    unsigned long long next_tile; // grid-wide tile counter: a CTA with a free stage claims the next tile
     long long first_empty;
     ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
     unsigned long long heavy_tiles;  // tiles the writers had to analyse themselves (feeds the role split of the next launch)
@@ -283,6 +319,17 @@ __device__ __forceinline__ uint32_t zero_pair_any(uint32_t wp, uint32_t w0, uint
     return (((mp - c) & ~mp) | ((m0 - c) & ~m0) | ((m1 - c) & ~m1) | ((m2 - c) & ~m2) | ((m3 - c) & ~m3)) & h;
 }
 
+// the same for the pairs that START inside the chunk [g0, g0 + 16): needs byte g0 + 16 only (low byte of wn)
+__device__ __forceinline__ uint32_t zero_pair_own(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wn)
+{
+    const uint32_t m0 = w0 | __funnelshift_r(w0, w1, 8);
+    const uint32_t m1 = w1 | __funnelshift_r(w1, w2, 8);
+    const uint32_t m2 = w2 | __funnelshift_r(w2, w3, 8);
+    const uint32_t m3 = w3 | __funnelshift_r(w3, wn, 8);
+    const uint32_t c = 0x01010101u, h = 0x80808080u;
+    return (((m0 - c) & ~m0) | ((m1 - c) & ~m1) | ((m2 - c) & ~m2) | ((m3 - c) & ~m3)) & h;
+}
+
 // cold path, kept out of line so that the hot loop stays small in the instruction cache
 __device__ __noinline__ uint3 analyze_cold(uint32_t wp, uint4 v, uint32_t wn, int64_t g0, int64_t size, int64_t own, int64_t evl)
 {
@@ -313,8 +360,9 @@ __device__ __noinline__ void emit_cold(uint32_t evsc, uint32_t deler, uint32_t m
 // 16-byte aligned global destination; Q selects the word offset at compile time, sh is the byte shift in bits.
 template <int Q>
 __device__ __forceinline__ void copy_vectors(uint8_t* __restrict__ dst16, const uint8_t* __restrict__ src16, uint32_t nv, uint32_t sh, int tid,
-                                             uint32_t nthreads = kWorkerThreads)
+                                             uint32_t nthreads = kWThreads)
 {
+#pragma unroll 4
     for (uint32_t vi = tid; vi < nv; vi += nthreads) {
         const uint4 lo = *reinterpret_cast<const uint4*>(src16 + (vi << 4));
         const uint4 hi = *reinterpret_cast<const uint4*>(src16 + (vi << 4) + 16);
@@ -362,23 +410,53 @@ __device__ __forceinline__ void copy_row_clean(uint8_t* __restrict__ dst, const 
     if ((uint32_t)lane < kRowBytes - done) { dst[done + lane] = src[done + lane]; }
 }
 
-// Scanner warp (one per grid): the chained scan over the tile aggregates.  Batch by batch (320 tiles, 10 per lane, in
-// stream order) it waits for the aggregates the analyser CTAs publish, combines them with shuffles / ballots and
-// publishes every tile's EXCLUSIVE prefix (start codes, kept bytes, ordered carry) into tile_excl[].  One reader per
-// aggregate and one 16-byte poll per tile replace an all-to-all look-back, whose polling traffic on a few cache lines
-// was measured to cost ~14k cycles per wave of 296 tiles.
-__device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl,
-                                             long long n_tiles, ScanHeader* __restrict__ hdr, int lane, uint32_t init_n, uint32_t init_kind)
+// Scanner CTA (the last CTA of the grid; it takes no tiles): the chained scan over the tile aggregates.  Batches of 32 x per_lane
+// consecutive tiles go round-robin to kScanWarps warps.  A warp waits for the aggregates the analyser control warps publish (one
+// reader and one 16-byte poll per aggregate: an all-to-all look-back over hundreds of CTAs costs more in polling traffic on a few
+// L2 lines than the whole pass, tests/micro/stream_ceiling.cu), scans them with shuffles / ballots, takes the running prefix from
+// the warp of the previous batch through SHARED memory (the only serial step: ~100 cycles per batch, while the L2 round trips of
+// the batches overlap across the warps) and publishes every tile's EXCLUSIVE prefix (start codes, kept bytes, ordered carry).
+constexpr int kScanWarps = 16;
+constexpr int kTimingIters = 256, kTimingEvents = 8;
+// running prefix handed from batch to batch: ONE 16-byte shared-memory word, so that taking it over and handing it on is one
+// vector load / store without fences: x = batches folded in so far (24 bits) | start codes (40 bits), y = kind | err | kept bytes
+typedef ulonglong2 ScanRun;
+__device__ __forceinline__ ulonglong2 lds_v2(const volatile ScanRun* p)
 {
-    unsigned long long runN = init_n, runK = 0;
-    uint32_t runKind = init_kind, runErr = 0;
-    for (long long base = 0; base < n_tiles; base += 32 * kScanPerLane) {
-        const long long first = base + (long long)lane * kScanPerLane;
+    ulonglong2 v;
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(smem_u32((const void*)p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2(volatile ScanRun* p, ulonglong2 v)
+{
+    asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(smem_u32((const void*)p)), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ ulonglong2 pack_run(unsigned long long seq, unsigned long long n, unsigned long long k, uint32_t kind, uint32_t err)
+{
+    return make_ulonglong2((seq << 40) | (n & ((1ull << 40) - 1)), ((unsigned long long)kind << 62) | ((unsigned long long)(err & 1u) << 61) | k);
+}
+__device__ __forceinline__ void scanner_warps(const ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, long long n_tiles,
+                                              ScanHeader* __restrict__ hdr, volatile ScanRun* run, int warp, int lane, int per_lane,
+                                              unsigned long long* __restrict__ tdbg)
+{
+#define SSTAMP(b, ev)                                                                                            \
+    do {                                                                                                         \
+        if (tdbg != nullptr && lane == 0 && ((b) & 7) == 0 && ((b) >> 3) < kTimingIters) {                       \
+            unsigned long long ts_;                                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                                              \
+            tdbg[((size_t)blockIdx.x * kTimingIters + (size_t)((b) >> 3)) * kTimingEvents + (ev)] = ts_;         \
+        }                                                                                                        \
+    } while (0)
+    const long long batch_tiles = 32ll * per_lane;
+    const long long n_batches = (n_tiles + batch_tiles - 1) / batch_tiles;
+    for (long long b = warp; b < n_batches; b += kScanWarps) {
+        const long long first = b * batch_tiles + (long long)lane * per_lane;
+        SSTAMP(b, 0);
         ulonglong2 sv[kScanPerLane];
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
             const long long idx = first + j;
-            if (idx < n_tiles) { sv[j] = ld_state(&tile_state[idx]); }
+            if (j < per_lane && idx < n_tiles) { sv[j] = ld_state(&tile_state[idx]); }
             else { sv[j] = pack_agg(0, 0, HEVCB_KIND_PASS, 0, 0ull); } // past the end: identity
         }
         for (;;) { // re-poll, one batch per round trip, the aggregates that are not published yet
@@ -386,12 +464,13 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
 #pragma unroll
             for (int j = 0; j < kScanPerLane; j++) { missing = missing || ((sv[j].x >> 62) == 0ull); }
             if (!__any_sync(0xFFFFFFFFu, missing)) { break; }
+            __nanosleep(64);
 #pragma unroll
             for (int j = 0; j < kScanPerLane; j++) {
                 if ((sv[j].x >> 62) == 0ull) { sv[j] = ld_state(&tile_state[first + j]); }
             }
         }
-        __threadfence(); // the aggregates observed above happen before the prefixes published below (writers re-read them)
+        SSTAMP(b, 1);
         // lane totals
         uint32_t ln = 0, lk = 0, lkind = HEVCB_KIND_PASS, lerr = 0;
 #pragma unroll
@@ -400,31 +479,41 @@ __device__ __forceinline__ void scanner_warp(const ulonglong2* __restrict__ tile
             lk += agg_k(sv[j]);
             hevcb_carry_combine(lkind, lerr, agg_kind(sv[j]), agg_err(sv[j]));
         }
-        // exclusive scan over lanes (ascending lane = stream order)
+        // exclusive scan over lanes (ascending lane = stream order), batch totals
         const uint32_t nin = warp_incl_scan(ln, lane), kin = warp_incl_scan(lk, lane);
         const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, lkind != HEVCB_KIND_PASS);
         const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lkind == HEVCB_KIND_SC3);
         const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, lerr != 0u);
-        uint32_t ck, ce;
+        uint32_t ck, ce, bk, be;
         warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+        warp_carry_total(Eb, Sb, Rb, bk, be);
+        const uint32_t totN = __shfl_sync(0xFFFFFFFFu, nin, 31), totK = __shfl_sync(0xFFFFFFFFu, kin, 31);
+        // serial step: running prefix of the batches before this one, handed on to the next batch's warp (every lane reads the
+        // same word: a broadcast load, no divergence)
+        ulonglong2 rw;
+        do { rw = lds_v2(run); } while ((rw.x >> 40) != (unsigned long long)b);
+        SSTAMP(b, 2);
+        const unsigned long long runN = rw.x & ((1ull << 40) - 1), runK = rw.y & ((1ull << 61) - 1);
+        const uint32_t runKind = (uint32_t)(rw.y >> 62), runErr = (uint32_t)(rw.y >> 61) & 1u;
+        if (lane == 0) {
+            uint32_t ok = runKind, oe = runErr;
+            hevcb_carry_combine(ok, oe, bk, be);
+            sts_v2(run, pack_run((unsigned long long)(b + 1), runN + totN, runK + totK, ok, oe));
+            if (b == n_batches - 1) { hdr->final_state = pack_state(kStatusPrefix, runN + totN, runK + totK, ok, oe); }
+        }
         uint32_t cKind = runKind, cErr = runErr; // carry entering this lane's first tile
         hevcb_carry_combine(cKind, cErr, ck, ce);
         unsigned long long cN = runN + (nin - ln), cK = runK + (kin - lk);
 #pragma unroll
         for (int j = 0; j < kScanPerLane; j++) {
             const long long idx = first + j;
-            if (idx < n_tiles) { st_state(&tile_excl[idx], pack_state(kStatusPrefix, cN, cK, cKind, cErr)); }
+            if (j < per_lane && idx < n_tiles) { st_state(&tile_excl[idx], pack_state(kStatusPrefix, cN, cK, cKind, cErr)); }
             cN += agg_n(sv[j]);
             cK += agg_k(sv[j]);
             hevcb_carry_combine(cKind, cErr, agg_kind(sv[j]), agg_err(sv[j]));
         }
-        // running state after the batch = lane 31's state after its last tile
-        runN = __shfl_sync(0xFFFFFFFFu, cN, 31);
-        runK = __shfl_sync(0xFFFFFFFFu, cK, 31);
-        runKind = __shfl_sync(0xFFFFFFFFu, cKind, 31);
-        runErr = __shfl_sync(0xFFFFFFFFu, cErr, 31);
+        SSTAMP(b, 3);
     }
-    if (lane == 0) { hdr->final_state = pack_state(kStatusPrefix, runN, runK, runKind, runErr); }
 }
 
 // per-row analysis shared by both roles: exact masks of one 512-byte row (lanes without two adjacent zero bytes nearby take
@@ -503,7 +592,7 @@ __device__ __forceinline__ void copy_span(uint8_t* __restrict__ dst, const uint8
 }
 __device__ __noinline__ void copy_tile(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int tid)
 {
-    copy_span(dst, src, L, tid, kWorkerThreads);
+    copy_span(dst, src, L, tid, kWThreads);
 }
 
 // boundary fix-ups of a staged tile: positions < 0 read as non-zero, positions >= size read as zero
@@ -513,9 +602,9 @@ __device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, 
     if (t == 0 || valid_end < kStageBytes) {
         if (t == 0 && tid < kLead) { st[tid] = 0xFF; }
         if (valid_end < kStageBytes) {
-            for (int i = (int)valid_end + tid; i < kStageBytes; i += kWorkerThreads) { st[i] = 0; }
+            for (int i = (int)valid_end + tid; i < kStageBytes; i += kAThreads) { st[i] = 0; }
         }
-        bar_sync(kBarWork, kWorkerThreads);
+        bar_sync(kBarWork, kAThreads);
     }
 }
 
@@ -531,7 +620,7 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
     const uint32_t below = (1u << lane) - 1u;
     uint32_t total = 0;
 #pragma unroll
-    for (int i = 0; i < kRowsPerWarp; i++) {
+    for (int i = 0; i < kARows; i++) {
         const bool mine = ((slow8 >> i) & 1u) != 0u;
         const uint32_t sb = __ballot_sync(0xFFFFFFFFu, mine);
         if (mine) { slowmap[total + (uint32_t)__popc(sb & below)] = (uint8_t)(i * 32 + lane); }
@@ -543,7 +632,7 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
         const uint32_t slot = base + (uint32_t)lane;
         uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu, chunk = 0u;
         if (slot < total) {
-            chunk = (uint32_t)(warp * kRowsPerWarp * 32) + slowmap[slot];
+            chunk = (uint32_t)(warp * kARows * 32) + slowmap[slot];
             const uint8_t* rp = st + kLead + chunk * 16u;
             const uint4 v = *reinterpret_cast<const uint4*>(rp);
             const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
@@ -579,162 +668,317 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
 }
 
 // ====================================================================================================================
-// The grid is split into two roles.
-//   ANALYSER CTAs walk the tiles (round-robin among themselves), build the exact predicates where two adjacent zero bytes
-//   occur, and publish one 16-byte aggregate per tile: start codes, kept bytes, ordered carry, and a 64-bit mask of the
-//   rows that need exact treatment.  They never wait for anything but their own TMA loads.
-//   The SCANNER warp turns aggregates into exclusive prefixes, in stream order.
-//   WRITER CTAs walk the same tiles some microseconds later (the second load of a tile is served by L2, so DRAM still sees
-//   every input byte once): they wait for the tile's prefix, redo the exact analysis of the flagged rows only, emit the
-//   NAL boundaries and write the EPB-free image.
-// The dependency analyser -> scanner -> writer is one-directional: no CTA ever waits on a CTA of its own kind, which is
-// what removes the wave-by-wave lock-step a single-role pipeline suffers from (its prefix round trip through L2 is as
-// long as the work on a tile).
+// One CTA per SM; every CTA is a pipeline of specialised warps over a ring of kStages tile buffers, CTA c takes the tiles
+// c, c + G, c + 2G, ...:
+//   PRODUCER (one thread)  waits until the writers have released a stage and reloads it with the CTA's next tile (TMA).
+//   ANALYSER warps         build the exact predicates where two adjacent zero bytes occur and leave per-warp aggregates;
+//   the analyser CONTROL warp publishes one 16-byte aggregate per tile: start codes, kept bytes, ordered carry, and either a
+//                          64-bit mask of the rows that need exact treatment or the number of event records left for the emit pass.
+//   The SCANNER warp (one per grid) turns aggregates into exclusive prefixes, in stream order.
+//   the writer CONTROL warp polls the prefix of the CTA's next tiles (a few tiles ahead) and hands it to the
+//   WRITER warps,          which write the EPB-free image out of the SAME stage (redoing the exact analysis of flagged rows
+//                          only) and emit the NAL boundaries of heavy tiles.
+// The tile is read from HBM once and never reloaded.  Inside a CTA the roles are coupled by mbarriers per stage only (full ->
+// done -> ready -> free): the analysers run ahead of the writers by as many tiles as the scanner needs to deliver a prefix,
+// so the prefix round trip through L2 (as long as the work on a tile) never stalls a warp that has work to do.
 // ====================================================================================================================
 __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_kernel(
-    const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, long long n_analysers, ScanHeader* __restrict__ hdr,
+    const uint8_t* __restrict__ buf, const ScanGeom geom, long long n_tiles, ScanHeader* __restrict__ hdr,
     ulonglong2* __restrict__ tile_state, ulonglong2* __restrict__ tile_excl, uint4* __restrict__ tile_events,
     int64_t* __restrict__ nal_start, int64_t* __restrict__ nal_end, int64_t cap_nals, uint8_t* __restrict__ rbsp,
-    int64_t* __restrict__ rbsp_off, int64_t* __restrict__ rbsp_end, long long debug_flags)
+    int64_t* __restrict__ rbsp_off, int64_t* __restrict__ rbsp_end, long long debug_flags, unsigned long long* __restrict__ tdbg)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    // measurement aid (HEVCB_SCAN_TIMING=1): globaltimer stamps of the pipeline events of the first kTimingIters tiles of every CTA
+#define TSTAMP(iter, ev)                                                                                         \
+    do {                                                                                                         \
+        if (tdbg != nullptr && (iter) < kTimingIters) {                                                          \
+            unsigned long long ts_;                                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                                              \
+            tdbg[((size_t)blockIdx.x * kTimingIters + (size_t)(iter)) * kTimingEvents + (ev)] = ts_;             \
+        }                                                                                                        \
+    } while (0)
+    const int role_warp = threadIdx.x >> 5;
     const unsigned dbg = (unsigned)debug_flags; // experiment switches, 0 in production
     const int64_t size = geom.size;
-    const bool analyser = (long long)blockIdx.x < n_analysers;
-    const long long G = analyser ? n_analysers : (long long)gridDim.x - n_analysers; // CTAs of this role
-    const long long first_tile = analyser ? (long long)blockIdx.x : (long long)blockIdx.x - n_analysers;
 
-    if (tid == kWorkerThreads) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&sm.mbar[s], 1); mbar_init(&sm.done[s], kWorkers); sm.evcount[s] = 0; }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fence_proxy_async();
-        for (int s = 0; s < kStages; s++) { // this CTA's first tiles
-            const long long t = first_tile + (long long)s * G;
-            if (t < n_tiles) { issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, t); }
-        }
-    }
-    __syncthreads();
-
-    if (warp == kWorkers + 1) { // scanner warp: one per grid, never joins the CTA's barriers
-        if (blockIdx.x == 0 && !(dbg & 1u)) { scanner_warp(tile_state, tile_excl, n_tiles, hdr, lane, geom.init_n, geom.init_kind); }
+    if (blockIdx.x == gridDim.x - 1) {
+        // ============================================ SCANNER CTA ============================================
+        volatile ScanRun* run = reinterpret_cast<volatile ScanRun*>(smem_raw);
+        if (threadIdx.x == 0) { sts_v2(run, pack_run(0ull, geom.init_n, 0ull, geom.init_kind, 0u)); }
+        __syncthreads();
+        if (role_warp < kScanWarps) { scanner_warps(tile_state, tile_excl, n_tiles, hdr, run, role_warp, lane, geom.scan_per_lane, tdbg); }
         return;
     }
 
-    if (!analyser && (dbg & 32u)) { return; } // experiment: writers off
-    if (analyser) {
-        // ============================================ ANALYSER ============================================
-        if (warp == kWorkers) {
-            // control warp: all workers are done with the stage -> publish the tile's aggregate, reload the stage
-            int s = 0;
-            uint32_t done_bits = 0;
-            long long seen_written = 0;
-            unsigned long long heavy_local = 0, flagged_local = 0;
-            for (long long t = first_tile; t < n_tiles; t += G) {
-                while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
-                done_bits ^= (1u << s);
-                uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0, adel = 0;
-                unsigned long long mask = 0ull;
-#pragma unroll
-                for (int w = 0; w < kWorkers; w++) {
-                    const WarpAgg a = sm.wagg[s][w];
-                    tile_n += a.n;
-                    tile_k += a.k;
-                    hevcb_carry_combine(ak, ae, a.kind, a.err);
-                    mask |= (unsigned long long)(a.rows & 0xFFu) << (w * kRowsPerWarp);
-                    adel |= a.del;
-                }
-                if (lane == 0) {
-                    // A tile whose bytes are all kept and whose event chunks fit into the record list looks CLEAN to the
-                    // writer (mask 0): its NAL boundaries are emitted from the records by hevcb_scan_emit_kernel.
-                    const uint32_t nrec = sm.evcount[s];
-                    sm.evcount[s] = 0;
-                    const bool light = (adel == 0u) && (nrec <= kEvCap) && (tile_k == (uint32_t)kTileBytes) && !(dbg & 1024u);
-                    st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
-                    if (!light && mask != 0ull) { heavy_local++; }
-                    flagged_local += (unsigned long long)__popcll(mask);
-                    const long long nt = t + (long long)kStages * G; // the tile that reuses this stage
-                    if (nt < n_tiles) {
-                        // stay within `window` tiles of the writers: what they load a second time is then still in L2
-                        while (nt > seen_written + geom.window) {
-                            unsigned long long w;
-                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&hdr->tiles_written) : "memory");
-                            seen_written = (long long)w;
-                            if (nt > seen_written + geom.window) { __nanosleep(200); }
-                        }
-                        fence_proxy_async();
-                        issue_tile_load(sm.stage[s], &sm.mbar[s], buf, size, nt);
-                    }
-                }
-                __syncwarp();
-                s = (s + 1 == kStages) ? 0 : s + 1;
-            }
-            if (lane == 0 && heavy_local) { atomicAdd(&hdr->heavy_tiles, heavy_local); }
-            if (lane == 0 && flagged_local) { atomicAdd(&hdr->flagged_rows, flagged_local); }
-            return;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&sm.full[s], 1); mbar_init(&sm.done[s], kAWarps); mbar_init(&sm.ready[s], 1); mbar_init(&sm.freeb[s], kWWarps);
+            mbar_init(&sm.pub[s], 1);
+            sm.evcount[s] = 0;
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (role_warp == kWarpProd) {
+        // ============================================ PRODUCER ============================================
+        // Tiles are claimed from a grid-wide counter the moment a stage is free, so a CTA that falls behind simply takes fewer
+        // tiles: aggregates are published in (nearly) tile order and a scanner batch never waits for a slow CTA's turn.
+        if (lane == 0) {
+            for (long long i = 0;; i++) {
+                const int s = (int)(i % kStages);
+                const uint32_t round = (uint32_t)(i / kStages);
+                if (round >= 1u) { while (!mbar_try_wait(&sm.freeb[s], (round - 1u) & 1u)) {} } // the writers have released the stage
+                const long long t = (long long)atomicAdd(&hdr->next_tile, 1ull);
+                TSTAMP(i, 0);
+                if (t >= n_tiles) { // end marker: travels through the roles like a tile
+                    sm.tile[s] = -1;
+                    mbar_arrive(&sm.full[s]);
+                    break;
+                }
+                sm.tile[s] = t;
+                fence_proxy_async();
+                issue_tile_load(sm.stage[s], &sm.full[s], buf, size, t);
+                // Every claimed tile also pulls the tile `prefetch` tiles further on from HBM into L2.  The ring of an SM is small
+                // (six tiles) and a tile cannot leave it before the prefixes of all earlier tiles are known, so the ring must not
+                // also have to cover HBM latency and its variance: with the prefetch the bulk copies are L2 hits.
+                const long long tp = t + geom.prefetch;
+                if (geom.prefetch > 0 && tp < n_tiles) {
+                    const int64_t p0 = (int64_t)tp * kTileBytes;
+                    const int64_t size16 = (size + 15) & ~(int64_t)15;
+                    const int64_t p1 = p0 + kTileBytes < size16 ? p0 + kTileBytes : size16;
+                    if (p1 > p0) { tma_prefetch_l2(buf + p0, (uint32_t)(p1 - p0)); }
+                }
+            }
+        }
+        return;
+    }
+
+    if (role_warp == kWarpAC) {
+        // ============================================ ANALYSER CONTROL ============================================
+        // all analyser warps are done with the stage -> publish the tile's aggregate
+        int s = 0;
+        uint32_t done_bits = 0;
+        unsigned long long heavy_local = 0, flagged_local = 0;
+        for (long long it_ac = 0;; it_ac++) {
+            while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
+            done_bits ^= (1u << s);
+            const long long t = sm.tile[s];
+            if (t < 0) {
+                if (lane == 0) { mbar_arrive(&sm.pub[s]); }
+                break;
+            }
+            if (lane == 0) { TSTAMP(it_ac, 2); }
+            uint32_t tile_n = 0, tile_k = 0, ak = HEVCB_KIND_PASS, ae = 0, adel = 0;
+            unsigned long long mask = 0ull;
+#pragma unroll
+            for (int w = 0; w < kAWarps; w++) {
+                const WarpAgg a = sm.wagg[s][w];
+                tile_n += a.n;
+                tile_k += a.k;
+                hevcb_carry_combine(ak, ae, a.kind, a.err);
+                mask |= (unsigned long long)(a.rows & ((1u << kARows) - 1u)) << (w * kARows);
+                adel |= a.del;
+            }
+            if (lane == 0) {
+                // A tile whose bytes are all kept and whose event chunks fit into the record list looks CLEAN to the
+                // writers (mask 0): its NAL boundaries are emitted from the records by hevcb_scan_emit_kernel.
+                const uint32_t nrec = sm.evcount[s];
+                sm.evcount[s] = 0;
+                const bool light = (adel == 0u) && (nrec <= kEvCap) && (tile_k == (uint32_t)kTileBytes) && !(dbg & 1024u);
+                st_state(&tile_state[t], light ? pack_agg(tile_n, tile_k, ak, ae, 0ull, nrec) : pack_agg(tile_n, tile_k, ak, ae, mask, kEvByWriter));
+                sm.aggmask[s] = light ? 0ull : mask;
+                mbar_arrive(&sm.pub[s]);
+                if (!light && mask != 0ull) { heavy_local++; }
+                flagged_local += (unsigned long long)__popcll(mask);
+            }
+            __syncwarp();
+            s = (s + 1 == kStages) ? 0 : s + 1;
+        }
+        if (lane == 0 && heavy_local) { atomicAdd(&hdr->heavy_tiles, heavy_local); }
+        if (lane == 0 && flagged_local) { atomicAdd(&hdr->flagged_rows, flagged_local); }
+        return;
+    }
+
+    if (role_warp == kWarpWC) {
+        // ============================================ WRITER CONTROL ============================================
+        // Lane j looks after the CTA's j-th next tile (kAhead tiles ahead of the writers): it waits until the tile's aggregate
+        // is published (then the tile index and row mask are known), then polls the tile's prefix, so that the L2 round trips
+        // never sit between two tiles.  Per tile: lane 0 has the prefix -> shared memory -> release the writers into the
+        // tile -> every lane hands its state down by one lane.
+        constexpr int kAhead = 4;
+        long long my_i = lane;          // iteration (position in this CTA's tile sequence) this lane looks after
+        long long tq = -2;              // its tile: -2 not known yet, -1 end marker
+        unsigned long long mk = 0ull;   // its row mask
+        ulonglong2 ex = make_ulonglong2(0ull, 0ull);
+        for (long long it_wc = 0;; it_wc++) {
+            const int s = (int)(it_wc % kStages);
+            for (;;) {
+                if (lane < kAhead) {
+                    const int ms = (int)(my_i % kStages);
+                    if (tq == -2 && mbar_test_wait(&sm.pub[ms], (uint32_t)(my_i / kStages) & 1u)) { tq = sm.tile[ms]; mk = sm.aggmask[ms]; }
+                    if (tq >= 0 && (ex.x >> 62) == 0ull) { ex = ld_state(&tile_excl[tq]); }
+                }
+                const bool ready = (tq == -1) || (tq >= 0 && (ex.x >> 62) != 0ull);
+                if (__shfl_sync(0xFFFFFFFFu, ready ? 1 : 0, 0)) { break; }
+                __nanosleep(20);
+            }
+            const long long t0q = __shfl_sync(0xFFFFFFFFu, tq, 0);
+            if (lane == 0) {
+                // pref[s] is free: the stage's previous tile was written before the stage could be reloaded and analysed again
+                if (tq >= 0) {
+                    TilePrefix tp;
+                    tp.n = ex.x & ((1ull << 40) - 1); tp.k = ex.y; tp.kind = (uint32_t)(ex.x >> 60) & 3u; tp.err = (uint32_t)(ex.x >> 59) & 1u;
+                    tp.mask = mk;
+                    sm.pref[s] = tp;
+                    TSTAMP(it_wc, 3);
+                }
+                mbar_arrive(&sm.ready[s]);
+            }
+            __syncwarp();
+            if (t0q < 0) { break; }
+            // hand down: lane j takes over what lane j + 1 knows so far; the last looking lane starts on a new tile
+            ex.x = __shfl_down_sync(0xFFFFFFFFu, ex.x, 1); ex.y = __shfl_down_sync(0xFFFFFFFFu, ex.y, 1);
+            tq = __shfl_down_sync(0xFFFFFFFFu, tq, 1); mk = __shfl_down_sync(0xFFFFFFFFu, mk, 1);
+            my_i += 1;
+            if (lane >= kAhead - 1) { ex = make_ulonglong2(0ull, 0ull); tq = -2; mk = 0ull; }
+        }
+        return;
+    }
+
+    if (role_warp < kAWarps) {
+        // ============================================ ANALYSER ============================================
+        const int tid = threadIdx.x;
         // workers: wait for the tile, analyse their rows, hand the warp aggregate to the control warp; they never wait for
         // it (the stage they move on to was loaded three tiles ago; a stage is only reloaded after its aggregate was read)
         uint32_t phase_bits = 0;
         int s = 0;
-        for (long long t = first_tile; t < n_tiles; t += G) {
-            const int64_t t0 = (int64_t)t * kTileBytes;
+        for (long long it_an = 0;; it_an++) {
             uint8_t* st = sm.stage[s];
-            while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
+            while (!mbar_try_wait(&sm.full[s], (phase_bits >> s) & 1u)) {}
             phase_bits ^= (1u << s);
+            const long long t = sm.tile[s];
+            if (t < 0) { // end marker: hand it on
+                if (lane == 0) { mbar_arrive(&sm.done[s]); }
+                break;
+            }
+            const int64_t t0 = (int64_t)t * kTileBytes;
+            // Which rows a warp takes rotates from tile to tile: in a stream of equally sized NALs the start codes keep falling
+            // into the same rows of every tile, and the exact analysis of such a row (about as long as the whole fast path)
+            // would otherwise always land on the same warp and set the pace of the CTA.
+            const int warp = (role_warp + (int)(it_an & (kAWarps - 1))) & (kAWarps - 1);
+            if (tid == 0) { TSTAMP(it_an, 1); }
             fix_stage(st, t, t0, size, tid);
             const bool interior = geom.evl - t0 >= (int64_t)kTileBytes + 32; // every byte (and its halo) owned and below the event limit
             uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, rows = 0, anydel = 0;
-            if (dbg & 64u) { wK = kRowsPerWarp * kRowBytes; rows = (dbg >> 8) & 0xFFu; } // experiment: analysis off, rows flagged as told
+            if (dbg & 64u) { wK = kARows * kRowBytes; rows = (dbg >> 8) & 0xFFu; } // experiment: analysis off, rows flagged as told
             else if (interior && !(dbg & 2048u)) {
-                // interior tile: SWAR zero-pair test of the warp's eight rows, four rows (independent instruction chains) at a
-                // time; one vote sends the common "no two adjacent zero bytes anywhere" case on, otherwise the slow chunks are
-                // analysed exactly, ranked in stream order (analyse_slow_chunks)
-                uint32_t slow8 = 0;
-#pragma unroll kAnalyserUnroll
-                for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
-                    const uint8_t* rp = st + kLead + (warp * kRowsPerWarp + i0) * kRowBytes + lane * 16;
-                    uint4 v[4];
+                // interior tile: which chunks have two adjacent zero bytes NEARBY (inside [g0 - 2, g0 + 18)) and need the exact masks?
+                // Every lane tests the pairs that START in its own chunk (needs one byte of the next chunk: a shuffle), one ballot per
+                // row collects them, and a chunk is slow when it, its predecessor or its successor starts a pair (a superset of the
+                // exact condition; the next / previous chunk of the warp's first / last chunk come from two single-lane halo loads).
+                // All rows are loaded up front: eight independent 16-byte shared-memory loads per lane in flight.
+                const uint8_t* wbase = st + kLead + (warp * kARows) * kRowBytes;
+                // (written in phases -- loads, shuffles, arithmetic, ballots -- because the warp-synchronous operations keep their
+                // program order: interleaving them row by row would serialise the rows' dependency chains)
+                uint4 v[kARows];
+                uint32_t wn[kARows];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { v[k] = *reinterpret_cast<const uint4*>(rp + k * kRowBytes); }
-                    uint32_t wp[4], wn[4];
+                for (int k = 0; k < kARows; k++) { v[k] = *reinterpret_cast<const uint4*>(wbase + k * kRowBytes + lane * 16); }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        wp[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes - 4);
-                        wn[k] = *reinterpret_cast<const uint32_t*>(rp + k * kRowBytes + 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        slow8 |= (zero_pair_any(wp[k], v[k].x, v[k].y, v[k].z, v[k].w, wn[k]) != 0u ? 1u : 0u) << (i0 + k);
-                    }
+                for (int k = 0; k < kARows; k++) { // lane 31: the word behind its chunk is the first word of the next row
+                    wn[k] = 0u;
+                    if (lane == 31) { wn[k] = *reinterpret_cast<const uint32_t*>(wbase + (k + 1) * kRowBytes); }
                 }
-                uint32_t wDel = 0;
-                const uint32_t rowany = __reduce_or_sync(0xFFFFFFFFu, slow8); // bit i: row i has a slow chunk
+                uint32_t edge = 0; // lane 0: the four bytes in front of the warp's rows; lane 31: the four bytes behind them
+                if (lane == 0) { edge = *reinterpret_cast<const uint32_t*>(wbase - 4); }
+                if (lane == 31) { edge = wn[kARows - 1]; }
+#pragma unroll
+                for (int k = 0; k < kARows; k++) {
+                    const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
+                    if (lane != 31) { wn[k] = nx; }
+                }
+                bool own[kARows];
+#pragma unroll
+                for (int k = 0; k < kARows; k++) { own[k] = zero_pair_own(v[k].x, v[k].y, v[k].z, v[k].w, wn[k]) != 0u; }
+                uint32_t P[kARows];
+#pragma unroll
+                for (int k = 0; k < kARows; k++) { P[k] = __ballot_sync(0xFFFFFFFFu, own[k]); }
+                // pairs that start in the two bytes in front of the warp's rows (or in the last of them with the row's first byte),
+                // and the pair made of the two bytes behind them
+                const bool pf = (lane == 0) && (((edge >> 16) == 0u) || (((edge >> 24) == 0u) && ((v[0].x & 0xFFu) == 0u)));
+                const bool nf = (lane == 31) && ((edge & 0xFFFFu) == 0u);
+                const uint32_t prevflag = __ballot_sync(0xFFFFFFFFu, pf) & 1u, nextflag = (__ballot_sync(0xFFFFFFFFu, nf) >> 31) & 1u;
+                uint32_t slow8 = 0, rowany = 0;
+#pragma unroll
+                for (int k = 0; k < kARows; k++) {
+                    const uint32_t before = (k > 0) ? (P[(k + kARows - 1) % kARows] >> 31) : prevflag;
+                    const uint32_t after = (k + 1 < kARows) ? (P[(k + 1) % kARows] & 1u) : nextflag;
+                    const uint32_t S = P[k] | (P[k] << 1) | (P[k] >> 1) | before | (after << 31);
+                    slow8 |= ((S >> lane) & 1u) << k;
+                    rowany |= (S != 0u ? 1u : 0u) << k;
+                }
+                if (tid == 0) { TSTAMP(it_an, 7); }
+                uint32_t wDel = 0; // rowany bit i: row i has a slow chunk
                 if (rowany != 0u) {
                     const uint32_t thr = (dbg & 0xF000u) ? ((dbg >> 12) & 15u) - 1u : 1u; // experiment switch; production: 1
                     if ((uint32_t)__popc(rowany) <= thr) {
-                        // a single flagged row: row by row (measured: shorter dependency chain than ranking the chunks first)
-                        uint32_t dummyK = 0;
+                        // A single flagged row (a stream of large NALs: the row a start code falls into): exact masks of the
+                        // flagged lanes straight from the registers the filter loaded, one row = one lane per chunk, so the ordered
+                        // carry is three ballots.  (Ranking the chunks first pays off when many rows are flagged.)
+                        // (a rolled loop with register selects instead of an unrolled one: this path runs once per tile in one or
+                        // two warps, its instructions are rarely in the instruction cache, so its size is what it costs)
+#pragma unroll 1
                         for (uint32_t rm = rowany; rm != 0u; rm &= rm - 1u) {
-                            const int i = __ffs((int)rm) - 1;
-                            const RowMasks r = analyze_staged_row(st, warp * kRowsPerWarp + i, lane, t0, geom, wN, dummyK, wKind, wErr);
-                            rows |= 1u << i;
-                            wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(r.deler & 0xFFFFu));
-                            if (((r.evsc & 0xFFFFu) | (r.deler >> 16)) != 0u) {
+                            const int k = __ffs((int)rm) - 1; // warp-uniform
+                            uint4 vk = v[0];
+                            uint32_t wnk = wn[0], pw = 0u;
+#pragma unroll
+                            for (int q = 1; q < kARows; q++) {
+                                if (k == q) { vk = v[q]; wnk = wn[q]; pw = v[q - 1].w; }
+                            }
+                            uint32_t wp = __shfl_up_sync(0xFFFFFFFFu, vk.w, 1);
+                            const uint32_t prow = __shfl_sync(0xFFFFFFFFu, pw, 31);
+                            if (lane == 0) { wp = (k > 0) ? prow : edge; }
+                            uint32_t ev = 0u, sc = 0u, del = 0u, er = 0u, scb = 0u;
+                            if ((slow8 >> k) & 1u) {
+                                const hevcb_chunk_masks m = hevcb_chunk_analyze_interior(wp, vk.x, vk.y, vk.z, vk.w, wnk);
+                                ev = m.ev; sc = m.sc; del = m.del; er = m.err; scb = m.scb;
+                            }
+                            uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // lane summary for the ordered carry
+                            if (ev != 0u) {
+                                const int tp = 31 - __clz((int)ev);
+                                lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                                le = ((er >> tp) >> 1) != 0u;
+                            }
+                            const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+                            const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+                            const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+                            const uint32_t Db = __ballot_sync(0xFFFFFFFFu, del != 0u);
+                            const uint32_t Cb = __ballot_sync(0xFFFFFFFFu, sc != 0u); // (Sb only tells whose LAST event is a start code)
+                            if (Cb != 0u) { wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc)); }
+                            if (Db != 0u) { wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(del)); }
+                            uint32_t rk, re;
+                            warp_carry_total(Eb, Sb, Rb, rk, re);
+                            hevcb_carry_combine(wKind, wErr, rk, re);
+                            rows |= 1u << k;
+                            if ((ev | er) != 0u) { // chunk with an event or an error position: leave a record for the emit pass
                                 const uint32_t slot = atomicAdd(&sm.evcount[s], 1u);
                                 if (slot < kEvCap) {
-                                    tile_events[(size_t)t * kEvCap + slot] = make_uint4((uint32_t)((warp * kRowsPerWarp + i) * 32 + lane), r.evsc, r.deler, r.misc);
+                                    tile_events[(size_t)t * kEvCap + slot] =
+                                        make_uint4((uint32_t)((warp * kARows + k) * 32 + lane), ev | (sc << 16), del | (er << 16), 0xFFFFu | (scb << 16));
                                 }
                             }
                         }
                     } else {
-                        analyse_slow_chunks(st, sm.slowmap[warp], warp, lane, slow8, t0, t, geom, &sm.evcount[s], tile_events, wN, wDel, wKind, wErr, rows);
+                        analyse_slow_chunks(st, sm.slowmapA[role_warp], warp, lane, slow8, t0, t, geom, &sm.evcount[s], tile_events, wN, wDel, wKind, wErr, rows);
                     }
                 }
-                wK = kRowsPerWarp * kRowBytes - wDel;
+                wK = kARows * kRowBytes - wDel;
                 anydel = wDel;
             }
             else
@@ -742,8 +986,8 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             // instruction chains, and one vote sends the common "no two adjacent zero bytes anywhere" case on.
             // (Loops over rows are kept rolled on purpose: two roles share the SM's instruction cache.)
 #pragma unroll kAnalyserUnroll
-            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
-                const int rbase = warp * kRowsPerWarp + i0;
+            for (int i0 = 0; i0 < kARows; i0 += 4) {
+                const int rbase = warp * kARows + i0;
                 const uint8_t* rp = st + kLead + rbase * kRowBytes + lane * 16;
                 uint4 v[4];
 #pragma unroll
@@ -786,6 +1030,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = anydel; a.rows = rows;
                 a.pad[0] = a.pad[1] = 0;
                 sm.wagg[s][warp] = a;
+                if (tid == 0) { TSTAMP(it_an, 6); }
                 mbar_arrive(&sm.done[s]);
             }
             __syncwarp();
@@ -795,94 +1040,43 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     }
 
     // ================================================ WRITER ================================================
-    if (warp == kWorkers) {
-        // control warp: lane j polls the prefix and the aggregate (row mask) of this CTA's tile number q + j, kAhead tiles
-        // ahead of the workers, so that the two L2 round trips never sit between two tiles.  Per tile: wait until lane 0 has
-        // both words -> shared memory -> [E] the workers are done with the previous stage -> reload it -> [P] release the
-        // workers into the tile -> every lane hands its words down by one lane.
-        constexpr int kAhead = 4;
-        if (first_tile >= n_tiles) { return; }
-        long long tq = first_tile + (long long)lane * G; // tile polled by this lane
-        ulonglong2 ex = make_ulonglong2(0ull, 0ull), ag = make_ulonglong2(0ull, 0ull);
-        int s = 0;
-        for (long long t = first_tile, it = 0; t < n_tiles; t += G, it++) {
-            for (;;) {
-                if (lane < kAhead && tq < n_tiles) {
-                    if (dbg & 1u) {
-                        ex = pack_state(kStatusPrefix, 0, (unsigned long long)tq * kTileBytes, HEVCB_KIND_Z3, 0);
-                        ag = pack_agg(0, 0, 0, 0, ~0ull);
-                    } else {
-                        if (dbg & 128u) { ex = pack_state(kStatusPrefix, 0, (unsigned long long)tq * kTileBytes, HEVCB_KIND_Z3, 0); } // experiment: scanner off the path
-                        else if ((ex.x >> 62) == 0ull) { ex = ld_state(&tile_excl[tq]); }
-                        if ((ag.x >> 62) == 0ull) { ag = ld_state(&tile_state[tq]); }
-                    }
-                }
-                const bool ready = (ex.x >> 62) != 0ull && (ag.x >> 62) != 0ull;
-                if (__shfl_sync(0xFFFFFFFFu, ready ? 1 : 0, 0)) { break; }
-                __nanosleep(20);
-            }
-            if (lane == 0) {
-                TilePrefix tp;
-                tp.n = ex.x & ((1ull << 40) - 1); tp.k = ex.y; tp.kind = (uint32_t)(ex.x >> 60) & 3u; tp.err = (uint32_t)(ex.x >> 59) & 1u;
-                tp.mask = ag.y;
-                sm.pref[it & 1] = tp;
-            }
-            __syncwarp();
-            if (it > 0) {
-                bar_sync(kBarE, kSyncThreads); // every worker finished reading the stage of the previous tile
-                if (lane == 0) { atomicAdd(&hdr->tiles_written, 1ull); }
-                const int ps = (s == 0) ? kStages - 1 : s - 1;
-                const long long nt = (t - G) + (long long)kStages * G;
-                if (lane == 0 && nt < n_tiles) {
-                    fence_proxy_async();
-                    issue_tile_load(sm.stage[ps], &sm.mbar[ps], buf, size, nt);
-                }
-            }
-            bar_arrive(kBarP, kSyncThreads);
-            // hand down: lane j takes over what lane j + 1 has polled so far; the last polling lane starts a new tile
-            ex.x = __shfl_down_sync(0xFFFFFFFFu, ex.x, 1); ex.y = __shfl_down_sync(0xFFFFFFFFu, ex.y, 1);
-            ag.x = __shfl_down_sync(0xFFFFFFFFu, ag.x, 1); ag.y = __shfl_down_sync(0xFFFFFFFFu, ag.y, 1);
-            tq += G;
-            if (lane >= kAhead - 1) { ex = make_ulonglong2(0ull, 0ull); ag = make_ulonglong2(0ull, 0ull); }
-            s = (s + 1 == kStages) ? 0 : s + 1;
-        }
-        bar_sync(kBarE, kSyncThreads); // the last tile
-        if (lane == 0) { atomicAdd(&hdr->tiles_written, 1ull); }
-        return;
-    }
-
+    const int tid = (int)threadIdx.x - kAThreads;
+    const int warp = tid >> 5;
     DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
     uint32_t phase_bits = 0;
     int s = 0;
-    for (long long t = first_tile, it = 0; t < n_tiles; t += G, it++) {
-        const int64_t t0 = (int64_t)t * kTileBytes;
+    for (long long it = 0;; it++) {
         uint8_t* st = sm.stage[s];
-        bar_sync(kBarP, kSyncThreads); // the tile's prefix and row mask are in shared memory
-        const TilePrefix pref = sm.pref[it & 1];
-        while (!mbar_try_wait(&sm.mbar[s], (phase_bits >> s) & 1u)) {}
+        while (!mbar_try_wait(&sm.ready[s], (phase_bits >> s) & 1u)) {} // the tile's prefix and row mask are in shared memory
+        const long long t = sm.tile[s];
+        if (t < 0) { break; } // end marker
+        const int64_t t0 = (int64_t)t * kTileBytes;
+        const TilePrefix pref = sm.pref[s];
+        while (!mbar_try_wait(&sm.full[s], (phase_bits >> s) & 1u)) {}
         phase_bits ^= (1u << s);
+        if (tid == 0) { TSTAMP(it, 4); }
         const long long tileN = (long long)pref.n;
         const long long tileK = (long long)pref.k;
 
         if (pref.mask == 0ull) {
             // ---- clean interior tile: aligned 16-byte vectors, funnel-shifted by the (tile-uniform) misalignment
             if (rbsp != nullptr && !(dbg & 4u)) { copy_tile(rbsp + tileK, st + kLead, kTileBytes, tid); }
-            bar_arrive(kBarE, kSyncThreads);
+            if (tid == 0) { TSTAMP(it, 5); }
+            release_stage(&sm.freeb[s], lane);
             s = (s + 1 == kStages) ? 0 : s + 1;
             continue;
         }
 
         // ---- tile with flagged rows: exact masks of those rows, warp aggregates, ordered emission, row-wise write-out
-        fix_stage(st, t, t0, size, tid);
         if (geom.evl - t0 >= (int64_t)kTileBytes + 32 && !(dbg & 65536u)) {
             // Interior tile.  The warp ranks the slow chunks of its eight rows in stream order and takes them 32 at a time
             // (every lane busy, see analyse_slow_chunks); pass 1 parks the masks and builds the warp aggregate, pass 2 emits.
-            uint8_t* const map = sm.slowmap[warp];
+            uint8_t* const map = sm.slowmapW[warp];
             const uint32_t below = (1u << lane) - 1u;
             uint32_t total = 0;
 #pragma unroll 1
-            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
-                const uint8_t* rp = st + kLead + (warp * kRowsPerWarp + i0) * kRowBytes + lane * 16;
+            for (int i0 = 0; i0 < kWRows; i0 += 4) {
+                const uint8_t* rp = st + kLead + (warp * kWRows + i0) * kRowBytes + lane * 16;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint4 v = *reinterpret_cast<const uint4*>(rp + k * kRowBytes);
@@ -895,7 +1089,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 }
             }
             __syncwarp();
-            constexpr int kBatches = kRowsPerWarp;
+            constexpr int kBatches = kWRows;
             uint32_t p_evsc[kBatches], p_deler[kBatches], p_misc[kBatches];
             uint32_t wN = 0, wDel = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
 #pragma unroll 1
@@ -904,7 +1098,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 if ((uint32_t)b * 32u >= total) { break; }
                 uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu;
                 if (slot < total) {
-                    const uint32_t chunk = (uint32_t)(warp * kRowsPerWarp * 32) + map[slot];
+                    const uint32_t chunk = (uint32_t)(warp * kWRows * 32) + map[slot];
                     const uint8_t* rp = st + kLead + chunk * 16u;
                     const uint4 v = *reinterpret_cast<const uint4*>(rp);
                     const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
@@ -931,17 +1125,17 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             }
             if (lane == 0) {
                 WarpAgg a;
-                a.n = wN; a.k = kRowsPerWarp * kRowBytes - wDel; a.kind = wKind; a.err = wErr; a.del = wDel; a.rows = 0;
+                a.n = wN; a.k = kWRows * kRowBytes - wDel; a.kind = wKind; a.err = wErr; a.del = wDel; a.rows = 0;
                 a.pad[0] = a.pad[1] = 0;
-                sm.wagg[it & 1][warp] = a;
+                sm.waggW[s][warp] = a;
             }
-            bar_sync(kBarWork, kWorkerThreads);
+            bar_sync(kBarW, kWThreads);
             uint32_t rN = 0, rK = 0, rKind = HEVCB_KIND_PASS, rErr = 0, tileDel = 0;
             {
                 uint32_t tn = 0, tk = 0, ak = HEVCB_KIND_PASS, ae = 0;
 #pragma unroll
-                for (int w = 0; w < kWorkers; w++) {
-                    const WarpAgg a = sm.wagg[it & 1][w];
+                for (int w = 0; w < kWWarps; w++) {
+                    const WarpAgg a = sm.waggW[s][w];
                     if (w == warp) { rN = tn; rK = tk; rKind = ak; rErr = ae; }
                     tn += a.n;
                     tk += a.k;
@@ -953,14 +1147,14 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             const bool compacting = write_img && tileDel != 0u && wDel != 0u; // this warp's rows lose bytes
             uint16_t* const dm = sm.delmask[warp];
             if (compacting) {
-                for (int e = lane * 8; e < kRowsPerWarp * 32; e += 256) { *reinterpret_cast<uint4*>(dm + e) = make_uint4(0u, 0u, 0u, 0u); }
+                for (int e = lane * 8; e < kWRows * 32; e += 256) { *reinterpret_cast<uint4*>(dm + e) = make_uint4(0u, 0u, 0u, 0u); }
                 __syncwarp();
             }
             // pass 2: ordered emission over the ranked chunks
             {
                 uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
                 hevcb_carry_combine(cKind, cErr, rKind, rErr);
-                uint32_t nrun = rN, drun = (uint32_t)(warp * kRowsPerWarp * kRowBytes) - rK; // start codes / removed bytes before, within the tile
+                uint32_t nrun = rN, drun = (uint32_t)(warp * kWRows * kRowBytes) - rK; // start codes / removed bytes before, within the tile
 #pragma unroll 1
                 for (int b = 0; b < kBatches; b++) {
                     const uint32_t slot = (uint32_t)b * 32u + (uint32_t)lane;
@@ -997,7 +1191,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                         if (compacting && del != 0u) { dm[local] = (uint16_t)del; }
                     }
                     if ((ev | er) != 0u) {
-                        const uint32_t chunk = (uint32_t)(warp * kRowsPerWarp * 32) + local;
+                        const uint32_t chunk = (uint32_t)(warp * kWRows * 32) + local;
                         emit_cold(evsc, deler, misc, t0 + (int64_t)chunk * 16, (int64_t)(tileN + nrun + (ninc - c)),
                                   (int64_t)(tileK + (long long)chunk * 16 - (long long)(drun + dinc - d)), ck, ce, sink);
                     }
@@ -1014,13 +1208,13 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 } else {
                     // tile with removed bytes: every warp closes the gaps of its own rows in place (shared memory), then copies
                     // its kept bytes out as one span
-                    uint8_t* const wb = st + kLead + warp * (kRowsPerWarp * kRowBytes);
-                    uint32_t out = kRowsPerWarp * kRowBytes;
+                    uint8_t* const wb = st + kLead + warp * (kWRows * kRowBytes);
+                    uint32_t out = kWRows * kRowBytes;
                     if (compacting) {
                         __syncwarp();
                         out = 0;
 #pragma unroll 1
-                        for (int i = 0; i < kRowsPerWarp; i++) {
+                        for (int i = 0; i < kWRows; i++) {
                             const uint32_t del = dm[i * 32 + lane];
                             if (out == (uint32_t)(i * kRowBytes) && !__any_sync(0xFFFFFFFFu, del != 0u)) { out += kRowBytes; continue; } // still in place
                             const uint4 v = *reinterpret_cast<const uint4*>(wb + i * kRowBytes + lane * 16);
@@ -1041,18 +1235,18 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     copy_span(rbsp + tileK + rK, wb, out, lane, 32u);
                 }
             }
-            bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
+            release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
             s = (s + 1 == kStages) ? 0 : s + 1;
             continue;
         }
-        const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kRowsPerWarp)) & 0xFFu;
+        const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kWRows)) & 0xFFu;
         // pass 1: aggregates of this warp's flagged rows; their masks are parked (thread-local memory) for pass 2
         uint32_t wN = 0, wK = 0, wKind = HEVCB_KIND_PASS, wErr = 0, anyD = 0;
-        uint32_t k_evsc[kRowsPerWarp], k_deler[kRowsPerWarp], k_misc[kRowsPerWarp], k_flags = 0;
+        uint32_t k_evsc[kWRows], k_deler[kWRows], k_misc[kWRows], k_flags = 0;
 #pragma unroll 1
-        for (int i = 0; i < kRowsPerWarp; i++) {
+        for (int i = 0; i < kWRows; i++) {
             if (!((myrows >> i) & 1u)) { wK += kRowBytes; continue; }
-            const RowMasks m = analyze_staged_row(st, warp * kRowsPerWarp + i, lane, t0, geom, wN, wK, wKind, wErr);
+            const RowMasks m = analyze_staged_row(st, warp * kWRows + i, lane, t0, geom, wN, wK, wKind, wErr);
             anyD |= (m.Db != 0u) ? 1u : 0u;
             k_evsc[i] = m.evsc; k_deler[i] = m.deler; k_misc[i] = m.misc;
             k_flags |= ((m.Xb != 0u) ? 1u : 0u) << i;
@@ -1062,16 +1256,16 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             WarpAgg a;
             a.n = wN; a.k = wK; a.kind = wKind; a.err = wErr; a.del = anyD; a.rows = myrows;
             a.pad[0] = a.pad[1] = 0;
-            sm.wagg[it & 1][warp] = a;
+            sm.waggW[s][warp] = a;
         }
-        bar_sync(kBarWork, kWorkerThreads);
+        bar_sync(kBarW, kWThreads);
         // aggregate of the warps before this one, tile totals
         uint32_t rN = 0, rK = 0, rKind = HEVCB_KIND_PASS, rErr = 0, compact = 0, tile_k = 0;
         {
             uint32_t tn = 0, ak = HEVCB_KIND_PASS, ae = 0;
 #pragma unroll
-            for (int w = 0; w < kWorkers; w++) {
-                const WarpAgg a = sm.wagg[it & 1][w];
+            for (int w = 0; w < kWWarps; w++) {
+                const WarpAgg a = sm.waggW[s][w];
                 if (w == warp) { rN = tn; rK = tile_k; rKind = ak; rErr = ae; }
                 tn += a.n;
                 tile_k += a.k;
@@ -1087,8 +1281,8 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
             hevcb_carry_combine(cKind, cErr, rKind, rErr);
 #pragma unroll 1
-            for (int i = 0; i < kRowsPerWarp; i++) {
-                const int r = warp * kRowsPerWarp + i;
+            for (int i = 0; i < kWRows; i++) {
+                const int r = warp * kWRows + i;
                 if (!((myrows >> i) & 1u)) {
                     if (dirty_out) { copy_row_clean(rbsp + tileK + rK, st + kLead + r * kRowBytes, lane); }
                     rK += kRowBytes;
@@ -1151,7 +1345,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         }
         // ---- tile without removed bytes: one shifted vector copy of the whole tile by all workers
         if (write_rows && !dirty_out) { copy_tile(rbsp + tileK, st + kLead, tile_k, tid); }
-        bar_arrive(kBarE, kSyncThreads); // the control warp may now reload this stage; workers do not wait
+        release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
         s = (s + 1 == kStages) ? 0 : s + 1;
     }
 }
@@ -1267,7 +1461,7 @@ __global__ void hevcb_scan_finalize_kernel(const uint8_t* __restrict__ buf, int6
 __global__ void hevcb_scan_init_kernel(ScanHeader* hdr, uint32_t init_n, int64_t* nal_start, int64_t* rbsp_off, int64_t cap_nals)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        hdr->tiles_written = 0ull;
+        hdr->next_tile = 0ull;
         hdr->heavy_tiles = 0ull;
         hdr->flagged_rows = 0ull;
         hdr->first_empty = 0x7FFFFFFFFFFFFFFFll;
@@ -1332,47 +1526,46 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
             if (nb < 1) { HEVCB_SET_ERR(ctx, "scan kernel does not fit on an SM"); return HEVCB_E_CUDA; }
             ctx->scan_blocks_per_sm = nb;
         }
-        long long grid = (long long)ctx->sm_count * ctx->scan_blocks_per_sm;
-        if (grid > 2 * n_tiles) { grid = 2 * n_tiles; }
-        if (grid < 2) { grid = 2; }
-        // analyser CTAs (the rest are writers): 60 % is the measured optimum when the writers mostly copy (NALs >= 4 KiB); when
-        // the previous launch on this context found that the writers had to analyse most tiles themselves (tiny NALs,
-        // EPB-dense payloads) they get the larger share.  Results do not depend on the split.
-        if (ctx->ev_stats && ctx->stats_pending && cudaEventQuery(ctx->ev_stats) == cudaSuccess) {
-            const unsigned long long* st = reinterpret_cast<const unsigned long long*>(ctx->pinned) + 64;
-            ctx->last_heavy_frac = st[2] ? (double)st[0] / (double)st[2] : 0.0;
-            ctx->last_flagged_frac = st[2] ? (double)st[1] / ((double)st[2] * kRows) : 0.0;
-            ctx->stats_pending = false;
-        }
-        // 3/8 analysers when the writers analyse most tiles themselves (tiny NALs, EPB-dense payloads); 65 % when more than a fifth
-        // of the rows needed exact analysis (NALs <= 2 KiB: the analysers are the bottleneck); 60 % otherwise (measured optima, 4 GiB)
-        const double ff = ctx->last_flagged_frac;
-        long long n_an = ctx->last_heavy_frac > 0.5 ? (grid * 3 + 4) / 8 : (ff > 0.2 ? (grid * 13 + 10) / 20 : (grid * 3 + 2) / 5);
-        if (n_an < 1) { n_an = 1; }
-        if (n_an > grid - 1) { n_an = grid - 1; }
-        if (const char* e = getenv("HEVCB_SCAN_ANALYSERS")) { const long long v = atoll(e); if (v >= 1 && v < grid) { n_an = v; } }
-        // cooperative launch: writers wait on the scanner, the scanner on the analysers: every CTA must be resident
+        // one CTA per SM (the ring takes most of the SM's shared memory); cooperative launch: writers wait on the scanner, the
+        // scanner on the analysers of every CTA, so every CTA must be resident
+        long long workers = (long long)ctx->sm_count * ctx->scan_blocks_per_sm - 1; // one SM runs the scanner CTA
+        if (workers > n_tiles) { workers = n_tiles; }
+        if (workers < 1) { HEVCB_SET_ERR(ctx, "scan kernel needs at least two SMs"); return HEVCB_E_CUDA; }
+        const long long grid = workers + 1;
         long long nt = n_tiles;
         long long dbg = ctx->scan_debug_flags;
         ScanGeom g = geom;
-        g.window = 1100; // tiles (34 MiB): more than both roles keep in flight (2 stages x grid) plus a scanner batch (measured, bench.py on one box: 1200 tiles 2259 GB/s, 1100 2241, below 1050 the analysers are throttled)
-        if (const char* e = getenv("HEVCB_SCAN_WINDOW")) { const long long v = atoll(e); if (v >= kStages * grid) { g.window = v; } }
-        if (g.window < kStages * grid) { g.window = kStages * grid; }
-        if (dbg & 32u) { g.window = 1ll << 40; } // experiment "writers off": nothing to wait for
-        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&n_an, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
-                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg};
+        // A scanner batch needs the aggregates of 32 x scan_per_lane consecutive tiles, and a tile is only written (its stage only
+        // freed) once its batch is complete, so the rings must be able to hold the batch of the oldest unwritten tile entirely
+        // (tiles are claimed in order, so the tiles the rings hold are a contiguous range of up to kStages x workers tiles that
+        // starts at the oldest unwritten one: two batches fit whenever the buffer has more tiles than the rings hold.)  Small
+        // batches keep the wait for a batch's last tile short: one tile per lane.
+        long long per_lane = HEVCB_SCAN_BATCH_PER_LANE;
+        while (per_lane > 1 && 64 * per_lane > (long long)kStages * workers && n_tiles > (long long)kStages * workers) { per_lane--; }
+        if (64 * per_lane > (long long)kStages * workers && n_tiles > (long long)kStages * workers) {
+            HEVCB_SET_ERR(ctx, "scan kernel: device has too few SMs for the tile ring");
+            return HEVCB_E_CUDA;
+        }
+        if (const char* e = getenv("HEVCB_SCAN_PERLANE_RT")) { const long long v = atoll(e); if (v >= 1 && v <= kScanPerLane && (64 * v <= (long long)kStages * workers || n_tiles <= (long long)kStages * workers)) { per_lane = v; } }
+        g.scan_per_lane = (int)per_lane;
+        g.prefetch = 4 * workers; // ~19 MB ahead of the claims on a whole B200: far more than the rings hold, a fraction of L2 (126 MB)
+        if (const char* e = getenv("HEVCB_SCAN_PREFETCH")) { g.prefetch = atoll(e); }
+        // the first tiles have no claim that would prefetch them: one bulk prefetch over that range in front of the kernel would
+        // only help the first microseconds, it is left out
+        unsigned long long* tdbg = nullptr;
+        if (getenv("HEVCB_SCAN_TIMING")) { // measurement aid: event stamps, dumped by tools/scan_timing.py through hevcb_scan_timing_dump
+            if (hevcb_reserve(ctx, &ctx->scan_timing, (size_t)grid * kTimingIters * kTimingEvents * 8) != HEVCB_OK) { return HEVCB_E_NOMEM; }
+            tdbg = reinterpret_cast<unsigned long long*>(ctx->scan_timing.p);
+            HEVCB_CUDA(ctx, cudaMemsetAsync(tdbg, 0, (size_t)grid * kTimingIters * kTimingEvents * 8, stream));
+            ctx->scan_timing_ctas = (int)grid;
+        }
+        void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
+                        (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg, (void*)&tdbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
         hevcb_scan_emit_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, stream>>>(n_tiles, hdr, states, excl, events, d_nal_start, d_nal_end, cap_nals,
                                                                                  d_rbsp_off, d_rbsp_end);
         ctx->launches += 2;
         HEVCB_CUDA(ctx, cudaGetLastError());
-        if (ctx->ev_stats && !ctx->stats_pending) { // heavy-tile count of this launch, read back without ever waiting for it
-            unsigned long long* st = reinterpret_cast<unsigned long long*>(ctx->pinned) + 64;
-            st[2] = (unsigned long long)n_tiles;
-            HEVCB_CUDA(ctx, cudaMemcpyAsync(&st[0], &hdr->heavy_tiles, 16, cudaMemcpyDeviceToHost, stream)); // heavy_tiles, flagged_rows
-            HEVCB_CUDA(ctx, cudaEventRecord(ctx->ev_stats, stream));
-            ctx->stats_pending = true;
-        }
     }
     *hdr_out = hdr;
     *n_tiles_out = n_tiles;
@@ -1388,7 +1581,7 @@ int hevcb_launch_scan_strip(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, 
         return HEVCB_E_ARG;
     }
     ScanGeom geom;
-    geom.size = size; geom.own = size; geom.evl = size - HEVCB_TAIL_ZONE; geom.init_n = 0; geom.init_kind = HEVCB_KIND_Z3; geom.window = 0;
+    geom.size = size; geom.own = size; geom.evl = size - HEVCB_TAIL_ZONE; geom.init_n = 0; geom.init_kind = HEVCB_KIND_Z3; geom.scan_per_lane = kScanPerLane; geom.prefetch = 0;
     ScanHeader* hdr = nullptr;
     long long n_tiles = 0;
     int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);
@@ -1415,7 +1608,8 @@ int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t 
     geom.evl = is_last ? own - HEVCB_TAIL_ZONE : own;
     geom.init_n = is_first ? 0u : 1u;
     geom.init_kind = is_first ? HEVCB_KIND_Z3 : HEVCB_KIND_SC3;
-    geom.window = 0;
+    geom.scan_per_lane = kScanPerLane;
+    geom.prefetch = 0;
     ScanHeader* hdr = nullptr;
     long long n_tiles = 0;
     int rc = launch_scan_common(ctx, d_buf, geom, d_nal_start, d_nal_end, cap_nals, d_rbsp, d_rbsp_off, d_rbsp_end, &hdr, &n_tiles, stream);
@@ -1425,4 +1619,13 @@ int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t 
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
+}
+
+// measurement aid: copies the event stamps of the last launch made with HEVCB_SCAN_TIMING set (ctas x 256 tiles x 8 events, ns)
+extern "C" HEVCB_API int64_t hevcb_scan_timing_dump(hevcb_ctx* ctx, unsigned long long* out, int64_t cap)
+{
+    if (!ctx || !ctx->scan_timing.p) { return 0; }
+    const int64_t n = (int64_t)ctx->scan_timing_ctas * kTimingIters * kTimingEvents;
+    if (out && cap >= n) { cudaMemcpy(out, ctx->scan_timing.p, (size_t)n * 8, cudaMemcpyDeviceToHost); }
+    return n;
 }

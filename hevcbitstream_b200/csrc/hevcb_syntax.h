@@ -129,19 +129,48 @@ struct hevcb_bits {
 // ------------------------------------------------------------------------------------------------
 // One sink type for both passes of the parser (count, then emit), so that both run the very same instantiation of
 // the walker: with `field` null it only counts.
-struct hevcb_sink {
+//
+// kTraceT = true is the read_debug variant (read_debug_hevc_nal_unit, hevc_stream.c:2343-3436; format process.pl:90-113): the
+// list then holds one record per element the reference PRINTS, in print order, each with the bit position of the reader
+// before the read: struct members as (field index, value), the f(n, v) elements and the NAL header under
+// HEVCB_TRACE_SPECIAL | id.  Values the reader stores without reading bits are kept too, marked HEVCB_TRACE_SILENT, so that
+// the record list still materialises the struct.
+enum hevcb_trace_id { // f(n, v) elements and the other lines of the dump that are not struct members
+    HEVCB_TI_FORBIDDEN_ZERO_BIT = 1, HEVCB_TI_NAL_UNIT_TYPE, HEVCB_TI_NAL_LAYER_ID, HEVCB_TI_NAL_TEMPORAL_ID_PLUS1,
+    HEVCB_TI_VPS_RESERVED_FFFF, HEVCB_TI_GENERAL_ZERO_34, HEVCB_TI_GENERAL_ZERO_43, HEVCB_TI_GENERAL_ZERO_BIT, HEVCB_TI_RESERVED_ZERO_XX,
+    HEVCB_TI_SUB_LAYER_ZERO_34, HEVCB_TI_SUB_LAYER_ZERO_43, HEVCB_TI_SUB_LAYER_ZERO_BIT, HEVCB_TI_RBSP_STOP_ONE, HEVCB_TI_RBSP_ALIGN_ZERO,
+    HEVCB_TI_ALIGN_ONE, HEVCB_TI_ALIGN_ZERO, HEVCB_TI_SLICE_RESERVED_FLAG, HEVCB_TI_SH_EXTENSION_DATA_BYTE,
+    HEVCB_TI_OPEN_LINE, // position prefix only, no newline: the "// ERROR" site of ref_pic_list_modification_flag_l1 (hevc_stream.c:3147)
+    HEVCB_TI_COUNT
+};
+template <bool kTraceT>
+struct hevcb_sink_t {
+    static constexpr bool kTrace = kTraceT;
     uint32_t* field;
     int32_t* value;
     uint32_t n;
+    uint32_t* bitpos; // trace only
     HEVCB_SHD void put(uint32_t f, int32_t v)
     {
         if (field) {
-            field[n] = f;
+            field[n] = kTraceT ? (f | HEVCB_TRACE_SILENT) : f;
             value[n] = v;
+            if (kTraceT) { bitpos[n] = 0u; }
+        }
+        n++;
+    }
+    HEVCB_SHD void trace(int64_t pos, uint32_t code, int32_t v)
+    {
+        if (field) {
+            field[n] = code;
+            value[n] = v;
+            bitpos[n] = pos > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)pos;
         }
         n++;
     }
 };
+typedef hevcb_sink_t<false> hevcb_sink;
+typedef hevcb_sink_t<true> hevcb_trace_sink;
 typedef hevcb_sink hevcb_count_sink;
 typedef hevcb_sink hevcb_emit_sink;
 
@@ -326,23 +355,28 @@ struct hevcb_walker {
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0), bw(nullptr), rp(nullptr) {}
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss, hevcb_bitwriter* w, hevcb_replay* r) : b(bb), s(ss), flags(0), bw(w), rp(r) {}
 
+    // one parsed element: (field, value) pair, or a trace record with the position the read started at
+    HEVCB_SHD void rep(uint32_t f, int32_t v, int64_t p0)
+    {
+        if constexpr (Sink::kTrace) { s.trace(p0, f, v); } else { (void)p0; s.put(f, v); }
+    }
     // value(x, u(n)) / u1 / u8 / ue / se : read + report, or load + write
     HEVCB_SHD int32_t u(uint32_t f, int n)
     {
         if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_u(n, (uint32_t)v); return v; }
-        else { const int32_t v = (int32_t)b.read_u(n); s.put(f, v); return v; }
+        else { const int64_t p0 = b.pos; const int32_t v = (int32_t)b.read_u(n); rep(f, v, p0); return v; }
     }
     HEVCB_SHD int32_t u1(uint32_t f) { return u(f, 1); }
     HEVCB_SHD int32_t u8(uint32_t f) { return u(f, 8); }
     HEVCB_SHD int32_t ue(uint32_t f)
     {
         if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_ue((uint32_t)v); return v; }
-        else { const int32_t v = (int32_t)b.read_ue(); s.put(f, v); return v; }
+        else { const int64_t p0 = b.pos; const int32_t v = (int32_t)b.read_ue(); rep(f, v, p0); return v; }
     }
     HEVCB_SHD int32_t se(uint32_t f)
     {
         if constexpr (kWrite) { const int32_t v = rp->load(f, false); bw->write_se(v); return v; }
-        else { const int32_t v = b.read_se(); s.put(f, v); return v; }
+        else { const int64_t p0 = b.pos; const int32_t v = b.read_se(); rep(f, v, p0); return v; }
     }
     // a field the reader stores several times (only the last value survives in the struct the writer reads)
     HEVCB_SHD int32_t se_multi(uint32_t f)
@@ -350,34 +384,48 @@ struct hevcb_walker {
         if constexpr (kWrite) { const int32_t v = rp->load(f, true); bw->write_se(v); return v; }
         else { return se(f); }
     }
-    // array element: reported only inside the reference's bounds
+    // array element: reported only inside the reference's bounds (the dump prints it either way)
     HEVCB_SHD int32_t au(uint32_t f, int idx, int bound, int n) { return raw_u(f + (uint32_t)idx, idx >= 0 && idx < bound, n); }
     HEVCB_SHD int32_t aue(uint32_t f, int idx, int bound)
     {
         const bool in = idx >= 0 && idx < bound;
         if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f + (uint32_t)idx, false); } else { flags |= 1u; } bw->write_ue((uint32_t)v); return v; }
-        else { const int32_t v = (int32_t)b.read_ue(); if (in) { s.put(f + (uint32_t)idx, v); } else { flags |= 1u; } return v; }
+        else {
+            const int64_t p0 = b.pos;
+            const int32_t v = (int32_t)b.read_ue();
+            if (in) { rep(f + (uint32_t)idx, v, p0); } else { flags |= 1u; }
+            return v;
+        }
     }
     HEVCB_SHD int32_t ase(uint32_t f, int idx, int bound) { return raw_se(f + (uint32_t)idx, idx >= 0 && idx < bound); }
     // element at an already computed field index; `in` = inside the reference's array
     HEVCB_SHD int32_t raw_u(uint32_t f, bool in, int n)
     {
         if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f, false); } else { flags |= 1u; } bw->write_u(n, (uint32_t)v); return v; }
-        else { const int32_t v = (int32_t)b.read_u(n); if (in) { s.put(f, v); } else { flags |= 1u; } return v; }
+        else { const int64_t p0 = b.pos; const int32_t v = (int32_t)b.read_u(n); if (in) { rep(f, v, p0); } else { flags |= 1u; } return v; }
     }
     HEVCB_SHD int32_t raw_se(uint32_t f, bool in)
     {
         if constexpr (kWrite) { int32_t v = 0; if (in) { v = rp->load(f, false); } else { flags |= 1u; } bw->write_se(v); return v; }
-        else { const int32_t v = b.read_se(); if (in) { s.put(f, v); } else { flags |= 1u; } return v; }
+        else { const int64_t p0 = b.pos; const int32_t v = b.read_se(); if (in) { rep(f, v, p0); } else { flags |= 1u; } return v; }
     }
-    HEVCB_SHD void put_idx(uint32_t f, int idx, int bound, int32_t v)
+    HEVCB_SHD void put_idx(uint32_t f, int idx, int bound, int32_t v, int64_t p0)
     {
-        if (idx >= 0 && idx < bound) { s.put(f + (uint32_t)idx, v); } else { flags |= 1u; }
+        if (idx >= 0 && idx < bound) { rep(f + (uint32_t)idx, v, p0); } else { flags |= 1u; }
     }
-    // f(n, v): bits the reader skips (bs_skip_u) and the writer emits as the constant v
-    HEVCB_SHD void fx(int n, uint32_t v)
+    // f(n, v): bits the reader skips (bs_skip_u) and the writer emits as the constant v; the read_debug variant reads and
+    // prints them under the element's name (id)
+    HEVCB_SHD void fx(int n, uint32_t v, int id)
     {
-        if constexpr (kWrite) { bw->write_u(n, v); } else { b.skip(n); }
+        if constexpr (kWrite) { (void)id; bw->write_u(n, v); }
+        else if constexpr (Sink::kTrace) {
+            const int64_t p0 = b.pos;
+            uint32_t r;
+            if (n <= 32) { r = b.read_u(n); }
+            else { r = 0u; for (int i = 0; i < n; i++) { r |= b.read_u1() << ((n - i - 1) & 31); } } // bs_read_u(b, 34 | 43): shift counts wrap on x86
+            s.trace(p0, HEVCB_TRACE_SPECIAL | (uint32_t)id, (int32_t)r);
+        }
+        else { (void)id; b.skip(n); }
     }
     // a value the reader stores without reading bits (init_slice_hevc, defaults): nothing is written
     HEVCB_SHD void syn(uint32_t f, int32_t v)
@@ -391,18 +439,19 @@ struct hevcb_walker {
         if constexpr (kWrite) { rp->skip_if(f); bw->write_ue((uint32_t)dflt); return dflt; }
         else { return ue(f); }
     }
-    // sub_layer_level_idc: read as u(8), written with bs_write_u1 by the generated writer (hevc_stream.c:751 vs :1845)
-    HEVCB_SHD int32_t level8(uint32_t f, int idx, int bound) { return au(f, idx, bound, kWrite ? 1 : 8); }
+    // sub_layer_level_idc: read as u(8) by read_hevc_*, with bs_read_u1 / bs_write_u1 by the generated read_debug and write
+    // variants (hevc_stream.c:751 vs :2939 and :1845)
+    HEVCB_SHD int32_t level8(uint32_t f, int idx, int bound) { return au(f, idx, bound, (kWrite || Sink::kTrace) ? 1 : 8); }
     HEVCB_SHD bool aligned() const
     {
         if constexpr (kWrite) { return bw->byte_aligned(); } else { return b.byte_aligned(); }
     }
 
     // 7.3.2.11 / 7.3.2.12: a one bit, then zero bits up to the byte boundary (hevc_stream.c:630-649 / :1724-1743)
-    HEVCB_SHD void trailing_bits()
+    HEVCB_SHD void trailing_bits(bool byte_alignment = false)
     {
-        fx(1, 1u);
-        while (!aligned()) { fx(1, 0u); }
+        fx(1, 1u, byte_alignment ? HEVCB_TI_ALIGN_ONE : HEVCB_TI_RBSP_STOP_ONE);
+        while (!aligned()) { fx(1, 0u, byte_alignment ? HEVCB_TI_ALIGN_ZERO : HEVCB_TI_RBSP_ALIGN_ZERO); }
     }
 
     // ---- 7.3.3 profile_tier_level (hevc_stream.c:652-755) --------------------------------------
@@ -428,14 +477,14 @@ struct hevcb_walker {
             u1(base + HF(P, general_intra_constraint_flag));
             u1(base + HF(P, general_one_picture_only_constraint_flag));
             u1(base + HF(P, general_lower_bit_rate_constraint_flag));
-            fx(34, 0u);
+            fx(34, 0u, HEVCB_TI_GENERAL_ZERO_34);
         } else {
-            fx(43, 0u);
+            fx(43, 0u, HEVCB_TI_GENERAL_ZERO_43);
         }
         if ((idc >= 1 && idc <= 5) || ((compat >> 1) & 1) || ((compat >> 2) & 1) || ((compat >> 3) & 1) || ((compat >> 4) & 1) || ((compat >> 5) & 1)) {
             u1(base + HF(P, general_inbld_flag));
         } else {
-            fx(1, 0u);
+            fx(1, 0u, HEVCB_TI_GENERAL_ZERO_BIT);
         }
         u8(base + HF(P, general_level_idc));
         uint32_t prof_present = 0, level_present = 0;
@@ -444,7 +493,7 @@ struct hevcb_walker {
             level_present |= (uint32_t)(au(base + HF(P, sub_layer_level_present_flag), i, HEVCB_MAX_SUBLAYERS, 1) & 1) << (i & 31);
         }
         if (max_sub_layers_minus1 > 0) {
-            for (int i = max_sub_layers_minus1; i < 8; i++) { fx(2, 0u); }
+            for (int i = max_sub_layers_minus1; i < 8; i++) { fx(2, 0u, HEVCB_TI_RESERVED_ZERO_XX); }
         }
         for (int i = 0; i < max_sub_layers_minus1; i++) {
             if ((prof_present >> (i & 31)) & 1u) {
@@ -470,9 +519,9 @@ struct hevcb_walker {
                     au(base + HF(P, sub_layer_intra_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
                     au(base + HF(P, sub_layer_one_picture_only_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
                     au(base + HF(P, sub_layer_lower_bit_rate_constraint_flag), i, HEVCB_MAX_SUBLAYERS, 1);
-                    fx(34, 0u);
+                    fx(34, 0u, HEVCB_TI_SUB_LAYER_ZERO_34);
                 } else {
-                    fx(43, 0u);
+                    fx(43, 0u, HEVCB_TI_SUB_LAYER_ZERO_43);
                 }
                 // the reference tests the ADDRESS of sub_layer_profile_compatibility_flag[1] (always true): App. A-10
                 au(base + HF(P, sub_layer_inbld_flag), i, HEVCB_MAX_SUBLAYERS, 1);
@@ -703,7 +752,7 @@ struct hevcb_walker {
         u(HF(V, vps_max_layers_minus1), 6);
         const int msl = u(HF(V, vps_max_sub_layers_minus1), 3);
         u1(HF(V, vps_temporal_id_nesting_flag));
-        fx(16, 0xFFFFu); // vps_reserved_0xffff_16bits
+        fx(16, 0xFFFFu, HEVCB_TI_VPS_RESERVED_FFFF);
         profile_tier_level(HF(V, ptl), msl);
         const int ordering = u1(HF(V, vps_sub_layer_ordering_info_present_flag));
         for (int i = (ordering ? 0 : msl); i <= msl; i++) {
@@ -961,7 +1010,7 @@ struct hevcb_walker {
         }
         cols.dependent_slice_segment_flag = dependent;
         if (!dependent) {
-            for (int i = 0; i < pps.num_extra_slice_header_bits; i++) { fx(1, 1u); } // slice_reserved_flag: the writer emits 1
+            for (int i = 0; i < pps.num_extra_slice_header_bits; i++) { fx(1, 1u, HEVCB_TI_SLICE_RESERVED_FLAG); } // the writer emits 1
             const int slice_type = ue(HF(H, slice_type));
             cols.slice_type = slice_type;
             if (pps.output_flag_present_flag) { u1(HF(H, pic_output_flag)); }
@@ -1034,6 +1083,9 @@ struct hevcb_walker {
                                 if (b.overrun() && i > 64) { break; }
                             }
                         }
+                        if constexpr (!kWrite && Sink::kTrace) { // B slices: the position prefix of the element that is never read
+                            if (slice_type == 0) { s.trace(b.pos, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_OPEN_LINE, 0); }
+                        }
                     }
                 }
                 if (slice_type == 0) { u1(HF(H, mvd_l1_zero_flag)); }
@@ -1079,8 +1131,9 @@ struct hevcb_walker {
                         raw_u(HF(H, entry_point_offset_minus1) + (uint32_t)i, i < HEVCB_MAX_PICS, w);
                     } else {
                         int32_t v;
+                        const int64_t p0 = b.pos;
                         if (w <= 32) { v = (int32_t)b.read_u(w); } else { b.skip(w - 32); v = (int32_t)b.read_u(32); flags |= 1u; }
-                        put_idx(HF(H, entry_point_offset_minus1), i, HEVCB_MAX_PICS, v);
+                        put_idx(HF(H, entry_point_offset_minus1), i, HEVCB_MAX_PICS, v, p0);
                     }
                     if (b.overrun() && i > 64) { break; }
                 }
@@ -1089,11 +1142,11 @@ struct hevcb_walker {
         if (pps.slice_segment_header_extension_present_flag) {
             const int len = ue(HF(H, slice_segment_header_extension_length));
             for (int i = 0; i < len; i++) {
-                fx(8, 0u); // slice_segment_header_extension_data_byte
+                fx(8, 0u, HEVCB_TI_SH_EXTENSION_DATA_BYTE);
                 if (b.overrun()) { break; }
             }
         }
-        trailing_bits(); // byte_alignment(): same bit pattern handling (hevc_stream.c:641-649)
+        trailing_bits(true); // byte_alignment(): same bit pattern handling (hevc_stream.c:641-649)
     }
 
     // ---- 7.3.6.3 pred_weight_table (hevc_stream.c:969-1029) ---------------------------------------
@@ -1164,10 +1217,16 @@ HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Si
 {
     hevcb_bits b;
     b.init(rbsp, rbsp_size);
-    b.skip(1); // forbidden_zero_bit is not validated (App. A-12)
+    const uint32_t fzb = b.read_u(1); // forbidden_zero_bit is not validated (App. A-12)
     r.nal_unit_type = (int32_t)b.read_u(6);
     r.nal_layer_id = (int32_t)b.read_u(6);
     r.nal_temporal_id_plus1 = (int32_t)b.read_u(3);
+    if constexpr (Sink::kTrace) { // the first four lines of every NAL's dump (hevc_stream.c:2363-2366)
+        sink.trace(0, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_FORBIDDEN_ZERO_BIT, (int32_t)fzb);
+        sink.trace(1, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_NAL_UNIT_TYPE, r.nal_unit_type);
+        sink.trace(7, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_NAL_LAYER_ID, r.nal_layer_id);
+        sink.trace(13, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_NAL_TEMPORAL_ID_PLUS1, r.nal_temporal_id_plus1);
+    }
     r.kind = HEVCB_KIND_NONE;
     r.ok = 0;
     r.hdr_end = 0;

@@ -124,8 +124,8 @@ def scan_strip_shard(ctx, buf, own: int, halo: int, is_first: bool, is_last: boo
     if sync:
         sc.record = ShardSummary.from_buffer_copy(d_sum.cpu().numpy().tobytes())
         if sc.record.overflow:
-            if auto_cap:
-                return scan_strip_shard(ctx, buf, own, halo, is_first, is_last, cap_nals=int(sc.record.n_nals) + 8, want_rbsp=want_rbsp,
+            if auto_cap:  # the record holds the true count of the shard
+                return scan_strip_shard(ctx, buf, own, halo, is_first, is_last, cap_nals=max(int(sc.record.n_nals) + 8, own // 3 + 8), want_rbsp=want_rbsp,
                                         extra_rbsp=extra_rbsp)
             raise HevcbError(-104, f"{sc.record.n_nals} NALs exceed cap_nals {cap_nals}")
     return sc

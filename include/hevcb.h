@@ -254,7 +254,25 @@ typedef struct hevcb_parse_buffers { /* device pointers for hevcb_parse_device, 
     uint32_t* pair_field; /* [cap_pairs] */
     int32_t* pair_value;  /* [cap_pairs] */
     int64_t cap_pairs;
+    uint32_t* pair_pos;   /* NULL, or [cap_pairs]: selects the TRACE variant of the parse, see below */
 } hevcb_parse_buffers;
+
+/* Trace variant (pair_pos != NULL): read_debug_hevc_nal_unit (hevc_stream.c:2343-3436) instead of read_hevc_nal_unit.  The list
+ * of NAL k then holds one record per line the reference prints for that NAL ("%ld.%d: <expr>: %d \n", process.pl:90-113), in
+ * print order: pair_pos = bit position of the reader before the element (byte = pos >> 3, bits_left = 8 - (pos & 7)),
+ * pair_value = the value printed, pair_field = the struct member's field index, or HEVCB_TRACE_SPECIAL | id for the lines that
+ * are not struct members (NAL header, f(n, v) elements; hevcb_trace_name resolves both to the text the reference prints).
+ * Values the reader stores without reading bits carry HEVCB_TRACE_SILENT (not printed) so that hevcb_materialize still rebuilds
+ * the struct from the list.  NALs of unsupported types contribute their four NAL header lines (rc stays -1).  The generated
+ * read_debug variant reads sub_layer_level_idc with ONE bit where read_hevc_nal_unit reads eight (hevc_stream.c:2939 vs :751);
+ * the trace variant follows it, so for such streams its state differs from the plain parse exactly as the reference's does.
+ * hevcb_rewrite_device needs the results of a plain parse. */
+#define HEVCB_TRACE_SPECIAL 0x80000000u
+#define HEVCB_TRACE_SILENT 0x40000000u
+#define HEVCB_TRACE_OPEN_LINE 19 /* id: position prefix only, no text, no newline (hevc_stream.c:3147) */
+/* Text of a trace record as the reference prints it ("sps->sps_max_dec_pic_buffering_minus1 [ i ]", "rbsp_stop_one_bit", ...).
+ * kind: HEVCB_KIND_* of the NAL.  Returns the length, 0 for records that print no text, -1 for an unknown code. */
+HEVCB_API int hevcb_trace_name(int kind, uint32_t code, char* out, int cap);
 
 typedef struct hevcb_parse_summary {
     int64_t n_nals;
@@ -361,6 +379,14 @@ HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size,
 /* Same, continuing from / handing on the parameter-set state of an earlier call (hevcb_parse_chain, all host pointers):
  * what lets a caller feed a stream piece by piece, like the reference's one-NAL-at-a-time read_hevc_nal_unit. */
 HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx, const hevcb_parse_chain* chain);
+
+/* Header parse of RBSPs the caller already holds (NAL payloads without start codes and without emulation prevention bytes, e.g.
+ * what nal_to_rbsp returned): n segments rbsp[rbsp_off[k] .. rbsp_end[k]) of one host buffer (a segment with rbsp_end[k] < 0 is
+ * treated as a failed nal_to_rbsp).  `out` holds HOST arrays sized for n / out->cap_pairs; rc[k] is the RBSP size or -1.  An empty
+ * segment is parsed like the reference parses a zero-length NAL: every read yields 0 bits (what hevc_analyze does with the
+ * zero-length "last NAL" of a window, hevc_analyze.c:190-205). */
+HEVCB_API int hevcb_parse_rbsp_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t rbsp_bytes, const int64_t* rbsp_off, const int64_t* rbsp_end,
+                                    int64_t n_nals, const hevcb_parse_buffers* out, hevcb_parse_summary* summary, const hevcb_parse_chain* chain);
 
 /* Applies NAL k of an index to caller-owned structs the way read_hevc_nal_unit updates hevc_stream_t: h->nal always
  * (unless nal_to_rbsp failed), and the struct selected by kind[k] is zeroed and refilled.  The struct pointers are the

@@ -4,7 +4,11 @@
  *     find_nal_unit / nal_to_rbsp / rbsp_to_nal          h264_stream.h:54-57  (h264_nal.c:38-200)
  *     hevc_new / hevc_free / peek_hevc_nal_unit           hevc_stream.h:571-572, hevc_nal.c:34,64,97
  *     read_hevc_nal_unit / write_hevc_nal_unit            hevc_stream.c:155-241 / :1249-1335
- * links against libhevcb200_compat.so + libhevcb200.so instead of libhevcbitstream and behaves the same.  Every call is
+ *     read_debug_hevc_nal_unit, debug_bytes, h264_dbgfile hevc_stream.c:2343, h264_stream.c:117,33
+ *     more_rbsp_data, ff-coded numbers, sei_new/free ...  h264_stream.c:42-137, h264_sei.c (declared in include/compat/*.h)
+ * links against libhevcb200_compat.so + libhevcb200.so instead of libhevcbitstream and behaves the same.  include/compat/
+ * holds headers under the reference's own names (bs.h, h264_stream.h, h264_sei.h, hevc_stream.h): the reference's
+ * hevc_analyze.c compiles against them unmodified and prints the same bytes (tests/test_compat_gpu.py).  Every call is
  * executed by the CUDA kernels of libhevcb200 (there is no CPU implementation: without a usable B200 hevc_new() returns
  * NULL and the byte-layer calls return -1 after printing the reason to stderr).
  *
@@ -19,6 +23,7 @@
 #define HEVCB_COMPAT_H
 
 #include <stdint.h>
+#include <stdio.h>
 
 #include "hevcb_layout.h"
 
@@ -57,6 +62,12 @@ HEVCB_COMPAT_API int rbsp_to_nal(const uint8_t* rbsp_buf, const int* rbsp_size, 
 HEVCB_COMPAT_API int read_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
 HEVCB_COMPAT_API int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
 HEVCB_COMPAT_API int peek_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
+/* hevc_stream.c:2343-3436: read_hevc_nal_unit + one "%ld.%d: <expr>: %d \n" line per syntax element on stdout (process.pl:90-113).
+ * The walk runs on the device in its read_debug variant (hevcb.h: trace variant of the parse), the lines are formatted here. */
+HEVCB_COMPAT_API int read_debug_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size);
+/* h264_stream.c:117-126: hex dump, 16 bytes per line, to h264_dbgfile (stdout when NULL) */
+HEVCB_COMPAT_API void debug_bytes(uint8_t* buf, int len);
+HEVCB_COMPAT_API extern FILE* h264_dbgfile; /* h264_stream.c:33 */
 
 #ifdef __cplusplus
 }

@@ -220,3 +220,67 @@ extern "C" int64_t hostsim_rewrite_all(const uint8_t* buf, int64_t size, const i
     memcpy(out, o.data(), o.size());
     return (int64_t)o.size();
 }
+
+// ------------------------------------------------------------------------------------------------
+// trace: the read_debug variant of the walker + hevcb_trace_name -> the text hevc_analyze prints
+// ------------------------------------------------------------------------------------------------
+#include <cstdio>
+#include <string>
+
+#include "hevcb_fields.cu" // host code only: field tables and hevcb_trace_name
+
+extern "C" int64_t hostsim_trace_all(const uint8_t* buf, const int64_t* starts, const int64_t* ends, int64_t n, int verbose, char* out,
+                                     int64_t out_cap)
+{
+    std::string text;
+    std::vector<uint8_t> rbsp;
+    std::vector<uint32_t> fld(1 << 16), pos(1 << 16);
+    std::vector<int32_t> val(1 << 16);
+    hevcb_sps_ctx* sps = new hevcb_sps_ctx();
+    hevcb_sps_ctx* sps_new = new hevcb_sps_ctx();
+    hevcb_pps_ctx* pps = new hevcb_pps_ctx();
+    memset(sps, 0, sizeof(*sps));
+    memset(pps, 0, sizeof(*pps));
+    char line[512], name[160];
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t size = ends[k] - starts[k];
+        if (verbose > 0) {
+            snprintf(line, sizeof(line), "!! Found NAL at offset %lld (0x%04llX), size %lld (0x%04llX) \n", (long long)starts[k], (long long)starts[k],
+                     (long long)size, (long long)size);
+            text += line;
+        }
+        int64_t consumed = 0;
+        const int64_t rs = strip(buf + starts[k], size, rbsp, &consumed);
+        if (rs < 0) { continue; }
+        rbsp.resize(rbsp.size() + 16, 0);
+        hevcb_nal_result res;
+        hevcb_trace_sink cs{nullptr, nullptr, 0, nullptr};
+        hevcb_pps_ctx pps_new;
+        memset(sps_new, 0, sizeof(*sps_new));
+        memset(&pps_new, 0, sizeof(pps_new));
+        hevcb_parse_nal(rbsp.data(), rs, cs, sps, pps, sps_new, &pps_new, res);
+        if (cs.n > fld.size()) { fld.resize(cs.n); val.resize(cs.n); pos.resize(cs.n); }
+        hevcb_trace_sink es{fld.data(), val.data(), 0, pos.data()};
+        memset(sps_new, 0, sizeof(*sps_new));
+        memset(&pps_new, 0, sizeof(pps_new));
+        hevcb_parse_nal(rbsp.data(), rs, es, sps, pps, sps_new, &pps_new, res);
+        if (es.n != cs.n) { return -2; }
+        if (res.kind == HEVCB_KIND_SPS) { *sps = *sps_new; }
+        if (res.kind == HEVCB_KIND_PPS) { *pps = pps_new; }
+        for (uint32_t i = 0; i < es.n; i++) {
+            if (!(fld[i] & HEVCB_TRACE_SPECIAL) && (fld[i] & HEVCB_TRACE_SILENT)) { continue; }
+            const int len = hevcb_trace_name(res.kind, fld[i], name, (int)sizeof(name));
+            if (len < 0) { return -3; }
+            if (fld[i] == (HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TRACE_OPEN_LINE)) {
+                snprintf(line, sizeof(line), "%ld.%d: ", (long)(pos[i] >> 3), 8 - (int)(pos[i] & 7u));
+            } else {
+                snprintf(line, sizeof(line), "%ld.%d: %s: %d \n", (long)(pos[i] >> 3), 8 - (int)(pos[i] & 7u), name, val[i]);
+            }
+            text += line;
+        }
+    }
+    delete sps; delete sps_new; delete pps;
+    if ((int64_t)text.size() > out_cap) { return -1; }
+    memcpy(out, text.data(), text.size());
+    return (int64_t)text.size();
+}

@@ -171,36 +171,67 @@ def test_write_hevc_nal_unit_matches_reference(compat):
         assert n_written > 250
 
 
-def test_analyze_tool_on_the_compat_api(tmp_path):
-    """tools/hevcb_analyze.c (a reader in the shape of hevc_analyze.c, plain C against hevcb_compat.h): its '!! Found NAL' lines
-    must be the reference CLI loop's, and its per-NAL summaries must agree with the reference parse"""
-    import re
+def _analyze_streams():
+    """(name, stream bytes) pairs for the CLI comparisons: the BASELINE config-1 shape cut to the reference's 32 MiB window, rich
+    generator streams (VUI / HRD / scaling lists / RPS / pred-weight / unsupported types / nal_to_rbsp failures), and the two ways a
+    stream makes the reference's loop end on return code 0 (its "last NAL" of size 0 is then dumped, hevc_analyze.c:190-205)."""
+    out = []
+    s = ref.gen_stream(seed=0, profile=0, n_slices=1200, payload_min=6680, payload_max=6680, idr_period=100)
+    out.append(("c1", s[: s.size - ref.PAD]))
+    for seed in (21, 22):
+        s = ref.gen_stream(seed=seed, profile=1, n_slices=400, payload_min=1, payload_max=400, zero_heavy_pct=20, extra_zero_pct=20, ps_period=40,
+                           unsupported_pct=5)
+        out.append((f"rich{seed}", s[: s.size - ref.PAD]))
+    s = ref.gen_stream(seed=23, profile=1, n_slices=60, payload_min=1, payload_max=200, ps_period=20)
+    body = s[: s.size - ref.PAD]
+    # (a stream that ends in 00 00 00 takes the same path but makes the reference itself crash: malloc(-1) + memcpy, App. A-11)
+    out.append(("tail_startcode", np.concatenate([body, np.array([0, 0, 1], np.uint8)])))
+    return out
+
+
+def _run_cli(exe, path, args, tmp_path, tag):
+    import subprocess
+
+    ofile = str(tmp_path / f"{tag}.dbg")
+    argv = [exe] + [a if a != "@O" else ofile for a in args] + [path]
+    r = subprocess.run(argv, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    dbg = open(ofile, "rb").read() if "@O" in args else b""
+    return r.stdout, dbg
+
+
+@pytest.mark.parametrize("args", [[], ["-v", "0"], ["-o", "@O"]])
+def test_reference_cli_unmodified_on_the_compat_library(tmp_path, args):
+    """oracle/_ref/hevc_analyze_compat is the reference's hevc_analyze.c, UNMODIFIED, compiled against include/compat/ (this
+    repo's bs.h / h264_stream.h / hevc_stream.h) and linked with libhevcb200_compat instead of the reference's library
+    (oracle/Makefile): find_nal_unit, read_debug_hevc_nal_unit and debug_bytes are then served by the CUDA library.  Its stdout
+    and its -o file must equal the reference binary's byte for byte."""
+    exe_ref, exe_b200 = ref.ANALYZE_BIN, os.path.join(os.path.dirname(ref.ANALYZE_BIN), "hevc_analyze_compat")
+    if not os.path.exists(exe_b200):
+        pytest.skip("oracle/_ref/hevc_analyze_compat not built")
+    for name, data in _analyze_streams():
+        path = str(tmp_path / f"{name}.h265")
+        data.tofile(path)
+        want = _run_cli(exe_ref, path, args, tmp_path, "ref_" + name)
+        got = _run_cli(exe_b200, path, args, tmp_path, "b200_" + name)
+        assert len(want[0]) > 1000
+        assert got[0] == want[0], f"{name} {args}: stdout differs at byte {next(i for i, (x, y) in enumerate(zip(got[0] + b'~', want[0] + b'~')) if x != y)}"
+        assert got[1] == want[1], f"{name} {args}: -o file differs"
+
+
+@pytest.mark.parametrize("args", [[], ["-v", "0"], ["-o", "@O"]])
+def test_batched_analyze_tool_prints_the_reference_dump(tmp_path, args):
+    """tools/hevcb_analyze.c: hevc_analyze's output from ONE batched call (hevcb_index_host in its trace variant + host formatting)"""
     import subprocess
 
     exe = str(tmp_path / "hevcb_analyze")
     libdir = os.path.join(ROOT, "hevcbitstream_b200")
     subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "hevcb_analyze.c"), "-L" + libdir,
-                           "-lhevcb200_compat", "-lhevcb200", "-Wl,-rpath," + libdir, "-o", exe])
-    s = ref.gen_stream(seed=21, profile=1, n_slices=300, payload_min=1, payload_max=400, zero_heavy_pct=20, extra_zero_pct=20, ps_period=40,
-                       unsupported_pct=5)
-    size = s.size - ref.PAD
-    path = str(tmp_path / "s.h265")
-    s[:size].tofile(path)
-    out = subprocess.run([exe, "-v", path], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    got = [l for l in out.stdout.splitlines() if l.startswith("!! Found NAL")]
-    refpath = str(tmp_path / "ref.txt")
-    assert ref.lib().ref_analyze_to_file(s.ctypes.data_as(C.c_void_p), C.c_int64(size), refpath.encode(), 1) == 0
-    want = [l.rstrip("\n") for l in open(refpath, errors="replace") if l.startswith("!! Found NAL")]
-    assert len(want) > 300 and got == want
-    st, en, _ = ref.scan_all_with_tail(s, size)
-    rec = ref.parse_all(s, st, en)["rec"]
-    lines = [l for l in out.stdout.splitlines() if l.startswith("nal_unit_type")]
-    assert len(lines) == len(st)
-    for k, l in enumerate(lines):
-        if rec["strip_rc"][k] >= 0:
-            assert int(re.match(r"nal_unit_type (\d+)", l).group(1)) == rec["nal_unit_type"][k]
-        assert ("not parsed" in l) == (rec["rc"][k] < 0)
-        m = re.search(r"slice_data (-?\d+) bytes", l)
-        if m:
-            assert int(m.group(1)) == rec["slice_data_size"][k]
+                           "-lhevcb200", "-Wl,-rpath," + libdir, "-o", exe])
+    for name, data in _analyze_streams():
+        path = str(tmp_path / f"{name}.h265")
+        data.tofile(path)
+        want = _run_cli(ref.ANALYZE_BIN, path, args, tmp_path, "ref_" + name)
+        got = _run_cli(exe, path, args, tmp_path, "tool_" + name)
+        assert got[0] == want[0], f"{name} {args}: stdout differs at byte {next(i for i, (x, y) in enumerate(zip(got[0] + b'~', want[0] + b'~')) if x != y)}"
+        assert got[1] == want[1], f"{name} {args}: -o file differs"

