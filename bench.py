@@ -6,8 +6,11 @@
 One "step" = one pass of the fused start-code scan + EPB strip (hevcb_scan_strip_device) over a synthetic Annex-B
 buffer that is already resident in HBM.  N = 1 runs BASELINE config[1]: a 4 GiB buffer; the headline `value` is quoted
 on 16 KiB NALs (escaped uniform-random payload) and `sweep` carries the other NAL sizes (64 B .. 1 MiB) plus the
-EPB-dense worst case.  N > 1 (torchrun, one rank per GPU) shards independent 4 GiB streams over the ranks (weak
-scaling, BASELINE config[5] first form); the only exchange is an all-gather of the per-shard NAL / RBSP-byte counts.
+EPB-dense worst case.  N > 1 (torchrun, one rank per GPU): the ranks' 4 GiB buffers are consecutive BYTE RANGES of one
+N x 4 GiB stream (weak scaling, BASELINE config[4]: 16-byte halo, NCCL all_gather of the ~190-byte shard records, stitch,
+patch of the boundary entries inside every step).  Before timing, a reference-written stream goes through the sharded
+scan + strip + header parse over the real process group and every rank checks its share against the reference
+(`sharded_parity`; the run fails otherwise).
 
 Printed (rank 0, one JSON line): metric/value/unit + `roofline` (algorithmic bytes / CUDA-event time of the step vs the
 measured HBM peak), `cpu_baseline` (the UNMODIFIED reference's find_nal_unit + nal_to_rbsp loop, oracle/_ref, one host
@@ -165,9 +168,114 @@ def cpu_reference_sample(unit: np.ndarray, reps: int = 3):
     return size / t / 1e9, n, t
 
 
+def sharded_parity_check(ctx, dev, world, rank):
+    """N > 1: a reference-written stream through the byte-range sharded scan + strip + header parse over the REAL process group
+    (NCCL): every rank checks the NALs it owns against the unmodified reference (oracle/_ref, the checker only): offsets,
+    nal_to_rbsp status / size, RBSP bytes, read_hevc_nal_unit return code, h->nal and the digest of every parsed struct.
+    Returns a short description; raises when any rank disagrees."""
+    import torch
+    import torch.distributed as dist
+
+    from hevcbitstream_b200 import shard as hs
+    from oracle import ref
+
+    if not ref.available():
+        return "skipped: oracle/_ref not built on this box"
+    from tests import parse_check
+
+    s = ref.gen_stream(seed=12, profile=1, n_slices=20000, payload_min=1, payload_max=1500, zero_heavy_pct=20, extra_zero_pct=10, ps_period=500,
+                       unsupported_pct=3)
+    size = s.size - ref.PAD
+    st, en, _ = ref.scan_all_with_tail(s, size)
+    sr = ref.strip_all(s, st, en)
+    R = ref.parse_all(s, st, en)["rec"]
+    bounds = hs.plan_shards(s, world, size)
+    own, halo, first, last = hs.shard_flags(bounds, rank)
+    lo = int(bounds[rank])
+    b = torch.zeros(own + halo + 32, dtype=torch.uint8, device=dev)
+    b[: own + halo] = torch.from_numpy(s[lo: lo + own + halo].copy()).to(dev)
+    err = ""
+    try:
+        sc, res = hs.scan_strip_sharded(ctx, b, own, halo, first, last, extra_rbsp=hs.HEAD_BYTES)
+        ps = hs.parse_sharded(ctx, b, own, halo, sc, res)
+        f, n, g = int(res.first_local[rank]), int(res.n_owned[rank]), int(res.nal_base[rank])
+        bb = int(res.byte_base[rank])
+        assert int(res.glob.n_nals) == len(st), "global NAL count"
+        assert np.array_equal(sc.nal_start[f:f + n].cpu().numpy() + bb, st[g:g + n]), "nal_start"
+        assert np.array_equal(sc.nal_end[f:f + n].cpu().numpy() + bb, en[g:g + n]), "nal_end"
+        ro, re_ = sc.rbsp_off[f:f + n].cpu().numpy(), sc.rbsp_end[f:f + n].cpu().numpy()
+        rc = sr["rc"][g:g + n].astype(np.int64)
+        assert np.array_equal(re_ < 0, rc < 0), "nal_to_rbsp status"
+        assert np.array_equal((re_ - ro)[rc >= 0], rc[rc >= 0]), "RBSP sizes"
+        img = sc.rbsp.cpu().numpy()
+        local_bytes = int(sc.record.rbsp_bytes)
+        for k in np.nonzero((rc >= 0) & (re_ <= local_bytes))[0][:: max(1, n // 4000)].tolist():  # NALs whose RBSP lies in the local image
+            a0 = int(sr["rbsp_off"][g + k])
+            assert np.array_equal(img[ro[k]: re_[k]], sr["rbsp"][a0: a0 + rc[k]]), f"RBSP bytes of NAL {g + k}"
+        prc, hdr, kind = ps["rc"][:n].cpu().numpy(), ps["nal_hdr"][:n].cpu().numpy().astype(np.int64), ps["kind"][:n].cpu().numpy()
+        assert np.array_equal(prc, R["rc"][g:g + n]), "read_hevc_nal_unit return codes"
+        okh = hdr != -1
+        assert np.array_equal((hdr & 0xFF)[okh], R["nal_unit_type"][g:g + n][okh]), "nal_unit_type"
+        npairs = int(ps["n_pairs"])
+        dg = parse_check.digests_from_pairs(kind, ps["pair_off"][: n + 1].cpu().numpy(), ps["pair_field"][:npairs].cpu().numpy().view(np.uint32),
+                                            ps["pair_value"][:npairs].cpu().numpy())
+        has = kind != 0
+        assert np.array_equal(dg[has], R["state_hash"][g:g + n][has]), "parsed struct digests"
+    except Exception as ex:  # every rank must reach the collective below
+        err = f"rank {rank}: {type(ex).__name__}: {ex}"
+    flag = torch.tensor([0.0 if err else 1.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if float(flag.item()) != 1.0:
+        raise SystemExit(f"sharded parity check FAILED ({err or 'on another rank'})")
+    return f"ok: {len(st)} NALs of a reference-written stream over {world} ranks (NCCL), offsets + RBSP + parsed structs vs oracle/_ref on every rank"
+
+
+def cpu_reference_extras():
+    """the reference's CLI and its edit loop on the host, on BASELINE config[0]'s stream (64 MB, Main
+    1920x1080, VPS/SPS/PPS + 10k slices written by the reference's writer).  One thread; bounded (a few seconds)."""
+    import tempfile
+
+    from oracle import ref
+
+    out = {}
+    s = ref.gen_stream(seed=0, profile=0, n_slices=10000, payload_min=6680, payload_max=6680, idr_period=100)
+    size = s.size - ref.PAD
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "c1.h265")
+        s[:size].tofile(path)
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with open(os.devnull, "wb") as dn:
+                subprocess.run([ref.ANALYZE_BIN, path], stdout=dn, stderr=dn, check=False)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["hevc_analyze_c1"] = {"seconds": best, "MBps": size / best / 1e6, "bytes": int(size),
+                                  "what": "wall time of `hevc_analyze c1.h265 > /dev/null` (oracle/_ref/hevc_analyze, -O2), best of 2"}
+    t, n = ref.time_loop(s, size, 2, 3)
+    out["read_loop_c1"] = {"seconds": t, "GBps": size / t / 1e9, "nal_per_s": n / t, "what": "in-memory find_nal_unit + read_hevc_nal_unit loop, best of 3"}
+    st, en, _ = ref.scan_all_with_tail(s, size)
+    t0 = time.perf_counter()
+    rw = ref.rewrite_all(s, size, st, en, qp_delta_add=2, vui_flip=1)
+    dt = time.perf_counter() - t0
+    out["rewrite_c4_composition"] = {"seconds": dt, "GBps": size / dt / 1e9, "bytes_out": int(rw["out"].size),
+                                     "what": "read_hevc_nal_unit -> edit slice_qp_delta / VUI flag -> write_hevc_nal_unit -> rbsp_to_nal over the same 64 MB "
+                                             "(SURVEY 3.4 composition, oracle/ref_harness.c), one pass"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # arms
 # ------------------------------------------------------------------------------------------------
+
+def workload_config(args, name, nal_size, size_bytes, world):
+    """`config` of the JSON line: identical in both arms (the reference arm walks the same bytes on the host)."""
+    return {"workload": f"BASELINE config[1]: fused start-code scan + EPB strip, {args.size_gib:g} GiB Annex-B buffer per GPU, NAL size {nal_size} B "
+                        f"({name}); 64 MiB synthetic unit (escaped uniform-random payload) tiled to the full size; input > L2 so no flush needed",
+            "nal_size": nal_size, "bytes_per_gpu": int(size_bytes), "l2": "inputs larger than L2 (4 GiB vs 126 MB)",
+            "sharding": ("one stream cut by byte range, one shard per rank: 16-byte halo, NCCL all_gather of the shard records, stitch "
+                         "(BASELINE config[4]); every step includes the exchange") if world > 1 else "single GPU"}
+
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -179,22 +287,44 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhevcref.so missing (reference sources not compiled)"}))
         return
     name, nal_size, dense = next(w for w in WORKLOADS if w[0] == args.workload)
-    unit = make_unit(nal_size, args.ref_sample_mib << 20, 1234, dense)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    unit = make_unit(nal_size, UNIT_BYTES, 1234, dense)  # rank 0's unit of the GPU arm
+    reps = max(1, int(args.size_gib * (1 << 30)) // unit.size)
+    size_total = unit.size * reps
+    # One step = the reference's find_nal_unit + nal_to_rbsp loop over the same bytes the GPU arm holds: the buffer is the unit
+    # tiled `reps` times and a unit begins with a start code, so the loop over one unit, run `reps` times, visits exactly the NALs
+    # of the whole buffer (the reference's API takes `int` sizes: pieces < 2 GiB cut at NAL boundaries).  --ref-passes
+    # bounds the passes per step (default: all of them); the throughput is per byte either way.
+    passes = reps if args.ref_passes <= 0 else min(reps, args.ref_passes)
     buf = ref.padded(unit)
     size = unit.size
+
+    def step():
+        t = 0.0
+        n = 0
+        for _ in range(passes):
+            dt, k = ref.time_loop(buf, size, 1, 1)
+            t += dt
+            n += k
+        return t, n
+
     for _ in range(args.warmup):
         ref.time_loop(buf, size, 1, 1)
     ts = []
+    nn = 0
     for _ in range(args.steps):
-        t, n = ref.time_loop(buf, size, 1, 1)
+        t, nn = step()
         ts.append(t)
     mean = float(np.mean(ts))
-    val = size / mean / 1e9
+    val = size * passes / mean / 1e9
+    cfg = workload_config(args, name, nal_size, size_total, world)
+    sample = (f"{passes} of {reps} passes over the 64 MiB unit per step (= {size * passes / 2**30:.2f} GiB of the {size_total / 2**30:.2f} GiB buffer), "
+              f"find_nal_unit + nal_to_rbsp loop of the unmodified reference (oracle/_ref), 1 thread (the reference is single-threaded), {nn} NALs per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"reference find_nal_unit + nal_to_rbsp loop over a {args.ref_sample_mib} MiB sample of {name} (NAL {nal_size} B)", "nal_size": nal_size},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"{args.ref_sample_mib} MiB of the {name} stream per step, 1 thread (the reference is single-threaded and not re-entrant)"},
+        "ms_per_step": mean * 1e3 * (reps / passes), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -221,6 +351,7 @@ def run_ours(args):
     ctx = hb.Context(local)
     size_target = int(args.size_gib * (1 << 30))
     peak, peak_src = measured_peak()
+    sharded_parity = sharded_parity_check(ctx, dev, world, rank) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -368,16 +499,18 @@ def run_ours(args):
                 del r
                 torch.cuda.empty_cache()
 
-    # ---- BASELINE config[3]: batched header parse of >= 1M header-bearing NALs (reference-written fixture, tiled)
+    # ---- BASELINE config[2]: batched header parse of >= 1M header-bearing NALs.  Primary number: 1 M DISTINCT headers written by the
+    # reference's own writer (oracle/_ref's generator: multi-slice, tiles / WPP entry points, long-term refs, RPS, pred-weight,
+    # VUI + HRD, re-sent parameter sets, unsupported types); second number: the small reference-written fixture tiled (every
+    # warp then holds identical headers after the shape sort: the best case for divergence).
     parse = None
     if not args.no_parse:
-        try:
-            unit_h = np.fromfile(os.path.join(ROOT, "tests", "golden", "headers_unit.bin"), dtype=np.uint8)
-            probe = ctx.scan_strip_device(torch.from_numpy(unit_h).to(dev), size=unit_h.size)
-            nals_per_unit = int(probe.n_nals)
-            reps = max(1, -(-args.parse_nals // nals_per_unit))
-            dh = torch.from_numpy(unit_h).to(dev).repeat(reps)
-            hsize = dh.numel()
+        def time_parse(unit_h, reps, label):
+            dh = torch.from_numpy(unit_h).to(dev)
+            if reps > 1:
+                dh = dh.repeat(reps)
+            dh = torch.cat([dh, torch.zeros(32, dtype=torch.uint8, device=dev)])
+            hsize = dh.numel() - 32
             scan = ctx.scan_strip_device(dh, size=hsize, cap_nals=hsize // 8 + 1024)
             n_h = int(scan.n_nals)
             for _ in range(3):
@@ -395,26 +528,40 @@ def run_ours(args):
             pms = e0.elapsed_time(e1) / k
             pl = (ctx.launch_count - l0) // k
             pout = ctx.parse_device(dh, scan)
-            # full pipeline (scan + strip + parse) device resident
             e0.record()
             for _ in range(k):
-                sc2 = ctx.scan_strip_device(dh, size=hsize, cap_nals=hsize // 8 + 1024, sync=False)
+                ctx.scan_strip_device(dh, size=hsize, cap_nals=hsize // 8 + 1024, sync=False)
             e1.record()
             barrier()
             sms = e0.elapsed_time(e1) / k
-            parse = {"n_nals": n_h, "ms_parse": pms, "nal_headers_per_s": n_h / (pms * 1e-3), "syntax_elements": int(pout["n_pairs"]),
-                     "elements_per_s": pout["n_pairs"] / (pms * 1e-3), "n_ok": int(pout["n_ok"]), "launches_per_parse": int(pl),
-                     "ms_scan_strip": sms, "nal_headers_per_s_incl_scan_strip": n_h / ((pms + sms) * 1e-3),
-                     "workload": f"tests/golden/headers_unit.bin (reference-written, {nals_per_unit} NALs: multi-slice, tiles/WPP, long-term refs, "
-                                 f"RPS, pred-weight, VUI/HRD) tiled x{reps} on the device; per rank"}
-            if rank == 0 and world == 1:
-                from oracle import ref as _ref
-                if _ref.available():
-                    ub = _ref.padded(unit_h)
-                    t_cpu, n_cpu = _ref.time_loop(ub, unit_h.size, 2, 5)
+            return {"n_nals": n_h, "ms_parse": pms, "nal_headers_per_s": n_h / (pms * 1e-3), "syntax_elements": int(pout["n_pairs"]),
+                    "elements_per_s": pout["n_pairs"] / (pms * 1e-3), "n_ok": int(pout["n_ok"]), "launches_per_parse": int(pl),
+                    "ms_scan_strip": sms, "nal_headers_per_s_incl_scan_strip": n_h / ((pms + sms) * 1e-3), "workload": label}
+
+        try:
+            from oracle import ref as _ref
+
+            fixture = np.fromfile(os.path.join(ROOT, "tests", "golden", "headers_unit.bin"), dtype=np.uint8)
+            if _ref.available():
+                t0 = time.perf_counter()
+                gs = _ref.gen_stream(seed=21 + rank, profile=1, n_slices=args.parse_nals, payload_min=1, payload_max=64, zero_heavy_pct=10, extra_zero_pct=5,
+                                     ps_period=500, unsupported_pct=2)
+                gen_s = time.perf_counter() - t0
+                distinct = gs[: gs.size - _ref.PAD]
+                parse = time_parse(distinct, 1, f"{args.parse_nals} DISTINCT slice headers (+ parameter sets every 500) written by the reference's writer "
+                                                f"(oracle/_ref generator, seed {21 + rank}, payload <= 64 B; generated on the host in {gen_s:.1f} s); per rank")
+                if rank == 0 and world == 1:  # CPU baseline of this leg: the reference's own loop over a bounded sample of the same stream
+                    # (a complete stream of its own: the reference crashes on a NAL that is cut short, App. A-11)
+                    n_cs = min(args.parse_nals, 300000)
+                    cs = _ref.gen_stream(seed=21 + rank, profile=1, n_slices=n_cs, payload_min=1, payload_max=64, zero_heavy_pct=10, extra_zero_pct=5,
+                                         ps_period=500, unsupported_pct=2)
+                    t_cpu, n_cpu = _ref.time_loop(cs, cs.size - _ref.PAD, 2, 3)
                     parse["cpu_reference_nal_headers_per_s"] = n_cpu / t_cpu
-                    parse["cpu_reference_note"] = "find_nal_unit + read_hevc_nal_unit loop of the unmodified reference, 1 thread, one unit, best of 5"
-            del dh, scan, pout
+                    parse["cpu_reference_note"] = f"find_nal_unit + read_hevc_nal_unit loop of the unmodified reference, 1 thread, {n_cs} slices of the same generator, best of 3"
+            else:
+                parse = {"note": "oracle/_ref not built: no generator for distinct headers on this box"}
+            reps = max(1, -(-args.parse_nals // 4106))
+            parse["tiled_fixture"] = time_parse(fixture, reps, f"tests/golden/headers_unit.bin (reference-written, 4106 NALs) tiled x{reps}: identical headers side by side after the shape sort")
         except Exception as ex:
             parse = {"error": repr(ex)}
 
@@ -439,7 +586,7 @@ def run_ours(args):
             barrier()
             ims = e0.elapsed_time(e1) / k
             s_ = ins["summary"].cpu().numpy()
-            alg_i = 2.0 * int(sres.rbsp_bytes) + float(s_[1]) + 24.0 * nn  # payload read by the count and the write pass, output written, offsets
+            alg_i = float(int(sres.rbsp_bytes)) + float(s_[1])  # N_rbsp + N_nal (a second read of the payload earns nothing)
             insert = {"ms": ims, "n_nals": nn, "out_bytes": int(s_[1]), "epb_inserted": int(s_[2]), "input_GBps": int(sres.rbsp_bytes) / (ims * 1e-3) / 1e9,
                       "algorithmic_GBps": alg_i / (ims * 1e-3) / 1e9, "frac_of_peak": alg_i / (ims * 1e-3) / 1e9 / peak,
                       "round_trip_identical": bool(int(s_[1]) == int(head["size_local"]) and torch.equal(ins["out"][: int(s_[1])], head["d"][: int(s_[1])])),
@@ -522,13 +669,15 @@ def run_ours(args):
             v, n, t = cpu_reference_sample(sample, reps=3)
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                    "sample": f"first {sample.size >> 20} MiB of the {name} stream, find_nal_unit + nal_to_rbsp loop (oracle/_ref), best of 3, {n} NALs"}
+            if not args.no_cpu_extras:
+                cpu["also"] = cpu_reference_extras()
         except Exception as ex:
             cpu = {"value": None, "unit": UNIT, "error": repr(ex)}
 
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same workload (profiles/)
     traffic = None
     try:
-        pj = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_strip_ncu.json")))
+        pj = json.load(open(os.path.join(ROOT, "profiles", "r2_scan_strip_ncu.json")))
         if pj.get("workload") == name and abs(pj.get("size_gib", 0) - args.size_gib) < 1e-6:
             traffic = pj["traffic_bytes_per_launch"]
     except Exception:
@@ -538,12 +687,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": head["in_gbs"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"BASELINE config[1]: fused start-code scan + EPB strip, {args.size_gib:g} GiB Annex-B buffer per GPU, NAL size {nal_size} B "
-                                   f"({name}); 64 MiB synthetic unit (escaped uniform-random payload) tiled on the device; input > L2 so no flush needed",
-                       "nal_size": nal_size, "bytes_per_gpu": int(head["size_local"]), "nals_per_step": int(head["n_nals"]),
-                       "nal_headers_located_per_s": head["n_nals"] / (head["ms"] * 1e-3), "l2": "inputs larger than L2 (4 GiB vs 126 MB)",
-                       "sharding": ("one stream cut by byte range, one shard per rank: 16-byte halo, NCCL all_gather of the shard records, host stitch "
-                                    "(BASELINE config[4]); every step includes the exchange") if world > 1 else "single GPU"},
+            "config": workload_config(args, name, nal_size, head["size_local"], world),
+            "detail": {"nals_per_step": int(head["n_nals"]), "nal_headers_located_per_s": head["n_nals"] / (head["ms"] * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": per_gpu_alg_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_alg_gbs / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": head["alg_bytes_per_gpu"], "peak_source": peak_src,
                          "algorithmic_bytes": "N_in + N_rbsp + 24*NALs per launch (SURVEY 8d), per GPU; time = CUDA-event mean over the timed steps (memset + init + scan + finalize launches)"},
@@ -554,6 +699,8 @@ def run_ours(args):
         }
         if head.get("stitched"):
             line["stitched"] = head["stitched"]
+        if sharded_parity is not None:
+            line["sharded_parity"] = sharded_parity
         if sweep:
             line["sweep"] = sweep
         if parse:
@@ -585,7 +732,9 @@ def main():
     ap.add_argument("--rewrite-gib", type=float, default=4.0)
     ap.add_argument("--rewrite-payload", type=int, default=16384)
     ap.add_argument("--ref-sample-mib", type=int, default=64)
+    ap.add_argument("--ref-passes", type=int, default=16, help="reference arm: passes over the 64 MiB unit per step (0 = the whole buffer)")
     ap.add_argument("--cpu-baseline-multi", action="store_true")
+    ap.add_argument("--no-cpu-extras", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -45,6 +45,10 @@ class ParseBuffers(C.Structure):
     ]
 
 
+class BsOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("value", C.c_int32), ("pad", C.c_int32)]
+
+
 class ParseSummary(C.Structure):
     _fields_ = [
         ("n_nals", C.c_int64), ("n_ok", C.c_int64), ("n_pairs", C.c_int64), ("n_vps", C.c_int64), ("n_sps", C.c_int64),
@@ -149,6 +153,12 @@ def load_library() -> C.CDLL:
     L.hevcb_rewrite_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), C.POINTER(EditSet), vp, i64, vp, vp, vp, vp]
     L.hevcb_field_index.restype = i64
     L.hevcb_field_index.argtypes = [C.c_int, C.c_char_p]
+    L.hevcb_bs_read_host.restype = C.c_int
+    L.hevcb_bs_read_host.argtypes = [vp, vp, i64, C.POINTER(BsOp), C.c_int, vp, vp, vp]
+    L.hevcb_bs_write_host.restype = C.c_int
+    L.hevcb_bs_write_host.argtypes = [vp, C.POINTER(BsOp), C.c_int, vp, i64, C.POINTER(i64), C.POINTER(C.c_int32)]
+    L.hevcb_parse_rbsp_host.restype = C.c_int
+    L.hevcb_parse_rbsp_host.argtypes = [vp, vp, i64, vp, vp, i64, C.POINTER(ParseBuffers), C.POINTER(ParseSummary), vp]
     L.hevcb_trace_name.restype = C.c_int
     L.hevcb_trace_name.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.c_int]
     L.hevcb_insert_device.restype = C.c_int

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import EditRule, EditSet, HevcbError, InsertSummary, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
+from ._lib import BsOp, EditRule, EditSet, HevcbError, InsertSummary, ParseBuffers, ParseSummary, ScanSummary, StreamIndex, load_library
 
 
 @dataclass
@@ -68,6 +68,38 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self._L.hevcb_sm_count(self._h))
+
+    # ---- the device bit reader / writer on their own (hevcb_bs_read_host / hevcb_bs_write_host) ----------
+    BS_KINDS = {"u": 0, "f": 0, "u1": 1, "u8": 2, "ue": 3, "se": 4, "skip": 5}
+
+    def bs_read(self, data: bytes, ops):
+        """ops: list of ("u", n) / ("u1",) / ("u8",) / ("ue",) / ("se",) / ("skip", n).  Returns (values, bitpos, overrun) lists."""
+        n = len(ops)
+        arr = (BsOp * max(n, 1))()
+        for i, op in enumerate(ops):
+            arr[i].kind = self.BS_KINDS[op[0]]
+            arr[i].n = int(op[1]) if len(op) > 1 else 0
+        buf = np.frombuffer(bytes(data), np.uint8).copy()
+        vals = np.zeros(max(n, 1), np.int32)
+        pos = np.zeros(max(n, 1), np.int64)
+        ovr = np.zeros(max(n, 1), np.int32)
+        self._check(self._L.hevcb_bs_read_host(self._h, _np_ptr(buf) if buf.size else None, int(buf.size), arr, n, _np_ptr(vals), _np_ptr(pos), _np_ptr(ovr)))
+        return vals[:n].tolist(), pos[:n].tolist(), ovr[:n].tolist()
+
+    def bs_write(self, ops, cap: int):
+        """ops: list of ("u", n, v) / ("u1", v) / ("u8", v) / ("ue", v) / ("se", v).  Returns (bytes, bits written, overrun)."""
+        n = len(ops)
+        arr = (BsOp * max(n, 1))()
+        for i, op in enumerate(ops):
+            arr[i].kind = self.BS_KINDS[op[0]]
+            arr[i].n = int(op[1]) if op[0] in ("u", "f") else 0
+            v = int(op[-1])
+            arr[i].value = v - (1 << 32) if v >= (1 << 31) else v
+        out = np.zeros(max(cap, 1), np.uint8)
+        bits = C.c_int64(0)
+        ovr = C.c_int32(0)
+        self._check(self._L.hevcb_bs_write_host(self._h, arr, n, _np_ptr(out), int(cap), C.byref(bits), C.byref(ovr)))
+        return out[:cap].tobytes(), int(bits.value), int(ovr.value)
 
     def trace_name(self, kind: int, code: int) -> str:
         """Text the reference prints for a trace record (hevcb_trace_name)."""

@@ -712,6 +712,102 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     return HEVCB_OK;
 }
 
+// ---- the device bit reader / writer on their own: a script of bs_* calls executed by hevcb_bits / hevcb_bitwriter ------------------
+namespace {
+__global__ void bs_read_kernel(const uint8_t* __restrict__ bytes, int64_t size, const hevcb_bs_op* __restrict__ ops, int n_ops, int32_t* __restrict__ values,
+                               int64_t* __restrict__ bitpos, int32_t* __restrict__ overrun)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+    hevcb_bits b;
+    b.init(bytes, size);
+    for (int i = 0; i < n_ops; i++) {
+        int32_t v = 0;
+        switch (ops[i].kind) {
+            case HEVCB_BS_U: v = (int32_t)b.read_u(ops[i].n); break;
+            case HEVCB_BS_U1: v = (int32_t)b.read_u1(); break;
+            case HEVCB_BS_U8: v = (int32_t)b.read_u8(); break;
+            case HEVCB_BS_UE: v = (int32_t)b.read_ue(); break;
+            case HEVCB_BS_SE: v = b.read_se(); break;
+            case HEVCB_BS_SKIP: b.skip(ops[i].n); break;
+            default: break;
+        }
+        values[i] = v;
+        bitpos[i] = b.pos;
+        overrun[i] = b.overrun() ? 1 : 0;
+    }
+}
+__global__ void bs_write_kernel(const hevcb_bs_op* __restrict__ ops, int n_ops, uint8_t* __restrict__ out, int64_t cap, int64_t* __restrict__ result)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+    hevcb_bitwriter w;
+    w.init(out, cap);
+    for (int i = 0; i < n_ops; i++) {
+        switch (ops[i].kind) {
+            case HEVCB_BS_U: w.write_u(ops[i].n, (uint32_t)ops[i].value); break;
+            case HEVCB_BS_U1: w.write_u(1, (uint32_t)ops[i].value); break;
+            case HEVCB_BS_U8: w.write_u(8, (uint32_t)ops[i].value); break;
+            case HEVCB_BS_UE: w.write_ue((uint32_t)ops[i].value); break;
+            case HEVCB_BS_SE: w.write_se(ops[i].value); break;
+            default: break;
+        }
+    }
+    // a pending partial byte is flushed the way the reference leaves it in memory: its bits at the top of the byte, the rest 0
+    if (w.nacc > 0 && (w.pos >> 3) < w.room) { out[w.pos >> 3] = (uint8_t)(w.acc << (8 - w.nacc)); }
+    result[0] = w.pos;
+    result[1] = w.overrun() ? 1 : 0;
+}
+} // namespace
+
+extern "C" HEVCB_API int hevcb_bs_read_host(hevcb_ctx* ctx, const uint8_t* bytes, int64_t size, const hevcb_bs_op* ops, int n_ops, int32_t* values,
+                                            int64_t* bitpos, int32_t* overrun)
+{
+    if (!ctx || size < 0 || n_ops < 0 || (size > 0 && !bytes) || (n_ops > 0 && (!ops || !values || !bitpos || !overrun))) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_ops == 0) { return HEVCB_OK; }
+    cudaStream_t st = ctx->stream;
+    const size_t o_ops = ((size_t)size + 64 + 255) & ~(size_t)255, o_val = o_ops + (((size_t)n_ops * sizeof(hevcb_bs_op) + 255) & ~(size_t)255);
+    const size_t o_pos = o_val + (((size_t)n_ops * 4 + 255) & ~(size_t)255), o_ovr = o_pos + (((size_t)n_ops * 8 + 255) & ~(size_t)255);
+    const size_t total = o_ovr + (size_t)n_ops * 4 + 256;
+    int rc = hevcb_reserve(ctx, &ctx->wstruct, total);
+    if (rc != HEVCB_OK) { return rc; }
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->wstruct.p);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(base, 0, o_ops, st)); // the reader's aligned 8-byte loads reach past the last byte
+    if (size > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(base, bytes, (size_t)size, cudaMemcpyHostToDevice, st)); }
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(base + o_ops, ops, (size_t)n_ops * sizeof(hevcb_bs_op), cudaMemcpyHostToDevice, st));
+    bs_read_kernel<<<1, 32, 0, st>>>(base, size, reinterpret_cast<const hevcb_bs_op*>(base + o_ops), n_ops, reinterpret_cast<int32_t*>(base + o_val),
+                                     reinterpret_cast<int64_t*>(base + o_pos), reinterpret_cast<int32_t*>(base + o_ovr));
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(values, base + o_val, (size_t)n_ops * 4, cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(bitpos, base + o_pos, (size_t)n_ops * 8, cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(overrun, base + o_ovr, (size_t)n_ops * 4, cudaMemcpyDeviceToHost, st));
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    return HEVCB_OK;
+}
+
+extern "C" HEVCB_API int hevcb_bs_write_host(hevcb_ctx* ctx, const hevcb_bs_op* ops, int n_ops, uint8_t* out, int64_t cap, int64_t* bits_written, int32_t* overrun)
+{
+    if (!ctx || n_ops < 0 || cap < 0 || (n_ops > 0 && !ops) || (cap > 0 && !out) || !bits_written || !overrun) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t o_ops = ((size_t)cap + 64 + 255) & ~(size_t)255, o_res = o_ops + (((size_t)n_ops * sizeof(hevcb_bs_op) + 255) & ~(size_t)255);
+    int rc = hevcb_reserve(ctx, &ctx->wstruct, o_res + 256);
+    if (rc != HEVCB_OK) { return rc; }
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->wstruct.p);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(base, 0, o_ops, st));
+    if (n_ops > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(base + o_ops, ops, (size_t)n_ops * sizeof(hevcb_bs_op), cudaMemcpyHostToDevice, st)); }
+    bs_write_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const hevcb_bs_op*>(base + o_ops), n_ops, base, cap, reinterpret_cast<int64_t*>(base + o_res));
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    int64_t res[2] = {0, 0};
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(res, base + o_res, 16, cudaMemcpyDeviceToHost, st));
+    if (cap > 0) { HEVCB_CUDA(ctx, cudaMemcpyAsync(out, base, (size_t)cap, cudaMemcpyDeviceToHost, st)); }
+    HEVCB_CUDA(ctx, cudaStreamSynchronize(st));
+    *bits_written = res[0];
+    *overrun = (int32_t)res[1];
+    return HEVCB_OK;
+}
+
 extern "C" HEVCB_API int hevcb_ps_context_bytes(int64_t* sps_bytes, int64_t* pps_bytes)
 {
     if (sps_bytes) { *sps_bytes = (int64_t)sizeof(hevcb_sps_ctx); }

@@ -117,7 +117,8 @@ struct hevcb_bits {
     HEVCB_SHD int32_t read_se() // bs.h:209-221
     {
         const int32_t r = (int32_t)read_ue();
-        return (r & 1) ? (int32_t)(((int64_t)r + 1) / 2) : -(r / 2);
+        // (r + 1) / 2 in 32-bit arithmetic that wraps, as the x86 reference computes it for r = INT_MAX
+        return (r & 1) ? (int32_t)((uint32_t)r + 1u) / 2 : -(r / 2);
     }
     HEVCB_SHD bool byte_aligned() const { return (pos & 7) == 0; }
     HEVCB_SHD int64_t byte_pos() const { return pos >> 3; }

@@ -118,7 +118,7 @@ static inline uint32_t bs_read_ue(bs_t* b)
 static inline int32_t bs_read_se(bs_t* b)
 {
     const int32_t k = (int32_t)bs_read_ue(b);
-    return (k & 1) ? (k + 1) / 2 : -(k / 2);
+    return (k & 1) ? (int32_t)((uint32_t)k + 1u) / 2 : -(k / 2); /* wraps for k = INT_MAX like the x86 reference */
 }
 
 static inline void bs_write_u1(bs_t* b, uint32_t v)

@@ -380,6 +380,28 @@ HEVCB_API int hevcb_index_host(hevcb_ctx* ctx, const uint8_t* buf, int64_t size,
  * what lets a caller feed a stream piece by piece, like the reference's one-NAL-at-a-time read_hevc_nal_unit. */
 HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t size, hevcb_stream_index* idx, const hevcb_parse_chain* chain);
 
+/* ---- the bit layer on its own --------------------------------------------------------------------
+ * bs_t's read / write calls (bs.h:126-331) as a script executed by the DEVICE bit reader (64-bit window, clz exp-Golomb) and
+ * bit writer the parser / writer kernels are built on: the hook that pins them directly against the reference's known answers
+ * (SURVEY Appendix B), independent of any syntax walk.  After op i: values[i] (reads), bitpos[i] = bits consumed so far (byte
+ * = pos >> 3, bits_left = 8 - (pos & 7)), overrun[i] = bs_overrun().  The writer returns the bytes as the reference leaves them
+ * in a zeroed buffer, the bit count and bs_overrun(); like bs_write_u1 it drops what does not fit into `cap` bytes. */
+#define HEVCB_BS_U 0    /* u(n) / f(n) */
+#define HEVCB_BS_U1 1
+#define HEVCB_BS_U8 2
+#define HEVCB_BS_UE 3
+#define HEVCB_BS_SE 4
+#define HEVCB_BS_SKIP 5 /* bs_skip_u(n); read side only */
+typedef struct hevcb_bs_op {
+    int32_t kind;
+    int32_t n;     /* bit count for U / SKIP */
+    int32_t value; /* value to write (write side) */
+    int32_t pad;
+} hevcb_bs_op;
+HEVCB_API int hevcb_bs_read_host(hevcb_ctx* ctx, const uint8_t* bytes, int64_t size, const hevcb_bs_op* ops, int n_ops, int32_t* values,
+                                 int64_t* bitpos, int32_t* overrun);
+HEVCB_API int hevcb_bs_write_host(hevcb_ctx* ctx, const hevcb_bs_op* ops, int n_ops, uint8_t* out, int64_t cap, int64_t* bits_written, int32_t* overrun);
+
 /* Header parse of RBSPs the caller already holds (NAL payloads without start codes and without emulation prevention bytes, e.g.
  * what nal_to_rbsp returned): n segments rbsp[rbsp_off[k] .. rbsp_end[k]) of one host buffer (a segment with rbsp_end[k] < 0 is
  * treated as a failed nal_to_rbsp).  `out` holds HOST arrays sized for n / out->cap_pairs; rc[k] is the RBSP size or -1.  An empty
