@@ -153,6 +153,10 @@ def load_library() -> C.CDLL:
     L.hevcb_rewrite_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(ParseBuffers), C.POINTER(EditSet), vp, i64, vp, vp, vp, vp]
     L.hevcb_field_index.restype = i64
     L.hevcb_field_index.argtypes = [C.c_int, C.c_char_p]
+    L.hevcb_reframe_device.restype = C.c_int
+    L.hevcb_reframe_device.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, i64, vp, vp, vp]
+    L.hevcb_lenpref_index_device.restype = C.c_int
+    L.hevcb_lenpref_index_device.argtypes = [vp, vp, i64, C.c_int, vp, i64, vp, vp, i64, vp, vp]
     L.hevcb_bs_read_host.restype = C.c_int
     L.hevcb_bs_read_host.argtypes = [vp, vp, i64, C.POINTER(BsOp), C.c_int, vp, vp, vp]
     L.hevcb_bs_write_host.restype = C.c_int

@@ -217,6 +217,49 @@ class Context:
                                               _np_ptr(out), out_cap, _np_ptr(out_off), C.byref(sm)))
         return out[: sm.out_bytes], out_off, int(sm.n_inserted)
 
+    # ---- length-prefixed framing <-> Annex-B ------------------------------------------------------
+    def reframe_device(self, buf, nal_start, nal_end, n_nals=None, start_code_len=0, len_size=0, out_cap=None, sync=True):
+        """Copies the NAL units buf[nal_start[k]:nal_end[k]] behind a start code (start_code_len 3 / 4) or a big-endian length
+        of len_size bytes (hevcb_reframe_device).  Returns dict(out, out_off, summary [, out_bytes])."""
+        import torch
+
+        n = int(nal_start.numel() if n_nals is None else n_nals)
+        dev = buf.device
+        if out_cap is None:
+            out_cap = int((nal_end[:n] - nal_start[:n]).clamp(min=0).sum().item()) + (start_code_len + len_size) * n + 64 if n else 64
+        out = dict(out=torch.empty(out_cap + 16, dtype=torch.uint8, device=dev), out_off=torch.empty(n + 1, dtype=torch.int64, device=dev),
+                   summary=torch.zeros(4, dtype=torch.int64, device=dev))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.hevcb_reframe_device(self._h, buf.data_ptr(), nal_start.data_ptr(), nal_end.data_ptr(), n, start_code_len, len_size,
+                                                 out["out"].data_ptr(), out_cap, out["out_off"].data_ptr(), out["summary"].data_ptr(), stream))
+        if sync:
+            s = out["summary"].cpu().numpy()
+            out["out_bytes"] = int(s[1])
+            if int(s[3]) & 0xFFFFFFFF:
+                raise HevcbError(-104, f"{out['out_bytes']} output bytes exceed out_cap {out_cap}")
+        return out
+
+    def lenpref_index_device(self, buf, size=None, len_size=4, sample_off=None, cap_nals=None):
+        """NAL extents of length-prefixed data (hevcb_lenpref_index_device).  sample_off: int64 CUDA tensor of n_samples + 1
+        boundaries or None.  Returns (nal_start, nal_end, n_nals, n_bad_samples)."""
+        import torch
+
+        size = int(buf.numel() if size is None else size)
+        dev = buf.device
+        if cap_nals is None:
+            cap_nals = size // (len_size + 1) + 8
+        ns = torch.empty(cap_nals, dtype=torch.int64, device=dev)
+        ne = torch.empty(cap_nals, dtype=torch.int64, device=dev)
+        tot = torch.zeros(2, dtype=torch.int64, device=dev)
+        n_samples = int(sample_off.numel() - 1) if sample_off is not None else 1
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.hevcb_lenpref_index_device(self._h, buf.data_ptr(), size, len_size, sample_off.data_ptr() if sample_off is not None else None,
+                                                       n_samples, ns.data_ptr(), ne.data_ptr(), cap_nals, tot.data_ptr(), stream))
+        t = tot.cpu().numpy()
+        if int(t[0]) > cap_nals:
+            raise HevcbError(-104, f"{int(t[0])} NALs exceed cap_nals {cap_nals}")
+        return ns, ne, int(t[0]), int(t[1])
+
     # ---- batched header parse -----------------------------------------------------------------
     def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False):
         """Header parse of every NAL found by scan_strip_device (device resident).  Returns a dict of torch tensors

@@ -360,6 +360,23 @@ HEVCB_API int hevcb_apply_patches_device(hevcb_ctx* ctx, const hevcb_stitch_resu
     return HEVCB_OK;
 }
 
+HEVCB_API int hevcb_reframe_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, int64_t n_nals,
+                                   int start_code_len, int len_size, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                                   hevcb_insert_summary* d_summary, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_frame(ctx, d_buf, d_nal_start, d_nal_end, n_nals, start_code_len, len_size, d_out, out_cap, d_out_off, d_summary, (cudaStream_t)stream);
+}
+
+HEVCB_API int hevcb_lenpref_index_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int len_size, const int64_t* d_sample_off, int64_t n_samples,
+                                         int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, int64_t* d_total, void* stream)
+{
+    if (!ctx) { return HEVCB_E_ARG; }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return hevcb_launch_lenpref_index(ctx, d_buf, size, len_size, d_sample_off, n_samples, d_nal_start, d_nal_end, cap_nals, d_total, (cudaStream_t)stream);
+}
+
 HEVCB_API int hevcb_rewrite_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, const int64_t* d_nal_start, const int64_t* d_nal_end,
                                    const uint8_t* d_rbsp, const int64_t* d_rbsp_off, const int64_t* d_rbsp_end, int64_t n_nals,
                                    const hevcb_parse_buffers* parsed, const hevcb_edit_set* edits, uint8_t* d_out, int64_t out_cap,

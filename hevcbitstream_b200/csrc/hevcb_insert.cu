@@ -141,7 +141,39 @@ struct AssembleParts {
     const uint8_t* b_base; const int64_t* b_off; const int64_t* b_end;       // escaped, continues the state of A
     int sc_len;      // start code written in front of every NAL (0: none)
     int skip_neg_b;  // hevcb_insert semantics: b_end < 0 => the NAL emits nothing at all
+    int len_size;    // 1 / 2 / 4: a big-endian length of the NAL's bytes is written in front of it (length-prefixed framing); 0: none
 };
+
+// one warp copies `len` bytes between arbitrarily aligned global addresses: 16-byte stores, the source taken as two aligned
+// 16-byte loads funnel-shifted by the (copy-uniform) misalignment between source and destination
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, int lane)
+{
+    if (len <= 0) { return; }
+    int64_t head = (int64_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    if (head > len) { head = len; }
+    if (lane < head) { dst[lane] = src[lane]; }
+    const int64_t nv = (len - head) >> 4;
+    const uint8_t* s0 = src + head;
+    const uint32_t mis = (uint32_t)((uintptr_t)s0 & 15u), q = mis >> 2, sh = (mis & 3u) * 8u;
+    const uint4* sa = reinterpret_cast<const uint4*>(s0 - mis);
+    uint4* da = reinterpret_cast<uint4*>(dst + head);
+    for (int64_t i = lane; i < nv; i += 32) {
+        const uint4 lo = __ldg(sa + i);
+        uint4 o4 = lo;
+        if (mis != 0u) {
+            const uint4 hi = __ldg(sa + i + 1); // stays inside the 16-byte block of the copy's last source byte
+            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            uint32_t x[5];
+#pragma unroll
+            for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[e + 3]; }
+            o4.x = __funnelshift_r(x[0], x[1], sh); o4.y = __funnelshift_r(x[1], x[2], sh);
+            o4.z = __funnelshift_r(x[2], x[3], sh); o4.w = __funnelshift_r(x[3], x[4], sh);
+        }
+        da[i] = o4;
+    }
+    const int64_t done = head + (nv << 4);
+    if (lane < len - done) { dst[done + lane] = src[done + lane]; }
+}
 
 // insertions of one escaped part (count pass)
 template <int kInsAhead>
@@ -300,7 +332,7 @@ __global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const Assembl
         const bool split = (bend - boff >= kSplitMin) && split_flag[k] != 0; // part B is counted piece by piece (extras_count_kernel)
         if (!split) { total += count_part(P.b_base, boff, bend, lane, run_m); }
         if (lane == 0) {
-            out_size[k] = (int64_t)P.sc_len + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) +
+            out_size[k] = (int64_t)P.sc_len + (int64_t)P.len_size + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) +
                           ((bend > boff && !split) ? bend - boff : 0) + (int64_t)total;
         }
         local_ins += total;
@@ -407,9 +439,14 @@ __global__ void __launch_bounds__(kInsThreads) insert_write_kernel(const Assembl
         if (out_off[k + 1] > out_cap) { continue; } // capacity overflow is reported by the summary
         if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
         o += P.sc_len;
+        if (P.len_size) { // big-endian length of what follows
+            const uint64_t nbytes = (uint64_t)(out_off[k + 1] - out_off[k] - P.len_size);
+            if (lane < P.len_size) { out[o + lane] = (uint8_t)(nbytes >> (8 * (P.len_size - 1 - lane))); }
+            o += P.len_size;
+        }
         if (P.raw_off) {
             const int64_t roff = P.raw_off[k], rend = P.raw_end[k];
-            for (int64_t i = roff + lane; i < rend; i += 32) { out[o + (i - roff)] = P.raw_base[i]; }
+            warp_copy_bytes(out + o, P.raw_base + roff, rend - roff, lane);
             if (rend > roff) { o += rend - roff; }
         }
         uint32_t run_m = 0;
@@ -594,6 +631,7 @@ int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_
     P.b_base = d_rbsp; P.b_off = d_off; P.b_end = d_end;
     P.sc_len = sc_len;
     P.skip_neg_b = 1;
+    P.len_size = 0;
     return launch_assemble(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
 }
 
@@ -612,5 +650,97 @@ int hevcb_launch_assemble3(hevcb_ctx* ctx, const uint8_t* raw_base, const int64_
     P.b_base = b_base; P.b_off = b_off; P.b_end = b_end;
     P.sc_len = 0;
     P.skip_neg_b = 0;
+    P.len_size = 0;
     return launch_assemble(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
+}
+
+// ---- length-prefixed framing (ISO/IEC 14496-15 sample format: hvcC / MP4 / Matroska) <-> Annex-B -----------------------------
+// A NAL unit is the same bytes in both framings (emulation prevention included); only what separates the units differs: a
+// start code in front (Annex-B) or a big-endian byte count of 1, 2 or 4 bytes (lengthSizeMinusOne + 1).  Both directions are
+// "copy the NAL bytes verbatim behind a freshly written prefix": the verbatim part of the assembly above.
+int hevcb_launch_frame(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, int64_t n, int sc_len, int len_size,
+                       uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    if (n < 0 || !d_out_off || !d_summary || (n > 0 && (!d_buf || !d_nal_start || !d_nal_end || !d_out)) || (sc_len != 0 && sc_len != 3 && sc_len != 4) ||
+        (len_size != 0 && len_size != 1 && len_size != 2 && len_size != 4) || (sc_len != 0 && len_size != 0)) {
+        HEVCB_SET_ERR(ctx, "hevcb frame conversion: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    AssembleParts P;
+    P.raw_base = d_buf; P.raw_off = d_nal_start; P.raw_end = d_nal_end;
+    P.a_base = nullptr; P.a_off = nullptr; P.a_end = nullptr;
+    P.b_base = nullptr; P.b_off = nullptr; P.b_end = nullptr;
+    P.sc_len = sc_len;
+    P.skip_neg_b = 0;
+    P.len_size = len_size;
+    return launch_assemble(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
+}
+
+namespace {
+// Walks the length fields of one sample (a run of length-prefixed NAL units that ends at a known position: the sample table of the
+// container knows it).  The fields chain -- every length tells where the next one is -- so a sample is walked by one thread; the
+// samples are independent.  count pass: NALs per sample (negative: the chain runs past the sample's end); fill pass: extents.
+template <bool kFill>
+__global__ void __launch_bounds__(256) lenpref_walk_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ sample_off, int64_t n_samples, int64_t size,
+                                                           int len_size, int64_t* __restrict__ count, const int64_t* __restrict__ first, int64_t* __restrict__ nal_start,
+                                                           int64_t* __restrict__ nal_end, int64_t cap_nals, unsigned long long* __restrict__ n_bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) { return; }
+    int64_t p = sample_off ? sample_off[i] : 0;
+    int64_t end = sample_off ? sample_off[i + 1] : size;
+    if (p < 0) { p = 0; }
+    if (end > size) { end = size; }
+    int64_t k = kFill ? first[i] : 0, n = 0;
+    bool bad = false;
+    while (p < end) {
+        if (p + len_size > end) { bad = true; break; }
+        uint64_t len = 0;
+        for (int b = 0; b < len_size; b++) { len = (len << 8) | buf[p + b]; }
+        p += len_size;
+        if ((int64_t)len > end - p) { bad = true; break; }
+        if (kFill && k < cap_nals) { nal_start[k] = p; nal_end[k] = p + (int64_t)len; }
+        k++; n++;
+        p += (int64_t)len;
+    }
+    if (!kFill) {
+        count[i] = n;
+        if (bad) { atomicAdd(n_bad, 1ull); }
+    }
+}
+} // namespace
+
+// length-prefixed samples -> NAL extents (d_nal_start / d_nal_end, positions of the NAL bytes inside d_buf); d_total: [0] NALs found,
+// [1] samples whose length chain is broken (the NALs in front of the break are kept)
+int hevcb_launch_lenpref_index(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int len_size, const int64_t* d_sample_off, int64_t n_samples,
+                               int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, int64_t* d_total, cudaStream_t stream)
+{
+    if (size < 0 || n_samples < 0 || (len_size != 1 && len_size != 2 && len_size != 4) || !d_total || (size > 0 && !d_buf) ||
+        (cap_nals > 0 && (!d_nal_start || !d_nal_end)) || cap_nals < 0) {
+        HEVCB_SET_ERR(ctx, "hevcb_lenpref_index: invalid argument");
+        return HEVCB_E_ARG;
+    }
+    const int64_t ns = d_sample_off ? n_samples : 1; // no sample table: the whole buffer is one sample (a serial walk)
+    const int64_t nb = (ns + kSTile - 1) / kSTile;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_cnt = 0, o_first = up((size_t)(ns + 1) * 8), o_bs = o_first + up((size_t)(ns + 2) * 8), need = o_bs + up((size_t)(nb + 2) * 8) + 256;
+    int rc = hevcb_reserve(ctx, &ctx->insert_scratch, need);
+    if (rc != HEVCB_OK) { return rc; }
+    uint8_t* sb = reinterpret_cast<uint8_t*>(ctx->insert_scratch.p);
+    int64_t* cnt = reinterpret_cast<int64_t*>(sb + o_cnt);
+    int64_t* first = reinterpret_cast<int64_t*>(sb + o_first);
+    long long* bs = reinterpret_cast<long long*>(sb + o_bs);
+    unsigned long long* n_bad = reinterpret_cast<unsigned long long*>(d_total + 1);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(d_total, 0, 16, stream));
+    if (ns == 0) { return HEVCB_OK; }
+    const unsigned g = (unsigned)((ns + 255) / 256);
+    lenpref_walk_kernel<false><<<g, 256, 0, stream>>>(d_buf, d_sample_off, ns, size, len_size, cnt, nullptr, nullptr, nullptr, 0, n_bad);
+    sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(cnt, ns, bs);
+    sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
+    sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(cnt, ns, bs, nb, first);
+    lenpref_walk_kernel<true><<<g, 256, 0, stream>>>(d_buf, d_sample_off, ns, size, len_size, nullptr, first, d_nal_start, d_nal_end, cap_nals, nullptr);
+    HEVCB_CUDA(ctx, cudaMemcpyAsync(d_total, first + ns, 8, cudaMemcpyDeviceToDevice, stream));
+    ctx->launches += 5;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
 }

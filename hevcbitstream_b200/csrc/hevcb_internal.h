@@ -100,6 +100,11 @@ int hevcb_launch_scan_strip_shard(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t 
                                   int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, uint8_t* d_rbsp, int64_t* d_rbsp_off,
                                   int64_t* d_rbsp_end, hevcb_shard_summary* d_summary, cudaStream_t stream);
 
+int hevcb_launch_frame(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, int64_t n, int sc_len, int len_size,
+                       uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream);
+int hevcb_launch_lenpref_index(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int len_size, const int64_t* d_sample_off, int64_t n_samples,
+                               int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, int64_t* d_total, cudaStream_t stream);
+
 int hevcb_launch_assemble3(hevcb_ctx* ctx, const uint8_t* raw_base, const int64_t* raw_off, const int64_t* raw_end, const uint8_t* a_base,
                            const int64_t* a_off, const int64_t* a_end, const uint8_t* b_base, const int64_t* b_off, const int64_t* b_end, int64_t n,
                            uint8_t* d_out, int64_t out_cap, int64_t* d_out_off, hevcb_insert_summary* d_summary, cudaStream_t stream);

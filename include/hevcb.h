@@ -220,6 +220,27 @@ HEVCB_API int hevcb_insert_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t rbs
                                 int64_t n_nals, int start_code_len, uint8_t* out, int64_t out_cap, int64_t* out_off,
                                 hevcb_insert_summary* summary);
 
+/* ---- length-prefixed framing <-> Annex-B -----------------------------------------------------------
+ *
+ * The step either side of the path in real pipelines: containers (MP4 / hvcC, Matroska) store every NAL unit behind a
+ * big-endian byte count of 1, 2 or 4 bytes (lengthSizeMinusOne + 1, ISO/IEC 14496-15) instead of a start code.  The NAL bytes
+ * themselves are identical in both framings (emulation prevention included), so a conversion copies them verbatim behind a
+ * freshly written prefix, on the device, from extents that are already there:
+ *   Annex-B -> length-prefixed   extents = nal_start / nal_end of hevcb_scan_strip_*;        start_code_len 0, len_size 1 | 2 | 4
+ *   length-prefixed -> Annex-B   extents = hevcb_lenpref_index_device (below);               start_code_len 3 | 4, len_size 0
+ * out[out_off[k] ..) = prefix, then buf[nal_start[k] .. nal_end[k]); out_off has n + 1 entries.  A NAL longer than the length
+ * field can express is written with the low bytes of its length (the caller chose len_size).  `buf` must be readable up to the
+ * next 16-byte boundary behind its last byte. */
+HEVCB_API int hevcb_reframe_device(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_nal_start, const int64_t* d_nal_end, int64_t n_nals,
+                                   int start_code_len, int len_size, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                                   hevcb_insert_summary* d_summary, void* stream);
+/* Finds the NAL units of length-prefixed data.  The length fields chain (each tells where the next one is), so the walk is
+ * sequential inside a sample; samples are independent and walked in parallel: d_sample_off[n_samples + 1] = the sample
+ * boundaries the container's sample table provides (NULL: the whole buffer is one sample).  d_total[0] = NALs found (extents
+ * beyond cap_nals are not stored), d_total[1] = samples whose chain runs past their end (their NALs up to the break are kept). */
+HEVCB_API int hevcb_lenpref_index_device(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, int len_size, const int64_t* d_sample_off, int64_t n_samples,
+                                         int64_t* d_nal_start, int64_t* d_nal_end, int64_t cap_nals, int64_t* d_total, void* stream);
+
 /* ---- batched header parse ----------------------------------------------------------------------
  *
  * read_hevc_nal_unit (hevc_stream.c:155-241) for every NAL of a stream at once, on the results of

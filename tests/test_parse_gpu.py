@@ -85,3 +85,35 @@ def test_device_api_one_million_headers(ctx):
     sl = idx.kind == 4
     assert sl.sum() == out["n_slices"]
     assert set(np.unique(cols[0][sl]).tolist()) <= {0, 1, 2}
+
+
+def test_cicc_o3_build_of_the_parser_matches_the_reference():
+    """hevcb_parse.cu is shipped with the NVVM optimiser at -O1 (csrc/Makefile): in round 1 the default -O3 made a few NALs parse
+    differently and the cause was never found.  With the current source the divergence no longer reproduces (tools/diag_cicc_o3.py:
+    0 of ~44 000 NALs differ); this test keeps the hazard tracked: when the diagnosis build exists (`make -C hevcbitstream_b200/csrc
+    o3`, ~9 minutes of cicc), the parity suite runs against it in a separate process."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "hevcbitstream_b200", "libhevcb200_cicc_o3.so")
+    if not os.path.exists(lib):
+        pytest.skip("diagnosis build libhevcb200_cicc_o3.so not present")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import hevcbitstream_b200 as hb\n"
+        "from oracle import ref\n"
+        "from tests import parse_check\n"
+        "ctx = hb.Context(0)\n"
+        "tot = 0\n"
+        "for seed in (1, 2, 3, 4, 5, 6, 21):\n"
+        "    s = ref.gen_stream(seed=seed, profile=1, n_slices=6000, payload_min=1, payload_max=64, zero_heavy_pct=20, extra_zero_pct=10, ps_period=37, unsupported_pct=5)\n"
+        "    size = s.size - ref.PAD\n"
+        "    idx = ctx.index_host(s[:size], size=size)\n"
+        "    n, ok = parse_check.compare_index(s, size, idx, tag='o3-%%d' %% seed)\n"
+        "    tot += n\n"
+        "print('O3_PARITY_OK', tot)\n" % root
+    )
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, HEVCB_LIB=lib), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "O3_PARITY_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]

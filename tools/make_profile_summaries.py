@@ -1,5 +1,6 @@
-"""Regenerates profiles/r1_scan_strip_ncu.{md,json} and profiles/r1_launch_summary.md from the scratch captures in gpurun_out/
-(scan_r1_aw_final.ncu-rep, r1_launches.csv) and profiles/r1_bench.json.  Run in the build container after a gpurun capture."""
+"""Regenerates the round-2 profile summaries under profiles/ from the scratch captures in gpurun_out/ (ncu --set full reports of
+hevcb_scan_strip_kernel on the nal16k / nal64 / epb_dense_4k bench workloads, the ncu launch list of a bench run) and
+profiles/r2_bench.json.  Run in the build container after the gpurun captures (commands are quoted in the outputs)."""
 import collections
 import csv
 import json
@@ -7,54 +8,96 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep = os.path.join(ROOT, "gpurun_out", "scan_r1_aw_final.ncu-rep")
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
-g = lambda k: (vals[hdr.index(k)], units[hdr.index(k)]) if k in hdr else ("n/a", "")
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
-        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
-tab = "\n".join(f"| `{k}` | {g(k)[0]} {g(k)[1]} |" for k in want)
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1, "us": 1e-3, "msecond": 1, "usecond": 1e-3}
 
 
-def num(k):
-    v, u = g(k)
-    v = float(v.replace(",", ""))
-    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1, "us": 1e-3, "msecond": 1, "usecond": 1e-3}.get(u, 1)
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    g = lambda k: (vals[hdr.index(k)], units[hdr.index(k)]) if k in hdr else ("n/a", "")
+    num = lambda k: float(g(k)[0].replace(",", "")) * UNIT.get(g(k)[1], 1)
+    return g, num
 
 
-rd, wr, ms = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gpu__time_duration.sum")
-b = json.load(open(os.path.join(ROOT, "profiles", "r1_bench.json")))
-alg = b["roofline"]["algorithmic_bytes_per_launch"]
-cmd = "ncu --set full --clock-control none --import-source on -k regex:hevcb_scan_strip_kernel -s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-sweep --no-parse --no-rewrite --no-insert"
-md = f"""# ncu --set full, hevcb_scan_strip_kernel, round 1 (analyser / writer design)
+def top_lines(rep, n=8):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    res, hdr, fil = [], None, ""
+    for r in rows:
+        if len(r) >= 2 and r[0] == "File Path":
+            fil = r[1]
+        elif len(r) > 6 and r[0] == "Line No":
+            hdr = r
+            si = r.index("# Samples")
+        elif hdr and len(r) > si and r[0].isdigit():
+            try:
+                res.append((int(r[si]), os.path.basename(fil), int(r[0]), r[1].strip()[:90]))
+            except ValueError:
+                pass
+    tot = sum(x[0] for x in res) or 1
+    return tot, sorted(res, reverse=True)[:n]
 
-`{cmd}` on one B200 (4 GiB buffer, 16 KiB NALs, 258 048 NALs).
-Report file: `gpurun_out/scan_r1_aw_final.ncu-rep` (scratch; numbers copied here by `tools/make_profile_summaries.py`).  Times under ncu are cold-cache and serialised; the bench value (CUDA events, no profiler) is in `profiles/r1_bench.json`.
+
+bench = json.load(open(os.path.join(ROOT, "profiles", "r2_bench.json")))
+alg16 = bench["roofline"]["algorithmic_bytes_per_launch"]
+sections = []
+for wl, title in (("nal16k", "headline: 4 GiB, 16 KiB NALs"), ("nal64", "4 GiB, 64-byte NALs (every chunk needs the exact masks)"),
+                  ("dense", "4 GiB, EPB-dense payload 00 00 03 01 (a quarter of the bytes removed)")):
+    rep = os.path.join(ROOT, "gpurun_out", f"r2_scan_{wl}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    g, num = raw(rep)
+    rd, wr, ms = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gpu__time_duration.sum")
+    tab = "\n".join(f"| `{k}` | {g(k)[0]} {g(k)[1]} |" for k in WANT)
+    tot, tops = top_lines(rep)
+    tl = "\n".join(f"| {100 * c / tot:.1f} % | `{f}:{ln}` | `{src}` |" for c, f, ln, src in tops)
+    wname = {"nal16k": "nal16k", "nal64": "nal64", "dense": "epb_dense_4k"}[wl]
+    cmd = (f"ncu --set full --clock-control none --import-source on -k regex:hevcb_scan_strip_kernel -s 3 -c 1 python bench.py --workload {wname} --steps 1 "
+           "--warmup 3 --no-sweep --no-parse --no-rewrite --no-insert --no-cpu-extras")
+    sec = f"""## {title}
+
+`{cmd}` (report: `gpurun_out/r2_scan_{wl}.ncu-rep`, scratch).
 
 | metric | value |
 |---|---|
 {tab}
 
-DRAM traffic per launch = read + write = {rd / 1e9:.3f} + {wr / 1e9:.3f} = **{(rd + wr) / 1e9:.3f} GB**; algorithmic bytes (N_in + N_rbsp + 24*NALs) = {alg / 1e9:.3f} GB -> traffic / algorithmic = {(rd + wr) / alg:.3f}.
-The image is written once.  The input is loaded twice (once by an analyser CTA, once by a writer CTA) but the second load is served by L2: the analysers stay within a 1100-tile (34 MiB) window of the writers' progress counter.  Measured sensitivity (same command, `HEVCB_SCAN_WINDOW`, 2 stages per CTA): 1200 tiles -> DRAM reads 1.27x the input, 1100 -> 1.11x, both at the same speed within 1 % (the kernel is not DRAM-bound); at 1050 and below the pipeline (2 tiles in flight per CTA in both roles = 592 tiles, plus one scanner batch of 320) is throttled.
-
-Where the time goes now (warp-state sampling of this capture, `--page source`): 31 % of all samples are the analysers' worker warps waiting for their bulk copies (`mbarrier.try_wait` loop), 15 % the writers' workers at the \"prefix ready\" barrier, 2 % the analysers' control warps polling the writers' progress (the L2 window); no single arithmetic instruction holds more than 1.5 %.  Issue slots are ~37 % used: the pass is bound by the latency of the memory system under the mixed load (the bare load pipeline alone sustains 4.0 TB/s, see DESIGN 4.1), not by DRAM bandwidth or instruction issue.  The previous single-role pipeline spent 38 % of all warp samples at one CTA barrier in lock-step with the scanner (`profiles/r1_scan_strip_ncu_v1.md`).
-
-SASS evidence of the async-copy path: `UBLKCP.S.G` (cp.async.bulk), `SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `REDUX`, `VOTE`, `LDG.E.128.STRONG.GPU` (tile-state polls) in `cuobjdump -sass hevcbitstream_b200/libhevcb200.so`.
+DRAM traffic per launch: read {rd / 1e9:.3f} GB + write {wr / 1e9:.3f} GB = **{(rd + wr) / 1e9:.3f} GB**.
 """
-open(os.path.join(ROOT, "profiles", "r1_scan_strip_ncu.md"), "w").write(md)
-json.dump({"kernel": "hevcb_scan_strip_kernel", "command": cmd, "workload": "nal16k", "size_gib": 4.0, "dram_bytes_read": rd, "dram_bytes_write": wr,
-           "traffic_bytes_per_launch": rd + wr, "duration_ms_under_ncu": ms}, open(os.path.join(ROOT, "profiles", "r1_scan_strip_ncu.json"), "w"), indent=1)
-print("scan:", rd, wr, ms, (rd + wr) / alg)
+    if wl == "nal16k":
+        sec += (f"Algorithmic bytes (N_in + N_rbsp + 24 x NALs) = {alg16 / 1e9:.3f} GB -> traffic / algorithmic = **{(rd + wr) / alg16:.3f}**: the input is read from "
+                "HBM once (the tile stays in shared memory until its prefix has arrived; the L2 prefetch pulls every byte exactly once), the image is written once.\n")
+        json.dump({"kernel": "hevcb_scan_strip_kernel", "command": cmd, "workload": "nal16k", "size_gib": 4.0, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "traffic_bytes_per_launch": rd + wr, "duration_ms_under_ncu": ms}, open(os.path.join(ROOT, "profiles", "r2_scan_strip_ncu.json"), "w"), indent=1)
+    sec += f"\nWarp-state samples by source line (top {len(tops)} of {tot} samples):\n\n| share | line | source |\n|---|---|---|\n{tl}\n"
+    sections.append(sec)
+sw = bench.get("sweep", {})
+swt = "\n".join(f"| {k} | {v['input_GBps']} | {v['algorithmic_GBps']} | {v['frac_of_peak']} |" for k, v in sw.items())
+md = f"""# ncu --set full, hevcb_scan_strip_kernel, round 2 (single-pass ring pipeline)
 
-rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_launches.csv"))) if r]
+Times under ncu are cold-cache and serialised; the bench values (CUDA events, no profiler) are in `profiles/r2_bench.json`:
+headline {bench['value']:.0f} GB/s of input = {bench['roofline']['achieved']:.0f} GB/s algorithmic = **{bench['roofline']['frac']:.3f}** of the measured HBM peak ({bench['roofline']['peak']} GB/s).
+
+| workload | input GB/s | algorithmic GB/s | fraction of measured peak |
+|---|---|---|---|
+{swt}
+
+""" + "\n".join(sections) + """
+SASS evidence of the async-copy path (`cuobjdump -sass hevcbitstream_b200/libhevcb200.so`): `UBLKCP.S.G` (cp.async.bulk global -> shared), `UBLKPF` (cp.async.bulk.prefetch.L2),
+`SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `REDUX`, `VOTE`, `LDG.E.128.STRONG.GPU` / `STG.E.128.STRONG.GPU` (tile-state words).
+"""
+open(os.path.join(ROOT, "profiles", "r2_scan_strip_ncu.md"), "w").write(md)
+
+rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r2_launches.csv"))) if r]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[hi]
 c = {h: i for i, h in enumerate(hdr)}
@@ -70,9 +113,10 @@ for r in rows[hi + 1:]:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-lines = ["# ncu launch list summary, round 1 (analyser / writer scan kernel)", "",
-         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 2 --warmup 3 --no-sweep --e2e-gib 0.25` (B200, cold-cache serialised launch times: compare SHARES, not absolutes).",
-         "Raw CSV: `profiles/r1_launches.csv` (warm-up + timed steps of the headline workload, then the e2e, parse, insert and rewrite sections of the bench).", "",
+lines = ["# ncu launch list summary, round 2", "",
+         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 2 --warmup 3 --no-sweep --e2e-gib 0.25 --no-cpu-extras` "
+         "(B200, cold-cache serialised launch times: compare SHARES, not absolutes).",
+         "Raw CSV: `profiles/r2_launches.csv` (warm-up + timed steps of the headline workload, then the e2e, parse, insert and rewrite sections of the bench).", "",
          "| kernel | launches | total us | share |", "|---|---|---|---|"]
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"| `{k}` | {n} | {us:.1f} | {100 * us / tot:.1f}% |")
@@ -82,5 +126,6 @@ lines += ["", f"Per scan step the launches are: memset (tile states), `hevcb_sca
           f"({per('hevcb_scan_strip_kernel'):.1f} us on average over the differently sized scans of the run, cooperative), `hevcb_scan_emit_kernel` ({per('hevcb_scan_emit_kernel'):.1f} us), "
           f"`hevcb_scan_finalize_kernel` ({per('hevcb_scan_finalize_kernel'):.1f} us): the strip kernel is {100 * per('hevcb_scan_strip_kernel') / step:.1f}% of a step's kernel time, "
           "which is the share `bench.py` attributes the roofline to (its CUDA-event time covers all of them)."]
-open(os.path.join(ROOT, "profiles", "r1_launch_summary.md"), "w").write("\n".join(lines) + "\n")
-print("\n".join(lines[7:14]))
+open(os.path.join(ROOT, "profiles", "r2_launch_summary.md"), "w").write("\n".join(lines) + "\n")
+print(md[:1500])
+print("\n".join(lines[7:16]))
