@@ -42,6 +42,7 @@ class ParseBuffers(C.Structure):
         ("rc", C.c_void_p), ("nal_hdr", C.c_void_p), ("kind", C.c_void_p), ("ubflag", C.c_void_p), ("hdr_end", C.c_void_p),
         ("cols", C.c_void_p), ("pair_off", C.c_void_p), ("pair_field", C.c_void_p), ("pair_value", C.c_void_p), ("cap_pairs", C.c_int64),
         ("pair_pos", C.c_void_p),  # None: plain parse; an array: the trace (read_debug) variant
+        ("flags", C.c_uint32), ("pad", C.c_uint32),  # HEVCB_PARSE_AUX = 1: extension mode (AUD / EOS / EOB / filler / SEI are parsed)
     ]
 
 

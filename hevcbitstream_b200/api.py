@@ -261,7 +261,7 @@ class Context:
         return ns, ne, int(t[0]), int(t[1])
 
     # ---- batched header parse -----------------------------------------------------------------
-    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False):
+    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False, aux=False):
         """Header parse of every NAL found by scan_strip_device (device resident).  Returns a dict of torch tensors
         (rc, nal_hdr, kind, ubflag, hdr_end, cols[8][n], pair_off[n+1], pair_field, pair_value) and `summary`.
         trace=True: the read_debug variant (include/hevcb.h): the lists hold what read_debug_hevc_nal_unit prints, with
@@ -285,6 +285,8 @@ class Context:
         if trace:
             out["pair_pos"] = torch.empty(cap_pairs, dtype=torch.int32, device=dev)
             pb.pair_pos = out["pair_pos"].data_ptr()
+        if aux:  # extension mode: AUD / EOS / EOB / filler / SEI NALs are parsed instead of returning -1 (kind 5)
+            pb.flags = 1
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self._L.hevcb_parse_device(self._h, buf.data_ptr(), scan.nal_start.data_ptr(), scan.nal_end.data_ptr(), scan.rbsp.data_ptr(),
                                                scan.rbsp_off.data_ptr(), scan.rbsp_end.data_ptr(), n, C.byref(pb), out["summary"].data_ptr(), stream))

@@ -580,6 +580,7 @@ HEVCB_API int hevcb_index_host_chain(hevcb_ctx* ctx, const uint8_t* buf, int64_t
     d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
     d.cap_pairs = idx->p.cap_pairs;
     d.pair_pos = idx->p.pair_pos ? reinterpret_cast<uint32_t*>(ctx->h_p[9].p) : nullptr; // host array given: the trace variant
+    d.flags = idx->p.flags; d.pad = 0;
     rc = hevcb_launch_parse(ctx, d_in, d_ns, d_ne, d_rbsp, d_ro, d_re, n, &d, d_psum, chain, st);
     if (rc != HEVCB_OK) { return rc; }
     HEVCB_CUDA(ctx, cudaMemcpyAsync(p_psum, d_psum, sizeof(hevcb_parse_summary), cudaMemcpyDeviceToHost, st));
@@ -667,6 +668,7 @@ HEVCB_API int hevcb_parse_rbsp_host(hevcb_ctx* ctx, const uint8_t* rbsp, int64_t
     d.pair_value = reinterpret_cast<int32_t*>(ctx->h_p[8].p);
     d.cap_pairs = out->cap_pairs;
     d.pair_pos = out->pair_pos ? reinterpret_cast<uint32_t*>(ctx->h_p[9].p) : nullptr;
+    d.flags = out->flags; d.pad = 0;
     // the RBSP doubles as "the NAL bytes": rc[k] is then the RBSP size (buf_size 1 keeps the trailing-00-00-03 rule, which is about
     // bytes the caller stripped, away from it)
     hevcb_parse_chain ch;

@@ -163,7 +163,7 @@ const char* const kSpecialNames[] = {
     "general_reserved_zero_34bits", "general_reserved_zero_43bits", "general_reserved_zero_bit", "reserved_zero_xxbits",
     "sub_layer_reserved_zero_34bits", "sub_layer_reserved_zero_43bits", "sub_layer_reserved_zero_bit", "rbsp_stop_one_bit",
     "rbsp_alignment_zero_bit", "alignment_bit_equal_to_one", "alignment_bit_equal_to_zero", "slice_reserved_flag",
-    "slice_segment_header_extension_data_byte", "" /* HEVCB_TRACE_OPEN_LINE */,
+    "slice_segment_header_extension_data_byte", "" /* HEVCB_TRACE_OPEN_LINE */, "ff_byte",
 };
 
 // innermost member that holds field index f of the struct described by (tbl, cnt)
@@ -199,6 +199,8 @@ extern "C" HEVCB_API int hevcb_trace_name(int kind, uint32_t code, char* out, in
         case HEVCB_KIND_SPS: tbl = tbl_hevc_sps_t; cnt = cnt_hevc_sps_t; break;
         case HEVCB_KIND_PPS: tbl = tbl_hevc_pps_t; cnt = cnt_hevc_pps_t; break;
         case HEVCB_KIND_SLICE: tbl = tbl_hevc_slice_header_t; cnt = cnt_hevc_slice_header_t; break;
+        case HEVCB_KIND_AUX: // extension mode: only the access unit delimiter has a printed struct member (hevc_stream.c:2707)
+            return code == HEVCB_AUX_AUD_PIC_TYPE ? snprintf(out, (size_t)cap, "h->aud->primary_pic_type") : -1;
         default: return -1;
     }
     const FieldDesc *owner = nullptr, *m = nullptr;

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int kCls_None = 0, kCls_Vps = 1, kCls_Sps = 2, kCls_Pps = 3, kCls_Slice = 4, kCls_Other = 5, kCls_StripErr = 255;
+constexpr int kCls_None = 0, kCls_Vps = 1, kCls_Sps = 2, kCls_Pps = 3, kCls_Slice = 4, kCls_Other = 5, kCls_Aux = 6, kCls_StripErr = 255;
 
 // ---- generic 3-kernel scan over a per-element functor -------------------------------------------------------
 constexpr int kScanThreads = 512;
@@ -151,7 +151,7 @@ int run_scan(hevcb_ctx* ctx, F f, int64_t n, TOut* out, long long* block_sums /*
 __global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t* __restrict__ rbsp_off, const int64_t* __restrict__ rbsp_end,
                                 int64_t n, uint8_t* __restrict__ cls, int32_t* __restrict__ nal_hdr, int32_t* __restrict__ rc,
                                 uint8_t* __restrict__ kind, uint8_t* __restrict__ ubflag, int32_t* __restrict__ cnt, int32_t* __restrict__ hdr_end,
-                                uint32_t* __restrict__ sortkey)
+                                uint32_t* __restrict__ sortkey, uint32_t flags)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) { return; }
@@ -178,6 +178,7 @@ __global__ void classify_kernel(const uint8_t* __restrict__ rbsp, const int64_t*
     else if (type == 32u) { c = (uint8_t)kCls_Vps; }
     else if (type == 33u) { c = (uint8_t)kCls_Sps; }
     else if (type == 34u) { c = (uint8_t)kCls_Pps; }
+    else if ((flags & HEVCB_PARSE_AUX) && type >= 35u && type <= 40u) { c = (uint8_t)kCls_Aux; } // extension mode
     cls[k] = c;
     if (c != (uint8_t)kCls_Other) {
         // shape key: NAL type, then the first payload bytes (first_slice_segment_in_pic_flag, ids, slice_type, ... live there):
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
     const int64_t k = a.perm[a.n - 1 - ti]; // shape order, last shape first: the long parameter-set walks start with the first blocks
     const int c = a.cls[k];
     const bool is_ps = (c == kCls_Vps || c == kCls_Sps || c == kCls_Pps);
-    const bool is_slice = (c == kCls_Slice) || (kTrace && c == kCls_Other);
+    const bool is_slice = (c == kCls_Slice) || (c == kCls_Aux) || (kTrace && c == kCls_Other); // no dependencies among these: one pass
     if (!kEmit) {
         if (kSlices ? !is_slice : !is_ps) { return; }
     } else {
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
     typedef hevcb_sink_t<kTrace> SinkT;
     if (!kEmit) {
         SinkT sink{nullptr, nullptr, 0, nullptr};
-        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux);
         a.cnt[k] = (int32_t)sink.n;
         a.kind[k] = (uint8_t)r.kind;
         a.ubflag[k] = (uint8_t)(r.flags & 0xFFu);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
         const int64_t pn = (int64_t)a.cnt[k];
         if (pn == 0 || po + pn > a.cap_pairs) { return; }
         SinkT sink{a.pair_field + po, a.pair_value + po, 0, kTrace ? a.pair_pos + po : nullptr};
-        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r);
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux);
         if (sink.n != (uint32_t)pn) { a.ubflag[k] |= 0x80u; a.cols[k] = (int32_t)r.end_bits; a.cols[a.n + k] = (int32_t)sink.n; } // self-check
     }
 }
@@ -648,7 +649,7 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
 
     const unsigned g128 = (unsigned)((n + 127) / 128);
     classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rbsp, d_rbsp_off, d_rbsp_end, n, cls, out->nal_hdr, out->rc, out->kind,
-                                                                    out->ubflag, cnt, out->hdr_end, sortkey);
+                                                                    out->ubflag, cnt, out->hdr_end, sortkey, out->flags);
     ctx->launches++;
     HEVCB_CUDA(ctx, cudaGetLastError());
     int rcp = hevcb_sort_perm(ctx, sortkey, n, perm, stream);

@@ -141,7 +141,8 @@ enum hevcb_trace_id { // f(n, v) elements and the other lines of the dump that a
     HEVCB_TI_VPS_RESERVED_FFFF, HEVCB_TI_GENERAL_ZERO_34, HEVCB_TI_GENERAL_ZERO_43, HEVCB_TI_GENERAL_ZERO_BIT, HEVCB_TI_RESERVED_ZERO_XX,
     HEVCB_TI_SUB_LAYER_ZERO_34, HEVCB_TI_SUB_LAYER_ZERO_43, HEVCB_TI_SUB_LAYER_ZERO_BIT, HEVCB_TI_RBSP_STOP_ONE, HEVCB_TI_RBSP_ALIGN_ZERO,
     HEVCB_TI_ALIGN_ONE, HEVCB_TI_ALIGN_ZERO, HEVCB_TI_SLICE_RESERVED_FLAG, HEVCB_TI_SH_EXTENSION_DATA_BYTE,
-    HEVCB_TI_OPEN_LINE, // position prefix only, no newline: the "// ERROR" site of ref_pic_list_modification_flag_l1 (hevc_stream.c:3147)
+    HEVCB_TI_OPEN_LINE, // (= 19) position prefix only, no newline: the "// ERROR" site of ref_pic_list_modification_flag_l1 (hevc_stream.c:3147)
+    HEVCB_TI_FF_BYTE, // (= 20) filler data, extension mode
     HEVCB_TI_COUNT
 };
 template <bool kTraceT>
@@ -960,6 +961,58 @@ struct hevcb_walker {
         trailing_bits();
     }
 
+    // ---- extension mode: the NAL types the reference defines readers for but never dispatches (hevc_stream.in.c:499-573; its
+    // switch returns -1 for them, which stays the default).  Fields are reported under kind HEVCB_KIND_AUX with the numbers of
+    // hevcb.h (HEVCB_AUX_*); SEI payload bytes stay in the image, a message is (type, size, offset of its payload in the RBSP).
+    HEVCB_SHD void access_unit_delimiter() // 7.3.2.5, hevc_stream.in.c:549-553
+    {
+        u(HEVCB_AUX_AUD_PIC_TYPE, 3);
+        trailing_bits();
+    }
+    HEVCB_SHD void filler_data() // 7.3.2.8, hevc_stream.in.c:566-573: bs_next_bits(b, 8) == 0xFF (zero bits behind the end)
+    {
+        int32_t n = 0;
+        while ((b.peek32() >> 24) == 0xFFu) { fx(8, 0xFFu, HEVCB_TI_FF_BYTE); n++; }
+        syn(HEVCB_AUX_FD_FF_BYTES, n);
+        trailing_bits();
+    }
+    HEVCB_SHD int32_t ff_coded_number() // _read_ff_coded_number, h264_stream.c:88-98
+    {
+        int32_t n1 = 0;
+        uint32_t n2;
+        do { n2 = b.read_u8(); n1 += (int32_t)n2; } while (n2 == 0xFFu);
+        return n1;
+    }
+    HEVCB_SHD bool more_rbsp_data(int64_t last_one_bit) const // h264_stream.c:62-84
+    {
+        if (b.byte_pos() >= b.size) { return false; }
+        return last_one_bit != b.pos; // the next bit is 0, or it is a 1 that is not the last 1 of the RBSP
+    }
+    HEVCB_SHD void sei_rbsp() // 7.3.2.4 / 7.3.5 (hevc_stream.in.c:499-546 under HAVE_SEI; payload: read_sei_payload, h264_sei.c:75-92)
+    {
+        int64_t last_one = -1; // bit position of the last 1 bit of the RBSP
+        for (int64_t i = b.size - 1; i >= 0; i--) {
+            const uint32_t x = b.base[i];
+            if (x) {
+                int tz = 0;
+                while (!((x >> tz) & 1u)) { tz++; }
+                last_one = i * 8 + (7 - tz);
+                break;
+            }
+        }
+        int32_t count = 0;
+        do {
+            const int32_t type = ff_coded_number();
+            const int32_t size = ff_coded_number();
+            syn(HEVCB_AUX_SEI_TYPE, type);
+            syn(HEVCB_AUX_SEI_SIZE, size);
+            syn(HEVCB_AUX_SEI_OFFSET, (int32_t)(b.pos >> 3));
+            if (size > 0) { b.pos += 8 * (int64_t)size; } // read_sei_payload: payloadSize bytes, kept in the image
+            count++;
+        } while (more_rbsp_data(last_one) && !b.overrun() && count < (1 << 20));
+        trailing_bits();
+    }
+
     // getNumPicTotalCurr (hevc_stream.in.c:35-59)
     HEVCB_SHD static int num_pic_total_curr(const hevcb_sps_ctx& sps, const hevcb_rps_entry& e, int num_lt_sps, int num_lt_pics,
                                             const int* lt_idx_sps, uint32_t used_lt_mask)
@@ -1214,7 +1267,7 @@ HEVCB_SHD inline bool hevcb_is_slice_type(int t) { return (t >= 0 && t <= 9) || 
 // (may be null when the caller does not need them).
 template <class Sink>
 HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Sink& sink, const hevcb_sps_ctx* sps_in, const hevcb_pps_ctx* pps_in,
-                                      hevcb_sps_ctx* sps_out, hevcb_pps_ctx* pps_out, hevcb_nal_result& r)
+                                      hevcb_sps_ctx* sps_out, hevcb_pps_ctx* pps_out, hevcb_nal_result& r, bool aux = false)
 {
     hevcb_bits b;
     b.init(rbsp, rbsp_size);
@@ -1250,6 +1303,12 @@ HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Si
     } else if (t == 34) {
         r.kind = HEVCB_KIND_PPS;
         w.pic_parameter_set(*pps_out);
+    } else if (aux && t >= 35 && t <= 40) { // extension mode only
+        r.kind = HEVCB_KIND_AUX;
+        if (t == 35) { w.access_unit_delimiter(); }
+        else if (t == 38) { w.filler_data(); }
+        else if (t >= 39) { w.sei_rbsp(); }
+        // 36 / 37: end of sequence / end of bitstream have no payload (hevc_stream.in.c:556-563)
     } else {
         r.flags = w.flags;
         return; // default: return -1 with h->nal already filled (hevc_stream.c:220-221)

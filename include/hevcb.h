@@ -276,7 +276,26 @@ typedef struct hevcb_parse_buffers { /* device pointers for hevcb_parse_device, 
     int32_t* pair_value;  /* [cap_pairs] */
     int64_t cap_pairs;
     uint32_t* pair_pos;   /* NULL, or [cap_pairs]: selects the TRACE variant of the parse, see below */
+    uint32_t flags;       /* HEVCB_PARSE_*; 0 = the reference's behaviour */
+    uint32_t pad;
 } hevcb_parse_buffers;
+
+/* Extension mode (flags & HEVCB_PARSE_AUX).  The reference defines readers for access unit delimiters, end of
+ * sequence / bitstream, filler data and SEI (hevc_stream.in.c:499-573) but never dispatches them: read_hevc_nal_unit returns -1
+ * for types 35..40, which stays the default here.  With the flag those NALs are parsed: kind[k] = HEVCB_KIND_AUX, rc[k] = bytes
+ * consumed (or -1 when the reader ran past the end), and the pair list holds, per NAL type:
+ *   35 AUD     (HEVCB_AUX_AUD_PIC_TYPE, primary_pic_type)
+ *   36 / 37    nothing (no payload)
+ *   38 filler  (HEVCB_AUX_FD_FF_BYTES, number of ff_byte)
+ *   39 / 40    per sei_message (ff-coded payloadType / payloadSize, h264_stream.c:88-98; raw payload, h264_sei.c:75-92), repeated while
+ *              more_rbsp_data (h264_stream.c:62-84): (HEVCB_AUX_SEI_TYPE, t) (HEVCB_AUX_SEI_SIZE, n) (HEVCB_AUX_SEI_OFFSET, o): the
+ *              payload is rbsp[rbsp_off[k] + o .. + n); the bytes stay in the image */
+#define HEVCB_PARSE_AUX 1u
+#define HEVCB_AUX_AUD_PIC_TYPE 0u
+#define HEVCB_AUX_FD_FF_BYTES 8u
+#define HEVCB_AUX_SEI_TYPE 16u
+#define HEVCB_AUX_SEI_SIZE 17u
+#define HEVCB_AUX_SEI_OFFSET 18u
 
 /* Trace variant (pair_pos != NULL): read_debug_hevc_nal_unit (hevc_stream.c:2343-3436) instead of read_hevc_nal_unit.  The list
  * of NAL k then holds one record per line the reference prints for that NAL ("%ld.%d: <expr>: %d \n", process.pl:90-113), in

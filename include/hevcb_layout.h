@@ -448,5 +448,6 @@ HEVCB_SIZE_CHECK(hevc_nal_t, 16)
 #define HEVCB_KIND_SPS 2
 #define HEVCB_KIND_PPS 3
 #define HEVCB_KIND_SLICE 4
+#define HEVCB_KIND_AUX 5 /* extension mode only: AUD / EOS / EOB / filler / SEI (hevcb.h, HEVCB_PARSE_AUX) */
 
 #endif /* HEVCB_LAYOUT_H */
