@@ -35,7 +35,8 @@ def test_product_library_does_not_link_the_oracle():
     out = subprocess.run(["ldd", hb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "hevcref" not in out and "hostsim" not in out
     syms = subprocess.run(["nm", "-D", "--defined-only", hb.LIB_PATH], capture_output=True, text=True).stdout
-    assert "oracle_" not in syms and "ref_" not in syms and "hostsim_" not in syms
+    names = [ln.split()[-1] for ln in syms.splitlines() if ln.strip()]
+    assert not [nm for nm in names if nm.startswith(("oracle_", "ref_", "hostsim_"))]
 
 
 def test_layout_header_compiles_as_c():
