@@ -15,6 +15,7 @@
 // header (escaped) and the original payload (escaped, the zero-run state continuing across the junction).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "hevcb_internal.h"
 
@@ -340,6 +341,63 @@ __global__ void __launch_bounds__(kInsThreads) insert_count_kernel(const Assembl
     if (lane == 0 && local_ins) { atomicAdd(n_ins_total, local_ins); }
 }
 
+// writes one analysed row at dst; returns the bytes written (warp uniform)
+__device__ __forceinline__ uint32_t write_row(const RowInfo& r, uint8_t* __restrict__ dst, int lane)
+{
+    const bool clean = r.fast || (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
+    uint32_t cnt = 16u, inc = ((uint32_t)lane + 1u) * 16u, row_total = 512u;
+    if (!clean) { // output offsets of the lanes: only rows with insertions or partial chunks need the scan
+        cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
+        inc = warp_incl_scan_u32(cnt, lane);
+        row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+    if (clean) {
+        // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
+        const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+        if (head != 0u) { // the bytes in front of the first / behind the last aligned vector, one per lane
+            // lanes 0..15 look at lane 0's chunk (head bytes), lanes 16..31 at lane 31's chunk (tail bytes)
+            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, r.v.x, lane < 16 ? 0 : 31), w1 = __shfl_sync(0xFFFFFFFFu, r.v.y, lane < 16 ? 0 : 31);
+            const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, r.v.z, lane < 16 ? 0 : 31), w3 = __shfl_sync(0xFFFFFFFFu, r.v.w, lane < 16 ? 0 : 31);
+            const uint32_t j = (uint32_t)lane & 15u;
+            const uint32_t w = (j < 4u) ? w0 : (j < 8u) ? w1 : (j < 12u) ? w2 : w3;
+            const uint8_t bv = (uint8_t)(w >> (8u * (j & 3u)));
+            if (lane < 16) { if (j < head) { dst[j] = bv; } }
+            else { if (j >= head) { dst[496u + j] = bv; } }
+        }
+        // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
+        uint4 nx;
+        nx.x = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
+        nx.y = __shfl_down_sync(0xFFFFFFFFu, r.v.y, 1);
+        nx.z = __shfl_down_sync(0xFFFFFFFFu, r.v.z, 1);
+        nx.w = __shfl_down_sync(0xFFFFFFFFu, r.v.w, 1);
+        if (head == 0u) {
+            *reinterpret_cast<uint4*>(dst + lane * 16) = r.v;
+        } else {
+            const uint32_t W[8] = {r.v.x, r.v.y, r.v.z, r.v.w, nx.x, nx.y, nx.z, nx.w};
+            const uint32_t q = head >> 2, sh = (head & 3u) * 8u;
+            uint32_t x[5];
+#pragma unroll
+            for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
+            uint4 o4;
+            o4.x = __funnelshift_r(x[0], x[1], sh);
+            o4.y = __funnelshift_r(x[1], x[2], sh);
+            o4.z = __funnelshift_r(x[2], x[3], sh);
+            o4.w = __funnelshift_r(x[3], x[4], sh);
+            if (lane < 31) { *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4; } // lane 31's 16 - head bytes were stored above
+        }
+    } else {
+        uint8_t* p = dst + (inc - cnt);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if ((r.valid >> j) & 1u) {
+                if ((r.ins >> j) & 1u) { *p++ = 3; }
+                *p++ = (uint8_t)byte_of(r.v, j);
+            }
+        }
+    }
+    return row_total;
+}
+
 // writes one escaped part at out + o; returns the bytes written (warp uniform)
 template <int kInsAhead>
 __device__ __forceinline__ int64_t write_part_n(const uint8_t* __restrict__ base, int64_t off, int64_t end, uint8_t* __restrict__ out, int64_t o, int lane,
@@ -348,68 +406,16 @@ __device__ __forceinline__ int64_t write_part_n(const uint8_t* __restrict__ base
     const int64_t o0 = o;
     const int64_t row0 = off & ~(int64_t)15;
     for (int64_t rowq = row0; rowq < end; rowq += 512 * kInsAhead) {
-      uint4 vq[kInsAhead];
+        uint4 vq[kInsAhead];
 #pragma unroll
-      for (int k = 0; k < kInsAhead; k++) { vq[k] = load_row_chunk(base, rowq + 512 * k, off, end, lane); }
+        for (int k = 0; k < kInsAhead; k++) { vq[k] = load_row_chunk(base, rowq + 512 * k, off, end, lane); }
 #pragma unroll
-      for (int k = 0; k < kInsAhead; k++) {
-        const int64_t row = rowq + 512 * k;
-        if (row >= end) { break; }
-        const RowInfo r = insert_row(vq[k], row, off, end, lane, run_m);
-        const bool clean = r.fast || (__ballot_sync(0xFFFFFFFFu, r.ins != 0u || r.valid != 0xFFFFu) == 0u);
-        uint32_t cnt = 16u, inc = ((uint32_t)lane + 1u) * 16u, row_total = 512u;
-        if (!clean) { // output offsets of the lanes: only rows with insertions or partial chunks need the scan
-            cnt = (uint32_t)__popc(r.valid) + (uint32_t)__popc(r.ins);
-            inc = warp_incl_scan_u32(cnt, lane);
-            row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        for (int k = 0; k < kInsAhead; k++) {
+            const int64_t row = rowq + 512 * k;
+            if (row >= end) { break; }
+            const RowInfo r = insert_row(vq[k], row, off, end, lane, run_m);
+            o += write_row(r, out + o, lane);
         }
-        uint8_t* dst = out + o;
-        if (clean) {
-            // full row without insertions: destination vector d (16-byte aligned) = source bytes [16 d + head - 16 ...]
-            const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-            if (head != 0u) { // the bytes in front of the first / behind the last aligned vector, one per lane
-                // lanes 0..15 look at lane 0's chunk (head bytes), lanes 16..31 at lane 31's chunk (tail bytes)
-                const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, r.v.x, lane < 16 ? 0 : 31), w1 = __shfl_sync(0xFFFFFFFFu, r.v.y, lane < 16 ? 0 : 31);
-                const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, r.v.z, lane < 16 ? 0 : 31), w3 = __shfl_sync(0xFFFFFFFFu, r.v.w, lane < 16 ? 0 : 31);
-                const uint32_t j = (uint32_t)lane & 15u;
-                const uint32_t w = (j < 4u) ? w0 : (j < 8u) ? w1 : (j < 12u) ? w2 : w3;
-                const uint8_t bv = (uint8_t)(w >> (8u * (j & 3u)));
-                if (lane < 16) { if (j < head) { dst[j] = bv; } }
-                else { if (j >= head) { dst[496u + j] = bv; } }
-            }
-            // lane l assembles destination bytes [head + 16 l, head + 16 l + 16) from its chunk and the next lane's
-            uint4 nx;
-            nx.x = __shfl_down_sync(0xFFFFFFFFu, r.v.x, 1);
-            nx.y = __shfl_down_sync(0xFFFFFFFFu, r.v.y, 1);
-            nx.z = __shfl_down_sync(0xFFFFFFFFu, r.v.z, 1);
-            nx.w = __shfl_down_sync(0xFFFFFFFFu, r.v.w, 1);
-            if (head == 0u) {
-                *reinterpret_cast<uint4*>(dst + lane * 16) = r.v;
-            } else {
-                const uint32_t W[8] = {r.v.x, r.v.y, r.v.z, r.v.w, nx.x, nx.y, nx.z, nx.w};
-                const uint32_t q = head >> 2, sh = (head & 3u) * 8u;
-                uint32_t x[5];
-#pragma unroll
-                for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[(e + 3) & 7]; }
-                uint4 o4;
-                o4.x = __funnelshift_r(x[0], x[1], sh);
-                o4.y = __funnelshift_r(x[1], x[2], sh);
-                o4.z = __funnelshift_r(x[2], x[3], sh);
-                o4.w = __funnelshift_r(x[3], x[4], sh);
-                if (lane < 31) { *reinterpret_cast<uint4*>(dst + head + lane * 16) = o4; } // lane 31's 16 - head bytes were stored above
-            }
-        } else {
-            uint8_t* p = dst + (inc - cnt);
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if ((r.valid >> j) & 1u) {
-                    if ((r.ins >> j) & 1u) { *p++ = 3; }
-                    *p++ = (uint8_t)byte_of(r.v, j);
-                }
-            }
-        }
-        o += row_total;
-      }
     }
     run_m -= (uint32_t)(row0 + ((end - row0 + 511) / 512) * 512 - end);
     return o - o0;
@@ -558,10 +564,412 @@ __global__ void __launch_bounds__(kSThreads) sizes_apply_kernel(const int64_t* i
     if (blockIdx.x == 0 && threadIdx.x == 0) { out[n] = bs[nb]; }
 }
 
+
+// ====================================================================================================================
+// Single-pass assembly: ONE read of every source byte (SURVEY 8d scores the insertion as N_rbsp + N_nal).
+//
+// The two-pass kernels above read every escaped byte twice (count, then write).  Here the work is cut into ITEMS -- pieces of at
+// most kPieceCap bytes of one part of one NAL -- and a CTA takes kFWarps consecutive items (a TILE, claimed with a ticket so
+// that every earlier tile is already running): each warp pulls its piece into shared memory with one TMA bulk copy, counts its
+// insertions there, the tile's size goes through a decoupled look-back over 8-byte tile states (aggregate / inclusive prefix),
+// and the warps write their pieces out of the SAME shared memory once the tile's output offset is known.  Pieces need nothing
+// from each other: rbsp_to_nal's state at a cut is a function of the zero run in front of it, which the piece's warp counts by
+// looking back from the cut (usually one byte).  NAL k's out_off is written by its first item.
+// Launches: plan -> 3-kernel scan of (items, plain bytes) per NAL -> item descriptors -> fused kernel -> summary.
+// ====================================================================================================================
+constexpr int kFWarps = 8, kFThreads = kFWarps * 32;
+constexpr int kPieceCap = 4224;                      // bytes of a piece (a multiple of 16; 8.25 rows: a 16 KiB NAL is four pieces at any alignment)
+constexpr int kPieceRows = (kPieceCap + 511) / 512;  // 9
+constexpr int kPieceSmem = kPieceCap + 32;           // + slack: the vector copies read up to 31 bytes behind a piece
+constexpr int kLook = 4;                             // look-back window: 32 x kLook tile states per round trip
+constexpr int kItemShift = 37;                       // packed per-NAL value: items << 37 | plain bytes (start code + prefix + parts, no insertions)
+constexpr unsigned long long kBytesMask = (1ull << kItemShift) - 1ull;
+
+struct FusedHeader {
+    unsigned long long ticket;
+    unsigned long long n_ins;
+    unsigned long long pad[2];
+};
+
+__device__ __forceinline__ int64_t piece_count(int64_t off, int64_t end)
+{
+    if (end <= off) { return 0; }
+    const int64_t L = end - (off & ~(int64_t)15);
+    return (L + kPieceCap - 1) / kPieceCap;
+}
+// piece j of np of the part [off, end): source window [s0, s0 + plen) with s0 16-byte aligned; the piece is its intersection with the part
+__device__ __forceinline__ void piece_bounds(int64_t off, int64_t end, int64_t np, int64_t j, int64_t& s0, int64_t& p0, int64_t& p1)
+{
+    const int64_t a0 = off & ~(int64_t)15, L = end - a0;
+    const int64_t plen = (((L + np - 1) / np) + 15) & ~(int64_t)15;
+    s0 = a0 + j * plen;
+    p0 = s0 > off ? s0 : off;
+    p1 = s0 + plen < end ? s0 + plen : end;
+    if (p1 < p0) { p1 = p0; }
+}
+
+__global__ void __launch_bounds__(256) fused_plan_kernel(const AssembleParts P, int64_t n, int64_t* __restrict__ packed)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) { return; }
+    const int64_t boff = P.b_off ? P.b_off[k] : 0, bend = P.b_off ? P.b_end[k] : 0;
+    unsigned long long items = 1, bytes = 0;
+    if (!(P.skip_neg_b && (bend < 0 || bend < boff))) {
+        const int64_t roff = P.raw_off ? P.raw_off[k] : 0, rend = P.raw_off ? P.raw_end[k] : 0;
+        const int64_t aoff = P.a_off ? P.a_off[k] : 0, aend = P.a_off ? P.a_end[k] : 0;
+        const int64_t ni = piece_count(roff, rend) + piece_count(aoff, aend) + piece_count(boff, bend);
+        items = (unsigned long long)(ni > 0 ? ni : 1);
+        bytes = (unsigned long long)((int64_t)P.sc_len + (int64_t)P.len_size + (rend > roff ? rend - roff : 0) + (aend > aoff ? aend - aoff : 0) + (bend > boff ? bend - boff : 0));
+    }
+    packed[k] = (int64_t)((items << kItemShift) | (bytes & kBytesMask));
+}
+
+// What a warp of the fused kernel needs to know about its item, written by fused_fill_kernel so that the fused kernel starts
+// with ONE load instead of a chain of dependent ones (item -> NAL -> extents -> the bytes in front of the piece).
+struct __align__(16) ItemDesc {
+    int64_t s0;       // source window start (16-byte aligned offset into the part's base)
+    int32_t lead;     // the piece starts at s0 + lead
+    int32_t len;      // bytes of the piece
+    int32_t k;        // NAL
+    uint32_t flags;   // bits 0..1: kItem*, bit 2: first item of its NAL, bit 3: the NAL produces nothing (hevcb_insert: nal_to_rbsp failed)
+    uint32_t run_m;   // escaped pieces: zero bytes that end right in front of the piece (rbsp_to_nal's state at the cut)
+    uint32_t raw_len; // bytes of the NAL's verbatim part (the length prefix of re-framed NALs)
+};
+enum { kItemNone = 0, kItemRaw = 1, kItemEscA = 2, kItemEscB = 3 };
+
+// zero bytes that end right in front of position p of base[], not looking below lo; all = the run reaches lo
+__device__ __forceinline__ uint32_t zeros_back_scalar(const uint8_t* __restrict__ base, int64_t lo, int64_t p, bool& all)
+{
+    uint32_t m = 0;
+    while (p > lo && base[p - 1] == 0) { p--; m++; }
+    all = (p <= lo);
+    return m;
+}
+
+__device__ __forceinline__ void fill_item(const AssembleParts& P, int64_t k, int64_t j, ItemDesc* __restrict__ d)
+{
+    ItemDesc it;
+    it.s0 = 0; it.lead = 0; it.len = 0; it.k = (int32_t)k; it.flags = (j == 0 ? 4u : 0u); it.run_m = 0; it.raw_len = 0;
+    const int64_t boff = P.b_off ? P.b_off[k] : 0, bend = P.b_off ? P.b_end[k] : 0;
+    if (P.skip_neg_b && (bend < 0 || bend < boff)) {
+        it.flags |= 8u;
+    } else {
+        const int64_t roff = P.raw_off ? P.raw_off[k] : 0, rend = P.raw_off ? P.raw_end[k] : 0;
+        const int64_t aoff = P.a_off ? P.a_off[k] : 0, aend = P.a_off ? P.a_end[k] : 0;
+        const int64_t nr = piece_count(roff, rend), na = piece_count(aoff, aend), nb = piece_count(boff, bend);
+        it.raw_len = (uint32_t)(rend > roff ? rend - roff : 0);
+        int64_t s0 = 0, p0 = 0, p1 = 0;
+        uint32_t kind = kItemNone;
+        bool all;
+        if (j < nr) {
+            kind = kItemRaw;
+            piece_bounds(roff, rend, nr, j, s0, p0, p1);
+        } else if (j < nr + na) {
+            kind = kItemEscA;
+            piece_bounds(aoff, aend, na, j - nr, s0, p0, p1);
+            it.run_m = zeros_back_scalar(P.a_base, aoff, p0, all);
+        } else if (j < nr + na + nb) {
+            kind = kItemEscB;
+            piece_bounds(boff, bend, nb, j - nr - na, s0, p0, p1);
+            it.run_m = zeros_back_scalar(P.b_base, boff, p0, all);
+            if (all && aend > aoff) { bool all2; it.run_m += zeros_back_scalar(P.a_base, aoff, aend, all2); } // the run continues into the header part
+        } // else: a NAL without bytes, its only item writes the prefix
+        if (p1 <= p0) { kind = kItemNone; }
+        it.s0 = s0; it.lead = (int32_t)(p0 - s0); it.len = (int32_t)(p1 - p0);
+        it.flags |= kind;
+    }
+    *d = it;
+}
+
+// item descriptors (items of one NAL are consecutive)
+__global__ void __launch_bounds__(256) fused_fill_kernel(const AssembleParts P, const int64_t* __restrict__ first, int64_t n, ItemDesc* __restrict__ items,
+                                                         int64_t cap_items)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t f = 0, cnt = 0;
+    if (k < n) {
+        f = (int64_t)((unsigned long long)first[k] >> kItemShift);
+        cnt = (int64_t)((unsigned long long)first[k + 1] >> kItemShift) - f;
+    }
+    if (cnt <= 8) {
+        for (int64_t j = 0; j < cnt; j++) { if (f + j < cap_items) { fill_item(P, k, j, &items[f + j]); } }
+    }
+    uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt > 8); // NALs of many pieces: the whole warp fills their range
+    while (big) {
+        const int src = __ffs((int)big) - 1;
+        big &= big - 1u;
+        const int64_t bf = __shfl_sync(0xFFFFFFFFu, f, src), bc = __shfl_sync(0xFFFFFFFFu, cnt, src), bk = __shfl_sync(0xFFFFFFFFu, k, src);
+        for (int64_t j = lane; j < bc; j += 32) { if (bf + j < cap_items) { fill_item(P, bk, j, &items[bf + j]); } }
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one warp copies len bytes from shared memory (any alignment) to global memory (any alignment): aligned 16-byte stores, the source as
+// two aligned 16-byte loads funnel-shifted by the (copy-uniform) misalignment between source and destination
+__device__ __forceinline__ void warp_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, int lane)
+{
+    if (len <= 0) { return; }
+    int64_t head = (int64_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    if (head > len) { head = len; }
+    if (lane < head) { dst[lane] = src[lane]; }
+    const int64_t nv = (len - head) >> 4;
+    const uint8_t* s0 = src + head;
+    const uint32_t mis = smem_addr(s0) & 15u, q = mis >> 2, sh = (mis & 3u) * 8u;
+    const uint8_t* sa = s0 - mis;
+    uint4* da = reinterpret_cast<uint4*>(dst + head);
+    for (int64_t i = lane; i < nv; i += 32) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(sa + (i << 4));
+        uint4 o4 = lo;
+        if (mis != 0u) {
+            const uint4 hi = *reinterpret_cast<const uint4*>(sa + (i << 4) + 16);
+            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            uint32_t x[5];
+#pragma unroll
+            for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[e + 3]; }
+            o4.x = __funnelshift_r(x[0], x[1], sh); o4.y = __funnelshift_r(x[1], x[2], sh);
+            o4.z = __funnelshift_r(x[2], x[3], sh); o4.w = __funnelshift_r(x[3], x[4], sh);
+        }
+        __stcs(da + i, o4);
+    }
+    const int64_t done = head + (nv << 4);
+    if (lane < len - done) { dst[done + lane] = src[done + lane]; }
+}
+
+// Scanner CTA of the fused kernel (the CTA that draws ticket 0): turns the tile aggregates into exclusive prefixes, in tile order.
+// Batches of 32 x kLook consecutive tiles go round-robin to the CTA's warps; a warp polls its batch's aggregates (one reader per state),
+// scans them with shuffles, takes the running total from the warp of the previous batch through ONE shared-memory word (the only serial
+// step) and publishes every tile's exclusive prefix.  (A look-back by the tiles themselves piles up: with ~900 tiles in flight most
+// predecessors hold only an aggregate, every tile walks hundreds of states back, and the chain of inclusive prefixes advances one window
+// per L2 round trip -- measured at 40 % of a tile's lifetime.)
+__device__ __forceinline__ void fused_scanner(const unsigned long long* __restrict__ tile_state, unsigned long long* __restrict__ tile_excl, int64_t n_tiles,
+                                              volatile ulonglong2* run, int warp, int lane, int64_t* __restrict__ total_out)
+{
+    const int64_t batch_tiles = 32 * kLook, n_batches = (n_tiles + batch_tiles - 1) / batch_tiles;
+    for (int64_t b = warp; b < n_batches; b += kFWarps) {
+        const int64_t first = b * batch_tiles + (int64_t)lane * kLook;
+        unsigned long long w[kLook];
+#pragma unroll
+        for (int q = 0; q < kLook; q++) { w[q] = (first + q < n_tiles) ? ld_relaxed_u64(&tile_state[first + q]) : (1ull << 62); }
+        for (;;) {
+            bool missing = false;
+#pragma unroll
+            for (int q = 0; q < kLook; q++) { missing = missing || ((w[q] >> 62) == 0ull); }
+            if (!__any_sync(0xFFFFFFFFu, missing)) { break; }
+            __nanosleep(64);
+#pragma unroll
+            for (int q = 0; q < kLook; q++) { if ((w[q] >> 62) == 0ull) { w[q] = ld_relaxed_u64(&tile_state[first + q]); } }
+        }
+        long long mine = 0;
+#pragma unroll
+        for (int q = 0; q < kLook; q++) { mine += (long long)(w[q] & ((1ull << 62) - 1ull)); }
+        long long inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) { inc += o; }
+        }
+        const long long tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        unsigned long long seq, base;
+        do { // the running total of the batches before this one (every lane reads the same word)
+            asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(seq), "=l"(base) : "r"(smem_addr((const void*)run)) : "memory");
+        } while (seq != (unsigned long long)b);
+        if (lane == 0) {
+            asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(smem_addr((const void*)run)), "l"((unsigned long long)(b + 1)), "l"(base + (unsigned long long)tot) : "memory");
+            if (b == n_batches - 1) { *total_out = (int64_t)(base + (unsigned long long)tot); }
+        }
+        long long e = (long long)base + inc - mine;
+#pragma unroll
+        for (int q = 0; q < kLook; q++) {
+            if (first + q < n_tiles) { st_relaxed_u64(&tile_excl[first + q], (1ull << 62) | (unsigned long long)e); }
+            e += (long long)(w[q] & ((1ull << 62) - 1ull));
+        }
+    }
+}
+
+struct __align__(16) FusedSmem {
+    uint8_t piece[kFWarps][kPieceSmem];
+    unsigned long long bar[kFWarps];
+    uint32_t run_in[kFWarps][kPieceRows + 1]; // zero run entering every row of an escaped piece (count pass -> write pass)
+    long long size[kFWarps];
+    long long excl;
+    long long ticket;
+};
+
+__global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const AssembleParts P, int64_t n, const int64_t* __restrict__ first,
+                                                                   const ItemDesc* __restrict__ items, int64_t cap_items,
+                                                                   unsigned long long* __restrict__ tile_state, unsigned long long* __restrict__ tile_excl,
+                                                                   FusedHeader* __restrict__ hdr, int64_t* __restrict__ out_off, uint8_t* __restrict__ out, int64_t out_cap)
+{
+    extern __shared__ __align__(128) uint8_t fsm_raw[];
+    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fsm_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
+    if (n_items > cap_items) { return; } // only when the sources alone exceed out_cap: the summary kernel reports the plain sizes
+    const int64_t n_tiles = (n_items + kFWarps - 1) / kFWarps;
+    if ((int64_t)blockIdx.x > n_tiles) { return; } // n_tiles CTAs take a tile each, one is the scanner
+    if (threadIdx.x == 0) {
+        sm.ticket = (long long)atomicAdd(&hdr->ticket, 1ull);
+        if (sm.ticket == 0) { reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[0] = 0ull; reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[1] = 0ull; }
+    }
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sm.bar[warp])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (sm.ticket == 0) { // the first CTA to start is the scanner: it takes no tile
+        fused_scanner(tile_state, tile_excl, n_tiles, reinterpret_cast<volatile ulonglong2*>(sm.piece[0]), warp, lane, out_off + n);
+        return;
+    }
+    const int64_t t = sm.ticket - 1;
+    const int64_t item = t * kFWarps + warp;
+    const bool active = item < n_items;
+    // ---- what this warp's item is
+    enum { kNone = 0, kRaw = 1, kEsc = 2 };
+    int kind = kNone;
+    bool first_item = false, nal_skipped = false;
+    int64_t k = 0, s0 = 0, p0 = 0, p1 = 0, nbytes_raw = 0;
+    const uint8_t* base = nullptr;
+    uint32_t run_m = 0;
+    uint8_t* const sp = sm.piece[warp];
+    if (active) {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&items[item])), d1 = __ldg(reinterpret_cast<const uint4*>(&items[item]) + 1);
+        s0 = (int64_t)(((unsigned long long)d0.y << 32) | d0.x);
+        p0 = s0 + (int32_t)d0.z;
+        p1 = p0 + (int32_t)d0.w;
+        k = (int32_t)d1.x;
+        const uint32_t fl = d1.y;
+        run_m = d1.z;
+        nbytes_raw = d1.w;
+        first_item = (fl & 4u) != 0u;
+        nal_skipped = (fl & 8u) != 0u;
+        const uint32_t ik = fl & 3u;
+        kind = (ik == kItemNone) ? kNone : (ik == kItemRaw ? kRaw : kEsc);
+        base = (ik == kItemRaw) ? P.raw_base : (ik == kItemEscA ? P.a_base : P.b_base);
+        if (kind != kNone && p1 <= p0) { kind = kNone; }
+        if (kind != kNone) {
+            const uint32_t bytes = (uint32_t)(((p1 + 15) & ~(int64_t)15) - s0);
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sm.bar[warp])), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sp)), "l"(base + s0),
+                             "r"(bytes), "r"(smem_addr(&sm.bar[warp]))
+                             : "memory");
+            }
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_addr(&sm.bar[warp])), "r"(0) : "memory");
+            }
+        }
+    }
+    // ---- count
+    const bool writes_prefix = active && first_item && !nal_skipped;
+    long long size = 0;
+    uint32_t fastmask = 0, n_ins = 0;
+    const int rows = (kind != kNone) ? (int)((p1 - s0 + 511) >> 9) : 0;
+    if (kind == kEsc) {
+        for (int r = 0; r < rows; r++) {
+            const int64_t row = s0 + ((int64_t)r << 9), cpos = row + lane * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cpos < p1 && cpos + 16 > p0) { v = *reinterpret_cast<const uint4*>(sp + (r << 9) + lane * 16); }
+            if (lane == 0) { sm.run_in[warp][r] = run_m; }
+            const RowInfo ri = insert_row(v, row, p0, p1, lane, run_m);
+            if (ri.fast) { fastmask |= 1u << r; }
+            else { n_ins += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(ri.ins)); }
+        }
+        size = (p1 - p0) + (long long)n_ins;
+    } else if (kind == kRaw) {
+        size = p1 - p0;
+    }
+    if (writes_prefix) { size += P.sc_len + P.len_size; }
+    if (lane == 0) { sm.size[warp] = size; }
+    __syncthreads();
+    // ---- the tile's output offset: the aggregate goes to the scanner CTA, which answers with the exclusive prefix
+    if (threadIdx.x == 0) {
+        long long total = 0;
+#pragma unroll
+        for (int w = 0; w < kFWarps; w++) { total += sm.size[w]; }
+        st_relaxed_u64(&tile_state[t], (1ull << 62) | (unsigned long long)total);
+        unsigned long long e;
+        while (((e = ld_relaxed_u64(&tile_excl[t])) >> 62) == 0ull) { __nanosleep(100); }
+        sm.excl = (long long)(e & ((1ull << 62) - 1ull));
+    }
+    __syncthreads();
+    if (!active) { return; }
+    long long o = sm.excl;
+    for (int w = 0; w < warp; w++) { o += sm.size[w]; }
+    if (first_item && lane == 0) { out_off[k] = o; }
+    if (n_ins && lane == 0) { atomicAdd(&hdr->n_ins, (unsigned long long)n_ins); }
+    if (o + size > out_cap) { return; } // capacity overflow is reported by the summary
+    if (writes_prefix) {
+        if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
+        o += P.sc_len;
+        if (P.len_size) { // big-endian length of what follows (verbatim NALs only: the launcher keeps escaped parts off this path)
+            if (lane < P.len_size) { out[o + lane] = (uint8_t)((uint64_t)nbytes_raw >> (8 * (P.len_size - 1 - lane))); }
+            o += P.len_size;
+        }
+    }
+    __syncwarp();
+    if (kind == kRaw) {
+        warp_copy_from_smem(out + o, sp + (p0 - s0), p1 - p0, lane);
+    } else if (kind == kEsc) {
+        int r = 0;
+        while (r < rows) {
+            if ((fastmask >> r) & 1u) { // a run of rows that take no insertion: one shifted vector copy
+                int r1 = r + 1;
+                while (r1 < rows && ((fastmask >> r1) & 1u)) { r1++; }
+                warp_copy_from_smem(out + o, sp + (r << 9), (int64_t)(r1 - r) << 9, lane);
+                o += (long long)(r1 - r) << 9;
+                r = r1;
+                continue;
+            }
+            const int64_t row = s0 + ((int64_t)r << 9), cpos = row + lane * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cpos < p1 && cpos + 16 > p0) { v = *reinterpret_cast<const uint4*>(sp + (r << 9) + lane * 16); }
+            uint32_t rm = sm.run_in[warp][r];
+            const RowInfo ri = insert_row(v, row, p0, p1, lane, rm);
+            o += write_row(ri, out + o, lane);
+            r++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fused_summary_kernel(const int64_t* __restrict__ first, int64_t n, int64_t cap_items, int64_t out_cap,
+                                                            const FusedHeader* __restrict__ hdr, int64_t* __restrict__ out_off, hevcb_insert_summary* s)
+{
+    const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
+    const bool plain = n_items > cap_items; // more pieces than the table holds: only when the sources alone exceed out_cap
+    if (plain) { // out_off = the sizes without insertions (a lower bound); the caller grows the buffer and runs again
+        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n; k += (int64_t)gridDim.x * blockDim.x) {
+            out_off[k] = (int64_t)((unsigned long long)first[k] & kBytesMask);
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int64_t total = plain ? (int64_t)((unsigned long long)first[n] & kBytesMask) : out_off[n];
+        s->n_nals = n;
+        s->out_bytes = total;
+        s->n_inserted = (int64_t)hdr->n_ins;
+        s->overflow = (plain || total > out_cap) ? 1 : 0;
+        s->pad = 0;
+    }
+}
+
 } // namespace
 
-static int launch_assemble(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
-                           hevcb_insert_summary* d_summary, cudaStream_t stream)
+static int launch_assemble_two_pass(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                                    hevcb_insert_summary* d_summary, cudaStream_t stream)
 {
     const int64_t nb = (n + kSTile - 1) / kSTile;
     const int64_t n1 = n > 0 ? n : 1;
@@ -612,6 +1020,63 @@ static int launch_assemble(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, ui
     ctx->launches += 10;
     HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
+}
+
+// single-pass path (see the comment in front of fused_assemble_kernel)
+static int launch_assemble_fused(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                                 hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    const int64_t nb = (n + kSTile - 1) / kSTile;
+    // every part of every NAL takes at most len / kPieceCap + 2 items, a NAL without bytes one: enough whenever the sources fit into out_cap
+    const int64_t n_parts = (P.raw_off ? 1 : 0) + (P.a_off ? 1 : 0) + (P.b_off ? 1 : 0);
+    const int64_t cap_items = (2 * n_parts + 1) * n + out_cap / kPieceCap + 64;
+    const int64_t cap_tiles = (cap_items + kFWarps - 1) / kFWarps;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_hdr = 0, o_state = 256, o_packed = o_state + up((size_t)cap_tiles * 8) * 2, o_first = o_packed + up((size_t)(n + 1) * 8);
+    const size_t o_bs = o_first + up((size_t)(n + 2) * 8), o_items = o_bs + up((size_t)(nb + 2) * 8), need = o_items + up((size_t)cap_items * sizeof(ItemDesc));
+    int rc = hevcb_reserve(ctx, &ctx->insert_scratch, need);
+    if (rc != HEVCB_OK) { return rc; }
+    uint8_t* sb = reinterpret_cast<uint8_t*>(ctx->insert_scratch.p);
+    FusedHeader* hdr = reinterpret_cast<FusedHeader*>(sb + o_hdr);
+    unsigned long long* states = reinterpret_cast<unsigned long long*>(sb + o_state);
+    unsigned long long* excl = reinterpret_cast<unsigned long long*>(sb + o_state + up((size_t)cap_tiles * 8));
+    int64_t* packed = reinterpret_cast<int64_t*>(sb + o_packed);
+    int64_t* first = reinterpret_cast<int64_t*>(sb + o_first);
+    long long* bs = reinterpret_cast<long long*>(sb + o_bs);
+    ItemDesc* items = reinterpret_cast<ItemDesc*>(sb + o_items);
+    HEVCB_CUDA(ctx, cudaMemsetAsync(sb, 0, o_packed, stream)); // header + tile states
+    if (!ctx->fused_smem_set) {
+        HEVCB_CUDA(ctx, cudaFuncSetAttribute(fused_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+        ctx->fused_smem_set = 1;
+    }
+    const unsigned gn = (unsigned)((n + 255) / 256);
+    fused_plan_kernel<<<gn, 256, 0, stream>>>(P, n, packed);
+    sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(packed, n, bs);
+    sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
+    sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(packed, n, bs, nb, first);
+    fused_fill_kernel<<<gn, 256, 0, stream>>>(P, first, n, items, cap_items);
+    fused_assemble_kernel<<<(unsigned)(cap_tiles + 1), kFThreads, sizeof(FusedSmem), stream>>>(P, n, first, items, cap_items, states, excl, hdr, d_out_off, d_out, out_cap);
+    fused_summary_kernel<<<gn < 1024u ? gn : 1024u, 256, 0, stream>>>(first, n, cap_items, out_cap, hdr, d_out_off, d_summary);
+    ctx->launches += 7;
+    HEVCB_CUDA(ctx, cudaGetLastError());
+    return HEVCB_OK;
+}
+
+// Which path: the single-pass kernel holds one piece per warp, so it pays off when NALs are not tiny (one warp-item per NAL part);
+// batches of very short NALs (average below kFusedMinAvg output bytes) stay with the two-pass kernels.  HEVCB_INSERT_PATH=fused|twopass
+// forces a path (tests run every case through both).
+constexpr int64_t kFusedMinAvg = 4096;
+static int launch_assemble(hevcb_ctx* ctx, const AssembleParts& P, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* d_out_off,
+                           hevcb_insert_summary* d_summary, cudaStream_t stream)
+{
+    bool can_fuse = n > 0 && n < (1ll << 26) && out_cap < (1ll << 36) && !(P.len_size != 0 && (P.a_off || P.b_off)) && (((uintptr_t)P.raw_base & 15u) == 0);
+    bool fused = can_fuse && out_cap / n >= kFusedMinAvg;
+    if (const char* e = getenv("HEVCB_INSERT_PATH")) {
+        if (e[0] == 'f') { fused = can_fuse; }
+        else if (e[0] == 't') { fused = false; }
+    }
+    return fused ? launch_assemble_fused(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream)
+                 : launch_assemble_two_pass(ctx, P, n, d_out, out_cap, d_out_off, d_summary, stream);
 }
 
 int hevcb_launch_insert(hevcb_ctx* ctx, const uint8_t* d_rbsp, const int64_t* d_off, const int64_t* d_end, int64_t n, int sc_len, uint8_t* d_out,

@@ -23,6 +23,7 @@ struct hevcb_ctx {
     int scan_timing_ctas = 0;
     hevcb_devbuf rewrite_slots;           // rewrite: per-NAL header slots of the first write pass
     hevcb_devbuf insert_scratch;          // insert: per-NAL output sizes + block sums
+    int fused_smem_set = 0;               // insert: the single-pass kernel's shared-memory attribute is set
     hevcb_devbuf rewrite_scratch, rewrite_staging; // rewrite: part arrays, written headers
     hevcb_devbuf wstruct;                 // hevcb_write_nal_host: uploaded structs, contexts, RBSP, NAL
     // what the last hevcb_parse_* left on the device (consumed by hevcb_rewrite_*)

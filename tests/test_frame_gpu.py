@@ -12,6 +12,14 @@ from tests import util
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
 
 
+@pytest.fixture(autouse=True, params=["fused", "twopass"])
+def insert_path(request, monkeypatch):
+    """every case runs through the single-pass assembly and through the two-pass kernels (HEVCB_INSERT_PATH, csrc/hevcb_insert.cu)"""
+    monkeypatch.setenv("HEVCB_INSERT_PATH", request.param)
+    return request.param
+
+
+
 def lenpref_numpy(s, st, en, len_size):
     parts = []
     for a, b in zip(st.tolist(), en.tolist()):

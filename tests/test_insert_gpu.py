@@ -10,6 +10,14 @@ from tests import util
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
 
 
+@pytest.fixture(autouse=True, params=["fused", "twopass"])
+def insert_path(request, monkeypatch):
+    """every case runs through the single-pass assembly and through the two-pass kernels (HEVCB_INSERT_PATH, csrc/hevcb_insert.cu)"""
+    monkeypatch.setenv("HEVCB_INSERT_PATH", request.param)
+    return request.param
+
+
+
 def zero_heavy(rng, n, alphabet):
     if alphabet == 0:
         vals, p = [0, 1, 2, 3, 4, 0x80], [0.55, 0.1, 0.08, 0.1, 0.07, 0.1]

@@ -9,6 +9,14 @@ from tests import rewrite_check as rc
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
 
 
+@pytest.fixture(autouse=True, params=["fused", "twopass"])
+def insert_path(request, monkeypatch):
+    """every case runs through the single-pass assembly and through the two-pass kernels (HEVCB_INSERT_PATH, csrc/hevcb_insert.cu)"""
+    monkeypatch.setenv("HEVCB_INSERT_PATH", request.param)
+    return request.param
+
+
+
 def device_rewrite(ctx, s, size, qp, vui):
     import torch
 

@@ -10,7 +10,9 @@ ctx = Context(0)
 g = torch.Generator(device="cuda").manual_seed(1)
 n_bytes = 1 << 30
 x = torch.randint(0, 256, (n_bytes,), dtype=torch.uint8, device="cuda", generator=g)
-for name, seg, zero_frac in [("64B", 64, 0), ("1KiB", 1024, 0), ("16KiB", 16384, 0), ("1MiB", 1 << 20, 0), ("16KiB-z50", 16384, 2)]:
+CASES = [("64B", 64, 0), ("1KiB", 1024, 0), ("4KiB", 4096, 0), ("16KiB", 16384, 0), ("1MiB", 1 << 20, 0), ("16KiB-z50", 16384, 2)]
+sel = os.environ.get("CASES")
+for name, seg, zero_frac in [c for c in CASES if not sel or c[0] in sel.split(",")]:
     y = x
     if zero_frac:
         m = torch.randint(0, 4, (n_bytes,), dtype=torch.uint8, device="cuda", generator=g)
