@@ -67,10 +67,11 @@ __device__ __forceinline__ uint4 load_row_chunk(const uint8_t* __restrict__ img,
     if (cpos < end && cpos + 16 > off) { v = *reinterpret_cast<const uint4*>(img + cpos); }
     return v;
 }
-__device__ __forceinline__ RowInfo insert_row(const uint4 v, int64_t row, int64_t off, int64_t end, int lane, uint32_t& run_m)
+template <typename I>
+__device__ __forceinline__ RowInfo insert_row(const uint4 v, I row, I off, I end, int lane, uint32_t& run_m)
 {
     RowInfo r;
-    const int64_t cpos = row + lane * 16;
+    const I cpos = row + lane * 16;
     r.v = v;
     if (row >= off && row + 512 <= end) {
         // Interior row, the common case: no insertion is possible when the row holds no two adjacent zero bytes and the run
@@ -92,7 +93,7 @@ __device__ __forceinline__ RowInfo insert_row(const uint4 v, int64_t row, int64_
         }
     }
     // validity of the 16 positions
-    const int64_t lo = off - cpos, hi = end - cpos; // valid j in [lo, hi)
+    const I lo = off - cpos, hi = end - cpos; // valid j in [lo, hi)
     uint32_t valid = 0xFFFFu;
     if (lo > 0) { valid &= (lo >= 16) ? 0u : (0xFFFFu << (int)lo); }
     if (hi < 16) { valid &= (hi <= 0) ? 0u : ((1u << (int)hi) - 1u); }
@@ -581,7 +582,10 @@ constexpr int kFWarps = 8, kFThreads = kFWarps * 32;
 constexpr int kPieceCap = 4224;                      // bytes of a piece (a multiple of 16; 8.25 rows: a 16 KiB NAL is four pieces at any alignment)
 constexpr int kPieceRows = (kPieceCap + 511) / 512;  // 9
 constexpr int kPieceSmem = kPieceCap + 32;           // + slack: the vector copies read up to 31 bytes behind a piece
-constexpr int kLook = 4;                             // look-back window: 32 x kLook tile states per round trip
+#ifndef HEVCB_FUSED_LOOK
+#define HEVCB_FUSED_LOOK 2
+#endif
+constexpr int kLook = HEVCB_FUSED_LOOK;              // a scanner batch is 32 x kLook tiles (it waits for the slowest of them)
 constexpr int kItemShift = 37;                       // packed per-NAL value: items << 37 | plain bytes (start code + prefix + parts, no insertions)
 constexpr unsigned long long kBytesMask = (1ull << kItemShift) - 1ull;
 
@@ -681,27 +685,19 @@ __device__ __forceinline__ void fill_item(const AssembleParts& P, int64_t k, int
     *d = it;
 }
 
-// item descriptors (items of one NAL are consecutive)
+// item descriptors (items of one NAL are consecutive): one thread per item, the NAL found by bisection of the scanned item counts
 __global__ void __launch_bounds__(256) fused_fill_kernel(const AssembleParts P, const int64_t* __restrict__ first, int64_t n, ItemDesc* __restrict__ items,
                                                          int64_t cap_items)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t f = 0, cnt = 0;
-    if (k < n) {
-        f = (int64_t)((unsigned long long)first[k] >> kItemShift);
-        cnt = (int64_t)((unsigned long long)first[k + 1] >> kItemShift) - f;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
+    if (i >= n_items || n_items > cap_items) { return; }
+    int64_t lo = 0, hi = n; // the NAL k with first[k] <= i < first[k + 1]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)((unsigned long long)first[mid] >> kItemShift) <= i) { lo = mid; } else { hi = mid; }
     }
-    if (cnt <= 8) {
-        for (int64_t j = 0; j < cnt; j++) { if (f + j < cap_items) { fill_item(P, k, j, &items[f + j]); } }
-    }
-    uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt > 8); // NALs of many pieces: the whole warp fills their range
-    while (big) {
-        const int src = __ffs((int)big) - 1;
-        big &= big - 1u;
-        const int64_t bf = __shfl_sync(0xFFFFFFFFu, f, src), bc = __shfl_sync(0xFFFFFFFFu, cnt, src), bk = __shfl_sync(0xFFFFFFFFu, k, src);
-        for (int64_t j = lane; j < bc; j += 32) { if (bf + j < cap_items) { fill_item(P, bk, j, &items[bf + j]); } }
-    }
+    fill_item(P, lo, i - (int64_t)((unsigned long long)first[lo] >> kItemShift), &items[i]);
 }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
@@ -717,7 +713,23 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // one warp copies len bytes from shared memory (any alignment) to global memory (any alignment): aligned 16-byte stores, the source as
-// two aligned 16-byte loads funnel-shifted by the (copy-uniform) misalignment between source and destination
+// two aligned 16-byte loads funnel-shifted by the (copy-uniform) misalignment between source and destination (Q = its word part)
+template <int Q>
+__device__ __forceinline__ void smem_vectors_out(uint4* __restrict__ da, const uint8_t* __restrict__ sa, int64_t nv, uint32_t sh, int lane)
+{
+#pragma unroll 2
+    for (int64_t i = lane; i < nv; i += 32) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(sa + (i << 4));
+        uint4 o4 = lo;
+        if (Q != 0 || sh != 0u) {
+            const uint4 hi = *reinterpret_cast<const uint4*>(sa + (i << 4) + 16);
+            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            o4.x = __funnelshift_r(W[Q], W[Q + 1], sh); o4.y = __funnelshift_r(W[Q + 1], W[Q + 2], sh);
+            o4.z = __funnelshift_r(W[Q + 2], W[Q + 3], sh); o4.w = __funnelshift_r(W[Q + 3], W[Q + 4], sh);
+        }
+        __stcs(da + i, o4);
+    }
+}
 __device__ __forceinline__ void warp_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, int lane)
 {
     if (len <= 0) { return; }
@@ -726,22 +738,14 @@ __device__ __forceinline__ void warp_copy_from_smem(uint8_t* __restrict__ dst, c
     if (lane < head) { dst[lane] = src[lane]; }
     const int64_t nv = (len - head) >> 4;
     const uint8_t* s0 = src + head;
-    const uint32_t mis = smem_addr(s0) & 15u, q = mis >> 2, sh = (mis & 3u) * 8u;
+    const uint32_t mis = smem_addr(s0) & 15u, sh = (mis & 3u) * 8u;
     const uint8_t* sa = s0 - mis;
     uint4* da = reinterpret_cast<uint4*>(dst + head);
-    for (int64_t i = lane; i < nv; i += 32) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(sa + (i << 4));
-        uint4 o4 = lo;
-        if (mis != 0u) {
-            const uint4 hi = *reinterpret_cast<const uint4*>(sa + (i << 4) + 16);
-            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            uint32_t x[5];
-#pragma unroll
-            for (int e = 0; e < 5; e++) { x[e] = (q == 0u) ? W[e] : (q == 1u) ? W[e + 1] : (q == 2u) ? W[e + 2] : W[e + 3]; }
-            o4.x = __funnelshift_r(x[0], x[1], sh); o4.y = __funnelshift_r(x[1], x[2], sh);
-            o4.z = __funnelshift_r(x[2], x[3], sh); o4.w = __funnelshift_r(x[3], x[4], sh);
-        }
-        __stcs(da + i, o4);
+    switch (mis >> 2) {
+        case 0: smem_vectors_out<0>(da, sa, nv, sh, lane); break;
+        case 1: smem_vectors_out<1>(da, sa, nv, sh, lane); break;
+        case 2: smem_vectors_out<2>(da, sa, nv, sh, lane); break;
+        default: smem_vectors_out<3>(da, sa, nv, sh, lane); break;
     }
     const int64_t done = head + (nv << 4);
     if (lane < len - done) { dst[done + lane] = src[done + lane]; }
@@ -810,7 +814,7 @@ struct __align__(16) FusedSmem {
 __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const AssembleParts P, int64_t n, const int64_t* __restrict__ first,
                                                                    const ItemDesc* __restrict__ items, int64_t cap_items,
                                                                    unsigned long long* __restrict__ tile_state, unsigned long long* __restrict__ tile_excl,
-                                                                   FusedHeader* __restrict__ hdr, int64_t* __restrict__ out_off, uint8_t* __restrict__ out, int64_t out_cap)
+                                                                   FusedHeader* __restrict__ hdr, int64_t* __restrict__ out_off, uint8_t* __restrict__ out, int64_t out_cap, int stagger_ns, int persistent)
 {
     extern __shared__ __align__(128) uint8_t fsm_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fsm_raw);
@@ -818,22 +822,30 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
     const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
     if (n_items > cap_items) { return; } // only when the sources alone exceed out_cap: the summary kernel reports the plain sizes
     const int64_t n_tiles = (n_items + kFWarps - 1) / kFWarps;
-    if ((int64_t)blockIdx.x > n_tiles) { return; } // n_tiles CTAs take a tile each, one is the scanner
-    if (threadIdx.x == 0) {
-        sm.ticket = (long long)atomicAdd(&hdr->ticket, 1ull);
-        if (sm.ticket == 0) { reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[0] = 0ull; reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[1] = 0ull; }
-    }
+    if (!persistent && (int64_t)blockIdx.x > n_tiles) { return; } // one tile per CTA: n_tiles workers and the scanner
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sm.bar[warp])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    uint32_t phase = 0; // parity of this warp's mbarrier (flips with every piece the warp loads)
+    // The CTAs of an SM start staggered: the in-order prefix couples the tiles in flight, and CTAs that all draw their tickets at the same
+    // moment keep loading, counting and writing in lock-step (read bursts, then write bursts) instead of overlapping the phases.
+    if (persistent && stagger_ns > 0 && gridDim.x > 1) { __nanosleep((unsigned)(blockIdx.x * 6ull / gridDim.x) * (unsigned)stagger_ns); }
+  // persistent CTAs: every round draws a ticket; ticket 0 makes its CTA the scanner, ticket i the worker of tile i - 1 (so every earlier
+  // tile is running or done, and so is the scanner)
+  for (;;) {
+    if (threadIdx.x == 0) {
+        sm.ticket = (long long)atomicAdd(&hdr->ticket, 1ull);
+        if (sm.ticket == 0) { reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[0] = 0ull; reinterpret_cast<volatile unsigned long long*>(sm.piece[0])[1] = 0ull; }
+    }
     __syncthreads();
-    if (sm.ticket == 0) { // the first CTA to start is the scanner: it takes no tile
+    if (sm.ticket == 0) {
         fused_scanner(tile_state, tile_excl, n_tiles, reinterpret_cast<volatile ulonglong2*>(sm.piece[0]), warp, lane, out_off + n);
         return;
     }
     const int64_t t = sm.ticket - 1;
+    if (t >= n_tiles) { return; }
     const int64_t item = t * kFWarps + warp;
     const bool active = item < n_items;
     // ---- what this warp's item is
@@ -870,24 +882,59 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
             uint32_t ok = 0;
             while (!ok) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(ok) : "r"(smem_addr(&sm.bar[warp])), "r"(0) : "memory");
+                             : "=r"(ok) : "r"(smem_addr(&sm.bar[warp])), "r"(phase) : "memory");
             }
+            phase ^= 1u;
         }
     }
     // ---- count
     const bool writes_prefix = active && first_item && !nal_skipped;
     long long size = 0;
     uint32_t fastmask = 0, n_ins = 0;
-    const int rows = (kind != kNone) ? (int)((p1 - s0 + 511) >> 9) : 0;
+    const int q0 = (int)(p0 - s0), q1 = (int)(p1 - s0); // the piece inside its shared-memory window (32-bit positions from here on)
+    const int rows = (kind != kNone) ? ((q1 + 511) >> 9) : 0;
     if (kind == kEsc) {
-        for (int r = 0; r < rows; r++) {
-            const int64_t row = s0 + ((int64_t)r << 9), cpos = row + lane * 16;
+        int r = 0;
+        while (r < rows) {
+            const int row = r << 9, cpos = row + lane * 16;
+            if (row >= q0 && row + 2048 <= q1) {
+                // Four interior rows at once (the common case): the zero-pair test of insert_row over 2 KiB with ONE vote.  A pair that
+                // straddles two rows of the group is seen through the next row's first word; the pair across the group's end is left to
+                // run_m, as in insert_row.
+                uint4 v[4];
+                uint32_t nx[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) { v[g] = *reinterpret_cast<const uint4*>(sp + cpos + (g << 9)); }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    nx[g] = __shfl_down_sync(0xFFFFFFFFu, v[g].x, 1);
+                    const uint32_t nrow = __shfl_sync(0xFFFFFFFFu, v[g < 3 ? g + 1 : 3].x, 0); // first word of the next row of the group
+                    if (lane == 31) { nx[g] = (g < 3) ? nrow : 0xFFFFFFFFu; }
+                }
+                uint32_t pair = 0;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t m0 = v[g].x | __funnelshift_r(v[g].x, v[g].y, 8), m1 = v[g].y | __funnelshift_r(v[g].y, v[g].z, 8);
+                    const uint32_t m2 = v[g].z | __funnelshift_r(v[g].z, v[g].w, 8), m3 = v[g].w | __funnelshift_r(v[g].w, nx[g], 8);
+                    const uint32_t c = 0x01010101u;
+                    pair |= ((m0 - c) & ~m0) | ((m1 - c) & ~m1) | ((m2 - c) & ~m2) | ((m3 - c) & ~m3);
+                }
+                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0) & 0xFFu, bl = __shfl_sync(0xFFFFFFFFu, v[3].w, 31) >> 24;
+                const bool entering = (run_m >= 1u && b0 == 0u) || (run_m >= 2u && b0 <= 3u);
+                if (!__any_sync(0xFFFFFFFFu, (pair & 0x80808080u) != 0u) && !entering) {
+                    fastmask |= 0xFu << r;
+                    run_m = (bl == 0u) ? 1u : 0u;
+                    r += 4;
+                    continue;
+                }
+            }
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (cpos < p1 && cpos + 16 > p0) { v = *reinterpret_cast<const uint4*>(sp + (r << 9) + lane * 16); }
+            if (cpos < q1 && cpos + 16 > q0) { v = *reinterpret_cast<const uint4*>(sp + cpos); }
             if (lane == 0) { sm.run_in[warp][r] = run_m; }
-            const RowInfo ri = insert_row(v, row, p0, p1, lane, run_m);
+            const RowInfo ri = insert_row<int>(v, row, q0, q1, lane, run_m);
             if (ri.fast) { fastmask |= 1u << r; }
             else { n_ins += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(ri.ins)); }
+            r++;
         }
         size = (p1 - p0) + (long long)n_ins;
     } else if (kind == kRaw) {
@@ -903,47 +950,49 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
         for (int w = 0; w < kFWarps; w++) { total += sm.size[w]; }
         st_relaxed_u64(&tile_state[t], (1ull << 62) | (unsigned long long)total);
         unsigned long long e;
-        while (((e = ld_relaxed_u64(&tile_excl[t])) >> 62) == 0ull) { __nanosleep(100); }
+        while (((e = ld_relaxed_u64(&tile_excl[t])) >> 62) == 0ull) { __nanosleep(32); }
         sm.excl = (long long)(e & ((1ull << 62) - 1ull));
     }
     __syncthreads();
-    if (!active) { return; }
     long long o = sm.excl;
     for (int w = 0; w < warp; w++) { o += sm.size[w]; }
-    if (first_item && lane == 0) { out_off[k] = o; }
+    if (active && first_item && lane == 0) { out_off[k] = o; }
     if (n_ins && lane == 0) { atomicAdd(&hdr->n_ins, (unsigned long long)n_ins); }
-    if (o + size > out_cap) { return; } // capacity overflow is reported by the summary
-    if (writes_prefix) {
-        if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
-        o += P.sc_len;
-        if (P.len_size) { // big-endian length of what follows (verbatim NALs only: the launcher keeps escaped parts off this path)
-            if (lane < P.len_size) { out[o + lane] = (uint8_t)((uint64_t)nbytes_raw >> (8 * (P.len_size - 1 - lane))); }
-            o += P.len_size;
-        }
-    }
-    __syncwarp();
-    if (kind == kRaw) {
-        warp_copy_from_smem(out + o, sp + (p0 - s0), p1 - p0, lane);
-    } else if (kind == kEsc) {
-        int r = 0;
-        while (r < rows) {
-            if ((fastmask >> r) & 1u) { // a run of rows that take no insertion: one shifted vector copy
-                int r1 = r + 1;
-                while (r1 < rows && ((fastmask >> r1) & 1u)) { r1++; }
-                warp_copy_from_smem(out + o, sp + (r << 9), (int64_t)(r1 - r) << 9, lane);
-                o += (long long)(r1 - r) << 9;
-                r = r1;
-                continue;
+    if (active && o + size <= out_cap) { // (capacity overflow is reported by the summary)
+        if (writes_prefix) {
+            if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
+            o += P.sc_len;
+            if (P.len_size) { // big-endian length of what follows (verbatim NALs only: the launcher keeps escaped parts off this path)
+                if (lane < P.len_size) { out[o + lane] = (uint8_t)((uint64_t)nbytes_raw >> (8 * (P.len_size - 1 - lane))); }
+                o += P.len_size;
             }
-            const int64_t row = s0 + ((int64_t)r << 9), cpos = row + lane * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (cpos < p1 && cpos + 16 > p0) { v = *reinterpret_cast<const uint4*>(sp + (r << 9) + lane * 16); }
-            uint32_t rm = sm.run_in[warp][r];
-            const RowInfo ri = insert_row(v, row, p0, p1, lane, rm);
-            o += write_row(ri, out + o, lane);
-            r++;
+        }
+        __syncwarp();
+        if (kind == kRaw) {
+            warp_copy_from_smem(out + o, sp + q0, (int64_t)(q1 - q0), lane);
+        } else if (kind == kEsc) {
+            int r = 0;
+            while (r < rows) {
+                if ((fastmask >> r) & 1u) { // a run of rows that take no insertion: one shifted vector copy
+                    const int nrun = __ffs((int)~(fastmask >> r)) - 1; // (bit 31 of fastmask is never set: at most kPieceRows rows)
+                    warp_copy_from_smem(out + o, sp + (r << 9), (int64_t)nrun << 9, lane);
+                    o += (long long)nrun << 9;
+                    r += nrun;
+                    continue;
+                }
+                const int row = r << 9, cpos = row + lane * 16;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (cpos < q1 && cpos + 16 > q0) { v = *reinterpret_cast<const uint4*>(sp + cpos); }
+                uint32_t rm = sm.run_in[warp][r];
+                const RowInfo ri = insert_row<int>(v, row, q0, q1, lane, rm);
+                o += write_row(ri, out + o, lane);
+                r++;
+            }
         }
     }
+    if (!persistent) { return; }
+    __syncthreads(); // the pieces, sizes and the ticket word are rewritten by the next round
+  }
 }
 
 __global__ void __launch_bounds__(256) fused_summary_kernel(const int64_t* __restrict__ first, int64_t n, int64_t cap_items, int64_t out_cap,
@@ -1050,12 +1099,18 @@ static int launch_assemble_fused(hevcb_ctx* ctx, const AssembleParts& P, int64_t
         ctx->fused_smem_set = 1;
     }
     const unsigned gn = (unsigned)((n + 255) / 256);
+    long long fgrid = (long long)ctx->sm_count * 6; // persistent: six resident CTAs per SM (shared memory), tiles drawn by ticket
+    if (fgrid > cap_tiles + 1) { fgrid = cap_tiles + 1; }
+    int stagger_ns = 0, persistent = 1;
+    if (const char* e = getenv("HEVCB_FUSED_PERSISTENT")) { persistent = atoi(e); }
+    if (!persistent) { fgrid = cap_tiles + 1; }
+    if (const char* e = getenv("HEVCB_FUSED_STAGGER")) { stagger_ns = atoi(e); }
     fused_plan_kernel<<<gn, 256, 0, stream>>>(P, n, packed);
     sizes_reduce_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(packed, n, bs);
     sizes_blocksums_kernel<<<1, kSThreads, 0, stream>>>(bs, nb);
     sizes_apply_kernel<<<(unsigned)nb, kSThreads, 0, stream>>>(packed, n, bs, nb, first);
-    fused_fill_kernel<<<gn, 256, 0, stream>>>(P, first, n, items, cap_items);
-    fused_assemble_kernel<<<(unsigned)(cap_tiles + 1), kFThreads, sizeof(FusedSmem), stream>>>(P, n, first, items, cap_items, states, excl, hdr, d_out_off, d_out, out_cap);
+    fused_fill_kernel<<<(unsigned)((cap_items + 255) / 256), 256, 0, stream>>>(P, first, n, items, cap_items);
+    fused_assemble_kernel<<<(unsigned)fgrid, kFThreads, sizeof(FusedSmem), stream>>>(P, n, first, items, cap_items, states, excl, hdr, d_out_off, d_out, out_cap, stagger_ns, persistent);
     fused_summary_kernel<<<gn < 1024u ? gn : 1024u, 256, 0, stream>>>(first, n, cap_items, out_cap, hdr, d_out_off, d_summary);
     ctx->launches += 7;
     HEVCB_CUDA(ctx, cudaGetLastError());
