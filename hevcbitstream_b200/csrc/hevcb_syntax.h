@@ -194,7 +194,8 @@ struct hevcb_sps_ctx {
     int32_t num_short_term_ref_pic_sets, long_term_ref_pics_present_flag, num_long_term_ref_pics_sps;
     int32_t sps_temporal_mvp_enabled_flag, sample_adaptive_offset_enabled_flag;
     uint32_t used_by_curr_pic_lt_sps_mask;
-    int32_t pad[3];
+    int32_t seq_parameter_set_id; // spec mode: the id slices resolve the SPS by
+    int32_t pad[2];
     hevcb_rps_entry rps[HEVCB_RPS_SLOTS];
 };
 
@@ -204,7 +205,25 @@ struct hevcb_pps_ctx {
     int32_t pps_slice_chroma_qp_offsets_present_flag, weighted_pred_flag, weighted_bipred_flag, tiles_enabled_flag;
     int32_t entropy_coding_sync_enabled_flag, pps_loop_filter_across_slices_enabled_flag, deblocking_filter_override_enabled_flag;
     int32_t lists_modification_present_flag, slice_segment_header_extension_present_flag, chroma_qp_offset_list_enabled_flag;
-    int32_t pad[3];
+    int32_t pic_parameter_set_id;                // spec mode: the id slices resolve the PPS by
+    int32_t pps_deblocking_filter_disabled_flag; // spec mode: inherited by slice_deblocking_filter_disabled_flag
+    int32_t pad[1];
+};
+
+// Spec-correct mode (HEVCB_PARSE_SPEC).  The default walk reproduces the reference, deviations from the HEVC syntax
+// included; the switch turns exactly these into what the standard says (oracle: the reference's own template
+// with the same fixes, oracle/make_spec_ref.py):
+//   A-1  the SPS ends with rbsp_trailing_bits        A-2/3  a slice resolves its PPS by pic_parameter_set_id and that PPS's SPS by
+//   seq_parameter_set_id (the most recent NAL with that id in front of the slice), derived RPS tables per SPS
+//   A-4  ref_pic_list_modification_flag_l1 / list_entry_l1 are read      A-5  use_delta_flag inferred 1
+//   A-6  PPS deblocking offsets present when the filter is NOT disabled   A-7  slice_deblocking_filter_disabled_flag inherits the PPS's
+//   A-8  HRD: cpb_cnt_minus1 present when low_delay_hrd_flag is 0, fixed_pic_rate_within_cvs_flag inferred 1, cpb_cnt_minus1 + 1 entries
+//        per sub-layer; VPS: cprms_present_flag[0] inferred 1
+// The tables of a parse: entry j (1-based) = the j-th SPS / PPS NAL of the stream, entry 0 = the zeroed state before any.
+struct hevcb_ps_lookup {
+    const hevcb_sps_ctx* sps_tab;
+    const hevcb_pps_ctx* pps_tab;
+    int sps_count, pps_count; // SPS / PPS NALs in front of the slice
 };
 
 // per-slice columns written besides the (field, value) pairs
@@ -353,6 +372,8 @@ struct hevcb_walker {
     uint32_t flags; // bit0: an index ran past the reference's array bounds (undefined behaviour there)
     hevcb_bitwriter* bw;
     hevcb_replay* rp;
+    bool spec = false;                    // spec-correct mode (HEVCB_PARSE_SPEC): the fixes listed at hevcb_ps_lookup below
+    const hevcb_ps_lookup* lookup = nullptr; // spec mode: the parameter sets a slice may refer to, resolved by id
 
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0), bw(nullptr), rp(nullptr) {}
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss, hevcb_bitwriter* w, hevcb_replay* r) : b(bb), s(ss), flags(0), bw(w), rp(r) {}
@@ -536,7 +557,7 @@ struct hevcb_walker {
     HEVCB_SHD void sub_layer_hrd(uint32_t base, int cpb_cnt, int sub_pic)
     {
         typedef hevc_sub_layer_hrd_t H;
-        for (int i = 0; i <= cpb_cnt; i++) {
+        for (int i = 0; i < cpb_cnt + (spec ? 0 : 1); i++) { // the reference walks one entry more than cpb_cnt_minus1 + 1 (App. A-8)
             aue(base + HF(H, bit_rate_value_minus1), i, HEVCB_MAX_CPB_CNT);
             aue(base + HF(H, cpb_size_value_minus1), i, HEVCB_MAX_CPB_CNT);
             if (sub_pic) {
@@ -575,9 +596,10 @@ struct hevcb_walker {
             const int general = au(base + HF(H, fixed_pic_rate_general_flag), i, HEVCB_MAX_SUBLAYERS, 1);
             int within = 0, low_delay = 0, cpb_cnt_minus1 = 0;
             if (!general) { within = au(base + HF(H, fixed_pic_rate_within_cvs_flag), i, HEVCB_MAX_SUBLAYERS, 1); }
+            else if (spec) { within = 1; if (i < HEVCB_MAX_SUBLAYERS) { syn(base + HF(H, fixed_pic_rate_within_cvs_flag) + (uint32_t)i, 1); } } // inferred
             if (within) { aue(base + HF(H, elemental_duration_in_tc_minus1), i, HEVCB_MAX_SUBLAYERS); }
             else { low_delay = au(base + HF(H, low_delay_hrd_flag), i, HEVCB_MAX_SUBLAYERS, 1); }
-            if (low_delay) { cpb_cnt_minus1 = aue(base + HF(H, cpb_cnt_minus1), i, HEVCB_MAX_SUBLAYERS); } // read when SET (App. A-8)
+            if (spec ? !low_delay : low_delay) { cpb_cnt_minus1 = aue(base + HF(H, cpb_cnt_minus1), i, HEVCB_MAX_SUBLAYERS); } // the reference reads it when SET (App. A-8)
             const uint32_t sl = (uint32_t)(sizeof(hevc_sub_layer_hrd_t) / sizeof(int));
             if (nal) { if (i < HEVCB_MAX_SUBLAYERS) { sub_layer_hrd(base + HF(H, sub_layer_hrd_nal) + (uint32_t)i * sl, cpb_cnt_minus1 + 1, sub_pic); } }
             if (vcl) { if (i < HEVCB_MAX_SUBLAYERS) { sub_layer_hrd(base + HF(H, sub_layer_hrd_vcl) + (uint32_t)i * sl, cpb_cnt_minus1 + 1, sub_pic); } }
@@ -625,6 +647,9 @@ struct hevcb_walker {
                 if (!ub) {
                     const int ud = au(base + HF(R, use_delta_flag), j, HEVCB_MAX_PICS, 1);
                     if (j < 64) { use_delta |= (uint64_t)(ud & 1) << j; }
+                } else if (spec) { // inferred 1
+                    if (j < HEVCB_MAX_PICS) { syn(base + HF(R, use_delta_flag) + (uint32_t)j, 1); }
+                    if (j < 64) { use_delta |= 1ull << j; }
                 }
             }
             // updateNumDeltaPocs, inter case
@@ -778,6 +803,7 @@ struct hevcb_walker {
                 aue(HF(V, hrd_layer_set_idx), i, HEVCB_MAX_HRD_PARAM);
                 int cprms = 0; // cprms_present_flag[0] is neither read nor inferred (App. A-8)
                 if (i > 0) { cprms = au(HF(V, cprms_present_flag), i, HEVCB_MAX_HRD_PARAM, 1); }
+                else if (spec) { cprms = 1; syn(HF(V, cprms_present_flag), 1); } // inferred
                 const uint32_t hs = (uint32_t)(sizeof(hevc_hrd_t) / sizeof(int));
                 if (i < HEVCB_MAX_HRD_PARAM) { hrd_parameters(HF(V, hrd) + (uint32_t)i * hs, cprms, msl); }
                 else if constexpr (kWrite) { flags |= 1u; }
@@ -796,7 +822,7 @@ struct hevcb_walker {
         const int msl = u(HF(S, sps_max_sub_layers_minus1), 3);
         u1(HF(S, sps_temporal_id_nesting_flag));
         profile_tier_level(HF(S, ptl), msl);
-        ue(HF(S, sps_seq_parameter_set_id));
+        c.seq_parameter_set_id = ue(HF(S, sps_seq_parameter_set_id));
         c.chroma_format_idc = ue(HF(S, chroma_format_idc));
         c.separate_colour_plane_flag = 0;
         if (c.chroma_format_idc == 3) { c.separate_colour_plane_flag = u1(HF(S, separate_colour_plane_flag)); }
@@ -884,13 +910,14 @@ struct hevcb_walker {
             u1(e + HF(E, persistent_rice_adaptation_enabled_flag));
             u1(e + HF(E, cabac_bypass_alignment_enabled_flag));
         }
+        if (spec) { trailing_bits(); } // the reference's SPS has none (App. A-1)
     }
 
     // ---- 7.3.2.3 PPS (hevc_stream.c:419-521) ------------------------------------------------------
     HEVCB_SHD void pic_parameter_set(hevcb_pps_ctx& c)
     {
         typedef hevc_pps_t P;
-        ue(HF(P, pic_parameter_set_id));
+        c.pic_parameter_set_id = ue(HF(P, pic_parameter_set_id));
         c.seq_parameter_set_id = ue(HF(P, seq_parameter_set_id));
         c.dependent_slice_segments_enabled_flag = u1(HF(P, dependent_slice_segments_enabled_flag));
         c.output_flag_present_flag = u1(HF(P, output_flag_present_flag));
@@ -922,9 +949,11 @@ struct hevcb_walker {
         }
         c.pps_loop_filter_across_slices_enabled_flag = u1(HF(P, pps_loop_filter_across_slices_enabled_flag));
         c.deblocking_filter_override_enabled_flag = 0;
+        c.pps_deblocking_filter_disabled_flag = 0;
         if (u1(HF(P, deblocking_filter_control_present_flag))) {
             c.deblocking_filter_override_enabled_flag = u1(HF(P, deblocking_filter_override_enabled_flag));
-            if (u1(HF(P, pps_deblocking_filter_disabled_flag))) { // offsets read when the filter is DISABLED (App. A-6)
+            c.pps_deblocking_filter_disabled_flag = u1(HF(P, pps_deblocking_filter_disabled_flag));
+            if (spec ? !c.pps_deblocking_filter_disabled_flag : c.pps_deblocking_filter_disabled_flag) { // the reference reads the offsets when the filter is DISABLED (App. A-6)
                 se(HF(P, pps_beta_offset_div2));
                 se(HF(P, pps_tc_offset_div2));
             }
@@ -1032,14 +1061,30 @@ struct hevcb_walker {
     // ---- 7.3.6 slice segment header (hevc_stream.c:782-941) --------------------------------------
     // Returns nothing; `cols` receives the per-slice columns.  `sps`/`pps` = the most recent SPS / PPS NAL that
     // precedes the slice in stream order (pointer indexing with id 0, not a table lookup).
-    HEVCB_SHD void slice_segment_header(int nal_unit_type, const hevcb_sps_ctx& sps, const hevcb_pps_ctx& pps, hevcb_slice_cols& cols)
+    HEVCB_SHD void slice_segment_header(int nal_unit_type, const hevcb_sps_ctx& sps_recent, const hevcb_pps_ctx& pps_recent, hevcb_slice_cols& cols)
     {
         typedef hevc_slice_header_t H;
         syn(HF(H, collocated_from_l0_flag), 1); // init_slice_hevc (hevc_stream.c:18-23)
         const int first = u1(HF(H, first_slice_segment_in_pic_flag));
         if (nal_unit_type >= 16 && nal_unit_type <= 23) { u1(HF(H, no_output_of_prior_pics_flag)); }
         const int pps_id = ue(HF(H, pic_parameter_set_id));
-        if (pps_id != 0 || pps.seq_parameter_set_id != 0) { flags |= 1u; } // the reference indexes past its single PPS / SPS
+        // The reference parses against the most recent PPS / SPS NAL whatever the ids say (it indexes its single structs).
+        // Spec mode: the most recent PPS NAL with this id in front of the slice, then the most recent SPS NAL with that PPS's
+        // seq_parameter_set_id (entry 0, the zeroed state, when there is none -- what the reference's calloc'ed tables hold).
+        const hevcb_sps_ctx* sps_p = &sps_recent;
+        const hevcb_pps_ctx* pps_p = &pps_recent;
+        if (spec && lookup != nullptr) {
+            int j = lookup->pps_count;
+            while (j > 0 && lookup->pps_tab[j].pic_parameter_set_id != pps_id) { j--; }
+            pps_p = &lookup->pps_tab[j];
+            int q = lookup->sps_count;
+            while (q > 0 && lookup->sps_tab[q].seq_parameter_set_id != pps_p->seq_parameter_set_id) { q--; }
+            sps_p = &lookup->sps_tab[q];
+            if (pps_id < 0 || pps_id > 255 || pps_p->seq_parameter_set_id < 0 || pps_p->seq_parameter_set_id > 31) { flags |= 1u; } // past the reference's tables
+        }
+        const hevcb_sps_ctx& sps = *sps_p;
+        const hevcb_pps_ctx& pps = *pps_p;
+        if (!spec && (pps_id != 0 || pps.seq_parameter_set_id != 0)) { flags |= 1u; } // the reference indexes past its single PPS / SPS
         int num_ref_idx_l0 = pps.num_ref_idx_l0_default_active_minus1, num_ref_idx_l1 = pps.num_ref_idx_l1_default_active_minus1;
         syn(HF(H, num_ref_idx_l0_active_minus1), num_ref_idx_l0);
         syn(HF(H, num_ref_idx_l1_active_minus1), num_ref_idx_l1);
@@ -1137,7 +1182,14 @@ struct hevcb_walker {
                                 if (b.overrun() && i > 64) { break; }
                             }
                         }
-                        if constexpr (!kWrite && Sink::kTrace) { // B slices: the position prefix of the element that is never read
+                        if (spec) {
+                            if (slice_type == 0 && u1(m + HF(M, ref_pic_list_modification_flag_l1))) {
+                                for (int i = 0; i <= num_ref_idx_l1; i++) {
+                                    au(m + HF(M, list_entry_l1), i, HEVCB_MAX_PICS, hevcb_ceil_log2(total));
+                                    if (b.overrun() && i > 64) { break; }
+                                }
+                            }
+                        } else if constexpr (!kWrite && Sink::kTrace) { // B slices: the position prefix of the element that is never read
                             if (slice_type == 0) { s.trace(b.pos, HEVCB_TRACE_SPECIAL | (uint32_t)HEVCB_TI_OPEN_LINE, 0); }
                         }
                     }
@@ -1162,6 +1214,7 @@ struct hevcb_walker {
             if (pps.chroma_qp_offset_list_enabled_flag) { u1(HF(H, cu_chroma_qp_offset_enabled_flag)); }
             int override_flag = 0, slice_deblocking_disabled = 0;
             if (pps.deblocking_filter_override_enabled_flag) { override_flag = u1(HF(H, deblocking_filter_override_flag)); }
+            if (spec) { slice_deblocking_disabled = pps.pps_deblocking_filter_disabled_flag; syn(HF(H, slice_deblocking_filter_disabled_flag), slice_deblocking_disabled); } // inherited
             if (override_flag) {
                 slice_deblocking_disabled = u1(HF(H, slice_deblocking_filter_disabled_flag));
                 if (!slice_deblocking_disabled) {
@@ -1267,7 +1320,8 @@ HEVCB_SHD inline bool hevcb_is_slice_type(int t) { return (t >= 0 && t <= 9) || 
 // (may be null when the caller does not need them).
 template <class Sink>
 HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Sink& sink, const hevcb_sps_ctx* sps_in, const hevcb_pps_ctx* pps_in,
-                                      hevcb_sps_ctx* sps_out, hevcb_pps_ctx* pps_out, hevcb_nal_result& r, bool aux = false)
+                                      hevcb_sps_ctx* sps_out, hevcb_pps_ctx* pps_out, hevcb_nal_result& r, bool aux = false, bool spec = false,
+                                      const hevcb_ps_lookup* lookup = nullptr)
 {
     hevcb_bits b;
     b.init(rbsp, rbsp_size);
@@ -1288,6 +1342,8 @@ HEVCB_SHD inline void hevcb_parse_nal(const uint8_t* rbsp, int64_t rbsp_size, Si
     r.end_bits = 0;
     r.cols = hevcb_slice_cols{0, 0, 0, 0, 0, 0, 0, 0};
     hevcb_walker<Sink> w(b, sink);
+    w.spec = spec;
+    w.lookup = lookup;
     const int t = r.nal_unit_type;
     if (hevcb_is_slice_type(t)) {
         r.kind = HEVCB_KIND_SLICE;

@@ -52,14 +52,30 @@ NAL_RECORD_DTYPE = np.dtype(
 )
 
 _lib = None
+_SPEC_LIB_PATH = os.path.join(_HERE, "_ref", "libhevcref_spec.so")
+_libs = {}
+_spec = False
+
+
+def spec_available() -> bool:
+    return os.path.exists(_SPEC_LIB_PATH)
+
+
+def use_spec(flag: bool) -> None:
+    """Selects which build every function of this module talks to: the unmodified reference (default) or the reference with
+    the spec fixes of oracle/make_spec_ref.py (the oracle of the spec-correct mode)."""
+    global _spec, _lib
+    _spec = bool(flag)
+    _lib = _libs.get(_spec)
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not available():
-            raise RuntimeError(f"{_LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(_LIB_PATH)
+        path = _SPEC_LIB_PATH if _spec else _LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle ref` / `python oracle/make_spec_ref.py` where /root/reference exists")
+        L = C.CDLL(path)
         p8 = C.POINTER(C.c_uint8)
         p64 = C.POINTER(C.c_int64)
         p32 = C.POINTER(C.c_int32)
@@ -101,6 +117,7 @@ def lib():
         L.ref_writer_read.restype = C.c_int
         L.ref_writer_read.argtypes = [C.c_void_p, C.c_int]
         _lib = L
+        _libs[_spec] = L
     return _lib
 
 

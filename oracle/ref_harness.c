@@ -50,8 +50,27 @@ static double now_s(void)
 
 /* Reset the reference's process-global derived RPS tables so that independent streams parsed in
  * one process do not see each other's state. */
+#ifdef REF_SPEC /* spec-correct build (oracle/make_spec_ref.py): the derived RPS tables exist once per SPS id; ids written by the generator */
+static int g_sps_ids[32], g_n_sps_ids, g_pps_ids[64], g_n_pps_ids;
+static void note_id(int* ids, int* n, int id)
+{
+    for (int i = 0; i < *n; i++) { if (ids[i] == id) { return; } }
+    ids[(*n)++] = id;
+}
+#endif
 REF_API void ref_reset_static_state(void)
 {
+#ifdef REF_SPEC
+    memset(NumDeltaPocs_, 0, sizeof(NumDeltaPocs_));
+    memset(NumNegativePics_, 0, sizeof(NumNegativePics_));
+    memset(NumPositivePics_, 0, sizeof(NumPositivePics_));
+    memset(DeltaPocS0_, 0, sizeof(DeltaPocS0_));
+    memset(UsedByCurrPicS0_, 0, sizeof(UsedByCurrPicS0_));
+    memset(DeltaPocS1_, 0, sizeof(DeltaPocS1_));
+    memset(UsedByCurrPicS1_, 0, sizeof(UsedByCurrPicS1_));
+    spec_rps_cur = 0;
+    return;
+#endif
     memset(NumDeltaPocs, 0, sizeof(NumDeltaPocs));
     memset(NumNegativePics, 0, sizeof(NumNegativePics));
     memset(NumPositivePics, 0, sizeof(NumPositivePics));
@@ -243,7 +262,15 @@ REF_API int64_t ref_parse_all(uint8_t* buf, const int64_t* starts, const int64_t
             r->strip_rc = nal_to_rbsp(nal, &ns, tmp, &rs);
             free(tmp);
         }
+        if (getenv("REF_GEN_DEBUG")) { fprintf(stderr, "parse %lld type %d\n", (long long)k, (nal[0] >> 1) & 63); }
         r->rc = read_hevc_nal_unit(h, nal, size);
+#ifdef REF_SPEC
+        if (getenv("REF_GEN_DEBUG") && ((nal[0] >> 1) & 63) < 22) {
+            hevc_pps_t* dp = h->pps_table[h->sh->pic_parameter_set_id & 255];
+            fprintf(stderr, "read slice k %lld pps %d sps %d tiles %d wpp %d nep %d rc %d dep %d st %d\n", (long long)k, h->sh->pic_parameter_set_id, dp->seq_parameter_set_id,
+                    dp->tiles_enabled_flag, dp->entropy_coding_sync_enabled_flag, h->sh->num_entry_point_offsets, r->rc, h->sh->dependent_slice_segment_flag, h->sh->slice_type);
+        }
+#endif
         r->nal_unit_type = h->nal->nal_unit_type;
         r->nal_layer_id = h->nal->nal_layer_id;
         r->nal_temporal_id_plus1 = h->nal->nal_temporal_id_plus1;
@@ -572,6 +599,14 @@ static void gen_hrd(hevc_hrd_t* hrd, int max_sub_layers_minus1)
             hrd->low_delay_hrd_flag[i] = rr(0, 1);
         }
         hrd->cpb_cnt_minus1[i] = hrd->low_delay_hrd_flag[i] ? rr(0, 4) : 0;
+#ifdef REF_SPEC /* the spec's conditions: within_cvs inferred 1 under general, cpb_cnt_minus1 present when low_delay is 0 */
+        if (hrd->fixed_pic_rate_general_flag[i]) {
+            hrd->fixed_pic_rate_within_cvs_flag[i] = 1;
+            hrd->elemental_duration_in_tc_minus1[i] = rr(0, 2047);
+            hrd->low_delay_hrd_flag[i] = 0;
+        }
+        hrd->cpb_cnt_minus1[i] = hrd->low_delay_hrd_flag[i] ? 0 : rr(0, 4);
+#endif
         gen_sub_layer_hrd(&hrd->sub_layer_hrd_nal[i]);
         gen_sub_layer_hrd(&hrd->sub_layer_hrd_vcl[i]);
     }
@@ -619,6 +654,9 @@ static void gen_vps(hevc_vps_t* vps, int rich)
         for (int i = 0; i < vps->vps_num_hrd_parameters; i++) {
             vps->hrd_layer_set_idx[i] = rr(0, 2);
             vps->cprms_present_flag[i] = (i > 0) ? rr(0, 1) : 0; /* [0] is never coded (App. A-8) */
+#ifdef REF_SPEC
+            if (i == 0) { vps->cprms_present_flag[i] = 1; } /* inferred 1 */
+#endif
             gen_hrd(&vps->hrd[i], vps->vps_max_sub_layers_minus1);
             if (!vps->cprms_present_flag[i]) {
                 /* common info not coded: a reader keeps zeros, which drive the sub-layer loops */
@@ -648,6 +686,9 @@ static void gen_st_rps(hevc_st_ref_pic_set_t* r, int idx, int num)
             for (int j = 0; j <= NumDeltaPocs[ref]; j++) {
                 r->used_by_curr_pic_flag[j] = rr(0, 1);
                 r->use_delta_flag[j] = r->used_by_curr_pic_flag[j] ? 0 : rr(0, 1);
+#ifdef REF_SPEC /* inferred 1 when not present */
+                if (r->used_by_curr_pic_flag[j]) { r->use_delta_flag[j] = 1; }
+#endif
             }
         }
     }
@@ -714,6 +755,11 @@ static void gen_sps(hevc_stream_t* h, int rich)
     sps->sps_temporal_id_nesting_flag = 1;
     gen_ptl(&sps->ptl, rich, sps->sps_max_sub_layers_minus1);
     sps->sps_seq_parameter_set_id = 0; /* must stay 0: slices index h->sps by pointer arithmetic */
+#ifdef REF_SPEC /* id-indexed tables: any id */
+    sps->sps_seq_parameter_set_id = rich ? rr(0, 3) : 0;
+    note_id(g_sps_ids, &g_n_sps_ids, sps->sps_seq_parameter_set_id);
+    spec_rps_cur = sps->sps_seq_parameter_set_id;
+#endif
     sps->chroma_format_idc = rich ? rr(0, 3) : 1;
     sps->separate_colour_plane_flag = (sps->chroma_format_idc == 3) ? rr(0, 1) : 0;
     if (rich) {
@@ -815,6 +861,11 @@ static void gen_pps(hevc_stream_t* h, int rich)
     memset(pps, 0, sizeof(*pps));
     pps->pic_parameter_set_id = 0; /* must stay 0 */
     pps->seq_parameter_set_id = 0;
+#ifdef REF_SPEC
+    pps->pic_parameter_set_id = rich ? rr(0, 5) : 0;
+    pps->seq_parameter_set_id = g_sps_ids[rr(0, g_n_sps_ids - 1)];
+    note_id(g_pps_ids, &g_n_pps_ids, pps->pic_parameter_set_id);
+#endif
     pps->init_qp_minus26 = rich ? rr(-20, 20) : 0;
     pps->cu_qp_delta_enabled_flag = rich ? rr(0, 1) : 1;
     pps->diff_cu_qp_delta_depth = rich ? rr(0, 3) : 0;
@@ -887,6 +938,12 @@ static void gen_slice(hevc_stream_t* h, int rich, int nut, int force_type)
     sh->first_slice_segment_in_pic_flag = rich ? pct(60) : 1;
     sh->no_output_of_prior_pics_flag = rich ? rr(0, 1) : 0;
     sh->pic_parameter_set_id = 0;
+#ifdef REF_SPEC /* the slice is generated against the parameter sets its ids select (the tables hold what a reader has seen) */
+    sh->pic_parameter_set_id = g_pps_ids[rr(0, g_n_pps_ids - 1)];
+    pps = h->pps_table[sh->pic_parameter_set_id];
+    sps = h->sps_table[pps->seq_parameter_set_id];
+    spec_rps_cur = pps->seq_parameter_set_id & 31;
+#endif
     sh->num_ref_idx_l0_active_minus1 = pps->num_ref_idx_l0_default_active_minus1;
     sh->num_ref_idx_l1_active_minus1 = pps->num_ref_idx_l1_default_active_minus1;
     if (!sh->first_slice_segment_in_pic_flag) {
@@ -983,6 +1040,9 @@ static void gen_slice(hevc_stream_t* h, int rich, int nut, int force_type)
     sh->slice_cr_qp_offset = rr(-12, 12);
     sh->cu_chroma_qp_offset_enabled_flag = rr(0, 1);
     if (pps->deblocking_filter_override_enabled_flag) { sh->deblocking_filter_override_flag = rr(0, 1); }
+#ifdef REF_SPEC /* inherited from the PPS unless overridden (the writer's conditions read the struct) */
+    sh->slice_deblocking_filter_disabled_flag = pps->pps_deblocking_filter_disabled_flag;
+#endif
     if (sh->deblocking_filter_override_flag) {
         sh->slice_deblocking_filter_disabled_flag = rr(0, 1);
         if (!sh->slice_deblocking_filter_disabled_flag) { sh->slice_beta_offset_div2 = rr(-6, 6); sh->slice_tc_offset_div2 = rr(-6, 6); }
@@ -1030,7 +1090,8 @@ static void emit_ps(hevc_stream_t* h, int nut, outbuf* o, int extra_zero_pct)
     if (nut == HEVC_NAL_UNIT_TYPE_SPS_NUT || nut == HEVC_NAL_UNIT_TYPE_PPS_NUT) {
         /* make the in-memory state equal to what any reader reconstructs from the bytes; a failing read
          * (the SPS writer drops its last partial byte, App. A-1) leaves the same partial state a reader gets */
-        (void)read_hevc_nal_unit(h, tmp, n);
+        int rrc = read_hevc_nal_unit(h, tmp, n);
+        if (getenv("REF_GEN_DEBUG")) { fprintf(stderr, "emit_ps type %d wrote %d reread rc %d\n", nut, n, rrc); }
     }
     ob_startcode(o, 1, extra_zero_pct);
     ob_put(o, tmp, n);
@@ -1043,6 +1104,9 @@ REF_API int64_t ref_gen_stream(const ref_gen_params* gp, uint8_t* out, int64_t c
     int rich = gp->profile == 1;
     g_rng = gp->seed ? gp->seed : 88172645463325252ull;
     ref_reset_static_state();
+#ifdef REF_SPEC
+    g_n_sps_ids = g_n_pps_ids = 0;
+#endif
 
     gen_vps(h->vps, rich);
     emit_ps(h, HEVC_NAL_UNIT_TYPE_VPS_NUT, &o, gp->extra_zero_pct);
@@ -1093,6 +1157,13 @@ REF_API int64_t ref_gen_stream(const ref_gen_params* gp, uint8_t* out, int64_t c
         h->nal->nal_temporal_id_plus1 = rich ? rr(1, 3) : 1;
         gen_slice(h, rich, nut, ftype);
         int n = write_hevc_nal_unit(h, tmp, cap_hdr);
+#ifdef REF_SPEC
+        if (getenv("REF_GEN_DEBUG")) {
+            hevc_pps_t* dp = h->pps_table[h->sh->pic_parameter_set_id];
+            fprintf(stderr, "gen slice %lld nut %d pps %d sps %d tiles %d wpp %d nep %d n %d dep %d st %d\n", (long long)s, nut, h->sh->pic_parameter_set_id, dp->seq_parameter_set_id,
+                    dp->tiles_enabled_flag, dp->entropy_coding_sync_enabled_flag, h->sh->num_entry_point_offsets, n, h->sh->dependent_slice_segment_flag, h->sh->slice_type);
+        }
+#endif
         if (n <= 0) { o.fail = 1; break; }
         int ns = n, rs = cap_nal;
         int r = nal_to_rbsp(tmp, &ns, rb, &rs);

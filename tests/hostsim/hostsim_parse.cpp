@@ -50,9 +50,14 @@ struct sim_record {
     uint64_t state_hash, slice_data_hash;
 };
 
-extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, const int64_t* ends, int64_t n, sim_record* rec,
-                                     int32_t* sh_dump, int64_t* n_pairs_total, uint32_t* flags_out)
+static int64_t parse_all_impl(const uint8_t* buf, const int64_t* starts, const int64_t* ends, int64_t n, sim_record* rec,
+                              int32_t* sh_dump, int64_t* n_pairs_total, uint32_t* flags_out, bool spec)
 {
+    // spec mode (HEVCB_PARSE_SPEC): the tables of every SPS / PPS NAL seen so far, entry 0 = the zeroed state (as the kernels keep them)
+    std::vector<hevcb_sps_ctx> sps_tab(1);
+    std::vector<hevcb_pps_ctx> pps_tab(1);
+    memset(&sps_tab[0], 0, sizeof(hevcb_sps_ctx));
+    memset(&pps_tab[0], 0, sizeof(hevcb_pps_ctx));
     std::vector<uint8_t> rbsp;
     std::vector<uint32_t> fld(1 << 16);
     std::vector<int32_t> val(1 << 16);
@@ -87,13 +92,14 @@ extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, 
         hevcb_pps_ctx pps_new;
         memset(sps_new, 0, sizeof(*sps_new));
         memset(&pps_new, 0, sizeof(pps_new));
-        hevcb_parse_nal(rbsp.data(), rs, cs, sps, pps, sps_new, &pps_new, res);
+        hevcb_ps_lookup lk{sps_tab.data(), pps_tab.data(), (int)sps_tab.size() - 1, (int)pps_tab.size() - 1};
+        hevcb_parse_nal(rbsp.data(), rs, cs, sps, pps, sps_new, &pps_new, res, false, spec, spec ? &lk : nullptr);
         if (cs.n > fld.size()) { fld.resize(cs.n); val.resize(cs.n); }
         hevcb_sink es{fld.data(), val.data(), 0};
         memset(sps_new, 0, sizeof(*sps_new));
         memset(&pps_new, 0, sizeof(pps_new));
         hevcb_nal_result res2;
-        hevcb_parse_nal(rbsp.data(), rs, es, sps, pps, sps_new, &pps_new, res2);
+        hevcb_parse_nal(rbsp.data(), rs, es, sps, pps, sps_new, &pps_new, res2, false, spec, spec ? &lk : nullptr);
         if (es.n != cs.n || res2.ok != res.ok) { return -2; }
         pairs += es.n;
         allflags |= res.flags;
@@ -105,8 +111,8 @@ extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, 
         size_t words = 0;
         if (res.kind == HEVCB_KIND_SLICE) { dst = (int32_t*)sh_s; words = sizeof(*sh_s) / 4; }
         else if (res.kind == HEVCB_KIND_VPS) { dst = (int32_t*)vps_s; words = sizeof(*vps_s) / 4; }
-        else if (res.kind == HEVCB_KIND_SPS) { dst = (int32_t*)sps_s; words = sizeof(*sps_s) / 4; *sps = *sps_new; }
-        else if (res.kind == HEVCB_KIND_PPS) { dst = (int32_t*)pps_s; words = sizeof(*pps_s) / 4; *pps = pps_new; }
+        else if (res.kind == HEVCB_KIND_SPS) { dst = (int32_t*)sps_s; words = sizeof(*sps_s) / 4; *sps = *sps_new; sps_tab.push_back(*sps_new); }
+        else if (res.kind == HEVCB_KIND_PPS) { dst = (int32_t*)pps_s; words = sizeof(*pps_s) / 4; *pps = pps_new; pps_tab.push_back(pps_new); }
         delete sps_new;
         if (dst) {
             memset(dst, 0, words * 4);
@@ -127,6 +133,18 @@ extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, 
     *flags_out = allflags;
     delete sps; delete pps; delete vps_s; delete sps_s; delete pps_s; delete sh_s;
     return ok;
+}
+
+extern "C" int64_t hostsim_parse_all(const uint8_t* buf, const int64_t* starts, const int64_t* ends, int64_t n, sim_record* rec,
+                                     int32_t* sh_dump, int64_t* n_pairs_total, uint32_t* flags_out)
+{
+    return parse_all_impl(buf, starts, ends, n, rec, sh_dump, n_pairs_total, flags_out, false);
+}
+// the same walk in spec-correct mode (oracle: oracle/_ref/libhevcref_spec.so)
+extern "C" int64_t hostsim_parse_all_spec(const uint8_t* buf, const int64_t* starts, const int64_t* ends, int64_t n, sim_record* rec,
+                                          int32_t* sh_dump, int64_t* n_pairs_total, uint32_t* flags_out)
+{
+    return parse_all_impl(buf, starts, ends, n, rec, sh_dump, n_pairs_total, flags_out, true);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,15 +11,16 @@ from oracle import ref
 pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
 
 
-def sim_parse(lib, buf, st, en):
+def sim_parse(lib, buf, st, en, fn="hostsim_parse_all"):
     n = len(st)
     rec = np.zeros(n, dtype=ref.NAL_RECORD_DTYPE)
     st = np.ascontiguousarray(st, np.int64)
     en = np.ascontiguousarray(en, np.int64)
     npairs = C.c_int64(0)
     fl = C.c_uint32(0)
-    lib.hostsim_parse_all.restype = C.c_int64
-    ok = lib.hostsim_parse_all(buf.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p), C.c_int64(n),
+    f = getattr(lib, fn)
+    f.restype = C.c_int64
+    ok = f(buf.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p), C.c_int64(n),
                                rec.ctypes.data_as(C.c_void_p), None, C.byref(npairs), C.byref(fl))
     return ok, rec, npairs.value, fl.value
 
