@@ -261,7 +261,7 @@ class Context:
         return ns, ne, int(t[0]), int(t[1])
 
     # ---- batched header parse -----------------------------------------------------------------
-    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False, aux=False):
+    def parse_device(self, buf, scan: "ScanResult", cap_pairs=None, sync=True, trace=False, aux=False, spec=False):
         """Header parse of every NAL found by scan_strip_device (device resident).  Returns a dict of torch tensors
         (rc, nal_hdr, kind, ubflag, hdr_end, cols[8][n], pair_off[n+1], pair_field, pair_value) and `summary`.
         trace=True: the read_debug variant (include/hevcb.h): the lists hold what read_debug_hevc_nal_unit prints, with
@@ -287,6 +287,8 @@ class Context:
             pb.pair_pos = out["pair_pos"].data_ptr()
         if aux:  # extension mode: AUD / EOS / EOB / filler / SEI NALs are parsed instead of returning -1 (kind 5)
             pb.flags = 1
+        if spec:  # spec-correct mode (HEVCB_PARSE_SPEC, include/hevcb.h): the standard's syntax where the reference departs from it
+            pb.flags |= 2
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self._L.hevcb_parse_device(self._h, buf.data_ptr(), scan.nal_start.data_ptr(), scan.nal_end.data_ptr(), scan.rbsp.data_ptr(),
                                                scan.rbsp_off.data_ptr(), scan.rbsp_end.data_ptr(), n, C.byref(pb), out["summary"].data_ptr(), stream))
@@ -336,7 +338,7 @@ class Context:
                 raise HevcbError(-104, f"{out['out_bytes']} output bytes exceed out_cap {out_cap}")
         return out
 
-    def index_host(self, buf: np.ndarray, size=None, cap_nals=None, cap_pairs=None, want_rbsp=True) -> "HostIndex":
+    def index_host(self, buf: np.ndarray, size=None, cap_nals=None, cap_pairs=None, want_rbsp=True, flags=0) -> "HostIndex":
         """Annex-B bytes in host memory -> full index (hevcb_index_host: scan + strip + parse, copies included)."""
         assert buf.dtype == np.uint8
         size = int(buf.size if size is None else size)
@@ -344,13 +346,13 @@ class Context:
             cap_nals = size // 3 + 8
         if cap_pairs is None:
             cap_pairs = 64 * min(cap_nals, size // 4 + 8) + 4096
-        return HostIndex(self, buf, size, cap_nals, cap_pairs, want_rbsp)
+        return HostIndex(self, buf, size, cap_nals, cap_pairs, want_rbsp, flags)
 
 
 class HostIndex:
     """Owns the host arrays of a hevcb_stream_index and exposes hevcb_materialize."""
 
-    def __init__(self, ctx: Context, buf, size, cap_nals, cap_pairs, want_rbsp):
+    def __init__(self, ctx: Context, buf, size, cap_nals, cap_pairs, want_rbsp, flags=0):
         self._L = ctx._L
         a = self.arrays = dict(
             nal_start=np.zeros(cap_nals, np.int64), nal_end=np.zeros(cap_nals, np.int64), rbsp_off=np.zeros(cap_nals, np.int64),
@@ -361,6 +363,7 @@ class HostIndex:
         )
         pb = ParseBuffers(_np_ptr(a["rc"]), _np_ptr(a["nal_hdr"]), _np_ptr(a["kind"]), _np_ptr(a["ubflag"]), _np_ptr(a["hdr_end"]), _np_ptr(a["cols"]),
                           _np_ptr(a["pair_off"]), _np_ptr(a["pair_field"]), _np_ptr(a["pair_value"]), cap_pairs)
+        pb.flags = int(flags)  # HEVCB_PARSE_AUX = 1, HEVCB_PARSE_SPEC = 2
         self.idx = StreamIndex(cap_nals, _np_ptr(a["nal_start"]), _np_ptr(a["nal_end"]), _np_ptr(a["rbsp_off"]), _np_ptr(a["rbsp_end"]),
                                _np_ptr(a["rbsp"]), pb, ScanSummary(), ParseSummary())
         ctx._check(self._L.hevcb_index_host(ctx._h, _np_ptr(buf), size, C.byref(self.idx)))

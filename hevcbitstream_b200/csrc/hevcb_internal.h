@@ -29,6 +29,7 @@ struct hevcb_ctx {
     // what the last hevcb_parse_* left on the device (consumed by hevcb_rewrite_*)
     struct {
         int64_t n = -1;
+        int spec = 0; // the parse ran with HEVCB_PARSE_SPEC
         const void *cls = nullptr, *sps_ord = nullptr, *pps_ord = nullptr, *cnt = nullptr, *perm = nullptr;
         void *sps_tab = nullptr, *pps_tab = nullptr, *sps_scratch = nullptr;
     } last_parse;

@@ -226,6 +226,7 @@ struct ParseArgs {
     int32_t* pair_value;
     uint32_t* pair_pos; // trace mode (read_debug variant): bit position of every record
     int64_t cap_pairs;
+    bool spec;          // HEVCB_PARSE_SPEC: the spec-correct walk (slices resolve their parameter sets by id over the whole tables)
 };
 
 // kTrace: the read_debug variant of the walk (hevcb_sink_t<true>): the lists hold what read_debug_hevc_nal_unit prints; NALs of
@@ -256,9 +257,11 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
     if (c == kCls_Pps) { pps_out = kEmit ? &a.pps_scratch[pps_count] : &a.pps_tab[pps_count]; }
     hevcb_nal_result r;
     typedef hevcb_sink_t<kTrace> SinkT;
+    const hevcb_ps_lookup lk{a.sps_tab, a.pps_tab, sps_count, pps_count}; // spec mode, slices: every SPS / PPS NAL in front of this one
+    const hevcb_ps_lookup* lkp = (a.spec && is_slice) ? &lk : nullptr;
     if (!kEmit) {
         SinkT sink{nullptr, nullptr, 0, nullptr};
-        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux);
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux, a.spec, lkp);
         a.cnt[k] = (int32_t)sink.n;
         a.kind[k] = (uint8_t)r.kind;
         a.ubflag[k] = (uint8_t)(r.flags & 0xFFu);
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(128) parse_kernel(ParseArgs a)
         const int64_t pn = (int64_t)a.cnt[k];
         if (pn == 0 || po + pn > a.cap_pairs) { return; }
         SinkT sink{a.pair_field + po, a.pair_value + po, 0, kTrace ? a.pair_pos + po : nullptr};
-        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux);
+        hevcb_parse_nal(a.rbsp + off, size, sink, sps_in, pps_in, sps_out, pps_out, r, c == kCls_Aux, a.spec, lkp);
         if (sink.n != (uint32_t)pn) { a.ubflag[k] |= 0x80u; a.cols[k] = (int32_t)r.end_bits; a.cols[a.n + k] = (int32_t)sink.n; } // self-check
     }
 }
@@ -518,6 +521,10 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
         HEVCB_SET_ERR(ctx, "hevcb_rewrite: invalid argument");
         return HEVCB_E_ARG;
     }
+    if (ctx->last_parse.n == n && ctx->last_parse.spec) {
+        HEVCB_SET_ERR(ctx, "hevcb_rewrite: results of a spec-correct parse (HEVCB_PARSE_SPEC) cannot be rewritten yet");
+        return HEVCB_E_ARG;
+    }
     if (ctx->last_parse.n != n) {
         HEVCB_SET_ERR(ctx, "hevcb_rewrite: must follow hevcb_parse_device of the same %lld NALs on this context", (long long)n);
         return HEVCB_E_ARG;
@@ -618,6 +625,10 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
         HEVCB_SET_ERR(ctx, "hevcb_parse: output buffers missing");
         return HEVCB_E_ARG;
     }
+    if (chain && (out->flags & HEVCB_PARSE_SPEC)) {
+        HEVCB_SET_ERR(ctx, "hevcb_parse: the spec-correct mode is not available for shard parses (a slice may refer to any earlier parameter set)");
+        return HEVCB_E_ARG;
+    }
     HEVCB_CUDA(ctx, cudaMemsetAsync(d_summary, 0, sizeof(hevcb_parse_summary), stream));
     ctx->last_parse.n = -1;
     if (n == 0) {
@@ -681,8 +692,10 @@ int hevcb_launch_parse(hevcb_ctx* ctx, const uint8_t* d_buf, const int64_t* d_na
     a.pps_scratch = reinterpret_cast<hevcb_pps_ctx*>(pb + 2 * sps_bytes + pps_bytes);
     a.rc = out->rc; a.kind = out->kind; a.ubflag = out->ubflag; a.cnt = cnt; a.hdr_end = out->hdr_end; a.cols = out->cols;
     a.pair_off = out->pair_off; a.pair_field = out->pair_field; a.pair_value = out->pair_value; a.cap_pairs = out->cap_pairs;
+    a.spec = (out->flags & HEVCB_PARSE_SPEC) != 0u;
 
     ctx->last_parse.n = n;
+    ctx->last_parse.spec = a.spec ? 1 : 0;
     ctx->last_parse.cls = cls; ctx->last_parse.sps_ord = sps_ord; ctx->last_parse.pps_ord = pps_ord; ctx->last_parse.cnt = cnt;
     ctx->last_parse.perm = perm;
     ctx->last_parse.sps_tab = a.sps_tab; ctx->last_parse.pps_tab = a.pps_tab; ctx->last_parse.sps_scratch = a.sps_scratch;

@@ -378,6 +378,13 @@ struct hevcb_walker {
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss) : b(bb), s(ss), flags(0), bw(nullptr), rp(nullptr) {}
     HEVCB_SHD hevcb_walker(hevcb_bits& bb, Sink& ss, hevcb_bitwriter* w, hevcb_replay* r) : b(bb), s(ss), flags(0), bw(w), rp(r) {}
 
+    // Loops whose trip count comes out of the bitstream stop once the reader (writer) has run past its buffer: every further
+    // element is 0 and the NAL fails anyway (rc -1), but a count of 2^31 read out of garbage -- a slice parsed against the wrong
+    // parameter set, say -- would otherwise keep one GPU thread busy for minutes.  (The reference walks on and crashes there.)
+    HEVCB_SHD bool runaway(int i) const
+    {
+        if constexpr (kWrite) { return i > 64 && bw->overrun(); } else { return i > 64 && b.overrun(); }
+    }
     // one parsed element: (field, value) pair, or a trace record with the position the read started at
     HEVCB_SHD void rep(uint32_t f, int32_t v, int64_t p0)
     {
@@ -557,7 +564,7 @@ struct hevcb_walker {
     HEVCB_SHD void sub_layer_hrd(uint32_t base, int cpb_cnt, int sub_pic)
     {
         typedef hevc_sub_layer_hrd_t H;
-        for (int i = 0; i < cpb_cnt + (spec ? 0 : 1); i++) { // the reference walks one entry more than cpb_cnt_minus1 + 1 (App. A-8)
+        for (int i = 0; i < cpb_cnt + (spec ? 0 : 1); i++) { if (runaway(i)) { break; } // the reference walks one entry more than cpb_cnt_minus1 + 1 (App. A-8)
             aue(base + HF(H, bit_rate_value_minus1), i, HEVCB_MAX_CPB_CNT);
             aue(base + HF(H, cpb_size_value_minus1), i, HEVCB_MAX_CPB_CNT);
             if (sub_pic) {
@@ -641,7 +648,7 @@ struct hevcb_walker {
             if (ref_idx < 0 || ref_idx >= HEVCB_RPS_SLOTS) { flags |= 1u; ref_idx = 0; } // out of bounds in the reference
             const hevcb_rps_entry& ref = tbl[ref_idx];
             uint64_t used = 0, use_delta = 0; // use_delta_flag stays 0 when used_by_curr_pic_flag is 1 (App. A-5)
-            for (int j = 0; j <= ref.num_delta; j++) {
+            for (int j = 0; j <= ref.num_delta; j++) { if (runaway(j)) { break; }
                 const int ub = au(base + HF(R, used_by_curr_pic_flag), j, HEVCB_MAX_PICS, 1);
                 if (j < 64) { used |= (uint64_t)(ub & 1) << j; }
                 if (!ub) {
@@ -699,14 +706,14 @@ struct hevcb_walker {
             const int nneg = ue(base + HF(R, num_negative_pics));
             const int npos = ue(base + HF(R, num_positive_pics));
             int32_t acc = 0;
-            for (int i = 0; i < nneg; i++) {
+            for (int i = 0; i < nneg; i++) { if (runaway(i)) { break; }
                 const int d = aue(base + HF(R, delta_poc_s0_minus1), i, HEVCB_MAX_PICS);
                 const int ub = au(base + HF(R, used_by_curr_pic_s0_flag), i, HEVCB_MAX_PICS, 1);
                 acc = (i == 0) ? -(d + 1) : acc - (d + 1);
                 if (i < 32) { cur.dpoc_s0[i] = acc; cur.used_s0 = (cur.used_s0 & ~(1u << i)) | ((uint32_t)(ub & 1) << i); }
             }
             acc = 0;
-            for (int i = 0; i < npos; i++) {
+            for (int i = 0; i < npos; i++) { if (runaway(i)) { break; }
                 const int d = aue(base + HF(R, delta_poc_s1_minus1), i, HEVCB_MAX_PICS);
                 const int ub = au(base + HF(R, used_by_curr_pic_s1_flag), i, HEVCB_MAX_PICS, 1);
                 acc = (i == 0) ? (d + 1) : acc + (d + 1);
@@ -790,7 +797,7 @@ struct hevcb_walker {
         const int max_layer_id = u(HF(V, vps_max_layer_id), 6);
         const int num_layer_sets_minus1 = ue(HF(V, vps_num_layer_sets_minus1));
         for (int i = 1; i <= num_layer_sets_minus1; i++) {
-            for (int j = 0; j <= max_layer_id; j++) {
+            for (int j = 0; j <= max_layer_id; j++) { if (runaway(j)) { break; }
                 raw_u(HF(V, layer_id_included_flag) + (uint32_t)(i * HEVCB_MAX_SUBLAYERS + j), i < HEVCB_MAX_SUBLAYERS && j < HEVCB_MAX_SUBLAYERS, 1);
             }
         }
@@ -799,7 +806,7 @@ struct hevcb_walker {
             u(HF(V, vps_time_scale), 32);
             if (u1(HF(V, vps_poc_proportional_to_timing_flag))) { ue(HF(V, vps_num_ticks_poc_diff_one_minus1)); }
             const int num_hrd = ue(HF(V, vps_num_hrd_parameters));
-            for (int i = 0; i < num_hrd; i++) {
+            for (int i = 0; i < num_hrd; i++) { if (runaway(i)) { break; }
                 aue(HF(V, hrd_layer_set_idx), i, HEVCB_MAX_HRD_PARAM);
                 int cprms = 0; // cprms_present_flag[0] is neither read nor inferred (App. A-8)
                 if (i > 0) { cprms = au(HF(V, cprms_present_flag), i, HEVCB_MAX_HRD_PARAM, 1); }
@@ -863,7 +870,7 @@ struct hevcb_walker {
         }
         c.num_short_term_ref_pic_sets = ue(HF(S, num_short_term_ref_pic_sets));
         const uint32_t rs = (uint32_t)(sizeof(hevc_st_ref_pic_set_t) / sizeof(int));
-        for (int i = 0; i < c.num_short_term_ref_pic_sets; i++) {
+        for (int i = 0; i < c.num_short_term_ref_pic_sets; i++) { if (runaway(i)) { break; }
             if (i < HEVCB_MAX_PICS) {
                 st_ref_pic_set(HF(S, st_ref_pic_set) + (uint32_t)i * rs, i, c.num_short_term_ref_pic_sets, c.rps, c.rps[i]);
             } else if constexpr (kWrite) {
@@ -881,7 +888,7 @@ struct hevcb_walker {
         c.used_by_curr_pic_lt_sps_mask = 0;
         if (c.long_term_ref_pics_present_flag) {
             c.num_long_term_ref_pics_sps = ue(HF(S, num_long_term_ref_pics_sps));
-            for (int i = 0; i < c.num_long_term_ref_pics_sps; i++) {
+            for (int i = 0; i < c.num_long_term_ref_pics_sps; i++) { if (runaway(i)) { break; }
                 au(HF(S, lt_ref_pic_poc_lsb_sps), i, HEVCB_MAX_PICS, c.log2_max_poc_lsb_minus4 + 4);
                 const int f = au(HF(S, used_by_curr_pic_lt_sps_flag), i, HEVCB_MAX_PICS, 1);
                 if (i < 32) { c.used_by_curr_pic_lt_sps_mask |= (uint32_t)(f & 1) << i; }
@@ -942,8 +949,8 @@ struct hevcb_walker {
             const int cols = ue(HF(P, num_tile_columns_minus1));
             const int rows = ue(HF(P, num_tile_rows_minus1));
             if (!u1(HF(P, uniform_spacing_flag))) {
-                for (int i = 0; i < cols; i++) { aue(HF(P, column_width_minus1), i, HEVCB_MAX_PICS); }
-                for (int i = 0; i < rows; i++) { aue(HF(P, row_height_minus1), i, HEVCB_MAX_PICS); }
+                for (int i = 0; i < cols; i++) { if (runaway(i)) { break; } aue(HF(P, column_width_minus1), i, HEVCB_MAX_PICS); }
+                for (int i = 0; i < rows; i++) { if (runaway(i)) { break; } aue(HF(P, row_height_minus1), i, HEVCB_MAX_PICS); }
             }
             u1(HF(P, loop_filter_across_tiles_enabled_flag));
         }
@@ -979,7 +986,7 @@ struct hevcb_walker {
             if (c.chroma_qp_offset_list_enabled_flag) {
                 ue(e + HF(E, diff_cu_chroma_qp_offset_depth));
                 const int len_minus1 = ue(e + HF(E, chroma_qp_offset_list_len_minus1));
-                for (int i = 0; i <= len_minus1; i++) {
+                for (int i = 0; i <= len_minus1; i++) { if (runaway(i)) { break; }
                     ase(e + HF(E, cb_qp_offset_list), i, HEVCB_MAX_PICS);
                     ase(e + HF(E, cr_qp_offset_list), i, HEVCB_MAX_PICS);
                 }
@@ -1049,11 +1056,18 @@ struct hevcb_walker {
         int n = 0;
         for (int i = 0; i < e.num_neg && i < 32; i++) { n += (e.used_s0 >> i) & 1u; }
         for (int i = 0; i < e.num_pos && i < 32; i++) { n += (e.used_s1 >> i) & 1u; }
-        for (int i = 0; i < num_lt_sps + num_lt_pics; i++) {
+        const long long total = (long long)num_lt_sps + (long long)num_lt_pics;
+        for (int i = 0; i < total && i < 32; i++) {
             int used;
-            if (i < num_lt_sps) { const int k = (i < 32) ? lt_idx_sps[i] : 0; used = (k >= 0 && k < 32) ? ((sps.used_by_curr_pic_lt_sps_mask >> k) & 1u) : 0; }
-            else { used = (i < 32) ? ((used_lt_mask >> i) & 1u) : 0; }
+            if (i < num_lt_sps) { const int k = lt_idx_sps[i]; used = (k >= 0 && k < 32) ? ((sps.used_by_curr_pic_lt_sps_mask >> k) & 1u) : 0; }
+            else { used = (used_lt_mask >> i) & 1u; }
             n += used;
+        }
+        // entries 32 and up (only on corrupt input; the counts come out of the bitstream): an SPS candidate counts as index 0, a
+        // slice-local one as unused -- in closed form, a count of 2^31 must not become a loop
+        if (total > 32 && num_lt_sps > 32) {
+            const long long m = ((long long)num_lt_sps < total ? (long long)num_lt_sps : total) - 32;
+            n += (int)(m * (long long)(sps.used_by_curr_pic_lt_sps_mask & 1u));
         }
         return n;
     }
@@ -1231,7 +1245,7 @@ struct hevcb_walker {
             cols.num_entry_point_offsets = n;
             if (n > 0) {
                 const int len_minus1 = ue(HF(H, offset_len_minus1));
-                for (int i = 0; i < n; i++) {
+                for (int i = 0; i < n; i++) { if (runaway(i)) { break; }
                     // u(offset_len_minus1 + 1): widths beyond 32 only occur on corrupt input
                     const int w = len_minus1 + 1;
                     if constexpr (kWrite) {
@@ -1248,7 +1262,7 @@ struct hevcb_walker {
         }
         if (pps.slice_segment_header_extension_present_flag) {
             const int len = ue(HF(H, slice_segment_header_extension_length));
-            for (int i = 0; i < len; i++) {
+            for (int i = 0; i < len; i++) { if (runaway(i)) { break; }
                 fx(8, 0u, HEVCB_TI_SH_EXTENSION_DATA_BYTE);
                 if (b.overrun()) { break; }
             }
@@ -1273,19 +1287,19 @@ struct hevcb_walker {
     HEVCB_SHD void one_list(uint32_t base, int cat, int n, uint32_t f_lw, uint32_t f_cw, uint32_t f_dl, uint32_t f_lo, uint32_t f_dcw, uint32_t f_dco)
     {
         uint64_t lw = 0, cw = 0; // chroma flags stay 0 (struct zeroed) when ChromaArrayType == 0
-        for (int i = 0; i <= n; i++) {
+        for (int i = 0; i <= n; i++) { if (runaway(i)) { break; }
             const int f = au(base + f_lw, i, HEVCB_MAX_PICS, 1);
             if (i < 64) { lw |= (uint64_t)(f & 1) << i; }
             if (b.overrun() && i > 64) { break; }
         }
         if (cat != 0) {
-            for (int i = 0; i <= n; i++) {
+            for (int i = 0; i <= n; i++) { if (runaway(i)) { break; }
                 const int f = au(base + f_cw, i, HEVCB_MAX_PICS, 1);
                 if (i < 64) { cw |= (uint64_t)(f & 1) << i; }
                 if (b.overrun() && i > 64) { break; }
             }
         }
-        for (int i = 0; i <= n; i++) {
+        for (int i = 0; i <= n; i++) { if (runaway(i)) { break; }
             if (i < 64 && ((lw >> i) & 1)) {
                 ase(base + f_dl, i, HEVCB_MAX_PICS);
                 ase(base + f_lo, i, HEVCB_MAX_PICS);

@@ -291,6 +291,17 @@ typedef struct hevcb_parse_buffers { /* device pointers for hevcb_parse_device, 
  *              more_rbsp_data (h264_stream.c:62-84): (HEVCB_AUX_SEI_TYPE, t) (HEVCB_AUX_SEI_SIZE, n) (HEVCB_AUX_SEI_OFFSET, o): the
  *              payload is rbsp[rbsp_off[k] + o .. + n); the bytes stay in the image */
 #define HEVCB_PARSE_AUX 1u
+/* Spec-correct mode (flags & HEVCB_PARSE_SPEC).  The default walk reproduces the reference including where it departs
+ * from the HEVC syntax: that is what parity is measured against, and it mis-parses most real encoder output.
+ * With the flag the walk follows the standard in exactly these places (the oracle is the reference's own template with the same
+ * fixes, regenerated by oracle/make_spec_ref.py): the SPS ends with rbsp_trailing_bits; a slice resolves its PPS by
+ * pic_parameter_set_id and that PPS's SPS by seq_parameter_set_id (the most recent NAL with the id in front of the slice; derived
+ * RPS tables per SPS); ref_pic_list_modification_flag_l1 / list_entry_l1 are read; use_delta_flag, fixed_pic_rate_within_cvs_flag
+ * and cprms_present_flag[0] take their inferred values; the PPS deblocking offsets are present when the filter is not disabled and
+ * slices inherit pps_deblocking_filter_disabled_flag; cpb_cnt_minus1 is present when low_delay_hrd_flag is 0 and a sub-layer has
+ * cpb_cnt_minus1 + 1 entries.  Structures stay the reference's (pairs index the same structs).  Not available for shard parses
+ * (hevcb_parse_shard_device) and not accepted by hevcb_rewrite_device yet: both return HEVCB_E_ARG. */
+#define HEVCB_PARSE_SPEC 2u
 #define HEVCB_AUX_AUD_PIC_TYPE 0u
 #define HEVCB_AUX_FD_FF_BYTES 8u
 #define HEVCB_AUX_SEI_TYPE 16u

@@ -93,6 +93,9 @@ def main():
     cmd = ["gcc", "-O2", "-std=gnu99", "-fPIC", "-w", "-DREF_SPEC=1", "-I" + OUT, "-I" + REF, "-shared", "-o", os.path.join(HERE, "_ref", "libhevcref_spec.so"),
            os.path.join(HERE, "ref_harness.c")] + srcs + ["-lm"]
     subprocess.check_call(cmd)
+    for f in ("hevc_stream.in.c", "hevc_stream.c"):  # the patched template and the generated file are intermediates: only the library stays
+        os.remove(os.path.join(OUT, f))
+    os.rmdir(OUT)
     print("built oracle/_ref/libhevcref_spec.so (reference template + spec fixes)")
     return 0
 

@@ -262,15 +262,7 @@ REF_API int64_t ref_parse_all(uint8_t* buf, const int64_t* starts, const int64_t
             r->strip_rc = nal_to_rbsp(nal, &ns, tmp, &rs);
             free(tmp);
         }
-        if (getenv("REF_GEN_DEBUG")) { fprintf(stderr, "parse %lld type %d\n", (long long)k, (nal[0] >> 1) & 63); }
         r->rc = read_hevc_nal_unit(h, nal, size);
-#ifdef REF_SPEC
-        if (getenv("REF_GEN_DEBUG") && ((nal[0] >> 1) & 63) < 22) {
-            hevc_pps_t* dp = h->pps_table[h->sh->pic_parameter_set_id & 255];
-            fprintf(stderr, "read slice k %lld pps %d sps %d tiles %d wpp %d nep %d rc %d dep %d st %d\n", (long long)k, h->sh->pic_parameter_set_id, dp->seq_parameter_set_id,
-                    dp->tiles_enabled_flag, dp->entropy_coding_sync_enabled_flag, h->sh->num_entry_point_offsets, r->rc, h->sh->dependent_slice_segment_flag, h->sh->slice_type);
-        }
-#endif
         r->nal_unit_type = h->nal->nal_unit_type;
         r->nal_layer_id = h->nal->nal_layer_id;
         r->nal_temporal_id_plus1 = h->nal->nal_temporal_id_plus1;
@@ -1090,8 +1082,7 @@ static void emit_ps(hevc_stream_t* h, int nut, outbuf* o, int extra_zero_pct)
     if (nut == HEVC_NAL_UNIT_TYPE_SPS_NUT || nut == HEVC_NAL_UNIT_TYPE_PPS_NUT) {
         /* make the in-memory state equal to what any reader reconstructs from the bytes; a failing read
          * (the SPS writer drops its last partial byte, App. A-1) leaves the same partial state a reader gets */
-        int rrc = read_hevc_nal_unit(h, tmp, n);
-        if (getenv("REF_GEN_DEBUG")) { fprintf(stderr, "emit_ps type %d wrote %d reread rc %d\n", nut, n, rrc); }
+        (void)read_hevc_nal_unit(h, tmp, n);
     }
     ob_startcode(o, 1, extra_zero_pct);
     ob_put(o, tmp, n);
@@ -1157,13 +1148,6 @@ REF_API int64_t ref_gen_stream(const ref_gen_params* gp, uint8_t* out, int64_t c
         h->nal->nal_temporal_id_plus1 = rich ? rr(1, 3) : 1;
         gen_slice(h, rich, nut, ftype);
         int n = write_hevc_nal_unit(h, tmp, cap_hdr);
-#ifdef REF_SPEC
-        if (getenv("REF_GEN_DEBUG")) {
-            hevc_pps_t* dp = h->pps_table[h->sh->pic_parameter_set_id];
-            fprintf(stderr, "gen slice %lld nut %d pps %d sps %d tiles %d wpp %d nep %d n %d dep %d st %d\n", (long long)s, nut, h->sh->pic_parameter_set_id, dp->seq_parameter_set_id,
-                    dp->tiles_enabled_flag, dp->entropy_coding_sync_enabled_flag, h->sh->num_entry_point_offsets, n, h->sh->dependent_slice_segment_flag, h->sh->slice_type);
-        }
-#endif
         if (n <= 0) { o.fail = 1; break; }
         int ns = n, rs = cap_nal;
         int r = nal_to_rbsp(tmp, &ns, rb, &rs);
