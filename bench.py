@@ -388,8 +388,8 @@ def run_ours(args):
             outs = hs.alloc_shard_outputs(d, size, cap)
             box = {}
 
-            def step():
-                box["sc"], box["res"] = hs.scan_strip_sharded(ctx, d, size, halo, is_first, is_last, out=outs)
+            def step():  # the join of the records and the patches run on the device: a step is queued without waiting for the host
+                box["sc"], _ = hs.scan_strip_sharded(ctx, d, size, halo, is_first, is_last, out=outs, sync=False)
         step()
         torch.cuda.synchronize()
         for _ in range(warmup):
@@ -410,7 +410,8 @@ def run_ours(args):
             n_nals, rbsp_bytes, n_epb = int(s[0]), int(s[5]), int(s[6])
             assert int(s[2] >> 32) == 0, "NAL capacity overflow in bench"
         else:
-            sc, res = box["sc"], box["res"]
+            sc = box["sc"]
+            res = hs.fetch_stitch(sc)
             n_nals, rbsp_bytes, n_epb = int(res.n_owned[rank]), int(sc.record.rbsp_bytes), int(sc.record.n_epb)
             stitched = {"global_n_nals": int(res.glob.n_nals), "global_rbsp_bytes": int(res.glob.rbsp_bytes), "last_rc": int(res.glob.last_rc),
                         "patches": int(res.n_patches), "owned_per_rank": [int(res.n_owned[r]) for r in range(world)]}

@@ -148,6 +148,8 @@ def load_library() -> C.CDLL:
     L.hevcb_apply_patches_device.argtypes = [vp, C.POINTER(StitchResult), C.c_int, vp, vp, vp, vp, i64, vp]
     L.hevcb_plan_shards.restype = C.c_int
     L.hevcb_plan_shards.argtypes = [vp, i64, C.c_int, vp]
+    L.hevcb_stitch_apply_device.restype = C.c_int
+    L.hevcb_stitch_apply_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i64, vp, vp]
     L.hevcb_stitch.restype = C.c_int
     L.hevcb_stitch.argtypes = [C.POINTER(ShardSummary), C.c_int, C.POINTER(StitchResult)]
     L.hevcb_rewrite_device.restype = C.c_int

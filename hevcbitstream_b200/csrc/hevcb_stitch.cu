@@ -1,12 +1,16 @@
-// hevcb_stitch.cu -- host side of the byte-range sharding (include/hevcb.h: hevcb_plan_shards, hevcb_stitch).
+// hevcb_stitch.cu -- the join of the byte-range sharding (include/hevcb.h: hevcb_plan_shards, hevcb_stitch, hevcb_stitch_apply_device).
 //
-// No device code here: the per-shard passes run on the GPUs (hevcb_scan_strip_shard_device); what is left is O(shards)
-// integer bookkeeping over the all-gathered shard records, plus the reference's end-of-buffer rules (h264_nal.c:46-72,
-// restated in hevcb_scan_tail) applied once to the last 8 bytes of the stream, which travel inside the last record.
+// The per-shard passes run on the GPUs (hevcb_scan_strip_shard_device); what is left is O(shards) integer bookkeeping over the
+// all-gathered shard records, plus the reference's end-of-buffer rules (h264_nal.c:46-72, restated in hevcb_scan_tail) applied once to
+// the last 8 bytes of the stream, which travel inside the last record.  The same function runs on the host (hevcb_stitch) and, so that
+// a distributed step needs no device->host round trip, as a one-thread kernel that also writes the shard's patches
+// (hevcb_stitch_apply_device).
 #include <stdint.h>
 #include <string.h>
 
-#include "../../include/hevcb.h"
+#include <cuda_runtime.h>
+
+#include "hevcb_internal.h"
 #include "hevcb_scan_core.h"
 
 extern "C" HEVCB_API int hevcb_plan_shards(const uint8_t* buf, int64_t size, int n_shards, int64_t* bounds)
@@ -39,7 +43,7 @@ struct TailFetch {
 };
 } // namespace
 
-extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shards, hevcb_stitch_result* out)
+static __host__ __device__ int stitch_core(const hevcb_shard_summary* sh, int n_shards, hevcb_stitch_result* out)
 {
     if (!sh || !out || n_shards < 1 || n_shards > HEVCB_MAX_SHARDS) { return HEVCB_E_ARG; }
     memset(out, 0, sizeof(*out));
@@ -197,5 +201,41 @@ extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shard
     out->global.last_rc = t.last_rc;
     out->global.last_start = base + t.last_start;
     out->global.last_end = base + t.last_end;
+    return HEVCB_OK;
+}
+
+extern "C" HEVCB_API int hevcb_stitch(const hevcb_shard_summary* sh, int n_shards, hevcb_stitch_result* out) { return stitch_core(sh, n_shards, out); }
+
+namespace {
+// the join on the device: one thread runs the same arithmetic over the gathered records (they are in device memory after the
+// all_gather) and writes the entries of this rank's arrays that the join decides (<= 2 per rank)
+__global__ void stitch_apply_kernel(const hevcb_shard_summary* __restrict__ recs, int n_shards, int shard, int64_t* ns, int64_t* ne, int64_t* ro,
+                                    int64_t* re, int64_t cap, hevcb_stitch_result* __restrict__ res)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+    const int rc = stitch_core(recs, n_shards, res);
+    if (rc != HEVCB_OK) { res->n_patches = -1; return; } // (reported by the host wrapper when the result is fetched)
+    for (int i = 0; i < res->n_patches; i++) {
+        const hevcb_stitch_patch& p = res->patches[i];
+        if (p.shard != shard || p.index < 0 || p.index >= cap) { continue; }
+        if (p.set_start) { ns[p.index] = p.nal_start; ro[p.index] = p.rbsp_off; }
+        ne[p.index] = p.nal_end;
+        re[p.index] = p.rbsp_end;
+    }
+}
+} // namespace
+
+extern "C" HEVCB_API int hevcb_stitch_apply_device(hevcb_ctx* ctx, const hevcb_shard_summary* d_records, int n_shards, int shard, int64_t* d_nal_start,
+                                                   int64_t* d_nal_end, int64_t* d_rbsp_off, int64_t* d_rbsp_end, int64_t cap_nals,
+                                                   hevcb_stitch_result* d_result, void* stream)
+{
+    if (!ctx || !d_records || !d_result || n_shards < 1 || n_shards > HEVCB_MAX_SHARDS || shard < 0 || shard >= n_shards || !d_nal_start || !d_nal_end ||
+        !d_rbsp_off || !d_rbsp_end) {
+        return HEVCB_E_ARG;
+    }
+    HEVCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    stitch_apply_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_records, n_shards, shard, d_nal_start, d_nal_end, d_rbsp_off, d_rbsp_end, cap_nals, d_result);
+    ctx->launches++;
+    HEVCB_CUDA(ctx, cudaGetLastError());
     return HEVCB_OK;
 }

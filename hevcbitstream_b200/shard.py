@@ -140,10 +140,12 @@ def apply_patches_device(ctx, res: StitchResult, shard: int, sc: ShardScan):
                                                  sc.rbsp_end.data_ptr(), sc.cap_nals, stream))
 
 
-def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw):
-    """The distributed pass: local shard scan, all_gather of the device-resident records (the only collective), one
-    device->host read, host stitch, one patch kernel.  Returns (ShardScan, StitchResult); the global index of local NAL j
-    is res.nal_base[rank] + j - res.first_local[rank]."""
+def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, sync=True, **kw):
+    """The distributed pass: local shard scan, all_gather of the device-resident records (the only collective), then ONE small kernel
+    that joins the records on the device and writes this rank's patches (hevcb_stitch_apply_device): nothing in the step waits for
+    the host.  Returns (ShardScan, StitchResult); the global index of local NAL j is res.nal_base[rank] + j - res.first_local[rank].
+    sync=False: the join's result stays on the device (the second value is None; `fetch_stitch(sc)` reads it when it is wanted),
+    so that steps can be queued back to back."""
     import torch
     import torch.distributed as dist
 
@@ -151,16 +153,30 @@ def scan_strip_sharded(ctx, buf, own, halo, is_first, is_last, group=None, **kw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     allrec = torch.empty(world * sc.summary.numel(), dtype=torch.uint8, device=buf.device)
     dist.all_gather_into_tensor(allrec, sc.summary, group=group)
-    raw = allrec.cpu().numpy().tobytes()
+    d_res = torch.empty(C.sizeof(StitchResult), dtype=torch.uint8, device=buf.device)
+    stream = torch.cuda.current_stream(buf.device).cuda_stream
+    ctx._check(ctx._L.hevcb_stitch_apply_device(ctx._h, allrec.data_ptr(), world, rank, sc.nal_start.data_ptr(), sc.nal_end.data_ptr(), sc.rbsp_off.data_ptr(),
+                                                sc.rbsp_end.data_ptr(), sc.cap_nals, d_res.data_ptr(), stream))
+    sc.allrec, sc.d_stitch, sc.world, sc.rank = allrec, d_res, world, rank
+    if not sync:
+        return sc, None
+    return sc, fetch_stitch(sc)
+
+
+def fetch_stitch(sc: ShardScan) -> StitchResult:
+    """Device -> host read of what the last scan_strip_sharded(..., sync=False) left on the device: the gathered records (sc.record =
+    this rank's) and the join's result.  Raises together on every rank (the inputs are identical everywhere)."""
+    raw = sc.allrec.cpu().numpy().tobytes()
     n = C.sizeof(ShardSummary)
-    records = [ShardSummary.from_buffer_copy(raw[i * n:(i + 1) * n]) for i in range(world)]
-    sc.record = records[rank]
-    over = [r for r in range(world) if records[r].overflow]
+    records = [ShardSummary.from_buffer_copy(raw[i * n:(i + 1) * n]) for i in range(sc.world)]
+    sc.record = records[sc.rank]
+    over = [r for r in range(sc.world) if records[r].overflow]
     if over:  # decided from the gathered records: every rank raises together, none is left waiting in a later collective
         raise HevcbError(-104, f"shard(s) {over}: more NALs than cap_nals ({records[over[0]].n_nals} on shard {over[0]}, cap {sc.cap_nals})")
-    res = stitch(records)
-    apply_patches_device(ctx, res, rank, sc)
-    return sc, res
+    res = StitchResult.from_buffer_copy(sc.d_stitch.cpu().numpy().tobytes())
+    if res.n_patches < 0:
+        raise HevcbError(-101, "hevcb_stitch: the shard records do not describe one stream (is_first / is_last flags)")
+    return res
 
 
 # ---- sharded header parse: parameter-set hand-over between ranks -------------------------------------------------------

@@ -189,6 +189,15 @@ HEVCB_API int hevcb_stitch(const hevcb_shard_summary* shards, int n_shards, hevc
 HEVCB_API int hevcb_apply_patches_device(hevcb_ctx* ctx, const hevcb_stitch_result* res, int shard, int64_t* d_nal_start, int64_t* d_nal_end,
                                          int64_t* d_rbsp_off, int64_t* d_rbsp_end, int64_t cap_nals, void* stream);
 
+/* The join and the patches in one small kernel, for a distributed step without a device->host round trip: d_records = the
+ * n_shards records as the all_gather left them in device memory (stream order), d_result = device memory for the join's result (copy
+ * it back when the global numbers are wanted; n_patches = -1 reports what hevcb_stitch reports as HEVCB_E_ARG).  The arrays are this
+ * rank's (shard `shard`).  For C callers with an ncclComm_t: ncclAllGather(d_summary, d_records, sizeof(hevcb_shard_summary), ncclChar,
+ * comm, stream) between hevcb_scan_strip_shard_device and this call is the whole exchange. */
+HEVCB_API int hevcb_stitch_apply_device(hevcb_ctx* ctx, const hevcb_shard_summary* d_records, int n_shards, int shard, int64_t* d_nal_start,
+                                        int64_t* d_nal_end, int64_t* d_rbsp_off, int64_t* d_rbsp_end, int64_t cap_nals,
+                                        hevcb_stitch_result* d_result, void* stream);
+
 /* ---- batched EPB insertion (rbsp_to_nal) ---------------------------------------------------------
  *
  * rbsp_to_nal (h264_nal.c:92-132) for n RBSP segments at once.  Segment k is rbsp[rbsp_off[k] .. rbsp_end[k]) of one

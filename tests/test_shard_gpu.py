@@ -97,6 +97,44 @@ def test_apply_patches_device_matches_host_patching(ctx):
             assert np.array_equal(h[:n], t.cpu().numpy()[:n])
 
 
+@pytest.mark.parametrize("n_shards", [2, 4, 7])
+def test_device_join_equals_host_join(ctx, n_shards):
+    """hevcb_stitch_apply_device (the join of the gathered records + this shard's patches as one kernel, what the NCCL step runs)
+    against hevcb_stitch + host patching: the result struct byte for byte, the patched arrays entry for entry"""
+    import ctypes as C
+
+    import torch
+
+    from hevcbitstream_b200 import shard as hs
+    from hevcbitstream_b200._lib import StitchResult
+
+    for seed, pmax in ((5, 2000), (6, 400000)):  # NALs inside shards; NALs that span several shards
+        s = ref.gen_stream(seed=seed, profile=1, n_slices=3000 if pmax < 10000 else 40, payload_min=1, payload_max=pmax, zero_heavy_pct=20, extra_zero_pct=10,
+                           ps_period=40)
+        size = s.size - ref.PAD
+        bounds = hs.plan_shards(s, n_shards, size)
+        scans = []
+        for r in range(n_shards):
+            own, halo, first, last = hs.shard_flags(bounds, r)
+            lo = int(bounds[r])
+            d = torch.zeros(own + halo + 32, dtype=torch.uint8, device="cuda")
+            d[: own + halo] = torch.from_numpy(s[lo: lo + own + halo].copy())
+            scans.append(hs.scan_strip_shard(ctx, d, own, halo, first, last))
+        res = hs.stitch([sc.record for sc in scans])
+        allrec = torch.cat([sc.summary for sc in scans])  # what all_gather_into_tensor leaves on every rank
+        stream = torch.cuda.current_stream().cuda_stream
+        for r, sc in enumerate(scans):
+            host = [t.cpu().numpy().copy() for t in (sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)]
+            hs.apply_patches(res, r, *host)
+            d_res = torch.zeros(C.sizeof(StitchResult), dtype=torch.uint8, device="cuda")
+            ctx._check(ctx._L.hevcb_stitch_apply_device(ctx._h, allrec.data_ptr(), n_shards, r, sc.nal_start.data_ptr(), sc.nal_end.data_ptr(),
+                                                        sc.rbsp_off.data_ptr(), sc.rbsp_end.data_ptr(), sc.cap_nals, d_res.data_ptr(), stream))
+            assert d_res.cpu().numpy().tobytes() == bytes(res), f"join differs on shard {r}"
+            n = int(res.first_local[r] + res.n_owned[r])
+            for h, t in zip(host, (sc.nal_start, sc.nal_end, sc.rbsp_off, sc.rbsp_end)):
+                assert np.array_equal(h[:n], t.cpu().numpy()[:n])
+
+
 def _pairs(p, k):
     a, b = int(p["pair_off"][k]), int(p["pair_off"][k + 1])
     return p["pair_field"][a:b], p["pair_value"][a:b]
