@@ -97,6 +97,46 @@ SASS evidence of the async-copy path (`cuobjdump -sass hevcbitstream_b200/libhev
 """
 open(os.path.join(ROOT, "profiles", "r2_scan_strip_ncu.md"), "w").write(md)
 
+# ---- the single-pass insertion kernel (fused_assemble_kernel) on the headline stream
+rep_i = os.path.join(ROOT, "gpurun_out", "r2_insert_fused.ncu-rep")
+if os.path.exists(rep_i):
+    g, num = raw(rep_i)
+    rd, wr, ms = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gpu__time_duration.sum")
+    tab = "\n".join(f"| `{k}` | {g(k)[0]} {g(k)[1]} |" for k in WANT)
+    tot, tops = top_lines(rep_i, 10)
+    tl = "\n".join(f"| {100 * c / tot:.1f} % | `{f}:{ln}` | `{src}` |" for c, f, ln, src in tops)
+    ins = bench.get("insert", {})
+    alg = float(ins.get("out_bytes", 0)) * 2.0
+    cmd_i = ("ncu --set full --clock-control none --import-source on -k regex:fused_assemble_kernel -s 2 -c 1 python bench.py --steps 4 --warmup 3 --no-sweep "
+             "--no-parse --no-rewrite --no-cpu-extras --e2e-gib 0.25")
+    md_i = f"""# ncu --set full, fused_assemble_kernel (single-pass rbsp_to_nal), round 2
+
+`{cmd_i}` (report: `gpurun_out/r2_insert_fused.ncu-rep`, scratch).  Workload: `hevcb_insert_device` over the image and extents of the 4 GiB
+headline stream (16 KiB NALs); the output must equal the original stream (checked in `bench.py`).
+Bench value (CUDA events, no profiler, all 7 launches of a call): {ins.get('ms', 0):.3f} ms = {ins.get('input_GBps', 0):.0f} GB/s of input = **{ins.get('frac_of_peak', 0):.3f}** of the
+measured HBM peak when scored as SURVEY 8d says (N_rbsp + N_nal); round 1 (count + scan + write, two reads of the payload): 2.77 ms, 0.47.
+
+| metric | value |
+|---|---|
+{tab}
+
+DRAM traffic per launch: read {rd / 1e9:.3f} GB + write {wr / 1e9:.3f} GB = **{(rd + wr) / 1e9:.3f} GB** = {(rd + wr) / alg if alg else 0:.3f}x the algorithmic bytes
+({alg / 1e9:.3f} GB): every source byte is read once (TMA bulk copies into shared memory), every output byte written once.
+
+Warp-state samples by source line (top {len(tops)} of {tot} samples):
+
+| share | line | source |
+|---|---|---|
+{tl}
+
+Reading: the samples at the `__syncthreads()` in front of `long long o = sm.excl;` are the seven warps of a tile waiting for warp 0 to
+receive the tile's exclusive prefix from the scanner CTA: about a third of a tile's lifetime.  The scanner answers within one or two
+L2 round trips of the last aggregate of its batch; what a tile waits for is the slowest EARLIER tile (in-order prefix), at six
+33 KiB tiles per SM (all of the shared memory).  SASS: `UBLKCP.S.G` (cp.async.bulk), `SYNCS.*TRANS64` (mbarrier), `LDG/STG.E.64.STRONG.GPU`
+(tile states).
+"""
+    open(os.path.join(ROOT, "profiles", "r2_insert_ncu.md"), "w").write(md_i)
+
 rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r2_launches.csv"))) if r]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[hi]
