@@ -342,6 +342,15 @@ class Context:
         """Annex-B bytes in host memory -> full index (hevcb_index_host: scan + strip + parse, copies included)."""
         assert buf.dtype == np.uint8
         size = int(buf.size if size is None else size)
+        if cap_nals is None and cap_pairs is None:
+            # a realistic bound first (one NAL per 64 bytes: 0.6 bytes of arrays per input byte); a denser stream reports
+            # HEVCB_E_CAPACITY and the call repeats with the worst case (a start code every 3 bytes: ~11 bytes per input byte)
+            try:
+                cn = size // 64 + 1024
+                return HostIndex(self, buf, size, cn, 64 * cn + 4096, want_rbsp, flags)
+            except HevcbError as e:
+                if e.code != -104:
+                    raise
         if cap_nals is None:
             cap_nals = size // 3 + 8
         if cap_pairs is None:

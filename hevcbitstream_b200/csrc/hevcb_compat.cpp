@@ -1,6 +1,7 @@
 // hevcb_compat.cpp -- the reference's per-NAL API on top of the batched C ABI (include/hevcb_compat.h).  Host code only:
 // buffers are handed to libhevcb200 (CUDA), results are unpacked into the reference's structs.
 #include <map>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,6 +15,11 @@
 namespace {
 
 hevcb_ctx* g_ctx = nullptr; // one context per process (device HEVCB_COMPAT_DEVICE, default 0)
+// The reference's byte-layer functions are pure; here they share one context, its scratch buffers and the scan cache below.  Every
+// exported function takes this lock, so concurrent callers are serialised instead of racing (two interleaved find_nal_unit loops
+// still evict each other's cached scan: correct, but every call then scans again).
+std::recursive_mutex g_mu;
+#define HEVCB_COMPAT_LOCK std::lock_guard<std::recursive_mutex> compat_lock_(g_mu)
 
 hevcb_ctx* context()
 {
@@ -35,7 +41,17 @@ struct ScanCache {
     std::vector<int64_t> ns, ne;
     hevcb_scan_summary sum;
     int64_t next = 0; // index of the NAL the next call of the loop asks for
+    uint64_t probe = 0; // digest of the buffer's first and last bytes at scan time: a buffer rewritten in place is scanned again
 } g_scan;
+
+uint64_t probe_bytes(const uint8_t* buf, int64_t size)
+{
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)size;
+    const int64_t n = size < 64 ? size : 64;
+    for (int64_t i = 0; i < n; i++) { h = (h ^ buf[i]) * 1099511628211ull; }
+    for (int64_t i = size - n; i < size; i++) { h = (h ^ buf[i]) * 1099511628211ull; }
+    return h;
+}
 
 bool scan_buffer(const uint8_t* buf, int64_t size)
 {
@@ -50,6 +66,7 @@ bool scan_buffer(const uint8_t* buf, int64_t size)
             g_scan.base = buf;
             g_scan.size = size;
             g_scan.next = 0;
+            g_scan.probe = probe_bytes(buf, size);
             return true;
         }
         if (rc != HEVCB_E_CAPACITY) { break; }
@@ -81,6 +98,7 @@ extern "C" {
 
 hevc_stream_t* hevc_new(void) // hevc_nal.c:34-55
 {
+    HEVCB_COMPAT_LOCK;
     if (!context()) { return nullptr; }
     hevc_stream_t* h = (hevc_stream_t*)calloc(1, sizeof(hevc_stream_t));
     h->nal = (hevc_nal_t*)calloc(1, sizeof(hevc_nal_t));
@@ -103,6 +121,7 @@ hevc_stream_t* hevc_new(void) // hevc_nal.c:34-55
 void hevc_free(hevc_stream_t* h) // hevc_nal.c:64-90 (which leaks slice_data->rbsp_buf; freed here)
 {
     if (!h) { return; }
+    HEVCB_COMPAT_LOCK;
     g_streams.erase(h);
     free(h->nal);
     for (int i = 0; i < 32; i++) { free(h->sps_table[i]); }
@@ -119,6 +138,7 @@ void hevc_free(hevc_stream_t* h) // hevc_nal.c:64-90 (which leaks slice_data->rb
 
 int find_nal_unit(uint8_t* buf, int size, int* nal_start, int* nal_end) // h264_nal.c:38-76
 {
+    HEVCB_COMPAT_LOCK;
     *nal_start = 0;
     *nal_end = 0;
     if (size < 0) { return 0; }
@@ -128,7 +148,7 @@ int find_nal_unit(uint8_t* buf, int size, int* nal_start, int* nal_end) // h264_
         const int64_t off = buf - g_scan.base;
         const int64_t k = g_scan.next;
         const int64_t expect = (k == 0) ? 0 : ((k - 1 < (int64_t)g_scan.ne.size() && k - 1 < g_scan.sum.n_terminated) ? g_scan.ne[(size_t)(k - 1)] : -1);
-        hit = (off == expect);
+        hit = (off == expect) && g_scan.probe == probe_bytes(g_scan.base, g_scan.size);
     }
     if (!hit) {
         if (!scan_buffer(buf, size)) { return -1; }
@@ -150,10 +170,19 @@ int find_nal_unit(uint8_t* buf, int size, int* nal_start, int* nal_end) // h264_
 
 int nal_to_rbsp(const uint8_t* nal_buf, int* nal_size, uint8_t* rbsp_buf, int* rbsp_size) // h264_nal.c:147-200
 {
+    HEVCB_COMPAT_LOCK;
     hevcb_ctx* ctx = context();
     if (!ctx || *nal_size < 0) { return -1; }
     const int64_t n = *nal_size;
     if (n == 0) { *rbsp_size = 0; return 0; } // nothing to convert (the loop of h264_nal.c:153 does not run)
+    if (n <= 2 && nal_buf[0] == 0 && nal_buf[n - 1] == 0) {
+        // {00} and {00 00}: the reference's pattern tests need three bytes (i + 2 < nal_size, h264_nal.c:156) and copy these through;
+        // behind a start code they would not be a NAL at all (the scanner reads 00 00 01 00 [00] as a zero-length unit)
+        if (n > *rbsp_size) { return -1; }
+        memset(rbsp_buf, 0, (size_t)n);
+        *rbsp_size = (int)n;
+        return (int)n;
+    }
     std::vector<uint8_t>& s = g_ib.stream;
     s.assign((size_t)n + 3 + 16, 0);
     s[2] = 1; // 00 00 01 in front: the NAL becomes the single unit of a stream
@@ -177,6 +206,7 @@ int nal_to_rbsp(const uint8_t* nal_buf, int* nal_size, uint8_t* rbsp_buf, int* r
 
 int rbsp_to_nal(const uint8_t* rbsp_buf, const int* rbsp_size, uint8_t* nal_buf, int* nal_size) // h264_nal.c:92-132
 {
+    HEVCB_COMPAT_LOCK;
     hevcb_ctx* ctx = context();
     if (!ctx || *rbsp_size < 0) { return -1; }
     const int64_t n = *rbsp_size;
@@ -211,6 +241,7 @@ namespace {
 // parse run in its trace variant and one line printed per record
 int read_nal(hevc_stream_t* h, uint8_t* buf, int size, bool debug)
 {
+    HEVCB_COMPAT_LOCK;
     hevcb_ctx* ctx = context();
     std::map<hevc_stream_t*, StreamState>::iterator it = g_streams.find(h);
     if (!ctx || it == g_streams.end() || size < 0) { return -1; }
@@ -402,6 +433,7 @@ void read_debug_sei_payload(sei_t* s, bs_t* b) // h264_sei.c:123-140
 
 int write_hevc_nal_unit(hevc_stream_t* h, uint8_t* buf, int size) // hevc_stream.c:1249-1335
 {
+    HEVCB_COMPAT_LOCK;
     hevcb_ctx* ctx = context();
     if (!ctx || !h || size < 0) { return -1; }
     int64_t n = -1;

@@ -17,7 +17,12 @@
  *   - find_nal_unit(p, n, ...) scans the WHOLE remaining buffer on its first call and answers the following calls of the
  *     canonical loop `while (find_nal_unit(p, sz, &s, &e) > 0) { ...; p += e; sz -= e; }` from that result;
  *   - new code should call the batched entry points of hevcb.h.
- * Not re-entrant, like the reference (h264_dbgfile, file-static tables).
+ * Threads: the reference's parser is not re-entrant (h264_dbgfile, file-static tables) and neither is this one; its byte-layer
+ * functions are pure, here they share one context and the scan cache, so every exported function takes one process-wide lock:
+ * concurrent callers are serialised, never racing.  The cached scan is validated against the buffer's size and a digest of its first
+ * and last 64 bytes; a caller that rewrites the MIDDLE of a buffer between two calls of one find_nal_unit loop must restart the loop.
+ * read_hevc_nal_unit parses slices against the parameter sets it has READ through this handle, not against edits made to h->sps /
+ * h->pps in between (write_hevc_nal_unit does use the caller's structs).
  */
 #ifndef HEVCB_COMPAT_H
 #define HEVCB_COMPAT_H

@@ -89,6 +89,27 @@ def test_nal_to_rbsp_and_back(compat):
     assert n_ok > 50 and n_err > 50
 
 
+def test_nal_to_rbsp_exhaustive_short_nals(compat):
+    """every NAL of up to 5 bytes over the alphabet {0, 1, 2, 3, 4}: return value, consumed size and bytes as the reference
+    (the two all-zero NALs {00} and {00 00} are not a NAL behind a start code and are answered without the scanner)"""
+    import itertools
+
+    n_cases = 0
+    for n in range(1, 6):
+        for t in itertools.product(range(5), repeat=n):
+            nal = np.array(t, np.uint8)
+            rc, nsz, rb = ref.nal_to_rbsp(bytes(nal))
+            src = util.padded(nal)
+            dst = np.zeros(n + 16, np.uint8)
+            ns, rs = C.c_int(n), C.c_int(n)
+            got = compat.nal_to_rbsp(src.ctypes.data, C.byref(ns), dst.ctypes.data, C.byref(rs))
+            assert got == rc, f"rc {got} != {rc} for {bytes(nal).hex()}"
+            if rc >= 0:
+                assert ns.value == nsz and rs.value == rc and bytes(dst[:rc]) == rb, bytes(nal).hex()
+            n_cases += 1
+    assert n_cases == 5 + 25 + 125 + 625 + 3125
+
+
 def test_read_hevc_nal_unit_matches_reference(compat):
     """NAL by NAL through hevc_new / read_hevc_nal_unit: return value, h->nal and the struct the NAL wrote (hashed) equal the
     reference's; the parameter-set state is carried from call to call"""
