@@ -351,6 +351,7 @@ struct RewriteArgs {
     const int64_t* slot_off; // [n + 2] exclusive scan of the slot sizes (SlotCap)
     int64_t *raw_off, *raw_end, *a_off, *a_end, *b_off, *b_end; // [n + 1]
     hevcb_edit_set edits;
+    bool spec; // the parse ran with HEVCB_PARSE_SPEC: the write walk follows the same rules (slices resolve their parameter sets by id)
 };
 
 template <bool kEmit>
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(128) write_kernel(RewriteArgs a)
     hevcb_bitwriter bw;
     if (kEmit) { bw.init(a.staging + a.woff[k], (int64_t)a.wlen[k]); } else { bw.init(a.slots + a.slot_off[k], wcap, room); }
     hevcb_write_result wr;
-    hevcb_write_nal(rp, bw, a.nal_hdr[k], sps_in, pps_in, scr, wr);
+    const hevcb_ps_lookup lk{a.sps_tab, a.pps_tab, sps_count, pps_count};
+    hevcb_write_nal(rp, bw, a.nal_hdr[k], sps_in, pps_in, scr, wr, a.spec, (a.spec && is_slice) ? &lk : nullptr);
     if (!kEmit) {
         const int64_t len = is_slice ? (int64_t)wr.hdr_bytes : wr.bytes;
         a.wlen[k] = (wr.ok && wr.bytes > 0 && len > 0 && len < (1 << 30)) ? (int32_t)len : 0;
@@ -523,10 +525,6 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
         HEVCB_SET_ERR(ctx, "hevcb_rewrite: invalid argument");
         return HEVCB_E_ARG;
     }
-    if (ctx->last_parse.n == n && ctx->last_parse.spec) {
-        HEVCB_SET_ERR(ctx, "hevcb_rewrite: results of a spec-correct parse (HEVCB_PARSE_SPEC) cannot be rewritten yet");
-        return HEVCB_E_ARG;
-    }
     if (ctx->last_parse.n != n) {
         HEVCB_SET_ERR(ctx, "hevcb_rewrite: must follow hevcb_parse_device of the same %lld NALs on this context", (long long)n);
         return HEVCB_E_ARG;
@@ -561,6 +559,7 @@ int hevcb_launch_rewrite(hevcb_ctx* ctx, const uint8_t* d_buf, int64_t size, con
     int64_t* parts = reinterpret_cast<int64_t*>(base + o_parts);
     a.raw_off = parts; a.raw_end = parts + m; a.a_off = parts + 2 * m; a.a_end = parts + 3 * m; a.b_off = parts + 4 * m; a.b_end = parts + 5 * m;
     if (edits) { a.edits = *edits; } else { a.edits.n = 0; }
+    a.spec = ctx->last_parse.spec != 0;
     int64_t* out_off = reinterpret_cast<int64_t*>(base + o_ooff);
     long long* bsums = reinterpret_cast<long long*>(base + o_bs);
     hevcb_insert_summary* isum = reinterpret_cast<hevcb_insert_summary*>(base + o_isum);

@@ -1402,7 +1402,7 @@ struct hevcb_write_result {
 // nal_hdr = nal_unit_type | nal_layer_id << 8 | nal_temporal_id_plus1 << 16 (what the parse left in h->nal).
 // `sps_scratch`: working copy for the derived RPS tables an SPS builds while it is walked.
 HEVCB_SHD inline void hevcb_write_nal(hevcb_replay& rp, hevcb_bitwriter& bw, int32_t nal_hdr, const hevcb_sps_ctx* sps_in, const hevcb_pps_ctx* pps_in,
-                                      hevcb_sps_ctx* sps_scratch, hevcb_write_result& r)
+                                      hevcb_sps_ctx* sps_scratch, hevcb_write_result& r, bool spec = false, const hevcb_ps_lookup* lookup = nullptr)
 {
     hevcb_bits nob;
     nob.init(nullptr, 0);
@@ -1417,6 +1417,8 @@ HEVCB_SHD inline void hevcb_write_nal(hevcb_replay& rp, hevcb_bitwriter& bw, int
     bw.write_u(6, (uint32_t)((nal_hdr >> 8) & 0xFF));
     bw.write_u(3, (uint32_t)((nal_hdr >> 16) & 0xFF));
     hevcb_walker<hevcb_sink, true> w(nob, nos, &bw, &rp);
+    w.spec = spec;
+    w.lookup = lookup;
     if (hevcb_is_slice_type(t)) {
         hevcb_slice_cols cols;
         w.slice_segment_header(t, *sps_in, *pps_in, cols);

@@ -308,8 +308,9 @@ typedef struct hevcb_parse_buffers { /* device pointers for hevcb_parse_device, 
  * RPS tables per SPS); ref_pic_list_modification_flag_l1 / list_entry_l1 are read; use_delta_flag, fixed_pic_rate_within_cvs_flag
  * and cprms_present_flag[0] take their inferred values; the PPS deblocking offsets are present when the filter is not disabled and
  * slices inherit pps_deblocking_filter_disabled_flag; cpb_cnt_minus1 is present when low_delay_hrd_flag is 0 and a sub-layer has
- * cpb_cnt_minus1 + 1 entries.  Structures stay the reference's (pairs index the same structs).  Not available for shard parses
- * (hevcb_parse_shard_device) and not accepted by hevcb_rewrite_device yet: both return HEVCB_E_ARG. */
+ * cpb_cnt_minus1 + 1 entries.  Structures stay the reference's (pairs index the same structs).  hevcb_rewrite_device writes the results
+ * of such a parse by the same rules (the SPS with its trailing bits, slices against the parameter sets their ids select).  Not
+ * available for shard parses (hevcb_parse_shard_device): HEVCB_E_ARG. */
 #define HEVCB_PARSE_SPEC 2u
 #define HEVCB_AUX_AUD_PIC_TYPE 0u
 #define HEVCB_AUX_FD_FF_BYTES 8u

@@ -57,8 +57,32 @@ def test_device_entry_point_and_mode_limits(ctx, spec_ref):
     n = scan.n_nals
     assert np.array_equal(out["rc"][:n].cpu().numpy(), host.rc) and np.array_equal(out["pair_off"].cpu().numpy(), host.pair_off)
     assert np.array_equal(out["pair_value"][: out["n_pairs"]].cpu().numpy(), host.pair_value)
-    # a rewrite of spec-mode results is refused (documented limit), a default parse afterwards is accepted again
-    with pytest.raises(HevcbError):
-        ctx.rewrite_device(d, scan, out, size=size)
-    out2 = ctx.parse_device(d, scan)
-    ctx.rewrite_device(d, scan, out2, size=size)
+
+
+@pytest.mark.parametrize("qp,vui", [(0, 0), (3, 1)])
+def test_rewrite_of_spec_results_matches_the_spec_reference(ctx, spec_ref, qp, vui):
+    """read -> edit -> write -> rbsp_to_nal in spec mode: byte-exact against the same composition run by the spec build of the reference
+    (its writer ends the SPS with trailing bits and resolves the slices' parameter sets through the id tables)"""
+    import torch
+
+    from tests import rewrite_check as rc
+
+    for seed in (1, 2):
+        s = ref.gen_stream(seed=seed, profile=1, n_slices=3000, payload_min=1, payload_max=3000, zero_heavy_pct=30, extra_zero_pct=10, ps_period=25, unsupported_pct=5)
+        size = s.size - ref.PAD
+        d = torch.zeros(size + 32, dtype=torch.uint8, device="cuda")
+        d[:size] = torch.from_numpy(s[:size].copy())
+        scan = ctx.scan_strip_device(d, size=size)
+        parsed = ctx.parse_device(d, scan, spec=True)
+        edits = []
+        if qp:
+            edits.append((rc.KIND_SLICE, "slice_qp_delta", rc.EDIT_ADD, qp))
+        if vui:
+            edits.append((rc.KIND_SPS, "vui.video_full_range_flag", rc.EDIT_XOR, 1))
+        out = ctx.rewrite_device(d, scan, parsed, edits, size=size)
+        n = scan.n_nals
+        st, en = scan.nal_start.cpu().numpy()[:n], scan.nal_end.cpu().numpy()[:n]
+        want = ref.rewrite_all(s, size, st, en, qp_delta_add=qp, vui_flip=vui)
+        assert out["n_rewritten"] > 3000
+        rc.compare_rewrite(out["out"].cpu().numpy()[: out["out_bytes"]], out["out_start"].cpu().numpy()[:n], out["out_end"].cpu().numpy()[:n], want,
+                           tag=f"spec-s{seed}-qp{qp}-vui{vui}")
