@@ -263,7 +263,7 @@ struct ScanHeader {
     unsigned long long next_tile; // grid-wide tile counter: a CTA with a free stage claims the next tile
     long long first_empty;
     ulonglong2 final_state; // inclusive prefix over all tiles, written by the scanner warp
-    unsigned long long heavy_tiles;  // tiles the writers had to analyse themselves (feeds the role split of the next launch)
+    unsigned long long heavy_tiles;  // tiles the writers had to analyse themselves (a statistic: no launch parameter depends on earlier calls)
     unsigned long long flagged_rows; // rows the analysers had to analyse exactly
     unsigned long long pad[2];
 };
