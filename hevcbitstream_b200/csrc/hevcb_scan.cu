@@ -595,6 +595,44 @@ __device__ __noinline__ void copy_tile(uint8_t* __restrict__ dst, const uint8_t*
     copy_span(dst, src, L, tid, kWThreads);
 }
 
+// one warp copies L bytes from shared memory at ANY alignment to global memory at any alignment: aligned 16-byte stores, the source as
+// two aligned 16-byte loads funnel-shifted by the (copy-uniform) misalignment between source and destination
+template <int Q>
+__device__ __forceinline__ void smem_vectors_out(uint4* __restrict__ da, const uint8_t* __restrict__ sa, uint32_t nv, uint32_t sh, int lane)
+{
+    for (uint32_t i = (uint32_t)lane; i < nv; i += 32u) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(sa + (i << 4));
+        uint4 o4 = lo;
+        if (Q != 0 || sh != 0u) {
+            const uint4 hi = *reinterpret_cast<const uint4*>(sa + (i << 4) + 16);
+            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            o4.x = __funnelshift_r(W[Q], W[Q + 1], sh); o4.y = __funnelshift_r(W[Q + 1], W[Q + 2], sh);
+            o4.z = __funnelshift_r(W[Q + 2], W[Q + 3], sh); o4.w = __funnelshift_r(W[Q + 3], W[Q + 4], sh);
+        }
+        __stcs(da + i, o4);
+    }
+}
+__device__ __noinline__ void copy_span_any(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t L, int lane)
+{
+    if (L == 0u) { return; }
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > L) { head = L; }
+    if ((uint32_t)lane < head) { dst[lane] = src[lane]; }
+    const uint32_t nv = (L - head) >> 4;
+    const uint8_t* s0 = src + head;
+    const uint32_t mis = smem_u32(s0) & 15u, sh = (mis & 3u) * 8u;
+    const uint8_t* sa = s0 - mis; // (reads stay inside the stage: at most 16 bytes behind the span, the stage has a 16-byte trailing halo)
+    uint4* da = reinterpret_cast<uint4*>(dst + head);
+    switch (mis >> 2) {
+        case 0: smem_vectors_out<0>(da, sa, nv, sh, lane); break;
+        case 1: smem_vectors_out<1>(da, sa, nv, sh, lane); break;
+        case 2: smem_vectors_out<2>(da, sa, nv, sh, lane); break;
+        default: smem_vectors_out<3>(da, sa, nv, sh, lane); break;
+    }
+    const uint32_t done = head + (nv << 4);
+    if ((uint32_t)lane < L - done) { dst[done + lane] = src[done + lane]; }
+}
+
 // boundary fix-ups of a staged tile: positions < 0 read as non-zero, positions >= size read as zero
 __device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, int64_t size, int tid)
 {
@@ -1074,8 +1112,12 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             uint8_t* const map = sm.slowmapW[warp];
             const uint32_t below = (1u << lane) - 1u;
             uint32_t total = 0;
+            // rows the analysers did not flag hold no slow chunk (their test is a superset of the one below): a tile with one removed
+            // byte -- a stream with an emulation prevention byte every few NALs -- is ranked in the few flagged rows only
+            const uint32_t flagged8 = (uint32_t)(pref.mask >> (warp * kWRows)) & ((1u << kWRows) - 1u);
 #pragma unroll 1
             for (int i0 = 0; i0 < kWRows; i0 += 4) {
+                if (((flagged8 >> i0) & 0xFu) == 0u) { continue; }
                 const uint8_t* rp = st + kLead + (warp * kWRows + i0) * kRowBytes + lane * 16;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -1210,6 +1252,35 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     // its kept bytes out as one span
                     uint8_t* const wb = st + kLead + warp * (kWRows * kRowBytes);
                     uint32_t out = kWRows * kRowBytes;
+                    if (compacting && wDel <= 4u) {
+                        // A few removed bytes (an emulation prevention byte in a slice header now and then: the common case of real
+                        // streams): the kept bytes are a few runs; each goes out as one vector copy of its own, nothing moves in
+                        // shared memory (closing the gaps byte by byte made this warp the straggler of its tile).
+                        __syncwarp();
+                        uint32_t cur = 0;
+                        uint8_t* dptr = rbsp + tileK + rK;
+#pragma unroll 1
+                        for (int i = 0; i < kWRows; i++) {
+                            const uint32_t del = dm[i * 32 + lane];
+                            uint32_t lanes = __ballot_sync(0xFFFFFFFFu, del != 0u);
+                            while (lanes) {
+                                const int src = __ffs((int)lanes) - 1;
+                                lanes &= lanes - 1u;
+                                uint32_t m = __shfl_sync(0xFFFFFFFFu, del, src);
+                                while (m) {
+                                    const uint32_t pos = (uint32_t)((i * 32 + src) * 16 + (__ffs((int)m) - 1));
+                                    m &= m - 1u;
+                                    copy_span_any(dptr, wb + cur, pos - cur, lane);
+                                    dptr += pos - cur;
+                                    cur = pos + 1u;
+                                }
+                            }
+                        }
+                        copy_span_any(dptr, wb + cur, (uint32_t)(kWRows * kRowBytes) - cur, lane);
+                        release_stage(&sm.freeb[s], lane);
+                        s = (s + 1 == kStages) ? 0 : s + 1;
+                        continue;
+                    }
                     if (compacting) {
                         __syncwarp();
                         out = 0;
