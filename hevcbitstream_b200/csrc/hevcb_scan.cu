@@ -1277,6 +1277,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                             }
                         }
                         copy_span_any(dptr, wb + cur, (uint32_t)(kWRows * kRowBytes) - cur, lane);
+                        if (tid == 0) { TSTAMP(it, 5); }
                         release_stage(&sm.freeb[s], lane);
                         s = (s + 1 == kStages) ? 0 : s + 1;
                         continue;
@@ -1306,6 +1307,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     copy_span(rbsp + tileK + rK, wb, out, lane, 32u);
                 }
             }
+            if (tid == 0) { TSTAMP(it, 5); }
             release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
             s = (s + 1 == kStages) ? 0 : s + 1;
             continue;
@@ -1416,6 +1418,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         }
         // ---- tile without removed bytes: one shifted vector copy of the whole tile by all workers
         if (write_rows && !dirty_out) { copy_tile(rbsp + tileK, st + kLead, tile_k, tid); }
+        if (tid == 0) { TSTAMP(it, 5); }
         release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
         s = (s + 1 == kStages) ? 0 : s + 1;
     }
