@@ -217,3 +217,27 @@ def test_side_list_of_pieces_can_fill_up(ctx):
         ctx.insert_host(rbsp, off, end, start_code_len=3, out_cap=2 << 20)
     assert e.value.code == -104
     check(ctx, rbsp, off[:6], end[:6], 3, "overlap-6")
+
+
+def test_back_to_back_launches_without_host_sync(ctx):
+    """the single-pass assembly reuses its scratch (tickets, tile states, batch prefixes) from launch to launch: twenty launches queued
+    without a host synchronisation in between must all produce the first launch's bytes (checked on the device)"""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n_bytes = 256 << 20
+    x = torch.randint(0, 256, (n_bytes,), dtype=torch.uint8, device="cuda", generator=g)
+    x[::4099] = 0
+    x[1::4099] = 0  # a few insertions
+    for seg in (16384, 4096 + 37):
+        n = n_bytes // seg
+        off = torch.arange(n, dtype=torch.int64, device="cuda") * seg
+        end = off + seg
+        first = ctx.insert_device(x, off, end, start_code_len=3)
+        total = first["out_bytes"]
+        outs = [ctx.insert_device(x, off, end, start_code_len=3, out_cap=total + 64, sync=False) for _ in range(20)]
+        torch.cuda.synchronize()
+        for o in outs:
+            assert int(o["summary"][1]) == total and int(o["summary"][2]) == first["n_inserted"]
+            assert torch.equal(o["out"][:total], first["out"][:total])
+            assert torch.equal(o["out_off"], first["out_off"])
