@@ -60,6 +60,9 @@ constexpr int kStageBytes = kLead + kTileBytes + 16;
 #define HEVCB_SCAN_STAGES 6
 #endif
 constexpr int kStages = HEVCB_SCAN_STAGES;       // ring of tiles per CTA: in flight / being analysed / waiting for their prefix / being written
+#ifndef HEVCB_SCAN_REFINE
+#define HEVCB_SCAN_REFINE 1 // analysers narrow the filter's superset of slow chunks to the exact set when it exceeds one batch
+#endif
 #ifndef HEVCB_SCAN_AUNROLL
 #define HEVCB_SCAN_AUNROLL 1
 #endif
@@ -197,6 +200,23 @@ __device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, uint32_t
         : "memory");
     return ok != 0;
 }
+// Blocking wait.  A failed try_wait comes back after ~20 cycles, so a bare retry loop issues an instruction every few cycles per
+// waiting warp: on streams of short NALs (long waits in both roles) a third of everything the SM issued were such polls, taken
+// from the warps that had work.  After HEVCB_WAIT_POLLS misses the warp sleeps between polls (the bare loop
+// is the form the compiler gives a YIELD; short waits -- the clean tiles of large NALs -- keep their wake-up latency).
+#ifndef HEVCB_WAIT_SLEEP_NS
+#define HEVCB_WAIT_SLEEP_NS 64
+#endif
+#ifndef HEVCB_WAIT_POLLS
+#define HEVCB_WAIT_POLLS 32 // bare polls (~20 cycles each) before the warp starts to sleep between them: short waits keep their latency
+#endif
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (HEVCB_WAIT_SLEEP_NS > 0 && ++polls > HEVCB_WAIT_POLLS) { __nanosleep(HEVCB_WAIT_SLEEP_NS); }
+    }
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -216,7 +236,6 @@ __device__ __forceinline__ void fence_proxy_async()
 // named barriers: 0 is __syncthreads; kBarWork = the analyser warps, kBarW = the writer warps
 constexpr int kBarWork = 1, kBarW = 2;
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // issue the bulk copies for tile `t` into stage buffer `st` (one elected thread)
 __device__ __forceinline__ void issue_tile_load(uint8_t* st, unsigned long long* bar, const uint8_t* buf, int64_t size, long long t)
@@ -439,6 +458,9 @@ __device__ __forceinline__ void scanner_warps(const ulonglong2* __restrict__ til
                                               ScanHeader* __restrict__ hdr, volatile ScanRun* run, int warp, int lane, int per_lane,
                                               unsigned long long* __restrict__ tdbg)
 {
+#ifndef HEVCB_SCAN_TIMING_BUILD
+#define SSTAMP(b, ev) do { } while (0)
+#else
 #define SSTAMP(b, ev)                                                                                            \
     do {                                                                                                         \
         if (tdbg != nullptr && lane == 0 && ((b) & 7) == 0 && ((b) >> 3) < kTimingIters) {                       \
@@ -447,6 +469,7 @@ __device__ __forceinline__ void scanner_warps(const ulonglong2* __restrict__ til
             tdbg[((size_t)blockIdx.x * kTimingIters + (size_t)((b) >> 3)) * kTimingEvents + (ev)] = ts_;         \
         }                                                                                                        \
     } while (0)
+#endif
     const long long batch_tiles = 32ll * per_lane;
     const long long n_batches = (n_tiles + batch_tiles - 1) / batch_tiles;
     for (long long b = warp; b < n_batches; b += kScanWarps) {
@@ -651,11 +674,34 @@ __device__ __forceinline__ void fix_stage(uint8_t* st, long long t, int64_t t0, 
 // them 32 at a time: one pass of the exact masks with every lane busy instead of one pass per flagged row with a few lanes
 // busy.  The ordered carry, the counts and the event records follow from ballots over the ranked chunks (the combine is
 // associative, chunks without a zero pair contribute nothing).  slow8 bit i: this lane's chunk of row i is slow.
-__device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st, uint8_t* __restrict__ slowmap, int warp, int lane, uint32_t slow8,
-                                                 int64_t t0, long long t, const ScanGeom& geom, uint32_t* evcount, uint4* __restrict__ tile_events,
-                                                 uint32_t& wN, uint32_t& wDel, uint32_t& wKind, uint32_t& wErr, uint32_t& rows)
+// (Results come back BY VALUE: reference parameters of an out-of-line function would pin the caller's running aggregates to the
+// stack for the whole tile loop -- a local-memory store and load on the critical path of every tile, and with 200 KB of the SM's
+// L1 carved out as shared memory those mostly miss.)
+struct SlowAgg {
+    uint32_t n, del, kind, err, rows;
+};
+__device__ __noinline__ SlowAgg analyse_slow_chunks(const uint8_t* __restrict__ st, uint8_t* __restrict__ slowmap, int warp, int lane, uint32_t slow8,
+                                                    long long t, uint32_t* evcount, uint4* __restrict__ tile_events)
 {
+    uint32_t wN = 0, wDel = 0, wKind = HEVCB_KIND_PASS, wErr = 0, rows = 0;
     const uint32_t below = (1u << lane) - 1u;
+    // The filter's "slow" is a superset (a chunk, its predecessor and its successor for every pair).  When that is more than one
+    // batch of exact masks (streams of short NALs, dense payloads), the exact condition is worth its price: a chunk needs the masks
+    // iff two adjacent zero bytes start inside it or in the two bytes in front of it (zero_pair_any, the writers' test) -- about a
+    // third of the superset.  (Operands re-read from the stage: the caller's hot loop keeps its registers to itself.)
+    if (HEVCB_SCAN_REFINE && __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(slow8)) > 32u) {
+#pragma unroll 1
+        for (int i = 0; i < kARows; i++) {
+            if ((slow8 >> i) & 1u) {
+                const uint8_t* rp = st + kLead + (warp * kARows + i) * kRowBytes + lane * 16;
+                const uint4 v = *reinterpret_cast<const uint4*>(rp);
+                const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
+                const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
+                if (zero_pair_any(wp, v.x, v.y, v.z, v.w, wn) == 0u) { slow8 &= ~(1u << i); }
+            }
+        }
+        __syncwarp();
+    }
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < kARows; i++) {
@@ -694,7 +740,9 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
         uint32_t rk, re;
         warp_carry_total(Eb, Sb, Rb, rk, re);
         hevcb_carry_combine(wKind, wErr, rk, re);
-        if (Xb != 0u) { // chunks with an event or an error position leave a record (one shared-memory atomic per batch)
+        // chunks with an event or an error position leave a record (one shared-memory atomic per batch) -- unless the tile already
+        // has more of them than the list takes: it then goes to the writers as a whole and its records are never read
+        if (Xb != 0u && *reinterpret_cast<volatile uint32_t*>(evcount) <= kEvCap) {
             uint32_t first = 0u;
             if (lane == 0) { first = atomicAdd(evcount, (uint32_t)__popc(Xb)); }
             first = __shfl_sync(0xFFFFFFFFu, first, 0);
@@ -703,6 +751,9 @@ __device__ __noinline__ void analyse_slow_chunks(const uint8_t* __restrict__ st,
         }
     }
     __syncwarp(); // the map is rewritten for the warp's next tile
+    SlowAgg r;
+    r.n = wN; r.del = wDel; r.kind = wKind; r.err = wErr; r.rows = rows;
+    return r;
 }
 
 // ====================================================================================================================
@@ -730,6 +781,11 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
     const int lane = threadIdx.x & 31;
     // measurement aid (HEVCB_SCAN_TIMING=1): globaltimer stamps of the pipeline events of the first kTimingIters tiles of every CTA
+    // (compiled in with -DHEVCB_SCAN_TIMING_BUILD only, `make EXTRA=-DHEVCB_SCAN_TIMING_BUILD`: the stamps' addresses and predicates
+    // cost the hot loops registers, and the writers kept them on the stack)
+#ifndef HEVCB_SCAN_TIMING_BUILD
+#define TSTAMP(iter, ev) do { } while (0)
+#else
 #define TSTAMP(iter, ev)                                                                                         \
     do {                                                                                                         \
         if (tdbg != nullptr && (iter) < kTimingIters) {                                                          \
@@ -738,6 +794,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             tdbg[((size_t)blockIdx.x * kTimingIters + (size_t)(iter)) * kTimingEvents + (ev)] = ts_;             \
         }                                                                                                        \
     } while (0)
+#endif
     const int role_warp = threadIdx.x >> 5;
     const unsigned dbg = (unsigned)debug_flags; // experiment switches, 0 in production
     const int64_t size = geom.size;
@@ -770,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             for (long long i = 0;; i++) {
                 const int s = (int)(i % kStages);
                 const uint32_t round = (uint32_t)(i / kStages);
-                if (round >= 1u) { while (!mbar_try_wait(&sm.freeb[s], (round - 1u) & 1u)) {} } // the writers have released the stage
+                if (round >= 1u) { mbar_wait(&sm.freeb[s], (round - 1u) & 1u); } // the writers have released the stage
                 const long long t = (long long)atomicAdd(&hdr->next_tile, 1ull);
                 TSTAMP(i, 0);
                 if (t >= n_tiles) { // end marker: travels through the roles like a tile
@@ -803,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         uint32_t done_bits = 0;
         unsigned long long heavy_local = 0, flagged_local = 0;
         for (long long it_ac = 0;; it_ac++) {
-            while (!mbar_try_wait(&sm.done[s], (done_bits >> s) & 1u)) {}
+            mbar_wait(&sm.done[s], (done_bits >> s) & 1u);
             done_bits ^= (1u << s);
             const long long t = sm.tile[s];
             if (t < 0) {
@@ -897,7 +954,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         int s = 0;
         for (long long it_an = 0;; it_an++) {
             uint8_t* st = sm.stage[s];
-            while (!mbar_try_wait(&sm.full[s], (phase_bits >> s) & 1u)) {}
+            mbar_wait(&sm.full[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
             const long long t = sm.tile[s];
             if (t < 0) { // end marker: hand it on
@@ -1013,7 +1070,8 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                             }
                         }
                     } else {
-                        analyse_slow_chunks(st, sm.slowmapA[role_warp], warp, lane, slow8, t0, t, geom, &sm.evcount[s], tile_events, wN, wDel, wKind, wErr, rows);
+                        const SlowAgg r = analyse_slow_chunks(st, sm.slowmapA[role_warp], warp, lane, slow8, t, &sm.evcount[s], tile_events);
+                        wN = r.n; wDel = r.del; wKind = r.kind; wErr = r.err; rows = r.rows;
                     }
                 }
                 wK = kARows * kRowBytes - wDel;
@@ -1081,17 +1139,18 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     const int tid = (int)threadIdx.x - kAThreads;
     const int warp = tid >> 5;
     DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
-    uint32_t phase_bits = 0;
-    int s = 0;
-    for (long long it = 0;; it++) {
+    // (one loop-carried value: the stage and its phase are derived from the iteration count; with three of them the compiler kept
+    // the loop state on the stack -- local memory in the hot loop, see SlowAgg)
+    for (uint32_t it = 0;; it++) {
+        const int s = (int)(it % (uint32_t)kStages);
+        const uint32_t phase = (it / (uint32_t)kStages) & 1u;
         uint8_t* st = sm.stage[s];
-        while (!mbar_try_wait(&sm.ready[s], (phase_bits >> s) & 1u)) {} // the tile's prefix and row mask are in shared memory
+        mbar_wait(&sm.ready[s], phase); // the tile's prefix and row mask are in shared memory
         const long long t = sm.tile[s];
         if (t < 0) { break; } // end marker
         const int64_t t0 = (int64_t)t * kTileBytes;
         const TilePrefix pref = sm.pref[s];
-        while (!mbar_try_wait(&sm.full[s], (phase_bits >> s) & 1u)) {}
-        phase_bits ^= (1u << s);
+        mbar_wait(&sm.full[s], phase);
         if (tid == 0) { TSTAMP(it, 4); }
         const long long tileN = (long long)pref.n;
         const long long tileK = (long long)pref.k;
@@ -1101,14 +1160,13 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             if (rbsp != nullptr && !(dbg & 4u)) { copy_tile(rbsp + tileK, st + kLead, kTileBytes, tid); }
             if (tid == 0) { TSTAMP(it, 5); }
             release_stage(&sm.freeb[s], lane);
-            s = (s + 1 == kStages) ? 0 : s + 1;
             continue;
         }
 
         // ---- tile with flagged rows: exact masks of those rows, warp aggregates, ordered emission, row-wise write-out
-        if (geom.evl - t0 >= (int64_t)kTileBytes + 32 && !(dbg & 65536u)) {
+        if (geom.evl - t0 >= (int64_t)kTileBytes + 32 && !(dbg & (65536u | 2048u | 64u))) {
             // Interior tile.  The warp ranks the slow chunks of its eight rows in stream order and takes them 32 at a time
-            // (every lane busy, see analyse_slow_chunks); pass 1 parks the masks and builds the warp aggregate, pass 2 emits.
+            // (every lane busy, see analyse_slow_chunks): exact masks and ordered emission in one pass.
             uint8_t* const map = sm.slowmapW[warp];
             const uint32_t below = (1u << lane) - 1u;
             uint32_t total = 0;
@@ -1132,57 +1190,35 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             }
             __syncwarp();
             constexpr int kBatches = kWRows;
-            uint32_t p_evsc[kBatches], p_deler[kBatches], p_misc[kBatches];
-            uint32_t wN = 0, wDel = 0, wKind = HEVCB_KIND_PASS, wErr = 0;
-#pragma unroll 1
-            for (int b = 0; b < kBatches; b++) {
-                const uint32_t slot = (uint32_t)b * 32u + (uint32_t)lane;
-                if ((uint32_t)b * 32u >= total) { break; }
-                uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu;
-                if (slot < total) {
-                    const uint32_t chunk = (uint32_t)(warp * kWRows * 32) + map[slot];
-                    const uint8_t* rp = st + kLead + chunk * 16u;
-                    const uint4 v = *reinterpret_cast<const uint4*>(rp);
-                    const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
-                    const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
-                    const uint3 m3 = analyze_interior_cold(wp, v, wn); // interior tile: no position limits
-                    evsc = m3.x; deler = m3.y; misc = m3.z;
-                }
-                p_evsc[b] = evsc; p_deler[b] = deler; p_misc[b] = misc;
-                const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
-                uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
-                if (ev != 0u) {
-                    const int tp = 31 - __clz((int)ev);
-                    lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
-                    le = ((er >> tp) >> 1) != 0u;
-                }
-                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
-                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-                wN += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sc));
-                wDel += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(del));
-                uint32_t rk, re;
-                warp_carry_total(Eb, Sb, Rb, rk, re);
-                hevcb_carry_combine(wKind, wErr, rk, re);
-            }
-            if (lane == 0) {
-                WarpAgg a;
-                a.n = wN; a.k = kWRows * kRowBytes - wDel; a.kind = wKind; a.err = wErr; a.del = wDel; a.rows = 0;
-                a.pad[0] = a.pad[1] = 0;
-                sm.waggW[s][warp] = a;
-            }
-            bar_sync(kBarW, kWThreads);
-            uint32_t rN = 0, rK = 0, rKind = HEVCB_KIND_PASS, rErr = 0, tileDel = 0;
+            // The warp aggregates of the tile are the ones the ANALYSERS left in shared memory (one per group of kARows rows; the
+            // stage is not reloaded, so they are not rewritten, before the writers release it): what lies in front of this warp's
+            // rows -- start codes, kept bytes, ordered carry -- and how many bytes the tile and this warp's rows lose are known
+            // before the warp looks at a single chunk.  The writers therefore build every exact mask once, emit straight from it,
+            // and do not wait for each other (only tiles that lose bytes keep one barrier, in front of the in-place compaction).
+            constexpr int kGroupsPerW = kWRows / kARows;
+            static_assert(kAWarps <= 32 && kWRows % kARows == 0, "one lane per analyser aggregate");
+            uint32_t rN, rK, rKind, rErr, tileDel, wDel;
+            bool moving = false;
             {
-                uint32_t tn = 0, tk = 0, ak = HEVCB_KIND_PASS, ae = 0;
-#pragma unroll
-                for (int w = 0; w < kWWarps; w++) {
-                    const WarpAgg a = sm.waggW[s][w];
-                    if (w == warp) { rN = tn; rK = tk; rKind = ak; rErr = ae; }
-                    tn += a.n;
-                    tk += a.k;
-                    hevcb_carry_combine(ak, ae, a.kind, a.err);
-                    tileDel += a.del;
+                uint32_t gn = 0, gk = 0, gkind = HEVCB_KIND_PASS, gerr = 0, gdel = 0;
+                if (lane < kAWarps) {
+                    const WarpAgg a = sm.wagg[s][lane];
+                    gn = a.n; gk = a.k; gkind = a.kind; gerr = a.err; gdel = a.del;
+                }
+                const int g0 = warp * kGroupsPerW;
+                const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, gkind != HEVCB_KIND_PASS);
+                const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, gkind == HEVCB_KIND_SC3);
+                const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, gerr != 0u);
+                warp_carry_in(Eb, Sb, Rb, g0, rKind, rErr);
+                rN = __reduce_add_sync(0xFFFFFFFFu, lane < g0 ? gn : 0u);
+                rK = __reduce_add_sync(0xFFFFFFFFu, lane < g0 ? gk : 0u);
+                tileDel = __reduce_add_sync(0xFFFFFFFFu, gdel);
+                wDel = 0;
+                if (tileDel != 0u) {
+                    static_assert(kGroupsPerW == 2, "a writer warp's rows are two analyser groups");
+                    const uint32_t pairdel = gdel + __shfl_xor_sync(0xFFFFFFFFu, gdel, 1);
+                    wDel = __shfl_sync(0xFFFFFFFFu, pairdel, g0);
+                    moving = __any_sync(0xFFFFFFFFu, pairdel > 4u); // some writer warp closes gaps in place (the same answer in every warp)
                 }
             }
             const bool write_img = (rbsp != nullptr) && !(dbg & 4u);
@@ -1192,7 +1228,7 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 for (int e = lane * 8; e < kWRows * 32; e += 256) { *reinterpret_cast<uint4*>(dm + e) = make_uint4(0u, 0u, 0u, 0u); }
                 __syncwarp();
             }
-            // pass 2: ordered emission over the ranked chunks
+            // one pass over the ranked chunks: exact masks, ordered emission
             {
                 uint32_t cKind = pref.kind, cErr = pref.err; // carry entering this warp = tile carry (+) warps before it
                 hevcb_carry_combine(cKind, cErr, rKind, rErr);
@@ -1201,9 +1237,17 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                 for (int b = 0; b < kBatches; b++) {
                     const uint32_t slot = (uint32_t)b * 32u + (uint32_t)lane;
                     if ((uint32_t)b * 32u >= total) { break; }
-                    const uint32_t evsc = p_evsc[b], deler = p_deler[b], misc = p_misc[b];
+                    uint32_t evsc = 0u, deler = 0u, misc = 0xFFFFu, local = 0u;
+                    if (slot < total) {
+                        local = (uint32_t)map[slot];
+                        const uint8_t* rp = st + kLead + ((uint32_t)(warp * kWRows * 32) + local) * 16u;
+                        const uint4 v = *reinterpret_cast<const uint4*>(rp);
+                        const uint32_t wp = *reinterpret_cast<const uint32_t*>(rp - 4);
+                        const uint32_t wn = *reinterpret_cast<const uint32_t*>(rp + 16);
+                        const uint3 m3 = analyze_interior_cold(wp, v, wn); // interior tile: no position limits
+                        evsc = m3.x; deler = m3.y; misc = m3.z;
+                    }
                     const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, del = deler & 0xFFFFu, er = deler >> 16;
-                    const uint32_t local = (slot < total) ? (uint32_t)map[slot] : 0u;
                     if (!__any_sync(0xFFFFFFFFu, (ev | er) != 0u)) {
                         // nothing to emit and no carry change in this batch (EPB-dense payload): only the removed bytes count
                         if (tileDel != 0u) {
@@ -1244,6 +1288,8 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                     if (tileDel != 0u) { drun += __shfl_sync(0xFFFFFFFFu, dinc, 31); }
                 }
             }
+            // bytes move inside the stage from here on: every writer warp must be through with its neighbours' edge bytes
+            if (write_img && moving) { bar_sync(kBarW, kWThreads); }
             if (write_img) {
                 if (tileDel == 0u) {
                     copy_tile(rbsp + tileK, st + kLead, kTileBytes, tid); // every byte kept: one shifted vector copy by all workers
@@ -1279,7 +1325,6 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
                         copy_span_any(dptr, wb + cur, (uint32_t)(kWRows * kRowBytes) - cur, lane);
                         if (tid == 0) { TSTAMP(it, 5); }
                         release_stage(&sm.freeb[s], lane);
-                        s = (s + 1 == kStages) ? 0 : s + 1;
                         continue;
                     }
                     if (compacting) {
@@ -1309,7 +1354,6 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
             }
             if (tid == 0) { TSTAMP(it, 5); }
             release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
-            s = (s + 1 == kStages) ? 0 : s + 1;
             continue;
         }
         const uint32_t myrows = (uint32_t)(pref.mask >> (warp * kWRows)) & 0xFFu;
@@ -1420,7 +1464,6 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
         if (write_rows && !dirty_out) { copy_tile(rbsp + tileK, st + kLead, tile_k, tid); }
         if (tid == 0) { TSTAMP(it, 5); }
         release_stage(&sm.freeb[s], lane); // the control warp may now reload this stage; workers do not wait
-        s = (s + 1 == kStages) ? 0 : s + 1;
     }
 }
 
@@ -1627,12 +1670,14 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         // the first tiles have no claim that would prefetch them: one bulk prefetch over that range in front of the kernel would
         // only help the first microseconds, it is left out
         unsigned long long* tdbg = nullptr;
+#ifdef HEVCB_SCAN_TIMING_BUILD
         if (getenv("HEVCB_SCAN_TIMING")) { // measurement aid: event stamps, dumped by tools/scan_timing.py through hevcb_scan_timing_dump
             if (hevcb_reserve(ctx, &ctx->scan_timing, (size_t)grid * kTimingIters * kTimingEvents * 8) != HEVCB_OK) { return HEVCB_E_NOMEM; }
             tdbg = reinterpret_cast<unsigned long long*>(ctx->scan_timing.p);
             HEVCB_CUDA(ctx, cudaMemsetAsync(tdbg, 0, (size_t)grid * kTimingIters * kTimingEvents * 8, stream));
             ctx->scan_timing_ctas = (int)grid;
         }
+#endif
         void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg, (void*)&tdbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));

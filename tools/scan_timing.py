@@ -1,5 +1,6 @@
 """Measurement aid: event stamps of the scan pipeline (HEVCB_SCAN_TIMING): per CTA and tile: 0 load issued, 1 tile seen by the
-analysers, 6 analyser warp 0 done, 2 aggregate published, 3 prefix arrived, 4 writers start, 5 writers done.  Prints latencies."""
+analysers, 6 analyser warp 0 done, 2 aggregate published, 3 prefix arrived, 4 writers start, 5 writers done.  Prints latencies.
+Needs a library built with the stamps compiled in: make -C hevcbitstream_b200/csrc clean all EXTRA=-DHEVCB_SCAN_TIMING_BUILD."""
 import ctypes as C
 import os
 import sys
