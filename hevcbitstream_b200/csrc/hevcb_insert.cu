@@ -905,6 +905,8 @@ struct __align__(16) FusedSmem {
     long long size[kFWarps];
     long long excl;
     long long ticket;
+    long long n_items, n_tiles; // (kept here rather than in registers: see the note on the kernel's register budget)
+    uint4 meta[kFWarps];        // per warp: what the write phase needs of the item (NAL, raw length, flags), parked across the prefix wait
 };
 
 __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const AssembleParts P, int64_t n, const int64_t* __restrict__ first,
@@ -915,10 +917,13 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
     extern __shared__ __align__(128) uint8_t fsm_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fsm_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
-    if (n_items > cap_items) { return; } // only when the sources alone exceed out_cap: the summary kernel reports the plain sizes
-    const int64_t n_tiles = (n_items + kFWarps - 1) / kFWarps;
-    if (!persistent && (int64_t)blockIdx.x > n_tiles) { return; } // one tile per CTA: n_tiles workers and the scanner
+    {
+        const int64_t n_items = (int64_t)((unsigned long long)first[n] >> kItemShift);
+        if (n_items > cap_items) { return; } // only when the sources alone exceed out_cap: the summary kernel reports the plain sizes
+        const int64_t n_tiles = (n_items + kFWarps - 1) / kFWarps;
+        if (!persistent && (int64_t)blockIdx.x > n_tiles) { return; } // one tile per CTA: n_tiles workers and the scanner
+        if (threadIdx.x == 0) { sm.n_items = n_items; sm.n_tiles = n_tiles; } // (read after the first __syncthreads of the loop)
+    }
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sm.bar[warp])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -937,26 +942,25 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
     }
     __syncthreads();
     if (sm.ticket == 0) {
-        fused_scanner(tile_state, tile_excl, n_tiles, reinterpret_cast<volatile ulonglong2*>(sm.piece[0]), warp, lane, out_off + n);
+        fused_scanner(tile_state, tile_excl, sm.n_tiles, reinterpret_cast<volatile ulonglong2*>(sm.piece[0]), warp, lane, out_off + n);
         return;
     }
-    const int64_t t = sm.ticket - 1;
-    if (t >= n_tiles) { return; }
-    const int64_t item = t * kFWarps + warp;
-    const bool active = item < n_items;
-    // ---- what this warp's item is
+    if (sm.ticket - 1 >= sm.n_tiles) { return; }
+    const int64_t item = (sm.ticket - 1) * kFWarps + warp;
+    const bool active = item < sm.n_items;
+    // ---- what this warp's item is.  (Everything that lives across the count, the wait for the prefix and the write is 32 bits wide
+    // and the tile index stays in shared memory: at 42 registers per thread -- six CTAs per SM -- the 64-bit positions of the
+    // descriptor used to live on the stack, and with the SM's L1 carved out as shared memory those loads go to L2.)
     enum { kNone = 0, kRaw = 1, kEsc = 2 };
     int kind = kNone;
     bool first_item = false, nal_skipped = false;
-    int64_t k = 0, s0 = 0, p0 = 0, p1 = 0, nbytes_raw = 0;
-    const uint8_t* base = nullptr;
-    uint32_t run_m = 0;
+    int k = 0, q0 = 0, q1 = 0; // NAL; the piece inside its shared-memory window [q0, q1)
+    uint32_t run_m = 0, nbytes_raw = 0;
     uint8_t* const sp = sm.piece[warp];
     if (active) {
         const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&items[item])), d1 = __ldg(reinterpret_cast<const uint4*>(&items[item]) + 1);
-        s0 = (int64_t)(((unsigned long long)d0.y << 32) | d0.x);
-        p0 = s0 + (int32_t)d0.z;
-        p1 = p0 + (int32_t)d0.w;
+        q0 = (int32_t)d0.z;
+        q1 = q0 + (int32_t)d0.w;
         k = (int32_t)d1.x;
         const uint32_t fl = d1.y;
         run_m = d1.z;
@@ -965,11 +969,12 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
         nal_skipped = (fl & 8u) != 0u;
         const uint32_t ik = fl & 3u;
         kind = (ik == kItemNone) ? kNone : (ik == kItemRaw ? kRaw : kEsc);
-        base = (ik == kItemRaw) ? P.raw_base : (ik == kItemEscA ? P.a_base : P.b_base);
-        if (kind != kNone && p1 <= p0) { kind = kNone; }
+        if (kind != kNone && q1 <= q0) { kind = kNone; }
         if (kind != kNone) {
-            const uint32_t bytes = (uint32_t)(((p1 + 15) & ~(int64_t)15) - s0);
+            const uint32_t bytes = (uint32_t)((q1 + 15) & ~15);
             if (lane == 0) {
+                const int64_t s0 = (int64_t)(((unsigned long long)d0.y << 32) | d0.x);
+                const uint8_t* base = (ik == kItemRaw) ? P.raw_base : (ik == kItemEscA ? P.a_base : P.b_base);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sm.bar[warp])), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sp)), "l"(base + s0),
                              "r"(bytes), "r"(smem_addr(&sm.bar[warp]))
@@ -985,9 +990,8 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
     }
     // ---- count
     const bool writes_prefix = active && first_item && !nal_skipped;
-    long long size = 0;
+    int size = 0;
     uint32_t fastmask = 0, n_ins = 0;
-    const int q0 = (int)(p0 - s0), q1 = (int)(p1 - s0); // the piece inside its shared-memory window (32-bit positions from here on)
     const int rows = (kind != kNone) ? ((q1 + 511) >> 9) : 0;
     if (kind == kEsc) {
         int r = 0;
@@ -1032,18 +1036,22 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
             else { n_ins += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(ri.ins)); }
             r++;
         }
-        size = (p1 - p0) + (long long)n_ins;
+        size = (q1 - q0) + (int)n_ins;
     } else if (kind == kRaw) {
-        size = p1 - p0;
+        size = q1 - q0;
     }
     if (writes_prefix) { size += P.sc_len + P.len_size; }
-    if (lane == 0) { sm.size[warp] = size; }
+    if (lane == 0) {
+        sm.size[warp] = size;
+        sm.meta[warp] = make_uint4((uint32_t)k, nbytes_raw, (first_item ? 1u : 0u) | (writes_prefix ? 2u : 0u), 0u);
+    }
     __syncthreads();
     // ---- the tile's output offset: the aggregate goes to the scanner CTA, which answers with the exclusive prefix
     if (threadIdx.x == 0) {
         long long total = 0;
 #pragma unroll
         for (int w = 0; w < kFWarps; w++) { total += sm.size[w]; }
+        const int64_t t = sm.ticket - 1;
         st_relaxed_u64(&tile_state[t], (1ull << 62) | (unsigned long long)total);
         unsigned long long e;
         while (((e = ld_relaxed_u64(&tile_excl[t])) >> 62) == 0ull) { __nanosleep(32); }
@@ -1052,14 +1060,16 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
     __syncthreads();
     long long o = sm.excl;
     for (int w = 0; w < warp; w++) { o += sm.size[w]; }
-    if (active && first_item && lane == 0) { out_off[k] = o; }
+    const uint4 meta = sm.meta[warp]; // (an inactive warp parked zeros: no NAL offset, no prefix, kind none, size 0)
+    if ((meta.z & 1u) && lane == 0) { out_off[(int32_t)meta.x] = o; }
     if (n_ins && lane == 0) { atomicAdd(&hdr->n_ins, (unsigned long long)n_ins); }
-    if (active && o + size <= out_cap) { // (capacity overflow is reported by the summary)
-        if (writes_prefix) {
+    if (kind != kNone || (meta.z & 2u)) {
+      if (o + sm.size[warp] <= out_cap) { // (capacity overflow is reported by the summary)
+        if (meta.z & 2u) {
             if (lane < P.sc_len) { out[o + lane] = (lane == P.sc_len - 1) ? 1 : 0; }
             o += P.sc_len;
             if (P.len_size) { // big-endian length of what follows (verbatim NALs only: the launcher keeps escaped parts off this path)
-                if (lane < P.len_size) { out[o + lane] = (uint8_t)((uint64_t)nbytes_raw >> (8 * (P.len_size - 1 - lane))); }
+                if (lane < P.len_size) { out[o + lane] = (uint8_t)((uint64_t)meta.y >> (8 * (P.len_size - 1 - lane))); }
                 o += P.len_size;
             }
         }
@@ -1085,6 +1095,7 @@ __global__ void __launch_bounds__(kFThreads, 6) fused_assemble_kernel(const Asse
                 r++;
             }
         }
+      }
     }
     if (!persistent) { return; }
     __syncthreads(); // the pieces, sizes and the ticket word are rewritten by the next round
