@@ -275,3 +275,63 @@ def test_sparse_patterns_in_random_payload(ctx, seed):
     res.rbsp_end = res.rbsp_end[:n].cpu().numpy()
     util.compare_scan(buf, size, res, res.rbsp.cpu().numpy(), tag=f"sparse{seed}")
     assert n > 300
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_removed_bytes_unevenly_spread_over_a_tile(ctx, seed):
+    """Tiles whose 4 KiB row groups (one writer warp each) lose very different numbers of bytes: none, one to four (the kept runs go out
+    as separate copies), many (the gaps are closed in place, behind the writers' barrier), with start codes and error patterns in
+    between.  The writers take the per-group counts and carries from the analysers' aggregates: every mix must reproduce the oracle."""
+    rng = np.random.default_rng(1700 + seed)
+    size = 12 << 20
+    x = rng.integers(4, 256, size).astype(np.uint8)
+    group = 4096
+    last = 0
+
+    def put(p, pat):
+        nonlocal last
+        if p < last + 8 or p + len(pat) > size - 64:
+            return
+        x[p: p + len(pat)] = pat
+        last = p + len(pat)
+
+    for g in range(size // group):
+        kind = int(rng.integers(0, 8))
+        base = g * group
+        if kind == 0:
+            continue  # a clean group
+        if kind in (1, 2):  # a few removed bytes
+            for _ in range(int(rng.integers(1, 5))):
+                put(base + int(rng.integers(0, group - 16)), [0, 0, 3, int(rng.integers(0, 4))])
+        elif kind in (3, 4):  # many removed bytes: 00 00 03 01 back to back over part of the group
+            lo = base + int(rng.integers(0, group // 2))
+            n = int(rng.integers(8, 300))
+            for i in range(n):
+                put(lo + 4 * i + (8 if i == 0 else 0), [0, 0, 3, 1])
+        elif kind == 5:  # start codes (short NALs) and a removed byte
+            p = base + int(rng.integers(0, 64))
+            while p < base + group - 80:
+                put(p, [0, 0, 1, 0x26, 1])
+                p += int(rng.integers(40, 400))
+            put(base + group - 40, [0, 0, 3, 2])
+        elif kind == 6:  # nal_to_rbsp error patterns inside a NAL, removed bytes around them
+            put(base + 100, [0, 0, 1, 0x40, 1])
+            put(base + 300, [0, 0, 3, 0, 0, 3, 1])
+            put(base + 900, [0, 0, 2])
+            put(base + 1500, [0, 0, 3, 200])
+            put(base + 2500, [0, 0, 0, 1, 0x42, 1])
+        else:  # patterns straddling the group's edges (rows of neighbouring writer warps)
+            put(base + group - 2, [0, 0, 3, 1, 0, 0, 3, 1])
+            put(base + 2046, [0, 0, 3, 0, 0, 1, 0x26])
+    buf = util.padded(x)
+    import torch
+
+    d = torch.from_numpy(buf[:size].copy()).cuda()
+    res = ctx.scan_strip_device(d, size=size)
+    n = res.n_nals
+    res.nal_start = res.nal_start[:n].cpu().numpy()
+    res.nal_end = res.nal_end[:n].cpu().numpy()
+    res.rbsp_off = res.rbsp_off[:n].cpu().numpy()
+    res.rbsp_end = res.rbsp_end[:n].cpu().numpy()
+    util.compare_scan(buf, size, res, res.rbsp.cpu().numpy(), tag=f"uneven{seed}")
+    assert n > 1000

@@ -19,6 +19,9 @@ def report(ctx):
     L.hevcb_scan_timing_dump.restype = C.c_int64
     L.hevcb_scan_timing_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     n = L.hevcb_scan_timing_dump(ctx._h, None, 0)
+    if n == 0:
+        print("no event stamps: build the library with make -C hevcbitstream_b200/csrc clean all EXTRA=-DHEVCB_SCAN_TIMING_BUILD")
+        return
     buf = np.zeros(n, np.uint64)
     L.hevcb_scan_timing_dump(ctx._h, buf.ctypes.data_as(C.c_void_p), n)
     T = buf.reshape(-1, 256, 8).astype(np.int64)
