@@ -1467,9 +1467,21 @@ __global__ void __launch_bounds__(kThreads, HEVCB_SCAN_CTAS) hevcb_scan_strip_ke
     }
 }
 
-// Emit pass: NAL boundaries of the tiles whose event chunks the analysers left as records (one warp per tile, one lane per
-// record).  Records are in arrival order: they are ranked by chunk index, then the lanes run the same ordered-carry logic
-// a row of the writer runs.  Tiles of that kind keep all their bytes, so a chunk's image offset is prefix + chunk * 16.
+// Emit pass: NAL boundaries of the tiles whose event chunks the analysers left as records.  Records are in arrival order: they are
+// ranked by chunk index, then walked with the same ordered-carry logic a row of the writer runs.  Tiles of that kind keep all their
+// bytes, so a chunk's image offset is prefix + chunk * 16.
+// A warp looks after kEmitTilesPerWarp consecutive tiles.  A tile with at most kEmitSerial records -- every tile of a stream of large NALs: a 32 KiB
+// tile of 16 KiB NALs holds two start codes -- is walked by ONE THREAD (a sorting network over registers, then hevcb_chunk_emit
+// record by record), the warp's tiles side by side.  (One warp per tile, ranking by 32 shuffles and emitting with ballots and scans,
+// cost ~500 instructions per tile whatever the record count: 105 us for the 131 072 tiles of the 4 GiB headline stream, 7 % of the
+// step.)  Tiles with more records are then taken one at a time by the whole warp, one lane per record.
+constexpr int kEmitSerial = 4;
+constexpr int kEmitTilesPerWarp = 4; // (not 32: the tiles with many records of a warp are taken one after the other, and the grid must still fill the GPU)
+constexpr int kEmitTilesPerBlock = 8 * kEmitTilesPerWarp;
+__device__ __forceinline__ void rec_cswap(uint4& a, uint4& b)
+{
+    if (b.x < a.x) { const uint4 t = a; a = b; b = t; }
+}
 __global__ void __launch_bounds__(256) hevcb_scan_emit_kernel(long long n_tiles, ScanHeader* __restrict__ hdr, const ulonglong2* __restrict__ tile_state,
                                                               const ulonglong2* __restrict__ tile_excl, const uint4* __restrict__ tile_events,
                                                               int64_t* __restrict__ nal_start, int64_t* __restrict__ nal_end, int64_t cap_nals,
@@ -1477,70 +1489,118 @@ __global__ void __launch_bounds__(256) hevcb_scan_emit_kernel(long long n_tiles,
 {
     __shared__ uint4 sorted[8][kEvCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long t = (long long)blockIdx.x * 8 + warp;
-    if (t >= n_tiles) { return; }
-    const ulonglong2 ag = tile_state[t];
-    const uint32_t nrec = agg_records(ag);
-    if (nrec == 0u || nrec == kEvByWriter) { return; }
-    const ulonglong2 ex = tile_excl[t];
-    const long long tileN = (long long)(ex.x & ((1ull << 40) - 1)), tileK = (long long)ex.y;
-    const uint32_t pKind = (uint32_t)(ex.x >> 60) & 3u, pErr = (uint32_t)(ex.x >> 59) & 1u;
-    // rank by chunk index (distinct per record); lane l holds records l, l + 32, l + 64, ...
-    constexpr int kPerLane = (int)(kEvCap / 32);
-    uint4 rec_[kPerLane];
-    uint32_t rank_[kPerLane];
+    const long long first_tile = ((long long)blockIdx.x * 8 + warp) * kEmitTilesPerWarp;
+    if (first_tile >= n_tiles) { return; }
+    DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
+    uint32_t my_nrec = 0;
+    {
+        const long long t = first_tile + lane;
+        if (lane < kEmitTilesPerWarp && t < n_tiles) {
+            my_nrec = agg_records(tile_state[t]);
+            if (my_nrec == kEvByWriter) { my_nrec = 0u; }
+        }
+        if (my_nrec != 0u && my_nrec <= (uint32_t)kEmitSerial) {
+            const ulonglong2 ex = tile_excl[t];
+            long long nbase = (long long)(ex.x & ((1ull << 40) - 1));
+            const long long tileK = (long long)ex.y;
+            uint32_t cKind = (uint32_t)(ex.x >> 60) & 3u, cErr = (uint32_t)(ex.x >> 59) & 1u;
+            uint4 rec[kEmitSerial];
 #pragma unroll
-    for (int q = 0; q < kPerLane; q++) {
-        rec_[q] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu);
-        rank_[q] = 0;
-        if ((uint32_t)(q * 32 + lane) < nrec) { rec_[q] = tile_events[(size_t)t * kEvCap + q * 32 + lane]; }
-    }
+            for (int q = 0; q < kEmitSerial; q++) {
+                rec[q] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu); // (sorts behind every record)
+                if ((uint32_t)q < my_nrec) { rec[q] = tile_events[(size_t)t * kEvCap + q]; }
+            }
+            static_assert(kEmitSerial == 4, "the sorting network below is for four records");
+            rec_cswap(rec[0], rec[1]); rec_cswap(rec[2], rec[3]); rec_cswap(rec[0], rec[2]); rec_cswap(rec[1], rec[3]); rec_cswap(rec[1], rec[2]);
 #pragma unroll
-    for (int p = 0; p < kPerLane; p++) {
-        if ((uint32_t)(p * 32) < nrec) { // warp-uniform: slots beyond the record count hold nothing
-#pragma unroll 4
-            for (int i = 0; i < 32; i++) {
-                const uint32_t other = __shfl_sync(0xFFFFFFFFu, rec_[p].x, i);
-#pragma unroll
-                for (int q = 0; q < kPerLane; q++) { rank_[q] += (other < rec_[q].x) ? 1u : 0u; }
+            for (int q = 0; q < kEmitSerial; q++) {
+                if ((uint32_t)q < my_nrec) {
+                    const uint32_t evsc = rec[q].y, deler = rec[q].z, misc = rec[q].w;
+                    const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
+                    if ((ev | er) != 0u) {
+                        const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec[q].x * 16;
+                        emit_cold(evsc, deler, misc, g0, (int64_t)nbase, (int64_t)(tileK + (long long)rec[q].x * 16), cKind, cErr, sink);
+                    }
+                    uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u); // the chunk's summary for the ordered carry
+                    if (ev != 0u) {
+                        const int tp = 31 - __clz((int)ev);
+                        lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                        le = ((er >> tp) >> 1) != 0u;
+                    }
+                    hevcb_carry_combine(cKind, cErr, lk, le);
+                    nbase += (long long)__popc(sc);
+                }
             }
         }
     }
+    // tiles with more records: one at a time, one lane per record
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, my_nrec > (uint32_t)kEmitSerial);
+    while (todo != 0u) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const long long t = first_tile + src;
+        const uint32_t nrec = __shfl_sync(0xFFFFFFFFu, my_nrec, src);
+        const ulonglong2 ex = tile_excl[t];
+        const long long tileN = (long long)(ex.x & ((1ull << 40) - 1)), tileK = (long long)ex.y;
+        const uint32_t pKind = (uint32_t)(ex.x >> 60) & 3u, pErr = (uint32_t)(ex.x >> 59) & 1u;
+        // rank by chunk index (distinct per record); lane l holds records l, l + 32, l + 64, ...
+        constexpr int kPerLane = (int)(kEvCap / 32);
+        uint4 rec_[kPerLane];
+        uint32_t rank_[kPerLane];
 #pragma unroll
-    for (int q = 0; q < kPerLane; q++) {
-        if ((uint32_t)(q * 32 + lane) < nrec) { sorted[warp][rank_[q]] = rec_[q]; }
-    }
-    __syncwarp();
-    uint32_t cKind = pKind, cErr = pErr; // carry entering the round
-    long long nbase = tileN;
-    DevSink sink{nal_start, nal_end, rbsp_off, rbsp_end, cap_nals, &hdr->first_empty};
-    for (uint32_t base = 0; base < nrec; base += 32) {
-        uint4 rec = make_uint4(0u, 0u, 0u, 0xFFFFu);
-        if (base + (uint32_t)lane < nrec) { rec = sorted[warp][base + lane]; }
-        const uint32_t evsc = rec.y, deler = rec.z, misc = rec.w;
-        const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
-        uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
-        if (ev != 0u) {
-            const int tp = 31 - __clz((int)ev);
-            lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
-            le = ((er >> tp) >> 1) != 0u;
+        for (int q = 0; q < kPerLane; q++) {
+            rec_[q] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0xFFFFu);
+            rank_[q] = 0;
+            if ((uint32_t)(q * 32 + lane) < nrec) { rec_[q] = tile_events[(size_t)t * kEvCap + q * 32 + lane]; }
         }
-        const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
-        const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
-        const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
-        uint32_t ck, ce;
-        warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
-        if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the round
-        const uint32_t c = (uint32_t)__popc(sc);
-        const uint32_t ninc = warp_incl_scan(c, lane);
-        if ((ev | er) != 0u) {
-            const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec.x * 16;
-            emit_cold(evsc, deler, misc, g0, (int64_t)(nbase + (ninc - c)), (int64_t)(tileK + (long long)rec.x * 16), ck, ce, sink);
+#pragma unroll
+        for (int p = 0; p < kPerLane; p++) {
+            if ((uint32_t)(p * 32) < nrec) { // warp-uniform: slots beyond the record count hold nothing
+                const int cnt = (int)(nrec - (uint32_t)(p * 32) < 32u ? nrec - (uint32_t)(p * 32) : 32u);
+#pragma unroll 4
+                for (int i = 0; i < cnt; i++) {
+                    const uint32_t other = __shfl_sync(0xFFFFFFFFu, rec_[p].x, i);
+#pragma unroll
+                    for (int q = 0; q < kPerLane; q++) { rank_[q] += (other < rec_[q].x) ? 1u : 0u; }
+                }
+            }
         }
-        uint32_t rk, re;
-        warp_carry_total(Eb, Sb, Rb, rk, re);
-        hevcb_carry_combine(cKind, cErr, rk, re);
-        nbase += __shfl_sync(0xFFFFFFFFu, ninc, 31);
+#pragma unroll
+        for (int q = 0; q < kPerLane; q++) {
+            if ((uint32_t)(q * 32 + lane) < nrec) { sorted[warp][rank_[q]] = rec_[q]; }
+        }
+        __syncwarp();
+        uint32_t cKind = pKind, cErr = pErr; // carry entering the round
+        long long nbase = tileN;
+        for (uint32_t base = 0; base < nrec; base += 32) {
+            uint4 rec = make_uint4(0u, 0u, 0u, 0xFFFFu);
+            if (base + (uint32_t)lane < nrec) { rec = sorted[warp][base + lane]; }
+            const uint32_t evsc = rec.y, deler = rec.z, misc = rec.w;
+            const uint32_t ev = evsc & 0xFFFFu, sc = evsc >> 16, er = deler >> 16;
+            uint32_t lk = HEVCB_KIND_PASS, le = (er != 0u);
+            if (ev != 0u) {
+                const int tp = 31 - __clz((int)ev);
+                lk = ((sc >> tp) & 1u) ? HEVCB_KIND_SC3 : HEVCB_KIND_Z3;
+                le = ((er >> tp) >> 1) != 0u;
+            }
+            const uint32_t Eb = __ballot_sync(0xFFFFFFFFu, ev != 0u);
+            const uint32_t Sb = __ballot_sync(0xFFFFFFFFu, lk == HEVCB_KIND_SC3);
+            const uint32_t Rb = __ballot_sync(0xFFFFFFFFu, le != 0u);
+            uint32_t ck, ce;
+            warp_carry_in(Eb, Sb, Rb, lane, ck, ce);
+            if (ck == HEVCB_KIND_PASS) { ck = cKind; ce |= cErr; } // inherit the carry entering the round
+            const uint32_t c = (uint32_t)__popc(sc);
+            const uint32_t ninc = warp_incl_scan(c, lane);
+            if ((ev | er) != 0u) {
+                const int64_t g0 = (int64_t)t * kTileBytes + (int64_t)rec.x * 16;
+                emit_cold(evsc, deler, misc, g0, (int64_t)(nbase + (ninc - c)), (int64_t)(tileK + (long long)rec.x * 16), ck, ce, sink);
+            }
+            uint32_t rk, re;
+            warp_carry_total(Eb, Sb, Rb, rk, re);
+            hevcb_carry_combine(cKind, cErr, rk, re);
+            nbase += __shfl_sync(0xFFFFFFFFu, ninc, 31);
+        }
+        __syncwarp(); // sorted[warp] is rewritten for the warp's next tile
     }
 }
 
@@ -1681,7 +1741,7 @@ static int launch_scan_common(hevcb_ctx* ctx, const uint8_t* d_buf, const ScanGe
         void* args[] = {(void*)&d_buf, (void*)&g, (void*)&nt, (void*)&hdr, (void*)&states, (void*)&excl, (void*)&events, (void*)&d_nal_start, (void*)&d_nal_end,
                         (void*)&cap_nals, (void*)&d_rbsp, (void*)&d_rbsp_off, (void*)&d_rbsp_end, (void*)&dbg, (void*)&tdbg};
         HEVCB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)hevcb_scan_strip_kernel, dim3((unsigned)grid), dim3(kThreads), args, smem, stream));
-        hevcb_scan_emit_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, stream>>>(n_tiles, hdr, states, excl, events, d_nal_start, d_nal_end, cap_nals,
+        hevcb_scan_emit_kernel<<<(unsigned)((n_tiles + kEmitTilesPerBlock - 1) / kEmitTilesPerBlock), 256, 0, stream>>>(n_tiles, hdr, states, excl, events, d_nal_start, d_nal_end, cap_nals,
                                                                                  d_rbsp_off, d_rbsp_end);
         ctx->launches += 2;
         HEVCB_CUDA(ctx, cudaGetLastError());
