@@ -117,7 +117,7 @@ struct __align__(16) SmemLayout {
     unsigned long long aggmask[kStages]; // rows of the tile that need exact treatment by the writers (0: clean or handed over as records)
     uint32_t evcount[kStages];         // event records the analysers wrote for the tile in the stage
     WarpAgg wagg[kStages][kAWarps];    // analysers: per-warp aggregates of the tile in a stage
-    WarpAgg waggW[kStages][kWWarps];   // writers: the same for tiles they analyse themselves
+    WarpAgg waggW[kStages][kWWarps];   // writers: the same for the tiles at the edges of the byte range (interior tiles: wagg)
     TilePrefix pref[kStages];          // prefix + row mask of the tile in a stage
     uint8_t slowmapA[kAWarps][kARows * 32]; // analyser warp: its chunks that need exact analysis, in stream order
     uint8_t slowmapW[kWWarps][kWRows * 32]; // writer warp: the same
